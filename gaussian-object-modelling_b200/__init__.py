@@ -1,0 +1,304 @@
+"""gaussian-object-modelling_b200 — B200-native GP-regression core (hot path of
+pacman-project/gaussian-object-modelling, include/gp_regression).
+
+The product is ``libgpr_b200.so`` (hand-written sm_100a CUDA behind the C-ABI in include/gpr_c_api.h)
+plus the C++ drop-in headers in include/gp_regression/.  This Python module is only the ctypes binding
+that tests/ and bench.py use to call the C-ABI; it mirrors the reference's regressor interface
+(create / evaluate / update over Data-like SoA arrays, gp_regressor.hpp:110,:194-357,:367) and its error
+behaviour.  It never computes anything itself and never imports the CPU oracle: if the CUDA library is
+missing or no GPU is usable, calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpr_b200.so")
+INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
+
+KINDS = {"thin_plate": 0, "gaussian": 1, "laplace": 2}
+GPR_OK, GPR_ERR_INVALID, GPR_ERR_NOT_SPD, GPR_ERR_CUDA, GPR_ERR_OOM = range(5)
+
+_dp = C.POINTER(C.c_double)
+
+
+class GPRegressionException(Exception):
+    """Counterpart of gp_regression::GPRegressionException (gp_regression_exception.h:9-17)."""
+
+    def __init__(self, message, code=GPR_ERR_INVALID, pivot=0):
+        super().__init__(message)
+        self.code = code
+        self.pivot = pivot
+
+
+class KernelT(C.Structure):
+    _fields_ = [("kind", C.c_int), ("p0", C.c_double), ("p1", C.c_double)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "cov_ms", "chol_ms", "solve_ms", "normals_ms", "fit_total_ms", "linv_ms",
+        "predict_mean_ms", "predict_var_ms", "predict_total_ms", "h2d_ms", "d2h_ms")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class ModelState(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("padded_n", C.c_size_t), ("kernel", KernelT), ("R", C.c_double),
+                ("xyz", C.c_void_p), ("alpha", C.c_void_p), ("linv", C.c_void_p)]
+
+
+def build(force=False):
+    """Compile libgpr_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    csrc = os.path.join(_HERE, "csrc")
+    cmd = ["make", "-C", csrc, "-j8"] + (["-B"] if force else [])
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it was not built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libgpr_b200.so is missing (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, sz, ci, cd = C.c_void_p, C.c_size_t, C.c_int, C.c_double
+        L.gpr_ctx_create.argtypes = [C.POINTER(ci), ci, C.POINTER(vp)]
+        L.gpr_ctx_destroy.argtypes = [vp]
+        L.gpr_ctx_num_devices.argtypes = [vp]
+        L.gpr_last_error.restype = C.c_char_p
+        L.gpr_last_pivot.restype = C.c_longlong
+        L.gpr_last_timings.argtypes = [vp, C.POINTER(Timings)]
+        L.gpr_fit.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, sz, KernelT, ci, C.POINTER(vp)]
+        L.gpr_model_destroy.argtypes = [vp]
+        L.gpr_model_size.argtypes = [vp]
+        L.gpr_model_size.restype = sz
+        L.gpr_model_get.argtypes = [vp, _dp, _dp, _dp]
+        L.gpr_model_get_factor.argtypes = [vp, _dp]
+        L.gpr_predict.argtypes = [vp, vp, _dp, _dp, _dp, sz, _dp, _dp, _dp, _dp, _dp]
+        L.gpr_predict_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
+        L.gpr_model_prepare_variance.argtypes = [vp, vp]
+        L.gpr_append.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, sz]
+        L.gpr_model_state_get.argtypes = [vp, vp, ci, C.POINTER(ModelState)]
+        L.gpr_model_create_replica.argtypes = [vp, sz, KernelT, cd, ci, C.POINTER(vp)]
+        L.gpr_selftest_gemm.argtypes = [_dp, _dp, ci, _dp, ci, ci, ci]
+        L.gpr_selftest_leaf.argtypes = [_dp, _dp, C.POINTER(ci)]
+        L.gpr_selftest_factor.argtypes = [_dp, ci, _dp, ci, C.POINTER(C.c_longlong)]
+        L.gpr_selftest_peak.argtypes = [ci, ci, _dp]
+        _lib = L
+    return _lib
+
+
+# Every symbol include/gpr_c_api.h declares (checked by the CPU test-suite without a GPU).
+C_ABI_SYMBOLS = [
+    "gpr_ctx_create", "gpr_ctx_destroy", "gpr_ctx_num_devices", "gpr_last_error", "gpr_last_pivot",
+    "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_get",
+    "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
+    "gpr_model_state_get", "gpr_model_create_replica", "gpr_selftest_gemm", "gpr_selftest_leaf",
+    "gpr_selftest_factor", "gpr_selftest_peak",
+]
+
+
+def _check(rc):
+    if rc != GPR_OK:
+        L = lib()
+        raise GPRegressionException(L.gpr_last_error().decode(), rc, L.gpr_last_pivot() if rc == GPR_ERR_NOT_SPD else 0)
+
+
+def _arr(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class Context:
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(lib().gpr_ctx_create(arr, len(devices), C.byref(self._h)))
+        else:
+            _check(lib().gpr_ctx_create(None, 0, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().gpr_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_devices(self):
+        return lib().gpr_ctx_num_devices(self._h)
+
+    def timings(self):
+        t = Timings()
+        _check(lib().gpr_last_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+
+class Model:
+    """Handle on a fitted model (gp_regression::Model, gp_regressor.hpp:71-87)."""
+
+    def __init__(self, ctx, handle, with_normals=False):
+        self.ctx, self._h, self.with_normals = ctx, handle, with_normals
+
+    def close(self):
+        if self._h:
+            lib().gpr_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n(self):
+        return lib().gpr_model_size(self._h)
+
+    def get(self):
+        n = self.n
+        alpha, R = np.zeros(n), C.c_double()
+        N = np.zeros((n, 3), order="F") if self.with_normals else None
+        _check(lib().gpr_model_get(self._h, _p(alpha), C.byref(R), _p(N)))
+        return {"alpha": alpha, "R": R.value, "normals": None if N is None else np.ascontiguousarray(N)}
+
+    @property
+    def alpha(self):
+        return self.get()["alpha"]
+
+    @property
+    def R(self):
+        return self.get()["R"]
+
+    def factor(self):
+        n = self.n
+        Lm = np.zeros((n, n), order="F")
+        _check(lib().gpr_model_get_factor(self._h, _p(Lm)))
+        return Lm
+
+    def state(self, with_linv=False):
+        s = ModelState()
+        _check(lib().gpr_model_state_get(self.ctx._h, self._h, int(with_linv), C.byref(s)))
+        return s
+
+
+class GPRegressor:
+    """Python mirror of gp_regression::GPRegressor<CovType> (gp_regressor.hpp:92-574) over the C-ABI.
+
+    kernel: 'thin_plate' (R), 'gaussian' (sigma, length) or 'laplace' (sigma, length); the defaults
+    are the reference's default constructors (R=1; sigma=length=1)."""
+
+    def __init__(self, kernel="thin_plate", p0=1.0, p1=1.0, ctx=None):
+        self.ctx = ctx or Context()
+        self.set_cov_function(kernel, p0, p1)
+
+    def set_cov_function(self, kernel, p0=1.0, p1=1.0):          # setCovFunction, :488-491
+        self.kernel = KernelT(KINDS[kernel], float(p0), float(p1))
+
+    def create(self, x, y, z, label, sigma2=None, with_normals=False):   # create<withNormals>, :110-182
+        if x is None:
+            raise GPRegressionException("Empty data pointer")
+        x, y, z, label, sigma2 = map(_arr, (x, y, z, label, sigma2))
+        if len(x) == 0 and len(y) == 0 and len(z) == 0 and len(label) == 0:
+            raise GPRegressionException("All input data is empty!")
+        h = C.c_void_p()
+        _check(lib().gpr_fit(self.ctx._h, _p(x), _p(y), _p(z), _p(label), _p(sigma2), len(x), self.kernel,
+                             int(with_normals), C.byref(h)))
+        return Model(self.ctx, h, with_normals)
+
+    def evaluate(self, model, qx, qy, qz, var=False, grad=False, tangent=False, label=None):
+        """The four evaluate overloads (:194, :222, :282, :332): returns f[, v[, N[, Tx, Ty]]]."""
+        if model is None or not model._h:
+            raise GPRegressionException("Empty Model pointer")
+        if qx is None:
+            raise GPRegressionException("Empty data pointer")
+        if label is not None and len(label):
+            raise GPRegressionException("Query is already labeled!")
+        qx, qy, qz = map(_arr, (qx, qy, qz))
+        q = len(qx)
+        if q == 0:
+            raise GPRegressionException("All input data is empty!")
+        grad = grad or tangent
+        f = np.zeros(q)
+        v = np.zeros(q) if var else None
+        g, tx, ty = (np.zeros((q, 3), order="F") if c else None for c in (grad, tangent, tangent))
+        _check(lib().gpr_predict(self.ctx._h, model._h, _p(qx), _p(qy), _p(qz), q, _p(f), _p(v), _p(g), _p(tx), _p(ty)))
+        out = [f]
+        if var:
+            out.append(v)
+        if grad:
+            out.append(np.ascontiguousarray(g))
+        if tangent:
+            out += [np.ascontiguousarray(tx), np.ascontiguousarray(ty)]
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def update(self, model, x, y, z, label, sigma2=None):        # update<withNormals>, :367-479
+        if model is None or not model._h:
+            raise GPRegressionException("Empty model pointer")
+        x, y, z, label, sigma2 = map(_arr, (x, y, z, label, sigma2))
+        _check(lib().gpr_append(self.ctx._h, model._h, _p(x), _p(y), _p(z), _p(label), _p(sigma2), len(x)))
+
+    def prepare_variance(self, model):
+        _check(lib().gpr_model_prepare_variance(self.ctx._h, model._h))
+
+    def evaluate_device(self, model, d_qx, d_qy, d_qz, q, d_f, d_var=None, d_grad=None):
+        """Device-pointer variant (ints from tensor.data_ptr()); no host copies."""
+        _check(lib().gpr_predict_device(self.ctx._h, model._h, d_qx, d_qy, d_qz, q, d_f, d_var, d_grad))
+
+    def create_replica(self, n, R, with_linv):
+        h = C.c_void_p()
+        _check(lib().gpr_model_create_replica(self.ctx._h, n, self.kernel, float(R), int(with_linv), C.byref(h)))
+        return Model(self.ctx, h, False)
+
+
+# ---- tile-engine self-tests (thin wrappers used by tests/) ----------------------------------------
+def selftest_gemm(A, B, b_kmajor=False):
+    """C = A @ B.T on the DMMA tile engine.  A: (M,k), B: (N,k); M, N multiples of 128, k of 16."""
+    A = np.asfortranarray(A, dtype=np.float64)
+    M, k = A.shape
+    Nn = B.shape[0]
+    Bm = np.asfortranarray(B.T if b_kmajor else B, dtype=np.float64)    # K-major source is k x N column-major
+    Cm = np.zeros((M, Nn), order="F")
+    _check(lib().gpr_selftest_gemm(_p(A), _p(Bm), int(b_kmajor), _p(Cm), M // 128, Nn // 128, k))
+    return np.ascontiguousarray(Cm)
+
+
+def selftest_leaf(T):
+    T = np.asfortranarray(T, dtype=np.float64).copy(order="F")
+    inv = np.zeros((128, 128), order="F")
+    info = C.c_int()
+    _check(lib().gpr_selftest_leaf(_p(T), _p(inv), C.byref(info)))
+    return np.ascontiguousarray(T), np.ascontiguousarray(inv), info.value
+
+
+def selftest_factor(A, want_inverse=False, serial=False):
+    A = np.asfortranarray(A, dtype=np.float64).copy(order="F")
+    N = A.shape[0]
+    X = np.zeros((N, N), order="F") if want_inverse else None
+    piv = C.c_longlong()
+    rc = lib().gpr_selftest_factor(_p(A), N // 128, _p(X), int(serial), C.byref(piv))
+    if rc not in (GPR_OK, GPR_ERR_NOT_SPD):
+        _check(rc)
+    return np.tril(A), (None if X is None else np.ascontiguousarray(X)), piv.value
+
+
+def selftest_peak(which, ctas_per_sm=4):
+    t = C.c_double()
+    _check(lib().gpr_selftest_peak(int(which), int(ctas_per_sm), C.byref(t)))
+    return t.value

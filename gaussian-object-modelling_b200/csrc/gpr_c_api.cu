@@ -1,0 +1,695 @@
+// gpr_c_api.cu — implementation of include/gpr_c_api.h: contexts, models, the fit / predict / append
+// orchestration over the kernels in this directory.  No CPU fallback anywhere: every compute entry
+// point needs a CUDA device and reports GPR_ERR_CUDA otherwise.
+#include "../../include/gpr_c_api.h"
+#include "gpr_kernels.h"
+#include "gpr_mma.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace gpr;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local long long g_pivot = 0;
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return fail(e__ == cudaErrorMemoryAllocation ? GPR_ERR_OOM : GPR_ERR_CUDA, b__);       \
+        }                                                                                          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context, workspaces
+// ------------------------------------------------------------------------------------------------
+struct Workspace {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {};
+    double* io = nullptr; size_t io_cap = 0;          // 14 * io_cap doubles: q(3) f var grad(3) tx(3) ty(3)
+    double* panel = nullptr; size_t panel_dbl = 0;
+    double* partial = nullptr; size_t partial_dbl = 0;
+};
+
+struct DeviceCtx {
+    int dev = 0;
+    int num_sms = 148;
+    std::mutex mu;
+    std::vector<Workspace*> free_ws;
+};
+
+struct gpr_ctx {
+    std::vector<DeviceCtx*> devs;
+    gpr_timings timings;
+    std::mutex tmu;
+    size_t query_tile = 0;     // queries per variance batch (multiple of 128)
+    int chol_serial = 0;
+};
+
+static int ws_acquire(DeviceCtx* dc, Workspace** out) {
+    {
+        std::lock_guard<std::mutex> lk(dc->mu);
+        if (!dc->free_ws.empty()) { *out = dc->free_ws.back(); dc->free_ws.pop_back(); return GPR_OK; }
+    }
+    Workspace* ws = new Workspace();
+    ws->dev = dc->dev;
+    CU(cudaSetDevice(dc->dev));
+    CU(cudaStreamCreateWithFlags(&ws->st, cudaStreamNonBlocking));
+    for (auto& e : ws->ev) CU(cudaEventCreate(&e));
+    *out = ws;
+    return GPR_OK;
+}
+static void ws_release(DeviceCtx* dc, Workspace* ws) {
+    std::lock_guard<std::mutex> lk(dc->mu);
+    dc->free_ws.push_back(ws);
+}
+static int ws_reserve(double** p, size_t* cap, size_t need) {
+    if (*cap >= need) return GPR_OK;
+    if (*p) CU(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    CU(cudaMalloc((void**)p, need * sizeof(double)));
+    *cap = need;
+    return GPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+struct ModelDev {            // what predict needs, per device
+    int dev = 0;
+    double* xyz = nullptr;   // 3N: x | y | z
+    double* alpha = nullptr; // N
+    double* linv = nullptr;  // N x N, lower tiles
+    bool have = false, have_linv = false;
+};
+
+struct gpr_model {
+    gpr_ctx* ctx = nullptr;
+    size_t n = 0, N = 0;
+    int nb = 0;
+    gpr_kernel_t kernel{};
+    KernParams kp{};
+    double R = 0.0, k0 = 0.0;
+    bool has_s2 = false, with_normals = false, replica = false;
+    // factor state on the primary device
+    double* label = nullptr; double* s2 = nullptr; double* zfwd = nullptr;
+    double* L = nullptr; double* Dinv = nullptr; int* scratch = nullptr;
+    std::vector<ModelDev> devs;
+    std::vector<double> hx, hy, hz, hlabel, hs2, h_alpha, h_normals;
+    std::mutex mu;
+};
+
+static KernParams make_kp(gpr_kernel_t k) {
+    KernParams kp;
+    kp.kind = k.kind; kp.p0 = k.p0; kp.p1 = k.p1;
+    kp.R3 = k.p0 * k.p0 * k.p0;                                    // thin_plate.hpp:31
+    if (k.kind == 1) { kp.amp = k.p0 * k.p0; kp.inv = 1.0 / (k.p1 * k.p1); }      // gaussian.hpp:40-41
+    else if (k.kind == 2) { kp.amp = 2 * k.p0; kp.inv = 1.0 / k.p1; }             // laplace.hpp:40, :62
+    else { kp.amp = 0; kp.inv = 0; }
+    return kp;
+}
+static double kernel_at_zero(const KernParams& kp) { return kp.kind == 0 ? kp.R3 : kp.amp; }
+
+static void free_factor(gpr_model* m) {
+    if (m->devs.empty()) return;
+    cudaSetDevice(m->devs[0].dev);
+    cudaFree(m->label); cudaFree(m->s2); cudaFree(m->zfwd); cudaFree(m->L); cudaFree(m->Dinv); cudaFree(m->scratch);
+    m->label = m->s2 = m->zfwd = m->L = m->Dinv = nullptr; m->scratch = nullptr;
+    for (auto& d : m->devs) {
+        cudaSetDevice(d.dev);
+        cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.linv);
+        d.xyz = d.alpha = d.linv = nullptr; d.have = d.have_linv = false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fit
+// ------------------------------------------------------------------------------------------------
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float t = 0; cudaEventElapsedTime(&t, a, b); return t; }
+
+// (Re)fit from the host copies held in the model.  keep_R: the reference's update() does not refresh R.
+static int fit_from_host(gpr_model* m, bool keep_R) {
+    gpr_ctx* ctx = m->ctx;
+    DeviceCtx* dc = ctx->devs[0];
+    CU(cudaSetDevice(dc->dev));
+    free_factor(m);
+    const size_t n = m->hx.size();
+    const size_t N = (n + TB - 1) / TB * TB;
+    const int nb = (int)(N / TB);
+    m->n = n; m->N = N; m->nb = nb;
+    m->devs.assign(ctx->devs.size(), ModelDev());
+    for (size_t i = 0; i < ctx->devs.size(); ++i) m->devs[i].dev = ctx->devs[i]->dev;
+    ModelDev& md = m->devs[0];
+
+    CU(cudaMalloc((void**)&md.xyz, 3 * N * sizeof(double)));
+    CU(cudaMalloc((void**)&md.alpha, N * sizeof(double)));
+    CU(cudaMalloc((void**)&m->label, N * sizeof(double)));
+    CU(cudaMalloc((void**)&m->s2, N * sizeof(double)));
+    CU(cudaMalloc((void**)&m->zfwd, N * sizeof(double)));
+    CU(cudaMalloc((void**)&m->L, N * N * sizeof(double)));
+    CU(cudaMalloc((void**)&m->Dinv, (size_t)nb * TB * TB * sizeof(double)));
+    CU(cudaMalloc((void**)&m->scratch, (8 + (size_t)nb * nb) * sizeof(int)));
+
+    Workspace* ws = nullptr;
+    int rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    cudaStream_t st = ws->st;
+
+    CU(cudaEventRecord(ws->ev[0], st));
+    CU(cudaMemsetAsync(md.xyz, 0, 3 * N * sizeof(double), st));
+    CU(cudaMemsetAsync(m->label, 0, N * sizeof(double), st));
+    CU(cudaMemsetAsync(m->s2, 0, N * sizeof(double), st));
+    CU(cudaMemcpyAsync(md.xyz, m->hx.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(md.xyz + N, m->hy.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(md.xyz + 2 * N, m->hz.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->label, m->hlabel.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (m->has_s2) CU(cudaMemcpyAsync(m->s2, m->hs2.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    // the max-distance accumulator lives in the last 8 bytes of the int scratch header
+    unsigned long long* rbits = reinterpret_cast<unsigned long long*>(m->zfwd);   // reused before zfwd is written
+    CU(cudaMemsetAsync(rbits, 0, sizeof(unsigned long long), st));
+    CU(cudaEventRecord(ws->ev[1], st));
+    CU(launch_cov_build(md.xyz, md.xyz + N, md.xyz + 2 * N, m->s2, (int)n, nb, 0, m->L, N, rbits, m->kp, st));
+    double Rbits_host = 0.0;
+    CU(cudaMemcpyAsync(&Rbits_host, rbits, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ws->ev[2], st));
+    CU(launch_cholesky(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st));
+    CU(cudaEventRecord(ws->ev[3], st));
+    int info[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (info[1] != 0) {
+        g_pivot = info[1];
+        char b[256];
+        snprintf(b, sizeof b, "covariance matrix is not positive definite: pivot %d of %zu is <= 0 "
+                 "(thin-plate R must be >= the largest pairwise distance, %.6g here)", info[1], n, Rbits_host);
+        return fail(GPR_ERR_NOT_SPD, b);
+    }
+    if (info[2] != 0) return fail(GPR_ERR_CUDA, "cholesky kernel aborted (dependency wait timed out)");
+    if (!keep_R) m->R = Rbits_host;
+    CU(launch_trsv(0, m->L, N, nb, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
+    CU(launch_trsv(1, m->L, N, nb, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
+    CU(cudaEventRecord(ws->ev[4], st));
+    m->h_alpha.resize(n);
+    CU(cudaMemcpyAsync(m->h_alpha.data(), md.alpha, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    m->h_normals.clear();
+    if (m->with_normals) {
+        // create<true>(): N_i = normalize(sum_j alpha_j k~(D_ij)(p_i - p_j))  (gp_regressor.hpp:166-181)
+        rc = ws_reserve(&ws->io, &ws->io_cap, 14 * N);
+        if (rc) return rc;
+        double* f = ws->io; double* g = ws->io + N;
+        CU(launch_predict(md.xyz, md.xyz + N, md.xyz + 2 * N, md.alpha, (int)n, (int)N, md.xyz, md.xyz + N, md.xyz + 2 * N,
+                          (int)n, f, g, N, nullptr, 0, m->kp, n <= 4096, st));
+        CU(launch_normalize_rows(g, N, (int)n, st));
+        m->h_normals.resize(3 * n);
+        for (int c = 0; c < 3; ++c)
+            CU(cudaMemcpyAsync(m->h_normals.data() + c * n, g + c * N, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaEventRecord(ws->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    int abortflag[4] = {0, 0, 0, 0};
+    CU(cudaMemcpy(abortflag, m->scratch, sizeof(abortflag), cudaMemcpyDeviceToHost));
+    if (abortflag[2] != 0) return fail(GPR_ERR_CUDA, "triangular solve kernel aborted (dependency wait timed out)");
+    md.have = true;
+    {
+        std::lock_guard<std::mutex> lk(ctx->tmu);
+        gpr_timings& t = ctx->timings;
+        t.h2d_ms = ev_ms(ws->ev[0], ws->ev[1]);
+        t.cov_ms = ev_ms(ws->ev[1], ws->ev[2]);
+        t.chol_ms = ev_ms(ws->ev[2], ws->ev[3]);
+        t.solve_ms = ev_ms(ws->ev[3], ws->ev[4]);
+        t.normals_ms = ev_ms(ws->ev[4], ws->ev[5]);
+        t.fit_total_ms = ev_ms(ws->ev[1], ws->ev[5]);
+    }
+    return GPR_OK;
+}
+
+// Build L^-1 on the primary device (lazily, for the variance path).  Caller holds m->mu.
+static int ensure_linv_primary(gpr_model* m) {
+    ModelDev& md = m->devs[0];
+    if (md.have_linv) return GPR_OK;
+    if (m->replica) return fail(GPR_ERR_INVALID, "replica model was created without L^-1");
+    DeviceCtx* dc = m->ctx->devs[0];
+    CU(cudaSetDevice(dc->dev));
+    if (!md.linv) CU(cudaMalloc((void**)&md.linv, m->N * m->N * sizeof(double)));
+    Workspace* ws = nullptr;
+    int rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    CU(cudaEventRecord(ws->ev[0], ws->st));
+    CU(launch_linv(m->L, md.linv, m->N, m->nb, m->Dinv, m->scratch, dc->num_sms, ws->st));
+    CU(cudaEventRecord(ws->ev[1], ws->st));
+    int flags[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(flags, m->scratch, sizeof(flags), cudaMemcpyDeviceToHost, ws->st));
+    CU(cudaStreamSynchronize(ws->st));
+    if (flags[2] != 0) return fail(GPR_ERR_CUDA, "L^-1 kernel aborted (dependency wait timed out)");
+    md.have_linv = true;
+    std::lock_guard<std::mutex> lk(m->ctx->tmu);
+    m->ctx->timings.linv_ms = ev_ms(ws->ev[0], ws->ev[1]);
+    return GPR_OK;
+}
+
+// Make sure device slot di holds the predict state (copied from the primary over NVLink).
+static int ensure_on_device(gpr_model* m, size_t di, bool need_linv) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (need_linv) { int rc = ensure_linv_primary(m); if (rc) return rc; }
+    if (di == 0) return GPR_OK;
+    ModelDev& src = m->devs[0];
+    ModelDev& dst = m->devs[di];
+    CU(cudaSetDevice(dst.dev));
+    if (!dst.have) {
+        CU(cudaMalloc((void**)&dst.xyz, 3 * m->N * sizeof(double)));
+        CU(cudaMalloc((void**)&dst.alpha, m->N * sizeof(double)));
+        CU(cudaMemcpyPeer(dst.xyz, dst.dev, src.xyz, src.dev, 3 * m->N * sizeof(double)));
+        CU(cudaMemcpyPeer(dst.alpha, dst.dev, src.alpha, src.dev, m->N * sizeof(double)));
+        dst.have = true;
+    }
+    if (need_linv && !dst.have_linv) {
+        if (!dst.linv) CU(cudaMalloc((void**)&dst.linv, m->N * m->N * sizeof(double)));
+        CU(cudaMemcpyPeer(dst.linv, dst.dev, src.linv, src.dev, m->N * m->N * sizeof(double)));
+        dst.have_linv = true;
+    }
+    return GPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// predict on one device.  in_dev/out_dev: pointers are device memory of that device.
+// ------------------------------------------------------------------------------------------------
+struct PredictIO {
+    const double* qx; const double* qy; const double* qz; size_t q;
+    double* f; double* var; double* grad; double* tx; double* ty;
+    size_t out_ld;          // leading dimension of grad/tx/ty in the caller's arrays
+    size_t offset;          // first query handled here
+    bool device_ptrs;
+};
+
+static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, double* mean_ms, double* var_ms,
+                             double* h2d_ms, double* d2h_ms) {
+    gpr_ctx* ctx = m->ctx;
+    DeviceCtx* dc = ctx->devs[di];
+    const bool want_var = io.var != nullptr, want_grad = io.grad != nullptr, want_t = io.tx != nullptr;
+    int rc = ensure_on_device(m, di, want_var);
+    if (rc) return rc;
+    CU(cudaSetDevice(dc->dev));
+    ModelDev& md = m->devs[di];
+    Workspace* ws = nullptr;
+    rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    cudaStream_t st = ws->st;
+    const size_t N = m->N;
+    const int n = (int)m->n;
+    const bool small_var = want_var && io.q <= 8;
+    size_t batch = io.q;
+    if (want_var && !small_var) batch = std::min(io.q, ctx->query_tile ? ctx->query_tile : (size_t)TB * dc->num_sms);
+    else batch = std::min(io.q, (size_t)1 << 22);
+    const size_t panel_ld_max = (batch + TB - 1) / TB * TB;
+    rc = ws_reserve(&ws->io, &ws->io_cap, 14 * std::max(batch, (size_t)TB));
+    if (rc) return rc;
+    const size_t cap = ws->io_cap / 14;
+    double* dq = ws->io; double* df = dq + 3 * cap; double* dv = df + cap; double* dg = dv + cap;
+    double* dtx = dg + 3 * cap; double* dty = dtx + 3 * cap;
+    if (want_var) {
+        rc = ws_reserve(&ws->panel, &ws->panel_dbl, N * panel_ld_max);
+        if (rc) return rc;
+        rc = ws_reserve(&ws->partial, &ws->partial_dbl, std::max((size_t)m->nb * panel_ld_max, (size_t)8 * 8 * N));
+        if (rc) return rc;
+    }
+    float t_mean = 0, t_var = 0, t_h2d = 0, t_d2h = 0;
+    for (size_t b0 = 0; b0 < io.q; b0 += batch) {
+        const size_t bq = std::min(batch, io.q - b0);
+        const size_t g0 = io.offset + b0;
+        const double *qx, *qy, *qz;
+        double *f, *v, *g;
+        size_t gld;
+        CU(cudaEventRecord(ws->ev[0], st));
+        if (io.device_ptrs) {
+            qx = io.qx + g0; qy = io.qy + g0; qz = io.qz + g0;
+            f = io.f + g0; v = want_var ? io.var + g0 : nullptr; g = want_grad ? io.grad + g0 : nullptr; gld = io.out_ld;
+        } else {
+            CU(cudaMemcpyAsync(dq, io.qx + g0, bq * sizeof(double), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(dq + cap, io.qy + g0, bq * sizeof(double), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(dq + 2 * cap, io.qz + g0, bq * sizeof(double), cudaMemcpyHostToDevice, st));
+            qx = dq; qy = dq + cap; qz = dq + 2 * cap;
+            f = df; v = want_var ? dv : nullptr; g = want_grad ? dg : nullptr; gld = cap;
+        }
+        CU(cudaEventRecord(ws->ev[1], st));
+        const size_t pld = small_var ? (size_t)TB : (bq + TB - 1) / TB * TB;
+        const bool warp_mode = small_var || (!want_var && bq <= (size_t)64 * dc->num_sms);
+        CU(launch_predict(md.xyz, md.xyz + N, md.xyz + 2 * N, md.alpha, n, (int)N, qx, qy, qz, (int)bq, f, g, gld,
+                          want_var ? ws->panel : nullptr, pld, m->kp, warp_mode, st));
+        CU(cudaEventRecord(ws->ev[2], st));
+        if (want_var) {
+            if (small_var) CU(launch_variance_small(md.linv, N, (int)N, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+            else CU(launch_variance(md.linv, N, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+        }
+        CU(cudaEventRecord(ws->ev[3], st));
+        if (want_t && !io.device_ptrs) CU(launch_tangent_basis(g, gld, (int)bq, dtx, dty, st));
+        if (!io.device_ptrs) {
+            CU(cudaMemcpyAsync(io.f + g0, f, bq * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (want_var) CU(cudaMemcpyAsync(io.var + g0, v, bq * sizeof(double), cudaMemcpyDeviceToHost, st));
+            for (int c = 0; c < 3; ++c) {
+                if (want_grad) CU(cudaMemcpyAsync(io.grad + c * io.out_ld + g0, g + c * gld, bq * sizeof(double), cudaMemcpyDeviceToHost, st));
+                if (want_t) {
+                    CU(cudaMemcpyAsync(io.tx + c * io.out_ld + g0, dtx + c * gld, bq * sizeof(double), cudaMemcpyDeviceToHost, st));
+                    CU(cudaMemcpyAsync(io.ty + c * io.out_ld + g0, dty + c * gld, bq * sizeof(double), cudaMemcpyDeviceToHost, st));
+                }
+            }
+        }
+        CU(cudaEventRecord(ws->ev[4], st));
+        CU(cudaStreamSynchronize(st));
+        t_h2d += ev_ms(ws->ev[0], ws->ev[1]); t_mean += ev_ms(ws->ev[1], ws->ev[2]);
+        t_var += ev_ms(ws->ev[2], ws->ev[3]); t_d2h += ev_ms(ws->ev[3], ws->ev[4]);
+    }
+    if (mean_ms) *mean_ms = t_mean;
+    if (var_ms) *var_ms = t_var;
+    if (h2d_ms) *h2d_ms = t_h2d;
+    if (d2h_ms) *d2h_ms = t_d2h;
+    return GPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* gpr_last_error(void) { return g_err.c_str(); }
+long long gpr_last_pivot(void) { return g_pivot; }
+
+int gpr_ctx_create(const int* devices, int ndev, gpr_ctx** out) {
+    if (!out) return fail(GPR_ERR_INVALID, "null output pointer");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(GPR_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    gpr_ctx* ctx = new gpr_ctx();
+    memset(&ctx->timings, 0, sizeof ctx->timings);
+    std::vector<int> devs;
+    if (!devices || ndev <= 0) devs.push_back(0);
+    else devs.assign(devices, devices + ndev);
+    for (int d : devs) {
+        if (d < 0 || d >= count) { delete ctx; return fail(GPR_ERR_INVALID, "device index out of range"); }
+        cudaDeviceProp p;
+        e = cudaGetDeviceProperties(&p, d);
+        if (e != cudaSuccess) { delete ctx; return fail(GPR_ERR_CUDA, cudaGetErrorString(e)); }
+        if (p.major < 10) { delete ctx; return fail(GPR_ERR_CUDA, "device is not sm_100 or newer; this library is built for sm_100a only"); }
+        DeviceCtx* dc = new DeviceCtx();
+        dc->dev = d; dc->num_sms = p.multiProcessorCount;
+        ctx->devs.push_back(dc);
+    }
+    for (size_t a = 0; a < devs.size(); ++a)
+        for (size_t b = 0; b < devs.size(); ++b) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devs[a], devs[b]);
+            if (can) { cudaSetDevice(devs[a]); cudaDeviceEnablePeerAccess(devs[b], 0); cudaGetLastError(); }
+        }
+    if (const char* s = getenv("GPR_QUERY_TILE")) {
+        long v = atol(s);
+        if (v > 0) ctx->query_tile = (size_t)(v + TB - 1) / TB * TB;
+    }
+    if (const char* s = getenv("GPR_CHOL_SERIAL")) ctx->chol_serial = atoi(s);
+    *out = ctx;
+    return GPR_OK;
+}
+
+int gpr_ctx_destroy(gpr_ctx* ctx) {
+    if (!ctx) return GPR_OK;
+    for (DeviceCtx* dc : ctx->devs) {
+        cudaSetDevice(dc->dev);
+        for (Workspace* ws : dc->free_ws) {
+            cudaFree(ws->io); cudaFree(ws->panel); cudaFree(ws->partial);
+            for (auto& e : ws->ev) cudaEventDestroy(e);
+            cudaStreamDestroy(ws->st);
+            delete ws;
+        }
+        delete dc;
+    }
+    delete ctx;
+    return GPR_OK;
+}
+
+int gpr_ctx_num_devices(const gpr_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int gpr_last_timings(const gpr_ctx* ctx, gpr_timings* out) {
+    if (!ctx || !out) return fail(GPR_ERR_INVALID, "null pointer");
+    std::lock_guard<std::mutex> lk(const_cast<gpr_ctx*>(ctx)->tmu);
+    *out = ctx->timings;
+    return GPR_OK;
+}
+
+int gpr_fit(gpr_ctx* ctx, const double* x, const double* y, const double* z, const double* label,
+            const double* sigma2, size_t n, gpr_kernel_t kernel, int with_normals, gpr_model** out) {
+    if (!ctx || !out) return fail(GPR_ERR_INVALID, "null context or output pointer");
+    if (!x || !y || !z || !label || n == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
+    if (kernel.kind < 0 || kernel.kind > 2) return fail(GPR_ERR_INVALID, "unknown kernel kind");
+    gpr_model* m = new gpr_model();
+    m->ctx = ctx; m->kernel = kernel; m->kp = make_kp(kernel); m->k0 = kernel_at_zero(m->kp);
+    m->has_s2 = sigma2 != nullptr; m->with_normals = with_normals != 0;
+    m->hx.assign(x, x + n); m->hy.assign(y, y + n); m->hz.assign(z, z + n); m->hlabel.assign(label, label + n);
+    if (sigma2) m->hs2.assign(sigma2, sigma2 + n);
+    int rc = fit_from_host(m, false);
+    if (rc) { free_factor(m); delete m; return rc; }
+    *out = m;
+    return GPR_OK;
+}
+
+int gpr_model_destroy(gpr_model* m) {
+    if (!m) return GPR_OK;
+    free_factor(m);
+    delete m;
+    return GPR_OK;
+}
+
+size_t gpr_model_size(const gpr_model* m) { return m ? m->n : 0; }
+
+int gpr_model_get(const gpr_model* m, double* alpha, double* R, double* normals) {
+    if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
+    if (alpha) {
+        if (m->h_alpha.size() != m->n) return fail(GPR_ERR_INVALID, "model holds no host alpha (replica)");
+        memcpy(alpha, m->h_alpha.data(), m->n * sizeof(double));
+    }
+    if (R) *R = m->R;
+    if (normals) {
+        if (m->h_normals.size() != 3 * m->n) return fail(GPR_ERR_INVALID, "model was fitted without normals");
+        memcpy(normals, m->h_normals.data(), 3 * m->n * sizeof(double));
+    }
+    return GPR_OK;
+}
+
+int gpr_model_get_factor(const gpr_model* m, double* L) {
+    if (!m || !L) return fail(GPR_ERR_INVALID, "null pointer");
+    if (!m->L) return fail(GPR_ERR_INVALID, "model holds no factor (replica)");
+    CU(cudaSetDevice(m->devs[0].dev));
+    CU(cudaMemcpy2D(L, m->n * sizeof(double), m->L, m->N * sizeof(double), m->n * sizeof(double), m->n, cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < m->n; ++c)
+        for (size_t r = 0; r < c; ++r) L[c * m->n + r] = 0.0;
+    return GPR_OK;
+}
+
+int gpr_predict(gpr_ctx* ctx, gpr_model* m, const double* qx, const double* qy, const double* qz, size_t q,
+                double* f, double* var, double* grad, double* tx, double* ty) {
+    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
+    if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
+    if (!qx || !qy || !qz || !f || q == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
+    if ((tx == nullptr) != (ty == nullptr) || (tx && !grad)) return fail(GPR_ERR_INVALID, "tx/ty need each other and grad");
+    const size_t nd = ctx->devs.size();
+    // Shard contiguous query ranges over the devices; tiny batches stay on the primary device.
+    const size_t use = (nd > 1 && q >= 4096 * nd) ? nd : 1;
+    std::vector<int> rcs(use, 0);
+    std::vector<std::string> errs(use);
+    std::vector<double> tm(use, 0), tv(use, 0), th(use, 0), td(use, 0);
+    auto work = [&](size_t di) {
+        PredictIO io;
+        const size_t a = q * di / use, b = q * (di + 1) / use;
+        io.qx = qx; io.qy = qy; io.qz = qz; io.q = b - a; io.offset = a;
+        io.f = f; io.var = var; io.grad = grad; io.tx = tx; io.ty = ty; io.out_ld = q; io.device_ptrs = false;
+        rcs[di] = predict_on_device(m, di, io, &tm[di], &tv[di], &th[di], &td[di]);
+        if (rcs[di]) errs[di] = g_err;
+    };
+    if (use == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (size_t di = 0; di < use; ++di) pool.emplace_back(work, di);
+        for (auto& t : pool) t.join();
+    }
+    for (size_t di = 0; di < use; ++di) if (rcs[di]) return fail(rcs[di], errs[di]);
+    std::lock_guard<std::mutex> lk(ctx->tmu);
+    gpr_timings& t = ctx->timings;
+    t.predict_mean_ms = *std::max_element(tm.begin(), tm.end());
+    t.predict_var_ms = *std::max_element(tv.begin(), tv.end());
+    t.h2d_ms = *std::max_element(th.begin(), th.end());
+    t.d2h_ms = *std::max_element(td.begin(), td.end());
+    t.predict_total_ms = t.predict_mean_ms + t.predict_var_ms + t.h2d_ms + t.d2h_ms;
+    return GPR_OK;
+}
+
+int gpr_predict_device(gpr_ctx* ctx, gpr_model* m, const double* d_qx, const double* d_qy, const double* d_qz,
+                       size_t q, double* d_f, double* d_var, double* d_grad) {
+    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
+    if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
+    if (!d_qx || !d_qy || !d_qz || !d_f || q == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
+    PredictIO io;
+    io.qx = d_qx; io.qy = d_qy; io.qz = d_qz; io.q = q; io.offset = 0;
+    io.f = d_f; io.var = d_var; io.grad = d_grad; io.tx = nullptr; io.ty = nullptr; io.out_ld = q; io.device_ptrs = true;
+    double tm = 0, tv = 0, th = 0, td = 0;
+    int rc = predict_on_device(m, 0, io, &tm, &tv, &th, &td);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->tmu);
+    ctx->timings.predict_mean_ms = tm; ctx->timings.predict_var_ms = tv;
+    ctx->timings.predict_total_ms = tm + tv;
+    return GPR_OK;
+}
+
+int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m) {
+    if (!ctx || !m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
+    for (size_t di = 0; di < ctx->devs.size(); ++di) {
+        int rc = ensure_on_device(m, di, true);
+        if (rc) return rc;
+    }
+    return GPR_OK;
+}
+
+int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
+               const double* sigma2, size_t k) {
+    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
+    if (!m) return fail(GPR_ERR_INVALID, "Empty model pointer");
+    if (!x || !y || !z || !label || k == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
+    if (m->replica) return fail(GPR_ERR_INVALID, "cannot append to a replica model");
+    std::lock_guard<std::mutex> lk(m->mu);
+    const size_t p = m->hx.size();
+    m->hx.insert(m->hx.end(), x, x + k); m->hy.insert(m->hy.end(), y, y + k); m->hz.insert(m->hz.end(), z, z + k);
+    m->hlabel.insert(m->hlabel.end(), label, label + k);
+    if (m->has_s2 || sigma2) {
+        // gp_regressor.hpp:449-450: S2 grows with the new block; absent entries are zero noise.
+        m->hs2.resize(p, 0.0);
+        if (sigma2) m->hs2.insert(m->hs2.end(), sigma2, sigma2 + k); else m->hs2.resize(p + k, 0.0);
+        m->has_s2 = true;
+    }
+    const bool normals = m->with_normals;
+    m->with_normals = false;                 // :462-477: normals are not refreshed by update()
+    std::vector<double> keep = m->h_normals;
+    int rc = fit_from_host(m, true);
+    m->with_normals = normals;
+    m->h_normals = keep;
+    return rc;
+}
+
+int gpr_model_state_get(gpr_ctx* ctx, gpr_model* m, int with_linv, gpr_model_state* out) {
+    if (!ctx || !m || !out) return fail(GPR_ERR_INVALID, "null pointer");
+    if (with_linv) { int rc = ensure_on_device(m, 0, true); if (rc) return rc; }
+    out->n = m->n; out->padded_n = m->N; out->kernel = m->kernel; out->R = m->R;
+    out->xyz = m->devs[0].xyz; out->alpha = m->devs[0].alpha;
+    out->linv = m->devs[0].have_linv ? m->devs[0].linv : nullptr;
+    return GPR_OK;
+}
+
+int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double R, int with_linv, gpr_model** out) {
+    if (!ctx || !out || n == 0) return fail(GPR_ERR_INVALID, "null pointer or empty model");
+    gpr_model* m = new gpr_model();
+    m->ctx = ctx; m->kernel = kernel; m->kp = make_kp(kernel); m->k0 = kernel_at_zero(m->kp); m->R = R;
+    m->replica = true;
+    m->n = n; m->N = (n + TB - 1) / TB * TB; m->nb = (int)(m->N / TB);
+    m->devs.assign(ctx->devs.size(), ModelDev());
+    for (size_t i = 0; i < ctx->devs.size(); ++i) m->devs[i].dev = ctx->devs[i]->dev;
+    ModelDev& md = m->devs[0];
+    auto bail = [&](int rc) { free_factor(m); delete m; return rc; };
+    if (cudaSetDevice(md.dev) != cudaSuccess) return bail(fail(GPR_ERR_CUDA, "cudaSetDevice failed"));
+    if (cudaMalloc((void**)&md.xyz, 3 * m->N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&md.alpha, m->N * sizeof(double)) != cudaSuccess)
+        return bail(fail(GPR_ERR_OOM, "out of device memory"));
+    md.have = true;
+    if (with_linv) {
+        if (cudaMalloc((void**)&md.linv, m->N * m->N * sizeof(double)) != cudaSuccess)
+            return bail(fail(GPR_ERR_OOM, "out of device memory"));
+        md.have_linv = true;
+    }
+    *out = m;
+    return GPR_OK;
+}
+
+// ---- self-tests ---------------------------------------------------------------------------------
+int gpr_selftest_gemm(const double* hA, const double* hB, int b_kmajor, double* hC, int mt, int nt, int k) {
+    if (k % KT) return fail(GPR_ERR_INVALID, "k must be a multiple of 16");
+    const size_t M = (size_t)mt * TB, Nn = (size_t)nt * TB;
+    double *A, *B, *C;
+    CU(cudaMalloc((void**)&A, M * k * sizeof(double)));
+    CU(cudaMalloc((void**)&B, Nn * k * sizeof(double)));
+    CU(cudaMalloc((void**)&C, M * Nn * sizeof(double)));
+    CU(cudaMemcpy(A, hA, M * k * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(B, hB, Nn * k * sizeof(double), cudaMemcpyHostToDevice));
+    CU(launch_gemm_selftest(A, M, B, b_kmajor ? (size_t)k : Nn, b_kmajor, C, M, mt, nt, k, 0));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(hC, C, M * Nn * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(A); cudaFree(B); cudaFree(C);
+    return GPR_OK;
+}
+
+int gpr_selftest_leaf(double* h_tile, double* h_inv, int* info) {
+    double *T, *I; int* d_info;
+    CU(cudaMalloc((void**)&T, TB * TB * sizeof(double)));
+    CU(cudaMalloc((void**)&I, TB * TB * sizeof(double)));
+    CU(cudaMalloc((void**)&d_info, sizeof(int)));
+    CU(cudaMemcpy(T, h_tile, TB * TB * sizeof(double), cudaMemcpyHostToDevice));
+    CU(launch_leaf_selftest(T, I, d_info, 0));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h_tile, T, TB * TB * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_inv, I, TB * TB * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(info, d_info, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(T); cudaFree(I); cudaFree(d_info);
+    return GPR_OK;
+}
+
+int gpr_selftest_factor(double* hA, int nb, double* h_linv, int serial, long long* pivot) {
+    const size_t N = (size_t)nb * TB;
+    double *A, *D, *X = nullptr; int* scratch;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    CU(cudaMalloc((void**)&A, N * N * sizeof(double)));
+    CU(cudaMalloc((void**)&D, (size_t)nb * TB * TB * sizeof(double)));
+    CU(cudaMalloc((void**)&scratch, (8 + (size_t)nb * nb) * sizeof(int)));
+    CU(cudaMemcpy(A, hA, N * N * sizeof(double), cudaMemcpyHostToDevice));
+    CU(launch_cholesky(A, N, nb, D, scratch, sms, serial, 0));
+    CU(cudaDeviceSynchronize());
+    int info[4];
+    CU(cudaMemcpy(info, scratch, sizeof info, cudaMemcpyDeviceToHost));
+    if (pivot) *pivot = info[1];
+    if (info[2] && !info[1]) return fail(GPR_ERR_CUDA, "cholesky kernel aborted");
+    CU(cudaMemcpy(hA, A, N * N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_linv && !info[1]) {
+        CU(cudaMalloc((void**)&X, N * N * sizeof(double)));
+        CU(cudaMemset(X, 0, N * N * sizeof(double)));
+        CU(launch_linv(A, X, N, nb, D, scratch, sms, 0));
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemcpy(info, scratch, sizeof info, cudaMemcpyDeviceToHost));
+        if (info[2]) return fail(GPR_ERR_CUDA, "L^-1 kernel aborted");
+        CU(cudaMemcpy(h_linv, X, N * N * sizeof(double), cudaMemcpyDeviceToHost));
+        cudaFree(X);
+    }
+    cudaFree(A); cudaFree(D); cudaFree(scratch);
+    return info[1] ? GPR_ERR_NOT_SPD : GPR_OK;
+}
+
+int gpr_selftest_peak(int which, int ctas_per_sm, double* tflops) {
+    if (!tflops) return fail(GPR_ERR_INVALID, "null pointer");
+    CU(run_peak_probe(which, ctas_per_sm, tflops));
+    return GPR_OK;
+}
+
+}  // extern "C"

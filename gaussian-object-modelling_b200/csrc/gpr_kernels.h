@@ -1,0 +1,41 @@
+// gpr_kernels.h — host-side launchers of the sm_100a kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include "gpr_common.cuh"
+
+namespace gpr {
+
+// K1 (gpr_cov.cu)
+cudaError_t launch_cov_build(const double* x, const double* y, const double* z, const double* sigma2, int n, int nb,
+                             int tile_row0, double* K, size_t ld, unsigned long long* rmax_bits, const KernParams& kp,
+                             cudaStream_t st);
+// K2 (gpr_factor.cu).  scratch: at least 4 + nb*nb ints.
+cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, int serial,
+                            cudaStream_t st);
+cudaError_t launch_linv(const double* L, double* X, size_t ld, int nb, const double* Dinv, int* scratch, int num_sms,
+                        cudaStream_t st);
+// K3 (gpr_solve.cu).  scratch: at least 4 + nb ints.
+cudaError_t launch_trsv(int backward, const double* L, size_t ld, int nb, const double* Dinv, const double* rhs,
+                        double* out, int* scratch, int num_sms, cudaStream_t st);
+// K4 (gpr_predict.cu)
+cudaError_t launch_predict(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
+                           const double* qx, const double* qy, const double* qz, int q, double* f, double* grad,
+                           size_t grad_ld, double* panel, size_t panel_ld, const KernParams& kp, int warp_mode,
+                           cudaStream_t st);
+cudaError_t launch_tangent_basis(const double* grad, size_t ld, int q, double* Tx, double* Ty, cudaStream_t st);
+cudaError_t launch_normalize_rows(double* g, size_t ld, int q, cudaStream_t st);
+// K3' (gpr_var.cu)
+cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* panel, size_t panel_ld, int q,
+                            double* partial, double k0, double* var, cudaStream_t st);
+cudaError_t launch_variance_small(const double* X, size_t ld, int N, const double* panel, size_t panel_ld, int q,
+                                  double* part, double k0, double* var, cudaStream_t st);
+// Engine self-test (gpr_selftest.cu): C = A * B^T on one 128x128 tile per CTA.
+cudaError_t launch_gemm_selftest(const double* A, size_t lda, const double* B, size_t ldb, int b_kmajor, double* C,
+                                 size_t ldc, int mt, int nt, int k, cudaStream_t st);
+cudaError_t launch_leaf_selftest(double* tile /*128x128 in/out: L*/, double* inv /*128x128 out*/, int* info,
+                                 cudaStream_t st);
+
+cudaError_t run_peak_probe(int which, int ctas_per_sm, double* tflops);
+
+}  // namespace gpr

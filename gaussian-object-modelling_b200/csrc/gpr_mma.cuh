@@ -1,0 +1,242 @@
+// gpr_mma.cuh — the FP64 tensor-pipe tile engine shared by the Cholesky, L^-1 and variance kernels.
+//
+// One CTA (256 threads, 8 warps) accumulates a 128x128 FP64 tile
+//        acc[i][j] += sum_k  Aop(i,k) * Bop(j,k)
+// with mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 — on sm_100a every FP64 mma shape lowers to it;
+// tcgen05.mma has no f64 kind, so there is no TMEM/UMMA path for this precision).
+//
+// Operand roles.  The "i operand" supplies the rows of the output tile and feeds the MMA *B*
+// fragment; the "j operand" supplies the columns and feeds the MMA *A* fragment.  With that
+// assignment the two accumulator registers of a thread are two rows of the same output column,
+// and with the row permutation below four consecutive rows: the tile is stored with 32-byte
+// contiguous pieces per thread and full 128-byte lines per quarter-warp.
+//
+// Shared-memory layouts of one k16 stage (all conflict-free for the fragment loads used):
+//   M-major  [k][m], pitch PM=132 doubles : fragment loads are LDS.128 of two adjacent m for one k.
+//   K-major  [m][k], pitch PK=20 doubles  : fragment loads are LDS.64 (j operand only).
+// A resident operand (a full 128x128 tile already in shared memory) uses pitch PM in either layout.
+//
+// Warp w owns rows i0 = 64*(w&1) .. +63 and columns j0 = 32*(w>>1) .. +31:
+//   8 n-tiles (i) x 4 m-tiles (j) of 8x8, i.e. 32 DMMA per k4 step and 6 LDS.128 per k4 step.
+// Fragment <-> tile index maps (g = lane>>2, t = lane&3):
+//   i operand, pair p (n-tiles 2p,2p+1):  rows  i0 + 16p + 2g + {0,1}   loaded as one LDS.128
+//   accumulators of pair p:               rows  i0 + 16p + 4t + {0,1,2,3} =
+//                                         acc[mt][2p][0], acc[mt][2p+1][0], acc[mt][2p][1], acc[mt][2p+1][1]
+//   j operand M-major, m-tile mt:         col   j0 + 16(mt>>1) + 2g + (mt&1)
+//   j operand K-major, m-tile mt:         col   j0 + 8mt + g
+#pragma once
+#include "gpr_common.cuh"
+
+namespace gpr {
+
+constexpr int KT = 16;                     // k extent of one pipeline stage
+constexpr int PM = 132;                    // pitch of M-major stage / resident tiles (doubles)
+constexpr int PK = 20;                     // pitch of K-major stage tiles (doubles)
+constexpr int STAGES = 4;
+constexpr int STAGE_I = KT * PM;           // doubles per i-operand stage (M-major)
+constexpr int STAGE_J = TB * PK;           // doubles per j-operand stage (max of both layouts: 2560 >= 2112)
+constexpr int R0_DBL = TB * PM;            // region 0: resident tile / i stages   (16896 doubles)
+constexpr int R1_DBL = STAGES * STAGE_J;   // region 1: j stages (or i stages when j is resident)
+constexpr size_t TILE_SMEM_BYTES = (size_t)(R0_DBL + R1_DBL) * sizeof(double);   // 217,088 B
+
+static_assert(STAGES * STAGE_I <= R0_DBL, "i stages must fit region 0");
+static_assert(STAGES * STAGE_I <= R1_DBL, "i stages must fit region 1");
+
+enum OperandMode { STREAM_M = 0, STREAM_K = 1, RES_M = 2, RES_K = 3 };
+
+typedef double Acc[4][8][2];
+
+__device__ __forceinline__ void acc_zero(Acc& acc) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
+}
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Warp / lane coordinates used by every tile routine.
+struct TileCoord {
+    int lane, warp, g, t, i0, j0;
+    __device__ __forceinline__ TileCoord() {
+        lane = threadIdx.x & 31; warp = threadIdx.x >> 5; g = lane >> 2; t = lane & 3;
+        i0 = (warp & 1) * 64; j0 = (warp >> 1) * 32;
+    }
+    // tile row of accumulator (pair p, e in 0..3)
+    __device__ __forceinline__ int row(int p, int e) const { return i0 + 16 * p + 4 * t + e; }
+    template <bool JK>
+    __device__ __forceinline__ int col(int mt) const {
+        return JK ? (j0 + 8 * mt + g) : (j0 + 16 * (mt >> 1) + 2 * g + (mt & 1));
+    }
+};
+
+// acc element for (mt, pair p, e): e=0 -> [2p][0], 1 -> [2p+1][0], 2 -> [2p][1], 3 -> [2p+1][1]
+#define GPR_ACC(acc, mt, p, e) (acc)[mt][2 * (p) + ((e) & 1)][(e) >> 1]
+
+// One k16 step.  As: i operand, element (k,m) at As[k*pa + m].  Bs: j operand; M-major element (k,m)
+// at Bs[k*pb + m]; K-major element (m,k) at Bs[m*pb + k].
+template <bool JK>
+__device__ __forceinline__ void compute_k16(Acc& acc, const double* __restrict__ As, int pa,
+                                            const double* __restrict__ Bs, int pb, const TileCoord& tc) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const int k = 4 * ks + tc.t;
+        double b[8], a[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            double2 v = *reinterpret_cast<const double2*>(As + k * pa + tc.i0 + 16 * p + 2 * tc.g);
+            b[2 * p] = v.x; b[2 * p + 1] = v.y;
+        }
+        if (JK) {
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) a[mt] = Bs[(tc.j0 + 8 * mt + tc.g) * pb + k];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                double2 v = *reinterpret_cast<const double2*>(Bs + k * pb + tc.j0 + 16 * q + 2 * tc.g);
+                a[2 * q] = v.x; a[2 * q + 1] = v.y;
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+}
+
+// Asynchronous copy of one k16 stage of a streamed operand.
+//   M-major source: element (m,k) at src[m + k*ld]   -> stage[k*PM + m]
+//   K-major source: element (m,k) at src[k + m*ld]   -> stage[m*PK + k]
+template <bool KMAJOR>
+__device__ __forceinline__ void load_stage(double* stage, const double* __restrict__ src, size_t ld) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        int chunk = tid + NTHREADS * c;           // 1024 chunks of 16 bytes
+        if (!KMAJOR) {
+            int k = chunk >> 6, m2 = chunk & 63;
+            cp_async16(stage + k * PM + 2 * m2, src + (size_t)k * ld + 2 * m2);
+        } else {
+            int m = chunk >> 3, k2 = chunk & 7;
+            cp_async16(stage + m * PK + 2 * k2, src + (size_t)m * ld + 2 * k2);
+        }
+    }
+}
+
+// Pipelined accumulation over nk16 k16-steps.
+//   IMODE in {STREAM_M, RES_M}; JMODE in {STREAM_M, STREAM_K, RES_M, RES_K}.
+//   Streamed operands: Ag/Bg point at (tile row 0, k = 0) of the operand; lda/ldb are its leading
+//   dimensions.  Resident operands: Ag/Bg are shared-memory tiles with pitch PM.
+//   waitf(kb) is called by ALL threads before the loads of k16-step 8*kb are issued (it may spin on a
+//   readiness flag in thread 0); it returns false to abandon the tile.  It must not contain a barrier.
+// Returns false if abandoned.  Ends with all async copies drained and a __syncthreads().
+template <int IMODE, int JMODE, class WaitF>
+__device__ __forceinline__ bool tile_mainloop(Acc& acc, const double* Ag, size_t lda, const double* Bg, size_t ldb,
+                                              int nk16, double* smem, int* s_abort, WaitF waitf) {
+    constexpr bool IS = (IMODE == STREAM_M);
+    constexpr bool JS = (JMODE == STREAM_M || JMODE == STREAM_K);
+    constexpr bool JK = (JMODE == STREAM_K || JMODE == RES_K);
+    constexpr bool JRES = !JS;
+    double* r0 = smem;
+    double* r1 = smem + R0_DBL;
+    double* istage = JRES ? r1 : r0;     // i stages move to region 1 when j is resident in region 0
+    double* jstage = r1;
+    const TileCoord tc;
+
+    auto issue = [&](int kk) {
+        const int s = kk % STAGES;
+        if (IS) load_stage<false>(istage + s * STAGE_I, Ag + (size_t)kk * KT * lda, lda);
+        if (JS) {
+            if (JK) load_stage<true>(jstage + s * STAGE_J, Bg + (size_t)kk * KT, ldb);
+            else load_stage<false>(jstage + s * STAGE_J, Bg + (size_t)kk * KT * ldb, ldb);
+        }
+    };
+
+    bool ok = true;
+    if (nk16 > 0) {
+        if (!waitf(0)) *s_abort = 1;
+    }
+    __syncthreads();
+    if (*s_abort) return false;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk16) issue(s);
+        cp_async_commit();
+    }
+    for (int kk = 0; kk < nk16; ++kk) {
+        cp_async_wait<STAGES - 2>();
+        const int nxt = kk + STAGES - 1;
+        if (nxt < nk16 && (nxt & 7) == 0) {
+            if (!waitf(nxt >> 3)) *s_abort = 1;
+        }
+        __syncthreads();
+        if (*s_abort) { ok = false; break; }
+        if (nxt < nk16) issue(nxt);
+        cp_async_commit();
+        const int s = kk % STAGES;
+        const double* As = IS ? (istage + s * STAGE_I) : (Ag + (size_t)kk * KT * PM);
+        const double* Bs = JS ? (jstage + s * STAGE_J) : (JK ? (Bg + kk * KT) : (Bg + (size_t)kk * KT * PM));
+        compute_k16<JK>(acc, As, IS ? PM : PM, Bs, JS ? (JK ? PK : PM) : PM, tc);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    return ok;
+}
+
+struct NoWait {
+    __device__ __forceinline__ bool operator()(int) const { return true; }
+};
+
+// ---- tile <-> memory helpers -------------------------------------------------------------------
+
+// Store accumulators as a column-major tile: element (row, col) -> dst[col*ld + row].
+// SIGN = +1 stores acc, -1 stores -acc.  Works for global or shared destinations.
+template <bool JK, int SIGN>
+__device__ __forceinline__ void store_tile(const Acc& acc, double* dst, size_t ld, const TileCoord& tc) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int c = tc.col<JK>(mt);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            double* d = dst + (size_t)c * ld + tc.row(p, 0);
+            double2 lo, hi;
+            lo.x = SIGN * GPR_ACC(acc, mt, p, 0); lo.y = SIGN * GPR_ACC(acc, mt, p, 1);
+            hi.x = SIGN * GPR_ACC(acc, mt, p, 2); hi.y = SIGN * GPR_ACC(acc, mt, p, 3);
+            reinterpret_cast<double2*>(d)[0] = lo;
+            reinterpret_cast<double2*>(d)[1] = hi;
+        }
+    }
+}
+
+// dst_smem (column-major, pitch PM) = G - acc, where G is a column-major global tile (read through L2).
+template <bool JK>
+__device__ __forceinline__ void residual_to_smem(const Acc& acc, const double* G, size_t ld, double* dst,
+                                                 const TileCoord& tc) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int c = tc.col<JK>(mt);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int r = tc.row(p, 0);
+            const double2* gp = reinterpret_cast<const double2*>(G + (size_t)c * ld + r);
+            double2 lo = __ldcg(gp), hi = __ldcg(gp + 1);
+            lo.x -= GPR_ACC(acc, mt, p, 0); lo.y -= GPR_ACC(acc, mt, p, 1);
+            hi.x -= GPR_ACC(acc, mt, p, 2); hi.y -= GPR_ACC(acc, mt, p, 3);
+            double2* d = reinterpret_cast<double2*>(dst + c * PM + r);
+            d[0] = lo; d[1] = hi;
+        }
+    }
+}
+
+}  // namespace gpr

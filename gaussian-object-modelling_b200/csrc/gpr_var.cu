@@ -1,0 +1,156 @@
+// gpr_var.cu — K3': predictive variance  v_q = k(0) - || L^-1 k*_q ||^2  for a batch of queries.
+//
+// Replaces, in the reference's evaluate(gp, query, f, v[, N]) overloads
+// (/root/reference/include/gp_regression/gp_regressor.hpp):
+//   :255-259, :308-312   Kpq = Kqp^T;  Kqq = k(dist(Q,Q))  (q x q, only its diagonal k(0) is used)
+//   :263, :316           V = cholesker.solve(Kpq)           (n x q solve, n^2 flop per query and factor)
+//   :265-266, :318-319   V = Kqq - Kqp*V; V.diagonal()      (q x q product for q numbers)
+// by a triangular matrix product on the FP64 tensor pipe against the precomputed inverse factor
+// X = L^-1 (gpr_factor.cu): V = X * K*^T has no dependency chain, streams X once per query tile through
+// L2, and its epilogue reduces the squared column norms so V itself is never written.
+//   algorithmic work: n^2 * q flop (one multiply-add per entry of the triangular factor per query).
+// Per-tile partial sums are written to a [row tile][query] scratch and summed in a fixed order by a
+// second small kernel, so the variance is bit-reproducible (no floating-point atomics).
+#include "gpr_mma.cuh"
+#include "gpr_kernels.h"
+
+namespace gpr {
+
+struct VarArgs {
+    const double* X; size_t ld; int nb;       // L^-1, lower triangular tiles
+    const double* panel; size_t panel_ld;     // K*: element (query, k) at panel[k*panel_ld + query]
+    int nqt;                                  // query tiles in this batch (panel_ld / 128)
+    double* partial;                          // nb x panel_ld
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) var_tiles_kernel(VarArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_abort;
+    __shared__ double sred[8][32];
+    const int b = blockIdx.x;
+    const int it = a.nb - 1 - b / a.nqt;      // heavy row tiles (long k range) are scheduled first
+    const int qt = b % a.nqt;
+    if (threadIdx.x == 0) s_abort = 0;
+    const TileCoord tc;
+    Acc acc;
+    acc_zero(acc);
+    tile_mainloop<STREAM_M, STREAM_M>(acc, a.X + (size_t)it * TB, a.ld, a.panel + (size_t)qt * TB, a.panel_ld,
+                                      8 * (it + 1), smem, &s_abort, NoWait());
+    // column sums of squares over this tile's 128 rows
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        double s = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s = fma(acc[mt][nt][0], acc[mt][nt][0], s);
+            s = fma(acc[mt][nt][1], acc[mt][nt][1], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (tc.t == 0) sred[tc.warp][tc.col<false>(mt) - tc.j0] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < TB) {
+        const int c = threadIdx.x, wj = c >> 5, lc = c & 31;
+        a.partial[(size_t)it * a.panel_ld + (size_t)qt * TB + c] = sred[2 * wj][lc] + sred[2 * wj + 1][lc];
+    }
+}
+
+__global__ void var_finalize_kernel(const double* partial, size_t panel_ld, int nb, int q, double k0, double* var) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    double s = 0.0;
+    for (int it = 0; it < nb; ++it) s += partial[(size_t)it * panel_ld + i];
+    var[i] = k0 - s;
+}
+
+cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* panel, size_t panel_ld, int q,
+                            double* partial, double k0, double* var, cudaStream_t st) {
+    static int attr_done = 0;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(var_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)TILE_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = 1;
+    }
+    if (q <= 0) return cudaSuccess;
+    VarArgs a;
+    a.X = X; a.ld = ld; a.nb = nb; a.panel = panel; a.panel_ld = panel_ld;
+    a.nqt = (int)(panel_ld / TB); a.partial = partial;
+    var_tiles_kernel<<<(unsigned)(a.nqt * nb), NTHREADS, TILE_SMEM_BYTES, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    var_finalize_kernel<<<(q + 255) / 256, 256, 0, st>>>(partial, panel_ld, nb, q, k0, var);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small-batch variance (q <= 8): the reference's callers ask for ONE query per call
+// (src/gp_node.cpp:1074, include/atlas/atlas_variance.hpp:78,:201).  v = X k* as a matrix-vector
+// product, bandwidth-bound: the lower triangle of X is read once for up to 8 queries.
+// Thread per row r (coalesced along r), k range split over blockIdx.y; partial dot products go to
+// part[split][r][8] and are combined in a fixed order by the finalize kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int VG_SPLIT = 8;
+
+template <int Q>
+__global__ void __launch_bounds__(256) var_gemv_kernel(const double* __restrict__ X, size_t ld, int N,
+                                                       const double* __restrict__ panel, size_t panel_ld,
+                                                       double* __restrict__ part) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    const int kspan = N / VG_SPLIT;                    // N is a multiple of 128
+    const int k0 = blockIdx.y * kspan;
+    const int rmax = min(N - 1, blockIdx.x * 256 + 255);
+    const int k1 = min(k0 + kspan, rmax + 1);
+    double s[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) s[i] = 0.0;
+    if (r < N) {
+        for (int k = k0; k < k1; ++k) {
+            if (k <= r) {
+                const double x = X[(size_t)k * ld + r];
+#pragma unroll
+                for (int i = 0; i < Q; ++i) s[i] = fma(x, __ldg(panel + (size_t)k * panel_ld + i), s[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < Q; ++i) part[((size_t)blockIdx.y * N + r) * 8 + i] = s[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) var_gemv_finalize_kernel(const double* part, int N, int q, double k0, double* var) {
+    __shared__ double red[256];
+    for (int i = 0; i < q; ++i) {
+        double s = 0.0;
+        for (int r = threadIdx.x; r < N; r += 256) {
+            double v = 0.0;
+            for (int y = 0; y < VG_SPLIT; ++y) v += part[((size_t)y * N + r) * 8 + i];
+            s = fma(v, v, s);
+        }
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) var[i] = k0 - red[0];
+        __syncthreads();
+    }
+}
+
+// part: VG_SPLIT * N * 8 doubles of scratch.
+cudaError_t launch_variance_small(const double* X, size_t ld, int N, const double* panel, size_t panel_ld, int q,
+                                  double* part, double k0, double* var, cudaStream_t st) {
+    if (q <= 0) return cudaSuccess;
+    dim3 grid((N + 255) / 256, VG_SPLIT);
+    if (q <= 1) var_gemv_kernel<1><<<grid, 256, 0, st>>>(X, ld, N, panel, panel_ld, part);
+    else if (q <= 2) var_gemv_kernel<2><<<grid, 256, 0, st>>>(X, ld, N, panel, panel_ld, part);
+    else if (q <= 4) var_gemv_kernel<4><<<grid, 256, 0, st>>>(X, ld, N, panel, panel_ld, part);
+    else var_gemv_kernel<8><<<grid, 256, 0, st>>>(X, ld, N, panel, panel_ld, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    var_gemv_finalize_kernel<<<1, 256, 0, st>>>(part, N, q, k0, var);
+    return cudaGetLastError();
+}
+
+}  // namespace gpr

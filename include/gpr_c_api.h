@@ -1,0 +1,117 @@
+/* gpr_c_api.h — C-ABI of the B200-native GP-regression core (libgpr_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of pacman-project/gaussian-object-modelling:
+ * everything that the reference's header-only template
+ *     /root/reference/include/gp_regression/gp_regressor.hpp   (class GPRegressor<CovType>)
+ * computes with Eigen on one CPU thread is computed here by hand-written sm_100a CUDA kernels.
+ * Plain C types only: SoA double arrays exactly as in gp_regression::Data
+ * (gp_regressor.hpp:49-55), sizes, opaque handles.  There is no CPU fallback: every entry point
+ * that computes fails with GPR_ERR_CUDA when no CUDA device is usable.
+ *
+ * The C++ headers in include/gp_regression/ are thin shims over this file and keep the reference's
+ * names, signatures and exception messages; INTEGRATION.md shows the binding.
+ *
+ * Matrices crossing this boundary are column-major with the stated leading dimension, like the
+ * Eigen::MatrixXd outputs of the reference (q x 3: all x, then all y, then all z).
+ */
+#ifndef GPR_C_API_H
+#define GPR_C_API_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpr_ctx gpr_ctx;
+typedef struct gpr_model gpr_model;
+
+/* Status codes.  GPR_ERR_NOT_SPD: the covariance matrix is not positive definite (for the
+ * thin-plate kernel: R smaller than the largest pairwise distance); the 1-based index of
+ * the failing pivot is returned by gpr_last_pivot(). */
+enum { GPR_OK = 0, GPR_ERR_INVALID = 1, GPR_ERR_NOT_SPD = 2, GPR_ERR_CUDA = 3, GPR_ERR_OOM = 4 };
+
+/* Covariance function = the reference's kernel classes:
+ *   kind 0  ThinPlate(R = p0)               kernels/thin_plate.hpp:12-38
+ *   kind 1  Gaussian(sigma = p0, length = p1)   kernels/gaussian.hpp:15-50   (sigma^2 exp(-d/length^2))
+ *   kind 2  Laplace(sigma = p0, length = p1)    kernels/laplace.hpp:37-70    (2 sigma exp(-d/length)) */
+typedef struct { int kind; double p0; double p1; } gpr_kernel_t;
+
+/* Per-phase device times of the last fit / predict on this context, CUDA-event measured (ms).
+ * Replaces the std::chrono prints of the reference's caller (src/gp_node.cpp:894, :923-925). */
+typedef struct {
+    double cov_ms, chol_ms, solve_ms, normals_ms, fit_total_ms;
+    double linv_ms;                 /* one-time L^-1 for the variance path */
+    double predict_mean_ms, predict_var_ms, predict_total_ms;
+    double h2d_ms, d2h_ms;
+} gpr_timings;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* devices == NULL or ndev <= 0: device 0 only.  With several devices, gpr_fit runs on devices[0]
+ * and gpr_predict shards the queries over all of them. */
+int gpr_ctx_create(const int* devices, int ndev, gpr_ctx** out);
+int gpr_ctx_destroy(gpr_ctx* ctx);
+int gpr_ctx_num_devices(const gpr_ctx* ctx);
+const char* gpr_last_error(void);          /* thread-local message of the last failing call */
+long long gpr_last_pivot(void);            /* thread-local, valid after GPR_ERR_NOT_SPD */
+int gpr_last_timings(const gpr_ctx* ctx, gpr_timings* out);
+
+/* ---- fit: GPRegressor::create<withNormals>  (gp_regressor.hpp:110-182) ---------------------- */
+/* x,y,z,label: n host doubles each; sigma2: n host doubles or NULL (Data::sigma2 empty, :154). */
+int gpr_fit(gpr_ctx* ctx, const double* x, const double* y, const double* z, const double* label,
+            const double* sigma2_or_null, size_t n, gpr_kernel_t kernel, int with_normals, gpr_model** out);
+int gpr_model_destroy(gpr_model* m);
+size_t gpr_model_size(const gpr_model* m);                 /* n */
+/* Model fields the reference exposes (gp_regressor.hpp:71-87): alpha[n], R, N (n x 3 column-major,
+ * only when fitted with normals).  Any output pointer may be NULL. */
+int gpr_model_get(const gpr_model* m, double* alpha, double* R, double* normals_or_null);
+/* Debug / parity access: the assembled covariance is not kept; the lower Cholesky factor is.
+ * L: n x n column-major, strict upper triangle zeroed. */
+int gpr_model_get_factor(const gpr_model* m, double* L);
+
+/* ---- predict: the four GPRegressor::evaluate overloads (gp_regressor.hpp:194,:222,:282,:332) - */
+/* qx,qy,qz: q host doubles.  f: q.  var: q or NULL.  grad: q x 3 column-major (leading dimension q),
+ * un-normalised as in the reference (:247-250), or NULL.  tx, ty: q x 3 tangent basis (:204-211), both
+ * or neither; they require grad.  Thread-safe on one model: concurrent calls use separate streams and
+ * workspaces (the reference is called from hundreds of threads, src/gp_node.cpp:1027-1038). */
+int gpr_predict(gpr_ctx* ctx, gpr_model* m, const double* qx, const double* qy, const double* qz, size_t q,
+                double* f, double* var_or_null, double* grad_or_null, double* tx_or_null, double* ty_or_null);
+/* Same, all pointers in device memory of the model's primary device (devices[0]); no host copies.
+ * Runs on an internal stream and returns after it has drained. */
+int gpr_predict_device(gpr_ctx* ctx, gpr_model* m, const double* d_qx, const double* d_qy, const double* d_qz,
+                       size_t q, double* d_f, double* d_var_or_null, double* d_grad_or_null);
+/* Builds L^-1 now (otherwise built by the first call that asks for a variance). */
+int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m);
+
+/* ---- update: GPRegressor::update<withNormals>  (gp_regressor.hpp:367-479) --------------------- */
+/* Appends k points; R and the normals are not refreshed, as in the reference (:454-455, :462-477). */
+int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
+               const double* sigma2_or_null, size_t k);
+
+/* ---- replication across processes (one process per GPU, bench.py / torch.distributed) -------- */
+/* The fitted state that predict needs, as raw device pointers on the primary device, so that the
+ * launcher can broadcast it with NCCL into a model created by gpr_model_create_replica on another rank.
+ * padded_n = 128*ceil(n/128); xyz: 3*padded_n (x | y | z); alpha: padded_n; linv: padded_n^2 (or NULL
+ * until the variance path was prepared). */
+typedef struct {
+    size_t n, padded_n;
+    gpr_kernel_t kernel;
+    double R;
+    double* xyz; double* alpha; double* linv;
+} gpr_model_state;
+int gpr_model_state_get(gpr_ctx* ctx, gpr_model* m, int with_linv, gpr_model_state* out);
+/* Allocates an un-fitted model of the given size on ctx's primary device; the caller fills the buffers
+ * returned by gpr_model_state_get(replica, ...) (e.g. as the destination of a broadcast). */
+int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double R, int with_linv, gpr_model** out);
+
+/* ---- self-tests of the tile engine (used by tests/, device pointers, one 128-tile granularity) -- */
+int gpr_selftest_gemm(const double* hA, const double* hB, int b_kmajor, double* hC, int m_tiles, int n_tiles, int k);
+int gpr_selftest_leaf(double* h_tile_inout, double* h_inv_out, int* info);
+int gpr_selftest_factor(double* hA_inout, int n_tiles, double* h_linv_or_null, int serial, long long* pivot);
+/* Raw pipe probes (CUDA-event timed): which = 0 FP64 tensor (DMMA.8x8x4), 1 FP64 FMA; TFLOP/s. */
+int gpr_selftest_peak(int which, int ctas_per_sm, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
