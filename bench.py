@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the GP-regression hot path on B200 (BASELINE.json).
+
+Workload (BASELINE config 3): synthetic cloud, seed 0, n = 16,384 (12,288 points on the unit
+sphere, label 0; 4,096 on the r = 2 sphere, label +1), sigma2 = 0.1, ThinPlate(R = 4.2); queries are the
+256^3 lattice on [-1.2, 1.2]^3, sharded over the ranks as contiguous index blocks (z-slabs).
+
+A "step" is one pass of the hot path over one batch of queries per GPU: fused mean + cross-covariance
+panel, then the variance product against L^-1 on the FP64 tensor pipe.  `value` is whole-job
+query points / s (mean + variance) with the queries already resident in HBM; `e2e` is the same through
+the host-pointer C-ABI call gpr_predict (pinned host buffers, H2D and D2H inside the timed region).
+The fit (covariance build + Cholesky + alpha) is timed separately and reported as fit_ms on the same line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL broadcast of the model)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRAIN = 16384
+GRID_RES = 256
+BATCHES_PER_STEP = 4           # variance batches (148*128 queries each) per step and GPU
+METRIC = "query_pts_per_sec_mean_var"
+UNIT = "points/s"
+
+
+def workload_config(extra=None):
+    cfg = {"workload": "config3: synthetic sphere cloud n=16384, ThinPlate(R=4.2), sigma2=0.1, mean+variance over the "
+                       "256^3 grid on [-1.2,1.2]^3 (z-slab shards)",
+           "n_train": N_TRAIN, "grid": GRID_RES, "kernel": "thin_plate", "R": 4.2,
+           "cache": "inputs larger than L2: each step streams L^-1 (1.07 GB) and a 2.5 GB cross-covariance panel"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, sample_q, threads_note=True):
+    """The CPU arm: the reference's mathematics with OpenBLAS LAPACK on all host cores (oracle.blas_*,
+    the "port" flavour of BASELINE.md §5 — the reference itself cannot be built here: Eigen is absent)."""
+    import oracle
+    import gpr_b200
+    W = gpr_b200.workloads
+    P, y, s2 = W.synthetic_cloud(N_TRAIN, seed=0)
+    cores = os.cpu_count()
+    t0 = time.perf_counter()
+    model = oracle.blas_fit(P, y, s2, "thin_plate", W.SYNTH_R, 0.0)
+    fit_s = time.perf_counter() - t0
+    rng = np.random.default_rng(0)
+    times = []
+    for s in range(warmup + steps):
+        z = int(rng.integers(0, GRID_RES))
+        Q = W.grid_slab(GRID_RES, z, z + 1)[:sample_q]
+        t0 = time.perf_counter()
+        oracle.blas_predict(model, Q, var=True)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times)
+    return {"value": sample_q * len(times) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d steps x %d queries of the same grid (mean+variance, dtrsm) after one dpotrf fit of n=%d "
+                      "(fit %.1f s, not in value)" % (len(times), sample_q, N_TRAIN, fit_s),
+            "fit_s": fit_s, "ms_per_step": 1e3 * dt / len(times)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fit-reps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res = cpu_reference_run(args.steps, args.warmup, sample_q=1024)
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config({"sample_queries_per_step": 1024}),
+                "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+                "fit_ms": 1e3 * res["fit_s"],
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import gpr_b200 as g
+    from gaussian_object_modelling_b200 import distributed as D
+    W = g.workloads
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    ctx = g.Context(devices=[local_rank])
+    reg = g.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    extras = {}
+
+    # ---- fit on rank 0 (the factorisation stays on one GPU), timed with the library's CUDA events ----
+    model = None
+    if rank == 0:
+        P, y, s2 = W.synthetic_cloud(N_TRAIN, seed=0)
+        fits = []
+        for rep in range(1 + args.fit_reps):
+            if model is not None:
+                model.close()
+            t0 = time.perf_counter()
+            model = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+            wall = 1e3 * (time.perf_counter() - t0)
+            t = ctx.timings()
+            if rep > 0:
+                fits.append((t["fit_total_ms"], t["cov_ms"], t["chol_ms"], t["solve_ms"], wall))
+        best = min(fits)
+        extras.update(fit_ms=best[0], fit_cov_ms=best[1], fit_chol_ms=best[2], fit_solve_ms=best[3], fit_wall_ms_e2e=best[4],
+                      fit_chol_tflops=N_TRAIN ** 3 / 3 / (best[2] * 1e-3) / 1e12)
+        reg.prepare_variance(model)
+        extras["linv_ms_once"] = ctx.timings()["linv_ms"]
+    bcast_bytes = 0
+    if world > 1:
+        t0 = time.perf_counter()
+        model, bcast_bytes = D.broadcast_model(reg, model, N_TRAIN, W.SYNTH_R, True, rank, dev, src=0)
+        barrier()
+        extras.update(broadcast_ms=1e3 * (time.perf_counter() - t0), broadcast_bytes=bcast_bytes)
+
+    # ---- this rank's block of the 256^3 query grid --------------------------------------------------
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    batch = 128 * sms
+    step_q = BATCHES_PER_STEP * batch
+    total_q = GRID_RES ** 3
+    a, b = D.shard_range(total_q, rank, world)
+    need = (args.warmup + args.steps) * step_q
+    z0 = a // (GRID_RES * GRID_RES)
+    nz = -(-need // (GRID_RES * GRID_RES)) + 1
+    Qh = W.grid_slab(GRID_RES, z0, min(GRID_RES, z0 + nz))
+    while len(Qh) < need:                                   # the shard is smaller than the run: wrap around
+        Qh = np.vstack([Qh, Qh])
+    Qh = np.ascontiguousarray(Qh[:need].T)                  # 3 x need, SoA like gp_regression::Data
+    Qd = torch.from_numpy(Qh).to(dev)
+    f_d = torch.empty(step_q, dtype=torch.float64, device=dev)
+    v_d = torch.empty(step_q, dtype=torch.float64, device=dev)
+
+    def step_device(s):
+        o = s * step_q
+        reg.evaluate_device(model, Qd[0, o:].data_ptr(), Qd[1, o:].data_ptr(), Qd[2, o:].data_ptr(), step_q,
+                            f_d.data_ptr(), v_d.data_ptr(), None)
+        t = ctx.timings()
+        return t["predict_var_ms"], t["predict_mean_ms"]
+
+    sampler = ClockSampler(local_rank)
+    for s in range(args.warmup):
+        step_device(s)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    var_ms = mean_ms = 0.0
+    for s in range(args.warmup, args.warmup + args.steps):
+        vm, mm = step_device(s)
+        var_ms += vm
+        mean_ms += mm
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms, var_ms, mean_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms, var_ms, mean_ms = (float(x) for x in tmax.tolist())
+    value = world * step_q * args.steps / (elapsed_ms * 1e-3)
+    assert bool(torch.isfinite(f_d).all()) and float(v_d.min()) > 0.0
+
+    # ---- e2e: the host-pointer C-ABI call, pinned host buffers, copies inside the timed region -------
+    Qp = torch.from_numpy(Qh).pin_memory()
+    fo = torch.empty(step_q, dtype=torch.float64).pin_memory()
+    vo = torch.empty(step_q, dtype=torch.float64).pin_memory()
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+
+    def step_host(s):
+        o = s * step_q
+        ptr = lambda t, off=0: C.cast(t.data_ptr() + 8 * off, dp)
+        rc = g.lib().gpr_predict(ctx._h, model._h, ptr(Qp[0], o), ptr(Qp[1], o), ptr(Qp[2], o), step_q, ptr(fo), ptr(vo), None, None, None)
+        if rc:
+            raise RuntimeError(g.lib().gpr_last_error().decode())
+
+    for s in range(min(2, args.warmup)):
+        step_host(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.warmup, args.warmup + args.steps):
+        step_host(s)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = world * step_q * args.steps / e2e_s
+    assert np.array_equal(fo.numpy(), f_d.cpu().numpy()) and np.array_equal(vo.numpy(), v_d.cpu().numpy())
+
+    if rank == 0:
+        launches_var = BATCHES_PER_STEP * args.steps
+        flops_per_launch = float(N_TRAIN) ** 2 * batch                # n^2 * q per variance batch
+        achieved = flops_per_launch / (var_ms / launches_var * 1e-3) / 1e12
+        dmma_peak = g.selftest_peak(0, 4)
+        a64 = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            a64 @ a64
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(); a64 @ a64; a64 @ a64; c1.record(); torch.cuda.synchronize(dev)
+        dgemm = 2 * 2 * 8192 ** 3 / (c0.elapsed_time(c1) * 1e-3) / 1e12
+        del a64
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config({"queries_per_step_per_gpu": step_q,
+                                                                               "parallelism": "query-sharded x%d" % world}),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * step_q, "d2h_bytes_per_step": 16 * step_q},
+                "gpu_launches": 3 * BATCHES_PER_STEP * args.steps,
+                "clocks": clocks,
+                "roofline": {"kernel": "var_tiles_kernel (variance product X*K*^T + column norms)", "bound": "tensor",
+                             "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
+                             "traffic": None,
+                             "peak_source": "FP64: measured in this run, raw DMMA.8x8x4 issue rate (gpr_selftest_peak); "
+                                            "MEASURED_PEAKS.json has no FP64 entry. cuBLAS DGEMM 8192^3 in this run: %.1f TF/s" % dgemm,
+                             "cublas_dgemm_tflops": dgemm, "share_of_step": var_ms / elapsed_ms,
+                             "mean_panel_kernel_ms_per_step": mean_ms / args.steps}}
+        line.update(extras)
+        if world == 1 and not args.no_cpu_baseline:
+            res = cpu_reference_run(2, 1, sample_q=1024)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["fit_s"] = res["fit_s"]
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,75 @@
+"""One-process-per-GPU plumbing for the query-sharded predict.
+
+The path shards by query point and has exactly one exchange step: after the fit on rank 0, the state
+that predict needs — X (3·N doubles), alpha (N) and, for variances, the inverse factor L^-1 (N² doubles)
+— is broadcast once (NCCL over NVLink on the GPU box, gloo in the CPU tests).  There is no per-query
+communication; every query is computed by exactly one rank with identical code, so sharded results are
+bit-identical to single-GPU results.  torch.distributed is plumbing only: the buffers being broadcast
+are the C-ABI library's own device allocations, wrapped without a copy.
+"""
+import numpy as np
+
+
+def shard_range(q, rank, world):
+    """Contiguous block of the query index range owned by `rank` (z-slabs for grids)."""
+    return (q * rank) // world, (q * (rank + 1)) // world
+
+
+class _DevicePtr:
+    """Zero-copy view of a raw device allocation for torch.as_tensor (CUDA array interface v3)."""
+
+    def __init__(self, ptr, n_doubles):
+        self.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def as_tensor(ptr, n_doubles, device):
+    import torch
+    return torch.as_tensor(_DevicePtr(ptr, n_doubles), device=device)
+
+
+def broadcast_model(reg, model, n, R, with_linv, rank, device, src=0):
+    """Rank `src` passes its fitted `model`; the other ranks pass model=None and receive a replica.
+    Returns (model, bytes_broadcast)."""
+    import torch
+    import torch.distributed as dist
+    meta = torch.tensor([float(n), float(R)], dtype=torch.float64, device=device)
+    dist.broadcast(meta, src=src)
+    n, R = int(meta[0].item()), float(meta[1].item())
+    if rank != src:
+        model = reg.create_replica(n, R, with_linv)
+    st = model.state(with_linv=with_linv)
+    N = st.padded_n
+    nbytes = 0
+    for ptr, cnt in ((st.xyz, 3 * N), (st.alpha, N)) + (((st.linv, N * N),) if with_linv else ()):
+        t = as_tensor(ptr, cnt, device)
+        # NCCL counts are 32-bit element counts in some paths: broadcast the factor in 1 GiB pieces
+        step = 1 << 27
+        for a in range(0, cnt, step):
+            dist.broadcast(t[a:a + step], src=src)
+        nbytes += 8 * cnt
+    torch.cuda.synchronize(device)
+    return model, nbytes
+
+
+def broadcast_arrays(arrays, src=0):
+    """gloo/CPU counterpart used by the tests: broadcast a list of numpy float64 arrays in place."""
+    import torch
+    import torch.distributed as dist
+    for a in arrays:
+        t = torch.from_numpy(a)
+        dist.broadcast(t, src=src)
+    return arrays
+
+
+def gather_shards(local, q, rank, world):
+    """All-gather variable-length query shards back into one array of length q (tests only)."""
+    import torch
+    import torch.distributed as dist
+    sizes = [shard_range(q, r, world)[1] - shard_range(q, r, world)[0] for r in range(world)]
+    m = max(sizes)
+    buf = np.zeros(m)
+    buf[:len(local)] = local
+    outs = [torch.zeros(m, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(outs, torch.from_numpy(buf))
+    return np.concatenate([o.numpy()[:s] for o, s in zip(outs, sizes)])

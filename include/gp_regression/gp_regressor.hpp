@@ -1,0 +1,243 @@
+// Drop-in for /root/reference/include/gp_regression/gp_regressor.hpp (namespace gp_regression):
+// Data, Model, GPRegressor<CovType> with create<bool> / four evaluate overloads / update<bool> /
+// setCovFunction, and the free function computeTangentBasis — same names, signatures, ownership and
+// exception messages.  All arithmetic runs in libgpr_b200.so (hand-written sm_100a CUDA behind
+// include/gpr_c_api.h); this header only validates, marshals the SoA vectors and copies results back.
+// There is no CPU fallback: without the library / a B200 the calls throw GPRegressionException.
+//
+// Differences a caller can observe (documented in INTEGRATION.md):
+//   * Model::Kpp, Kppdiff, Kppdiffdiff stay empty and there is no Model::cholesker — no caller reads
+//     them; the factor lives on the device behind Model::device.
+//   * create() throws GPRegressionException("covariance matrix is not positive definite …") where
+//     Eigen's pivoted LDLT would carry on with an indefinite matrix.
+//   * outputs N are zero-initialised before accumulation (the reference adds into uninitialised
+//     storage, gp_regressor.hpp:241/:247).
+//   * computeTangentBasis is inline (the reference defines it non-inline in a header, :29).
+#pragma once
+
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#if defined(__has_include)
+#if __has_include(<Eigen/Core>) && !defined(GPR_FORCE_MINI_EIGEN)
+#include <Eigen/Core>
+#define GPR_HAVE_EIGEN 1
+#endif
+#endif
+#ifndef GPR_HAVE_EIGEN
+#include "mini_eigen.h"
+#endif
+
+#include "../gpr_c_api.h"
+#include "cov_functions.h"
+#include "gp_regression_exception.h"
+
+namespace gp_regression {
+
+// gp_regressor.hpp:29-44.  N = grad/|grad|; Tx = e - N (N.e) normalised with e = X unless N is within
+// 1e-3 of X (Eigen isApprox), then e = Y; Ty = N x Tx normalised.
+inline void computeTangentBasis(const Eigen::Vector3d& grad, Eigen::Vector3d& N, Eigen::Vector3d& Tx,
+                                Eigen::Vector3d& Ty) {
+    N = grad.normalized();
+    const double dx = N(0) - 1.0;
+    const double diff2 = dx * dx + N(1) * N(1) + N(2) * N(2);
+    const double nn = N(0) * N(0) + N(1) * N(1) + N(2) * N(2);
+    const bool near_x = diff2 <= 1e-6 * (nn < 1.0 ? nn : 1.0);
+    Eigen::Vector3d e = near_x ? Eigen::Vector3d(0, 1, 0) : Eigen::Vector3d(1, 0, 0);
+    const double ne = N.dot(e);
+    Tx = Eigen::Vector3d(e(0) - N(0) * ne, e(1) - N(1) * ne, e(2) - N(2) * ne);
+    Tx.normalize();
+    Ty = N.cross(Tx);
+    Ty.normalize();
+}
+
+// gp_regressor.hpp:49-66
+struct Data {
+    std::vector<double> coord_x, coord_y, coord_z, label, sigma2;
+    typedef std::shared_ptr<Data> Ptr;
+    typedef std::shared_ptr<const Data> ConstPtr;
+    void clear() { coord_x.clear(); coord_y.clear(); coord_z.clear(); label.clear(); sigma2.clear(); }
+};
+
+// gp_regressor.hpp:71-87
+struct Model {
+    double R = 0.0;             // largest pairwise training distance
+    Eigen::MatrixXd P;          // n x 3 points
+    Eigen::VectorXd Y, S2;      // labels, noise
+    Eigen::MatrixXd N;          // normals at the training points (create<true>)
+    Eigen::MatrixXd Tx, Ty;     // never filled by the reference either
+    Eigen::MatrixXd Kpp;        // left empty: K is assembled and factorised on the device
+    Eigen::VectorXd alpha;      // weights
+    Eigen::MatrixXd Kppdiff, Kppdiffdiff;   // left empty
+    std::shared_ptr<void> device;           // gpr_model*, freed with the last Model::Ptr
+    typedef std::shared_ptr<Model> Ptr;
+    typedef std::shared_ptr<const Model> ConstPtr;
+};
+
+namespace detail {
+
+inline void raise(int rc) {
+    throw GPRegressionException(gpr_last_error(), rc, rc == GPR_ERR_NOT_SPD ? gpr_last_pivot() : 0);
+}
+
+// One process-wide context, created on first use.  GPR_DEVICES="0,1,2,3" selects the GPUs that share
+// the query load (default: device 0).
+inline gpr_ctx* context() {
+    static gpr_ctx* ctx = nullptr;
+    static std::once_flag once;
+    static int rc = 0;
+    std::call_once(once, [] {
+        std::vector<int> devs;
+        if (const char* s = std::getenv("GPR_DEVICES")) {
+            std::stringstream ss(s);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(std::atoi(tok.c_str()));
+        }
+        rc = gpr_ctx_create(devs.empty() ? nullptr : devs.data(), (int)devs.size(), &ctx);
+    });
+    if (!ctx) throw GPRegressionException(std::string("cannot create GPU context: ") + gpr_last_error(), rc ? rc : GPR_ERR_CUDA);
+    return ctx;
+}
+
+inline gpr_model* handle(const Model& m) { return static_cast<gpr_model*>(m.device.get()); }
+
+inline void vec_to(Eigen::VectorXd& dst, const std::vector<double>& src) {
+    dst.resize((Eigen::Index)src.size());
+    for (size_t i = 0; i < src.size(); ++i) dst((Eigen::Index)i) = src[i];
+}
+
+}  // namespace detail
+
+template <typename CovType>
+class GPRegressor {
+public:
+    std::shared_ptr<CovType> kernel_;       // gp_regressor.hpp:97
+
+    virtual ~GPRegressor() {}
+    GPRegressor() : kernel_(std::make_shared<CovType>()) {}                             // :497-500
+    void setCovFunction(const std::shared_ptr<CovType>& kernel) { kernel_ = kernel; }   // :488-491
+
+    // :110-182.  Replaces gp with a fresh Model (":117 we dont care what there was there").
+    template <bool withNormals>
+    void create(Data::ConstPtr data, Model::Ptr& gp) {
+        assertData(data);
+        const size_t n = data->coord_x.size();
+        if (data->coord_y.size() != n || data->coord_z.size() != n || data->label.size() != n ||
+            (!data->sigma2.empty() && data->sigma2.size() < n))
+            throw GPRegressionException("Inconsistent input data sizes");
+        gp = std::make_shared<Model>();
+        gpr_model* h = nullptr;
+        const int rc = gpr_fit(detail::context(), data->coord_x.data(), data->coord_y.data(), data->coord_z.data(),
+                               data->label.data(), data->sigma2.empty() ? nullptr : data->sigma2.data(), n,
+                               kernel_->descriptor(), withNormals ? 1 : 0, &h);
+        if (rc != GPR_OK) detail::raise(rc);
+        gp->device = std::shared_ptr<void>(h, [](void* p) { gpr_model_destroy(static_cast<gpr_model*>(p)); });
+        refreshHostMirror(*data, *gp, withNormals, 0);
+    }
+
+    // :194-212
+    void evaluate(Model::ConstPtr gp, Data::ConstPtr query, std::vector<double>& f, std::vector<double>& v,
+                  Eigen::MatrixXd& N, Eigen::MatrixXd& Tx, Eigen::MatrixXd& Ty) {
+        run(gp, query, f, &v, &N, &Tx, &Ty);
+    }
+    // :222-273  (N is the un-normalised gradient, :250)
+    void evaluate(Model::ConstPtr gp, Data::ConstPtr query, std::vector<double>& f, std::vector<double>& v,
+                  Eigen::MatrixXd& N) {
+        run(gp, query, f, &v, &N, nullptr, nullptr);
+    }
+    // :282-324
+    void evaluate(Model::ConstPtr gp, Data::ConstPtr query, std::vector<double>& f, std::vector<double>& v) {
+        run(gp, query, f, &v, nullptr, nullptr, nullptr);
+    }
+    // :332-357
+    void evaluate(Model::ConstPtr gp, Data::ConstPtr query, std::vector<double>& f) {
+        run(gp, query, f, nullptr, nullptr, nullptr, nullptr);
+    }
+
+    // :367-479.  Appends new_data and re-solves; R and the normals are not refreshed (:454-455, :462-477).
+    template <bool withNormals>
+    void update(Data::ConstPtr new_data, Model::Ptr gp) {
+        assertData(new_data);
+        if (!gp) throw GPRegressionException("Empty model pointer");
+        if (!gp->device) throw GPRegressionException("Model was not created by this regressor");
+        const size_t k = new_data->label.size();                                       // :383
+        if (new_data->coord_x.size() != k || new_data->coord_y.size() != k || new_data->coord_z.size() != k ||
+            (!new_data->sigma2.empty() && new_data->sigma2.size() < k))
+            throw GPRegressionException("Inconsistent input data sizes");
+        const size_t p = (size_t)gp->Y.size();
+        const int rc = gpr_append(detail::context(), detail::handle(*gp), new_data->coord_x.data(),
+                                  new_data->coord_y.data(), new_data->coord_z.data(), new_data->label.data(),
+                                  new_data->sigma2.empty() ? nullptr : new_data->sigma2.data(), k);
+        if (rc != GPR_OK) detail::raise(rc);
+        refreshHostMirror(*new_data, *gp, false, p);
+    }
+
+private:
+    // :563-572
+    void assertData(Data::ConstPtr data) const {
+        if (!data) throw GPRegressionException("Empty data pointer");
+        if (data->coord_x.empty() && data->coord_y.empty() && data->coord_z.empty() && data->label.empty())
+            throw GPRegressionException("All input data is empty!");
+    }
+
+    // Host mirrors of the fields the reference's Model exposes: P, Y, S2 (appended from `added`
+    // starting at row `first`), alpha, R, N.
+    void refreshHostMirror(const Data& added, Model& gp, bool normals, size_t first) const {
+        gpr_model* h = detail::handle(gp);
+        const size_t n = gpr_model_size(h);
+        Eigen::MatrixXd P((Eigen::Index)n, 3);
+        Eigen::VectorXd Y, S2;
+        Y.resize((Eigen::Index)n);
+        const bool s2 = !added.sigma2.empty() || gp.S2.size() > 0;
+        if (s2) S2.resize((Eigen::Index)n);
+        for (size_t i = 0; i < first; ++i) {
+            for (int c = 0; c < 3; ++c) P((Eigen::Index)i, c) = gp.P((Eigen::Index)i, c);
+            Y((Eigen::Index)i) = gp.Y((Eigen::Index)i);
+            if (s2) S2((Eigen::Index)i) = gp.S2.size() > (Eigen::Index)i ? gp.S2((Eigen::Index)i) : 0.0;
+        }
+        for (size_t i = first; i < n; ++i) {
+            const size_t s = i - first;
+            P((Eigen::Index)i, 0) = added.coord_x[s]; P((Eigen::Index)i, 1) = added.coord_y[s]; P((Eigen::Index)i, 2) = added.coord_z[s];
+            Y((Eigen::Index)i) = added.label[s];
+            if (s2) S2((Eigen::Index)i) = s < added.sigma2.size() ? added.sigma2[s] : 0.0;
+        }
+        gp.P = P; gp.Y = Y; gp.S2 = S2;
+        std::vector<double> alpha(n), nrm(normals ? 3 * n : 0);
+        double R = 0.0;
+        const int rc = gpr_model_get(h, alpha.data(), &R, normals ? nrm.data() : nullptr);
+        if (rc != GPR_OK) detail::raise(rc);
+        detail::vec_to(gp.alpha, alpha);
+        gp.R = R;
+        if (normals) {
+            gp.N.resize((Eigen::Index)n, 3);
+            for (size_t i = 0; i < n; ++i)
+                for (int c = 0; c < 3; ++c) gp.N((Eigen::Index)i, c) = nrm[(size_t)c * n + i];
+        }
+    }
+
+    void run(const Model::ConstPtr& gp, const Data::ConstPtr& query, std::vector<double>& f, std::vector<double>* v,
+             Eigen::MatrixXd* N, Eigen::MatrixXd* Tx, Eigen::MatrixXd* Ty) {
+        if (!gp) throw GPRegressionException("Empty Model pointer");                    // :197, :224, :284, :334
+        assertData(query);                                                             // :228, :288, :338
+        if (!query->label.empty()) throw GPRegressionException("Query is already labeled!");   // :230, :290, :340
+        if (!gp->device) throw GPRegressionException("Model was not created by this regressor");
+        const size_t q = query->coord_x.size();
+        if (query->coord_y.size() != q || query->coord_z.size() != q)
+            throw GPRegressionException("Inconsistent query sizes");
+        f.assign(q, 0.0);
+        if (v) v->assign(q, 0.0);
+        if (N) N->resize((Eigen::Index)q, 3);
+        if (Tx) Tx->resize((Eigen::Index)q, 3);
+        if (Ty) Ty->resize((Eigen::Index)q, 3);
+        const int rc = gpr_predict(detail::context(), detail::handle(*gp), query->coord_x.data(), query->coord_y.data(),
+                                   query->coord_z.data(), q, f.data(), v ? v->data() : nullptr, N ? N->data() : nullptr,
+                                   Tx ? Tx->data() : nullptr, Ty ? Ty->data() : nullptr);
+        if (rc != GPR_OK) detail::raise(rc);
+    }
+};
+
+}  // namespace gp_regression

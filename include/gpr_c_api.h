@@ -88,7 +88,7 @@ int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m);
 int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
                const double* sigma2_or_null, size_t k);
 
-/* ---- replication across processes (one process per GPU, bench.py / torch.distributed) -------- */
+/* ---- replication across processes (one process per GPU, launched by bench.py) ----------------- */
 /* The fitted state that predict needs, as raw device pointers on the primary device, so that the
  * launcher can broadcast it with NCCL into a model created by gpr_model_create_replica on another rank.
  * padded_n = 128*ceil(n/128); xyz: 3*padded_n (x | y | z); alpha: padded_n; linv: padded_n^2 (or NULL

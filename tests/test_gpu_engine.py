@@ -1,0 +1,81 @@
+"""GPU suite, part 1: the DMMA tile engine and the shared-memory leaves, piece by piece against numpy
+(float64 reference of the same op).  Tolerances: products of O(1) numbers with k terms accumulate
+k*eps relative error; factorisations are compared with LAPACK at cond*eps."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _spd(n, seed):
+    rng = np.random.default_rng(seed)
+    M = rng.standard_normal((n, n))
+    return M @ M.T / n + np.eye(n)
+
+
+@pytest.mark.parametrize("kmajor", [False, True])
+@pytest.mark.parametrize("shape", [(128, 128, 16), (256, 384, 64), (128, 256, 160), (384, 128, 1040)])
+def test_tile_gemm_matches_numpy(gpr, kmajor, shape):
+    M, N, k = shape
+    rng = np.random.default_rng(M + N + k)
+    A, B = rng.standard_normal((M, k)), rng.standard_normal((N, k))
+    C = gpr.selftest_gemm(A, B, kmajor)
+    assert relerr(C, A @ B.T) <= 1e-14 * np.sqrt(k)
+
+
+def test_tile_gemm_is_exact_on_small_integers(gpr):
+    rng = np.random.default_rng(0)
+    A = rng.integers(-8, 9, size=(256, 96)).astype(float)
+    B = rng.integers(-8, 9, size=(128, 96)).astype(float)
+    for kmajor in (False, True):
+        assert np.array_equal(gpr.selftest_gemm(A, B, kmajor), A @ B.T)      # fragment maps are exact
+
+
+def test_leaf_cholesky_and_inverse(gpr):
+    A = _spd(128, 3)
+    L, inv, info = gpr.selftest_leaf(A)
+    Lr = np.linalg.cholesky(A)
+    assert info == 0
+    assert relerr(np.tril(L), Lr) <= 1e-14 and np.abs(np.triu(L, 1)).max() == 0.0
+    assert relerr(inv, np.linalg.inv(Lr)) <= 1e-13 and np.abs(np.triu(inv, 1)).max() == 0.0
+
+
+@pytest.mark.parametrize("col", [0, 15, 16, 77, 127])
+def test_leaf_reports_first_bad_pivot(gpr, col):
+    A = _spd(128, 4)
+    A[col, col] = -5.0
+    assert gpr.selftest_leaf(A)[2] == col + 1
+
+
+@pytest.mark.parametrize("nb,serial", [(1, True), (2, True), (3, True), (3, False), (8, False), (24, False)])
+def test_tile_cholesky_and_inverse(gpr, nb, serial):
+    """The persistent tile-task kernels (dependency flags) and the one-launch-per-column debug mode."""
+    A = _spd(128 * nb, 10 + nb)
+    L, X, piv = gpr.selftest_factor(A, True, serial)
+    Lr = np.linalg.cholesky(A)
+    assert piv == 0
+    assert relerr(L, Lr) <= 1e-13
+    assert relerr(np.tril(X), np.linalg.inv(Lr)) <= 1e-12
+    assert relerr(np.tril(X) @ L, np.eye(len(A))) <= 1e-12
+
+
+def test_tile_cholesky_is_bit_reproducible(gpr):
+    A = _spd(128 * 12, 99)
+    L1, _, _ = gpr.selftest_factor(A, False, False)
+    L2, _, _ = gpr.selftest_factor(A, False, False)
+    L3, _, _ = gpr.selftest_factor(A, False, True)
+    assert np.array_equal(L1, L2) and np.array_equal(L1, L3)     # scheduling never changes the arithmetic
+
+
+def test_tile_cholesky_rejects_indefinite(gpr):
+    A = _spd(128 * 4, 5)
+    A[300, 300] = -1.0
+    _, _, piv = gpr.selftest_factor(A, False, False)
+    assert piv == 301
+
+
+def test_fp64_pipe_probes(gpr):
+    dmma, dfma = gpr.selftest_peak(0, 4), gpr.selftest_peak(1, 4)
+    assert 20.0 < dmma < 60.0 and 20.0 < dfma < 60.0       # B200: ~37 TF/s on either FP64 pipe

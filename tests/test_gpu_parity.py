@@ -1,0 +1,271 @@
+"""GPU suite, part 2: parity of the CUDA path with the oracle and with the reference fixtures, always
+through the C-ABI (ctypes binding) — the tests read like the reference's own usage:
+create<>() then the evaluate overloads, then update<>().
+
+Tolerances (BASELINE.json north_star): relative error <= 1e-9 on mean and alpha, <= 1e-7 on variance,
+identical sign of f on every query.  alpha is compared with max(1e-9, 4 x the oracle's own distance to an
+80-bit solve) where cond(K) makes 1e-9 unreachable for ANY double implementation."""
+import os
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_ALPHA, TOL_MEAN, TOL_VAR = 1e-9, 1e-9, 1e-7
+CASES = ["ref_mugD_thinplate", "ref_kettle_gaussian", "ref_jug_gaussian", "ref_jug_laplace"]
+
+
+@pytest.fixture(scope="module")
+def ctx(gpr):
+    return gpr.Context()
+
+
+def _reg(gpr, ctx, g):
+    return gpr.GPRegressor(g["kind"], g["p0"], g["p1"], ctx=ctx)
+
+
+def _signs_agree(f, fo):
+    mask = np.abs(fo) > 1e-9
+    return int((np.sign(f) != np.sign(fo))[mask].sum()) == 0
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_parity_with_reference_fixtures(gpr, orc, ctx, case):
+    """Configs 1 and 2: PCD clouds, node preprocessing, all four evaluate overloads + normals."""
+    g = load_golden(case)
+    P, Q = g["P"], g["Q"]
+    normals = "normals" in g
+    reg = _reg(gpr, ctx, g)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"], with_normals=normals)
+    got = m.get()
+    assert abs(got["R"] - g["R"]) <= 1e-15 * g["R"]
+    assert relerr(got["alpha"], g["alpha"]) <= TOL_ALPHA
+    f1 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2])
+    f2, v2 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    f3, v3, g3 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True)
+    f4, v4, g4, tx, ty = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, tangent=True)
+    for f in (f1, f2, f3, f4):
+        assert relerr(f, g["f"]) <= TOL_MEAN and _signs_agree(f, g["f"])
+    for v in (v2, v3, v4):
+        assert np.abs(v - g["v"]).max() <= TOL_VAR * np.abs(g["v"]).max()
+    for gr in (g3, g4):
+        assert relerr(gr, g["grad"]) <= TOL_MEAN
+    assert np.abs(tx - g["Tx"]).max() <= 1e-8 and np.abs(ty - g["Ty"]).max() <= 1e-8
+    if normals:
+        assert np.abs(got["normals"] - g["normals"]).max() <= 1e-8
+    # the thin-plate covariance build is bit-identical to the oracle's difference-form K
+    o = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"], g["kind"], g["p0"], g["p1"], factor="llt", dist="diff")
+    Lo = np.tril(o.get(factor=True)["factor"])
+    assert relerr(m.factor(), Lo) <= 1e-11
+    assert relerr(got["alpha"], o.alpha) <= TOL_ALPHA
+
+
+def test_single_query_calls_match_batched(gpr, ctx):
+    """Every real caller passes q = 1 (src/gp_node.cpp:1074): warp-per-query mean + matrix-vector variance."""
+    g = load_golden("ref_mugD_thinplate")
+    P, Q = g["P"], g["Q"]
+    reg = _reg(gpr, ctx, g)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"])
+    for i in (0, 17, 100, 251):
+        f, v, gr = reg.evaluate(m, Q[i:i + 1, 0], Q[i:i + 1, 1], Q[i:i + 1, 2], var=True, grad=True)
+        assert abs(f[0] - g["f"][i]) <= TOL_MEAN * np.abs(g["f"]).max()
+        assert abs(v[0] - g["v"][i]) <= TOL_VAR * np.abs(g["v"]).max()
+        assert np.abs(gr[0] - g["grad"][i]).max() <= TOL_MEAN * np.abs(g["grad"]).max()
+    for q in (2, 3, 5, 8, 9, 130):
+        f, v = reg.evaluate(m, Q[:q, 0], Q[:q, 1], Q[:q, 2], var=True)
+        assert relerr(f, g["f"][:q]) <= TOL_MEAN and np.abs(v - g["v"][:q]).max() <= TOL_VAR * np.abs(g["v"]).max()
+
+
+def test_update_matches_reference_fixture(gpr, ctx):
+    g = load_golden("ref_mugD_thinplate")
+    P, Q, Pu = g["P"], g["Q"], g["Pu"]
+    reg = _reg(gpr, ctx, g)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"])
+    reg.update(m, Pu[:, 0], Pu[:, 1], Pu[:, 2], g["yu"], g["su"])
+    assert m.n == len(P) + len(Pu)
+    assert relerr(m.alpha, g["alpha_updated"]) <= TOL_ALPHA
+    assert m.R == pytest.approx(g["R"], rel=1e-15)                 # not refreshed (gp_regressor.hpp:454-455)
+    assert relerr(reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2]), g["f_updated"]) <= TOL_MEAN
+
+
+def test_not_spd_is_reported_never_nan(gpr, ctx):
+    """Appendix B.7: the node's ThinPlate(2.0) setting is indefinite; pivot = first external point."""
+    g = load_golden("ref_mugD_thinplate")
+    P = g["P"]
+    reg = gpr.GPRegressor("thin_plate", 2.0, ctx=ctx)
+    with pytest.raises(gpr.GPRegressionException) as e:
+        reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"])
+    assert e.value.code == gpr.GPR_ERR_NOT_SPD and e.value.pivot == 263
+
+
+def test_closed_form_posteriors(gpr, ctx):
+    """Appendix B.3 / B.4 on the GPU."""
+    reg = gpr.GPRegressor("thin_plate", 2.0, ctx=ctx)
+    m = reg.create([0.5], [0.0], [0.0], [1.0], [0.1])
+    f, v, gr = reg.evaluate(m, [1.5], [0.0], [0.0], var=True, grad=True)
+    assert abs(m.alpha[0] - 1 / 8.1) <= 1e-15 and abs(f[0] - 4 / 8.1) <= 1e-14
+    assert abs(v[0] - (8 - 16 / 8.1)) <= 1e-13 and np.abs(gr[0] - [-6 / 8.1, 0, 0]).max() <= 1e-14
+    d0, s, R = 0.7, 0.05, 2.0
+    a, b = R ** 3 + s, 2 * d0 ** 3 - 3 * R * d0 ** 2 + R ** 3
+    y = np.array([1.0, -0.5])
+    m2 = reg.create([0.0, d0], [0, 0], [0, 0], y, [s, s])
+    assert relerr(m2.alpha, (a * y - b * y[::-1]) / (a * a - b * b)) <= 1e-13
+
+
+def test_interpolation_without_noise(gpr, ctx):
+    """Appendix B.5 (sigma2 empty): f(p_i) = y_i, v(p_i) = 0."""
+    rng = np.random.default_rng(3)
+    P = rng.uniform(-1, 1, size=(60, 3))
+    y = rng.standard_normal(60)
+    reg = gpr.GPRegressor("gaussian", 1.0, 1.0, ctx=ctx)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, None)
+    f, v = reg.evaluate(m, P[:, 0], P[:, 1], P[:, 2], var=True)
+    assert np.abs(f - y).max() <= 1e-9 and np.abs(v).max() <= 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 300, 1025])
+def test_ragged_sizes(gpr, orc, ctx, n):
+    """Training sets that do not fill whole 128-tiles (identity padding) and ragged query counts."""
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(max(n, 4), seed=n)
+    P, y, s2 = P[-n:], y[-n:], s2[-n:]
+    Q = W.grid_slab(7, 0, 7)[: 3 * n + 5]
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2, with_normals=True)
+    o = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, "thin_plate", W.SYNTH_R, 0.0, factor="llt", with_normals=True)
+    assert relerr(m.alpha, o.alpha) <= TOL_ALPHA and abs(m.R - o.R) <= 1e-15
+    f, v, gr = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True)
+    fo, vo, go = o.predict(Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True, threads=8)
+    assert relerr(f, fo) <= TOL_MEAN and np.abs(v - vo).max() <= TOL_VAR * np.abs(vo).max() and relerr(gr, go) <= TOL_MEAN
+    if n > 1:
+        assert np.abs(m.get()["normals"] - o.get()["normals"]).max() <= 1e-8
+
+
+def test_synthetic_2048_all_outputs(gpr, orc, ctx):
+    """Config-3 generator at a size the oracle finishes in seconds; alpha judged against the 80-bit solve."""
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(2048, seed=0)
+    Q = W.grid_slab(24, 0, 24)[::5]
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+    o = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, "thin_plate", W.SYNTH_R, 0.0, factor="llt")
+    ld = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, "thin_plate", W.SYNTH_R, 0.0, factor="llt", precision="longdouble")
+    err_ref, err_gpu = relerr(o.alpha, ld.alpha), relerr(m.alpha, ld.alpha)
+    assert err_gpu <= max(TOL_ALPHA, 4 * err_ref)
+    f, v = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    fo, vo, _ = ld.predict(Q[:, 0], Q[:, 1], Q[:, 2], var=True, threads=8)
+    assert relerr(f, fo) <= TOL_MEAN and np.abs(v - vo).max() <= TOL_VAR * np.abs(vo).max() and _signs_agree(f, fo)
+    assert v.min() > 0.0
+
+
+def test_query_batches_and_shards_are_bit_identical(gpr):
+    """each query is computed by one device with identical code, so splitting the query set
+    (across batches, calls or GPUs) never changes a bit.  Shards stay >= 9472 queries (thread-per-query path)."""
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(1536, seed=2)
+    Q = W.grid_slab(40, 0, 16)                      # 25,600 queries
+    os.environ["GPR_QUERY_TILE"] = "4096"           # force several variance batches per call
+    try:
+        small = gpr.Context()
+    finally:
+        del os.environ["GPR_QUERY_TILE"]
+    big = gpr.Context()
+    out = []
+    for c in (small, big):
+        reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=c)
+        m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+        out.append(reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True))
+        if c is big:
+            h = len(Q) // 2
+            parts = [reg.evaluate(m, Q[a:b, 0], Q[a:b, 1], Q[a:b, 2], var=True, grad=True) for a, b in ((0, h), (h, len(Q)))]
+            out.append(tuple(np.concatenate([p[i] for p in parts]) for i in range(3)))
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            assert np.array_equal(a, b)
+
+
+def test_fit_is_bit_reproducible(gpr, ctx):
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(3000, seed=4)
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    a1 = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2).alpha
+    a2 = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2).alpha
+    assert np.array_equal(a1, a2)
+
+
+def test_concurrent_single_query_calls(gpr, ctx):
+    """The node evaluates from hundreds of threads on one shared model (src/gp_node.cpp:1027-1038)."""
+    g = load_golden("ref_jug_gaussian")
+    P, Q = g["P"], g["Q"]
+    reg = _reg(gpr, ctx, g)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"])
+    reg.prepare_variance(m)
+    res = [None] * len(Q)
+
+    def work(i):
+        res[i] = reg.evaluate(m, Q[i:i + 1, 0], Q[i:i + 1, 1], Q[i:i + 1, 2], var=True)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(Q))]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    f = np.array([r[0][0] for r in res]); v = np.array([r[1][0] for r in res])
+    assert relerr(f, g["f"]) <= TOL_MEAN and np.abs(v - g["v"]).max() <= TOL_VAR * np.abs(g["v"]).max()
+
+
+def test_full_size_properties_config3(gpr, ctx):
+    """BASELINE config 3 at full size (n = 16,384, ThinPlate): size-independent properties.
+    (K alpha)_i = y_i on a row subset (numpy, float64); variances positive and below k(0); the mean is
+    ~0 on the unit sphere and ~1 on the outer sphere; timings are recorded."""
+    W = gpr.workloads
+    n = 16384
+    P, y, s2 = W.synthetic_cloud(n, seed=0)
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+    a = m.alpha
+    idx = np.arange(0, n, 128)
+    d = np.sqrt(((P[idx, None, :] - P[None, :, :]) ** 2).sum(-1))
+    K = 2 * d ** 3 - 3 * W.SYNTH_R * d ** 2 + W.SYNTH_R ** 3
+    K[np.arange(len(idx)), idx] += s2[idx]
+    assert np.abs(K @ a - y[idx]).max() <= 1e-9
+    Q = W.grid_slab(256, 128, 129)[:148 * 128]
+    f, v = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    assert np.isfinite(f).all() and v.min() > 0.0 and v.max() < W.SYNTH_R ** 3
+    fs = reg.evaluate(m, P[::64, 0], P[::64, 1], P[::64, 2])
+    assert np.abs(fs - y[::64]).max() < 0.2          # sigma2 = 0.1 smoothing, not interpolation
+    t = ctx.timings()
+    assert t["predict_var_ms"] > 0 and t["linv_ms"] > 0
+
+
+def test_cxx_dropin_headers_end_to_end(gpr, orc, tmp_path):
+    """The reference-facing C++ API (include/gp_regression/*.h) compiled as C++11 and run on the GPU."""
+    from test_host import _build_driver
+    exe = _build_driver(str(tmp_path))
+    g = load_golden("ref_mugD_thinplate")
+    P, Q, Pu = g["P"], g["Q"][:40], g["Pu"]
+    with open(tmp_path / "in.txt", "w") as fh:
+        fh.write("0 %r 0.0\n%d %d %d 1\n" % (g["R"], len(P), len(Q), len(Pu)))
+        for p, l, s in zip(P, g["y"], g["s2"]):
+            fh.write("%r %r %r %r %r\n" % (p[0], p[1], p[2], l, s))
+        for p in Q:
+            fh.write("%r %r %r\n" % tuple(p))
+        for p, l, s in zip(Pu, g["yu"], g["su"]):
+            fh.write("%r %r %r %r %r\n" % (p[0], p[1], p[2], l, s))
+    subprocess.run([exe, str(tmp_path / "in.txt"), str(tmp_path / "out.txt")], check=True)
+    rows = {ln.split()[0]: np.array(ln.split()[1:], dtype=float) for ln in open(tmp_path / "out.txt") if not ln.startswith("exception")}
+    q = len(Q)
+    assert abs(rows["R"][0] - g["R"]) <= 1e-14 and relerr(rows["alpha"], g["alpha"]) <= TOL_ALPHA
+    assert np.abs(rows["normals"].reshape(3, -1).T - g["normals"]).max() <= 1e-8
+    for k in ("f1", "f2", "f3", "f4"):
+        assert relerr(rows[k], g["f"][:q]) <= TOL_MEAN
+    for k in ("v2", "v3", "v4"):
+        assert np.abs(rows[k] - g["v"][:q]).max() <= TOL_VAR * np.abs(g["v"]).max()
+    assert relerr(rows["N3"].reshape(3, -1).T, g["grad"][:q]) <= TOL_MEAN
+    assert np.abs(rows["Tx"].reshape(3, -1).T - g["Tx"][:q]).max() <= 1e-8
+    assert abs(rows["single"][0] - g["f"][0]) <= 1e-9 and abs(rows["single"][1] - g["v"][0]) <= 1e-7 * np.abs(g["v"]).max()
+    assert relerr(rows["alpha_updated"], g["alpha_updated"]) <= TOL_ALPHA
+    assert relerr(rows["f_updated"], g["f_updated"][:q]) <= TOL_MEAN and rows["R_updated"][0] == rows["R"][0]
