@@ -248,13 +248,14 @@ def test_cxx_dropin_headers_end_to_end(gpr, orc, tmp_path):
     g = load_golden("ref_mugD_thinplate")
     P, Q, Pu = g["P"], g["Q"][:40], g["Pu"]
     with open(tmp_path / "in.txt", "w") as fh:
-        fh.write("0 %r 0.0\n%d %d %d 1\n" % (g["R"], len(P), len(Q), len(Pu)))
+        row = lambda *v: " ".join(repr(float(x)) for x in v) + "\n"
+        fh.write("0 %r 0.0\n%d %d %d 1\n" % (float(g["R"]), len(P), len(Q), len(Pu)))
         for p, l, s in zip(P, g["y"], g["s2"]):
-            fh.write("%r %r %r %r %r\n" % (p[0], p[1], p[2], l, s))
+            fh.write(row(p[0], p[1], p[2], l, s))
         for p in Q:
-            fh.write("%r %r %r\n" % tuple(p))
+            fh.write(row(*p))
         for p, l, s in zip(Pu, g["yu"], g["su"]):
-            fh.write("%r %r %r %r %r\n" % (p[0], p[1], p[2], l, s))
+            fh.write(row(p[0], p[1], p[2], l, s))
     subprocess.run([exe, str(tmp_path / "in.txt"), str(tmp_path / "out.txt")], check=True)
     rows = {ln.split()[0]: np.array(ln.split()[1:], dtype=float) for ln in open(tmp_path / "out.txt") if not ln.startswith("exception")}
     q = len(Q)
