@@ -92,6 +92,7 @@ def lib():
         L.gpr_selftest_leaf.argtypes = [_dp, _dp, C.POINTER(ci)]
         L.gpr_selftest_factor.argtypes = [_dp, ci, _dp, ci, C.POINTER(C.c_longlong)]
         L.gpr_selftest_peak.argtypes = [ci, ci, _dp]
+        L.gpr_selftest_factor_trace.argtypes = [ci, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         _lib = L
     return _lib
 
@@ -102,7 +103,7 @@ C_ABI_SYMBOLS = [
     "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_get",
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
     "gpr_model_state_get", "gpr_model_create_replica", "gpr_selftest_gemm", "gpr_selftest_leaf",
-    "gpr_selftest_factor", "gpr_selftest_peak",
+    "gpr_selftest_factor", "gpr_selftest_peak", "gpr_selftest_factor_trace",
 ]
 
 
@@ -302,3 +303,13 @@ def selftest_peak(which, ctas_per_sm=4):
     t = C.c_double()
     _check(lib().gpr_selftest_peak(int(which), int(ctas_per_sm), C.byref(t)))
     return t.value
+
+
+def selftest_factor_trace(n_tiles):
+    """(trace[ntasks,4] in ns relative to the first claim, leaf_cycles[2]) of the tile-task Cholesky."""
+    nt = n_tiles * (n_tiles + 1) // 2
+    tr = (C.c_longlong * (4 * nt))()
+    cy = (C.c_longlong * 8)()
+    _check(lib().gpr_selftest_factor_trace(n_tiles, tr, cy))
+    t = np.frombuffer(tr, dtype=np.int64).reshape(nt, 4).copy()
+    return t - t[:, 0].min(), np.array(list(cy))

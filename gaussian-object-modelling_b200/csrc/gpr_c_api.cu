@@ -626,7 +626,7 @@ int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double
 
 // ---- self-tests ---------------------------------------------------------------------------------
 int gpr_selftest_gemm(const double* hA, const double* hB, int b_kmajor, double* hC, int mt, int nt, int k) {
-    if (k % KT) return fail(GPR_ERR_INVALID, "k must be a multiple of 16");
+    if (k % (2 * KT)) return fail(GPR_ERR_INVALID, "k must be a multiple of 32 (the mainloop works on pairs of k16 stages)");
     const size_t M = (size_t)mt * TB, Nn = (size_t)nt * TB;
     double *A, *B, *C;
     CU(cudaMalloc((void**)&A, M * k * sizeof(double)));
@@ -684,6 +684,49 @@ int gpr_selftest_factor(double* hA, int nb, double* h_linv, int serial, long lon
     }
     cudaFree(A); cudaFree(D); cudaFree(scratch);
     return info[1] ? GPR_ERR_NOT_SPD : GPR_OK;
+}
+
+// Timeline of the tile-task Cholesky on an SPD test matrix of n_tiles x n_tiles tiles: 4 globaltimer
+// stamps (ns) per task in task order (claimed, accumulation done, tile solved, flag published).
+int gpr_selftest_factor_trace(int nb, long long* h_trace, long long* leaf_cycles) {
+    const size_t N = (size_t)nb * TB;
+    std::vector<double> hA(N * N, 0.0);
+    for (size_t c = 0; c < N; ++c)
+        for (size_t r = c; r < N; ++r) hA[c * N + r] = (r == c) ? 4.0 + 0.001 * (double)(r % 7) : 1.0 / (1.0 + (double)(r - c));
+    double *A, *D; int* scratch; long long* tr;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const size_t ntasks = (size_t)nb * (nb + 1) / 2;
+    CU(cudaMalloc((void**)&A, N * N * sizeof(double)));
+    CU(cudaMalloc((void**)&D, (size_t)nb * TB * TB * sizeof(double)));
+    CU(cudaMalloc((void**)&scratch, (8 + (size_t)nb * nb) * sizeof(int)));
+    CU(cudaMalloc((void**)&tr, 4 * ntasks * sizeof(long long)));
+    for (int rep = 0; rep < 2; ++rep) {
+        CU(cudaMemcpy(A, hA.data(), N * N * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemset(tr, 0, 4 * ntasks * sizeof(long long)));
+        CU(launch_cholesky(A, N, nb, D, scratch, sms, 0, 0, tr));
+        CU(cudaDeviceSynchronize());
+    }
+    int info[4];
+    CU(cudaMemcpy(info, scratch, sizeof info, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_trace, tr, 4 * ntasks * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (leaf_cycles) {
+        double* I; int* di; long long* cy;
+        CU(cudaMalloc((void**)&I, TB * TB * sizeof(double)));
+        CU(cudaMalloc((void**)&di, sizeof(int)));
+        CU(cudaMalloc((void**)&cy, 8 * sizeof(long long)));
+        std::vector<double> t(TB * TB);
+        for (int c = 0; c < TB; ++c) for (int r = 0; r < TB; ++r) t[c * TB + r] = (r == c) ? 4.0 : 1.0 / (1.0 + std::abs(r - c));
+        for (int rep = 0; rep < 2; ++rep) {
+            CU(cudaMemcpy(A, t.data(), TB * TB * sizeof(double), cudaMemcpyHostToDevice));
+            CU(launch_leaf_selftest(A, I, di, 0, cy));
+            CU(cudaDeviceSynchronize());
+        }
+        CU(cudaMemcpy(leaf_cycles, cy, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(I); cudaFree(di); cudaFree(cy);
+    }
+    cudaFree(A); cudaFree(D); cudaFree(scratch); cudaFree(tr);
+    return info[1] || info[2] ? GPR_ERR_CUDA : GPR_OK;
 }
 
 int gpr_selftest_peak(int which, int ctas_per_sm, double* tflops) {

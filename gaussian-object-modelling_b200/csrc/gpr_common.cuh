@@ -77,6 +77,12 @@ __device__ __forceinline__ int ld_volatile(const int* p) {
     return v;
 }
 
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Spin until *flag != 0.  Returns false if another CTA raised *abort or ~2 s passed (then raises it).
 // Tasks are claimed from an atomic counter in an order in which every dependency has a smaller
 // index, so a waiting CTA always waits on a CTA that is already running: no deadlock by construction;
@@ -90,6 +96,21 @@ __device__ __forceinline__ bool spin_wait(const int* flag, int* abort) {
         if (clock64() - t0 > 4000000000LL) { atomicExch(abort, 2); return false; }
         __nanosleep(64);
     }
+}
+
+// Block-uniform length of the leading run of ready items among [0, n): every thread tests a strided
+// subset with flag_ok(t) (an acquire load), the first failures are min-reduced through *s_min, which the
+// caller has set to a value >= n before the preceding barrier.  Contains one __syncthreads().
+template <class FlagOk>
+__device__ __forceinline__ int ready_prefix(int n, FlagOk flag_ok, int* s_min) {
+    int first_bad = n;
+    for (int t = threadIdx.x; t < n; t += NTHREADS) {
+        if (!flag_ok(t)) { first_bad = t; break; }
+    }
+    first_bad = __reduce_min_sync(0xffffffffu, first_bad);
+    if ((threadIdx.x & 31) == 0) atomicMin(s_min, first_bad);
+    __syncthreads();
+    return *s_min;
 }
 
 }  // namespace gpr

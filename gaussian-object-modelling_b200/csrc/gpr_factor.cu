@@ -36,11 +36,13 @@ struct CholArgs {
     int task_end;
     int* info;        // 0, or 1 + global index of the first non-positive pivot
     int* abort;       // raised on failure so that waiting CTAs leave
+    long long* trace; // optional: 4 globaltimer stamps per task (claim, accumulated, solved, published)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ int s_task, s_abort, s_fail;
+    __shared__ int s_task, s_abort, s_fail, s_upto;
+    __shared__ double s_inv[TB];
     const int tid = threadIdx.x;
     const TileCoord tc;
     for (;;) {
@@ -48,33 +50,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
             s_task = a.task_begin + atomicAdd(a.counter, 1);
             s_abort = ld_volatile(a.abort) != 0;
             s_fail = 1 << 20;
+            s_upto = 1 << 30;
         }
         __syncthreads();
         int task = s_task;
         if (task >= a.task_end || s_abort) return;
+        const int task_id = task;
         int j = 0;
         while (task >= a.nb - j) { task -= a.nb - j; ++j; }
         const int i = j + task;
+        if (a.trace && tid == 0) a.trace[4 * (size_t)task_id + 0] = globaltimer_ns();
 
         Acc acc;
         acc_zero(acc);
         const double* Li = a.A + (size_t)i * TB;     // row panel i, k = 0
         const double* Lj = a.A + (size_t)j * TB;
+        // One bulk look at the readiness flags of both row panels: the k-blocks [0, upto) are complete
+        // (almost always all but the last one or two), so the mainloop only polls beyond that prefix
+        // instead of paying an L2 round trip in front of a barrier at every 128-wide block.
+        const int* fi = a.ready + (size_t)i * a.nb;
+        const int* fj = a.ready + (size_t)j * a.nb;
+        const int upto = ready_prefix(j, [&](int t) { return ld_acquire(fi + t) != 0 && ld_acquire(fj + t) != 0; }, &s_upto);
         auto waitf = [&](int kb) -> bool {
-            if (tid != 0) return true;
-            if (!spin_wait(a.ready + (size_t)i * a.nb + kb, a.abort)) return false;
-            if (i != j && !spin_wait(a.ready + (size_t)j * a.nb + kb, a.abort)) return false;
+            if (tid != 0 || kb < upto) return true;
+            if (!spin_wait(fi + kb, a.abort)) return false;
+            if (i != j && !spin_wait(fj + kb, a.abort)) return false;
             return true;
         };
         if (!tile_mainloop<STREAM_M, STREAM_M>(acc, Li, a.ld, Lj, a.ld, 8 * j, smem, &s_abort, waitf)) return;
 
+        if (a.trace && tid == 0) a.trace[4 * (size_t)task_id + 1] = globaltimer_ns();
         double* T = smem;   // region 0, column-major pitch PM
         double* Gij = a.A + (size_t)j * TB * a.ld + (size_t)i * TB;
         residual_to_smem<false>(acc, Gij, a.ld, T, tc);
         __syncthreads();
 
         if (i == j) {
-            potrf128_smem(T, &s_fail);
+            potrf128_smem(T, s_inv, &s_fail);
             if (s_fail < TB) {
                 if (tid == 0) {
                     atomicCAS(a.info, 0, j * TB + s_fail + 1);
@@ -82,11 +94,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
                 }
                 return;
             }
-            for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-                const int r = idx & (TB - 1), c = idx >> 7;
-                Gij[(size_t)c * a.ld + r] = T[c * PM + r];
-            }
-            trinv128_smem(T, a.Dinv + (size_t)j * TB * TB);
+            store_lower_tile(T, Gij, a.ld);
+            __syncthreads();
+            trinv128_smem(T, s_inv, smem + R0_DBL);
+            store_lower_tile(T, a.Dinv + (size_t)j * TB * TB, TB);
         } else {
             if (tid == 0 && !spin_wait(a.ready + (size_t)j * a.nb + j, a.abort)) s_abort = 1;
             __syncthreads();
@@ -96,11 +107,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
             tile_mainloop<RES_M, STREAM_M>(acc, T, 0, a.Dinv + (size_t)j * TB * TB, TB, 8, smem, &s_abort, NoWait());
             store_tile<false, 1>(acc, Gij, a.ld, tc);
         }
+        if (a.trace && tid == 0) a.trace[4 * (size_t)task_id + 2] = globaltimer_ns();
         __threadfence();
         __syncthreads();
         if (tid == 0) {
             __threadfence();
             st_release(a.ready + (size_t)i * a.nb + j, 1);
+            if (a.trace) a.trace[4 * (size_t)task_id + 3] = globaltimer_ns();
         }
     }
 }
@@ -124,13 +137,14 @@ struct LinvArgs {
 
 __global__ void __launch_bounds__(NTHREADS, 1) linv_tiles_kernel(LinvArgs a) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ int s_task, s_abort;
+    __shared__ int s_task, s_abort, s_upto;
     const int tid = threadIdx.x;
     const TileCoord tc;
     for (;;) {
         if (tid == 0) {
             s_task = atomicAdd(a.counter, 1);
             s_abort = ld_volatile(a.abort) != 0;
+            s_upto = 1 << 30;
         }
         __syncthreads();
         int task = s_task;
@@ -153,8 +167,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) linv_tiles_kernel(LinvArgs a) {
             const double* Li = a.L + (size_t)j * TB * a.ld + (size_t)i * TB;
             // j operand: X[k, j-tile cols] K-major, element (c,k) at X[(j*128+c)*ld + k], k from j*128
             const double* Xj = a.X + (size_t)j * TB * a.ld + (size_t)j * TB;
+            const int upto = ready_prefix(d, [&](int t) { return ld_acquire(a.ready + (size_t)(j + t) * a.nb + j) != 0; }, &s_upto);
             auto waitf = [&](int kb) -> bool {
-                if (tid != 0) return true;
+                if (tid != 0 || kb < upto) return true;
                 return spin_wait(a.ready + (size_t)(j + kb) * a.nb + j, a.abort);
             };
             if (!tile_mainloop<STREAM_M, STREAM_K>(acc, Li, a.ld, Xj, a.ld, 8 * d, smem, &s_abort, waitf)) return;
@@ -191,13 +206,13 @@ static cudaError_t ensure_attrs() {
 
 // sync: the scratch ints are [0]=counter [1]=info [2]=abort followed by nb*nb ready flags.
 cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, int serial,
-                            cudaStream_t st) {
+                            cudaStream_t st, long long* trace) {
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(scratch, 0, sizeof(int) * (4 + (size_t)nb * nb), st);
     if (e != cudaSuccess) return e;
     CholArgs a;
-    a.A = A; a.ld = ld; a.nb = nb; a.Dinv = Dinv;
+    a.A = A; a.ld = ld; a.nb = nb; a.Dinv = Dinv; a.trace = trace;
     a.counter = scratch; a.info = scratch + 1; a.abort = scratch + 2; a.ready = scratch + 4;
     const int ntasks = nb * (nb + 1) / 2;
     a.task_begin = 0;

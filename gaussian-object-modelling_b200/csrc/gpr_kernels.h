@@ -12,7 +12,7 @@ cudaError_t launch_cov_build(const double* x, const double* y, const double* z, 
                              cudaStream_t st);
 // K2 (gpr_factor.cu).  scratch: at least 4 + nb*nb ints.
 cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, int serial,
-                            cudaStream_t st);
+                            cudaStream_t st, long long* trace = nullptr);
 cudaError_t launch_linv(const double* L, double* X, size_t ld, int nb, const double* Dinv, int* scratch, int num_sms,
                         cudaStream_t st);
 // K3 (gpr_solve.cu).  scratch: at least 4 + nb ints.
@@ -34,7 +34,7 @@ cudaError_t launch_variance_small(const double* X, size_t ld, int N, const doubl
 cudaError_t launch_gemm_selftest(const double* A, size_t lda, const double* B, size_t ldb, int b_kmajor, double* C,
                                  size_t ldc, int mt, int nt, int k, cudaStream_t st);
 cudaError_t launch_leaf_selftest(double* tile /*128x128 in/out: L*/, double* inv /*128x128 out*/, int* info,
-                                 cudaStream_t st);
+                                 cudaStream_t st, long long* cycles = nullptr);
 
 cudaError_t run_peak_probe(int which, int ctas_per_sm, double* tflops);
 

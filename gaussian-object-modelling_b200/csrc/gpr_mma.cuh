@@ -84,13 +84,13 @@ struct TileCoord {
 // acc element for (mt, pair p, e): e=0 -> [2p][0], 1 -> [2p+1][0], 2 -> [2p][1], 3 -> [2p+1][1]
 #define GPR_ACC(acc, mt, p, e) (acc)[mt][2 * (p) + ((e) & 1)][(e) >> 1]
 
-// One k16 step.  As: i operand, element (k,m) at As[k*pa + m].  Bs: j operand; M-major element (k,m)
-// at Bs[k*pb + m]; K-major element (m,k) at Bs[m*pb + k].
-template <bool JK>
-__device__ __forceinline__ void compute_k16(Acc& acc, const double* __restrict__ As, int pa,
-                                            const double* __restrict__ Bs, int pb, const TileCoord& tc) {
+// k4 sub-steps [KS0, KS1) of one k16 stage.  As: i operand, element (k,m) at As[k*pa + m].  Bs: j operand;
+// M-major element (k,m) at Bs[k*pb + m]; K-major element (m,k) at Bs[m*pb + k].
+template <bool JK, int KS0, int KS1>
+__device__ __forceinline__ void compute_ks(Acc& acc, const double* __restrict__ As, int pa,
+                                           const double* __restrict__ Bs, int pb, const TileCoord& tc) {
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int ks = KS0; ks < KS1; ++ks) {
         const int k = 4 * ks + tc.t;
         double b[8], a[4];
 #pragma unroll
@@ -115,31 +115,46 @@ __device__ __forceinline__ void compute_k16(Acc& acc, const double* __restrict__
     }
 }
 
-// Asynchronous copy of one k16 stage of a streamed operand.
-//   M-major source: element (m,k) at src[m + k*ld]   -> stage[k*PM + m]
-//   K-major source: element (m,k) at src[k + m*ld]   -> stage[m*PK + k]
-template <bool KMAJOR>
-__device__ __forceinline__ void load_stage(double* stage, const double* __restrict__ src, size_t ld) {
-    const int tid = threadIdx.x;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        int chunk = tid + NTHREADS * c;           // 1024 chunks of 16 bytes
+// Per-thread addressing of the asynchronous stage copies, computed once per tile.  One k16 stage of an
+// operand is 1024 chunks of 16 bytes, 4 per thread:
+//   M-major source: element (m,k) at src[m + k*ld] -> stage[k*PM + m]; thread owns k = tid>>6 (+4c), m = 2(tid&63)
+//   K-major source: element (m,k) at src[k + m*ld] -> stage[m*PK + k]; thread owns m = tid>>3 (+32c), k = 2(tid&7)
+struct StageCopy {
+    const double* src;     // this thread's first chunk at k16 stage 0
+    size_t chunk_stride;   // source elements between the thread's consecutive chunks
+    size_t stage_stride;   // source elements between consecutive k16 stages
+    int dst;               // offset of the first chunk inside a stage buffer
+    int dst_stride;        // stage-buffer elements between consecutive chunks
+    template <bool KMAJOR>
+    __device__ __forceinline__ void init(const double* base, size_t ld) {
+        const int tid = threadIdx.x;
         if (!KMAJOR) {
-            int k = chunk >> 6, m2 = chunk & 63;
-            cp_async16(stage + k * PM + 2 * m2, src + (size_t)k * ld + 2 * m2);
+            src = base + (size_t)(tid >> 6) * ld + 2 * (tid & 63);
+            chunk_stride = 4 * ld; stage_stride = (size_t)KT * ld;
+            dst = (tid >> 6) * PM + 2 * (tid & 63); dst_stride = 4 * PM;
         } else {
-            int m = chunk >> 3, k2 = chunk & 7;
-            cp_async16(stage + m * PK + 2 * k2, src + (size_t)m * ld + 2 * k2);
+            src = base + (size_t)(tid >> 3) * ld + 2 * (tid & 7);
+            chunk_stride = 32 * ld; stage_stride = KT;
+            dst = (tid >> 3) * PK + 2 * (tid & 7); dst_stride = 32 * PK;
         }
     }
-}
+    __device__ __forceinline__ void issue(double* stage, int kk) const {
+        const double* g = src + (size_t)kk * stage_stride;
+        double* d = stage + dst;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cp_async16(d + c * dst_stride, g + c * chunk_stride);
+    }
+};
 
-// Pipelined accumulation over nk16 k16-steps.
+// Pipelined accumulation over nk16 k16-steps (nk16 even).
 //   IMODE in {STREAM_M, RES_M}; JMODE in {STREAM_M, STREAM_K, RES_M, RES_K}.
 //   Streamed operands: Ag/Bg point at (tile row 0, k = 0) of the operand; lda/ldb are its leading
 //   dimensions.  Resident operands: Ag/Bg are shared-memory tiles with pitch PM.
 //   waitf(kb) is called by ALL threads before the loads of k16-step 8*kb are issued (it may spin on a
 //   readiness flag in thread 0); it returns false to abandon the tile.  It must not contain a barrier.
+// The k16 stages are processed in pairs: one barrier per 32 k, the copies of the next pair are issued
+// in the middle of the current pair's DMMA stream (so their address arithmetic and the barrier do not
+// sit in front of a block of tensor instructions), four stage buffers = two pairs in flight.
 // Returns false if abandoned.  Ends with all async copies drained and a __syncthreads().
 template <int IMODE, int JMODE, class WaitF>
 __device__ __forceinline__ bool tile_mainloop(Acc& acc, const double* Ag, size_t lda, const double* Bg, size_t ldb,
@@ -148,19 +163,30 @@ __device__ __forceinline__ bool tile_mainloop(Acc& acc, const double* Ag, size_t
     constexpr bool JS = (JMODE == STREAM_M || JMODE == STREAM_K);
     constexpr bool JK = (JMODE == STREAM_K || JMODE == RES_K);
     constexpr bool JRES = !JS;
+    constexpr int PB = JS ? (JK ? PK : PM) : PM;
     double* r0 = smem;
     double* r1 = smem + R0_DBL;
     double* istage = JRES ? r1 : r0;     // i stages move to region 1 when j is resident in region 0
     double* jstage = r1;
     const TileCoord tc;
+    StageCopy ci, cj;
+    if (IS) ci.template init<false>(Ag, lda);
+    if (JS) cj.template init<JK>(Bg, ldb);
 
-    auto issue = [&](int kk) {
-        const int s = kk % STAGES;
-        if (IS) load_stage<false>(istage + s * STAGE_I, Ag + (size_t)kk * KT * lda, lda);
-        if (JS) {
-            if (JK) load_stage<true>(jstage + s * STAGE_J, Bg + (size_t)kk * KT, ldb);
-            else load_stage<false>(jstage + s * STAGE_J, Bg + (size_t)kk * KT * ldb, ldb);
+    auto issue_pair = [&](int kk) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int s = (kk + h) & (STAGES - 1);
+            if (IS) ci.issue(istage + s * STAGE_I, kk + h);
+            if (JS) cj.issue(jstage + s * STAGE_J, kk + h);
         }
+        cp_async_commit();
+    };
+    auto a_of = [&](int kk) -> const double* {
+        return IS ? (istage + (kk & (STAGES - 1)) * STAGE_I) : (Ag + (size_t)kk * KT * PM);
+    };
+    auto b_of = [&](int kk) -> const double* {
+        return JS ? (jstage + (kk & (STAGES - 1)) * STAGE_J) : (JK ? (Bg + kk * KT) : (Bg + (size_t)kk * KT * PM));
     };
 
     bool ok = true;
@@ -169,25 +195,19 @@ __device__ __forceinline__ bool tile_mainloop(Acc& acc, const double* Ag, size_t
     }
     __syncthreads();
     if (*s_abort) return false;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk16) issue(s);
-        cp_async_commit();
-    }
-    for (int kk = 0; kk < nk16; ++kk) {
-        cp_async_wait<STAGES - 2>();
-        const int nxt = kk + STAGES - 1;
+    if (nk16 > 0) issue_pair(0);
+    for (int kk = 0; kk < nk16; kk += 2) {
+        cp_async_wait<0>();
+        const int nxt = kk + 2;
         if (nxt < nk16 && (nxt & 7) == 0) {
             if (!waitf(nxt >> 3)) *s_abort = 1;
         }
         __syncthreads();
         if (*s_abort) { ok = false; break; }
-        if (nxt < nk16) issue(nxt);
-        cp_async_commit();
-        const int s = kk % STAGES;
-        const double* As = IS ? (istage + s * STAGE_I) : (Ag + (size_t)kk * KT * PM);
-        const double* Bs = JS ? (jstage + s * STAGE_J) : (JK ? (Bg + kk * KT) : (Bg + (size_t)kk * KT * PM));
-        compute_k16<JK>(acc, As, IS ? PM : PM, Bs, JS ? (JK ? PK : PM) : PM, tc);
+        compute_ks<JK, 0, 2>(acc, a_of(kk), PM, b_of(kk), PB, tc);
+        if (nxt < nk16) issue_pair(nxt);
+        compute_ks<JK, 2, 4>(acc, a_of(kk), PM, b_of(kk), PB, tc);
+        compute_ks<JK, 0, 4>(acc, a_of(kk + 1), PM, b_of(kk + 1), PB, tc);
     }
     cp_async_wait<0>();
     __syncthreads();

@@ -39,23 +39,30 @@ cudaError_t launch_gemm_selftest(const double* A, size_t lda, const double* B, s
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) leaf_selftest_kernel(double* tile, double* inv, int* info) {
+__global__ void __launch_bounds__(NTHREADS, 1) leaf_selftest_kernel(double* tile, double* inv, int* info, long long* cycles) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_fail;
+    __shared__ double s_inv[TB];
     if (threadIdx.x == 0) s_fail = 1 << 20;
     for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) smem[(idx >> 7) * PM + (idx & 127)] = tile[idx];
     __syncthreads();
-    potrf128_smem(smem, &s_fail);
+    long long c0 = clock64();
+    potrf128_smem(smem, s_inv, &s_fail, cycles ? cycles + 2 : nullptr);
+    long long c1 = clock64();
     if (threadIdx.x == 0) *info = s_fail < TB ? s_fail + 1 : 0;
-    for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) tile[idx] = smem[(idx >> 7) * PM + (idx & 127)];
+    store_lower_tile(smem, tile, TB);
     __syncthreads();
-    trinv128_smem(smem, inv);
+    long long c2 = clock64();
+    trinv128_smem(smem, s_inv, smem + R0_DBL);
+    long long c3 = clock64();
+    store_lower_tile(smem, inv, TB);
+    if (cycles && threadIdx.x == 0) { cycles[0] = c1 - c0; cycles[1] = c3 - c2; }
 }
 
-cudaError_t launch_leaf_selftest(double* tile, double* inv, int* info, cudaStream_t st) {
+cudaError_t launch_leaf_selftest(double* tile, double* inv, int* info, cudaStream_t st, long long* cycles) {
     cudaError_t e = cudaFuncSetAttribute(leaf_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    leaf_selftest_kernel<<<1, NTHREADS, TILE_SMEM_BYTES, st>>>(tile, inv, info);
+    leaf_selftest_kernel<<<1, NTHREADS, TILE_SMEM_BYTES, st>>>(tile, inv, info, cycles);
     return cudaGetLastError();
 }
 

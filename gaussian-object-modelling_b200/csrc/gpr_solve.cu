@@ -6,10 +6,14 @@
 //   forward  L z = y      : block i accumulates s_i = sum_{k<i} L_ik z_k as the z_k become ready,
 //                           then z_i = Dinv_i (y_i - s_i)
 //   backward L^T a = z    : block i accumulates s_i = sum_{k>i} L_ki^T a_k, then a_i = Dinv_i^T (z_i - s_i)
-// HBM-bound: each solve reads the lower triangle of L once (4 n^2 bytes); Dinv_i = L_ii^-1 comes from
-// the factorisation.  Blocks are claimed from an atomic counter in dependency order, so a waiting CTA
-// only ever waits on a CTA that is already running (same argument as gpr_factor.cu).
-#include "gpr_common.cuh"
+// HBM-bound in volume (each solve reads the lower triangle of L once, 4 n^2 bytes) but latency-bound in
+// practice: nb dependent steps.  The step is kept short by taking everything that does not depend on
+// the incoming vector off the critical path: Dinv_i = L_ii^-1 (from the factorisation) is staged in
+// shared memory with cp.async when the CTA starts, and the next L tile is loaded into registers
+// (64 doubles per thread) right after the current one has been consumed, i.e. before the flag of the
+// next block is awaited.  Blocks are claimed from an atomic counter in dependency order, so a waiting
+// CTA only ever waits on a CTA that is already running (same argument as gpr_factor.cu).
+#include "gpr_mma.cuh"
 #include "gpr_kernels.h"
 
 namespace gpr {
@@ -24,7 +28,15 @@ struct TrsvArgs {
     int* abort;
 };
 
-__global__ void __launch_bounds__(256) trsv_forward_kernel(TrsvArgs a) {
+constexpr size_t TRSV_SMEM = (size_t)TB * TB * sizeof(double);
+
+__device__ __forceinline__ void stage_dinv(double* sD, const double* D) {
+    for (int c = threadIdx.x; c < TB * TB / 2; c += 256) cp_async16(sD + 2 * c, D + 2 * c);
+    cp_async_commit();
+}
+
+__global__ void __launch_bounds__(256, 1) trsv_forward_kernel(TrsvArgs a) {
+    extern __shared__ __align__(16) double sD[];   // Dinv_i, column-major ld 128
     __shared__ double zs[TB];
     __shared__ double part[2][TB];
     __shared__ int s_blk, s_abort;
@@ -34,6 +46,14 @@ __global__ void __launch_bounds__(256) trsv_forward_kernel(TrsvArgs a) {
         __syncthreads();
         const int i = s_blk;
         if (i >= a.nb || s_abort) return;
+        stage_dinv(sD, a.Dinv + (size_t)i * TB * TB);
+        // thread (r,h) owns row r and the 64 columns [64h, 64h+64) of every tile of block row i
+        const double* Lrow = a.L + (size_t)(64 * h) * a.ld + (size_t)i * TB + r;
+        double cur[64];
+        if (i > 0) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) cur[c] = __ldcs(Lrow + (size_t)c * a.ld);
+        }
         double s = 0.0;
         for (int k = 0; k < i; ++k) {
             if (tid == 0 && !spin_wait(a.ready + k, a.abort)) s_abort = 1;
@@ -41,19 +61,25 @@ __global__ void __launch_bounds__(256) trsv_forward_kernel(TrsvArgs a) {
             if (s_abort) return;
             if (tid < TB) zs[tid] = __ldcg(a.out + (size_t)k * TB + tid);
             __syncthreads();
-            const double* Lp = a.L + ((size_t)k * TB + 64 * h) * a.ld + (size_t)i * TB + r;
-#pragma unroll 8
-            for (int c = 0; c < 64; ++c) s = fma(Lp[(size_t)c * a.ld], zs[64 * h + c], s);
+#pragma unroll
+            for (int c = 0; c < 64; ++c) s = fma(cur[c], zs[64 * h + c], s);
+            if (k + 1 < i) {
+                const double* nxt = Lrow + (size_t)(k + 1) * TB * a.ld;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) cur[c] = __ldcs(nxt + (size_t)c * a.ld);
+            }
         }
         part[h][r] = s;
+        cp_async_wait<0>();
         __syncthreads();
         if (tid < TB) zs[tid] = a.rhs[(size_t)i * TB + tid] - (part[0][tid] + part[1][tid]);
         __syncthreads();
-        // z_i = Dinv_i * t   (Dinv_i lower triangular, column-major ld 128)
-        const double* D = a.Dinv + (size_t)i * TB * TB + (size_t)(64 * h) * TB + r;
+        // z_i = Dinv_i * t
         double z = 0.0;
-#pragma unroll 8
-        for (int c = 0; c < 64; ++c) z = fma(D[(size_t)c * TB], zs[64 * h + c], z);
+        const double* D = sD + (size_t)(64 * h) * TB + r;
+#pragma unroll 16
+        for (int c = 0; c < 64; ++c) z = fma(D[c * TB], zs[64 * h + c], z);
+        __syncthreads();
         part[h][r] = z;
         __syncthreads();
         if (tid < TB) a.out[(size_t)i * TB + tid] = part[0][tid] + part[1][tid];
@@ -63,7 +89,8 @@ __global__ void __launch_bounds__(256) trsv_forward_kernel(TrsvArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(256) trsv_backward_kernel(TrsvArgs a) {
+__global__ void __launch_bounds__(256, 1) trsv_backward_kernel(TrsvArgs a) {
+    extern __shared__ __align__(16) double sD[];
     __shared__ double as[TB];
     __shared__ double ts[TB];
     __shared__ int s_blk, s_abort;
@@ -73,24 +100,39 @@ __global__ void __launch_bounds__(256) trsv_backward_kernel(TrsvArgs a) {
         __syncthreads();
         if (s_blk >= a.nb || s_abort) return;
         const int i = a.nb - 1 - s_blk;
+        stage_dinv(sD, a.Dinv + (size_t)i * TB * TB);
         // warp w owns columns c = 16w .. 16w+15 of block column i; lane covers rows lane + 32m
+        const double* Lcol = a.L + ((size_t)i * TB + 16 * warp) * a.ld + lane;
+        double cur[16][4];
         double acc[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc[c] = 0.0;
+        if (i < a.nb - 1) {
+            const double* p = Lcol + (size_t)(a.nb - 1) * TB;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) cur[c][m] = __ldcs(p + (size_t)c * a.ld + 32 * m);
+        }
         for (int k = a.nb - 1; k > i; --k) {
             if (tid == 0 && !spin_wait(a.ready + k, a.abort)) s_abort = 1;
             __syncthreads();
             if (s_abort) return;
             if (tid < TB) as[tid] = __ldcg(a.out + (size_t)k * TB + tid);
             __syncthreads();
-            const double* Lp = a.L + ((size_t)i * TB + 16 * warp) * a.ld + (size_t)k * TB + lane;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                const double* col = Lp + (size_t)c * a.ld;
                 double v = acc[c];
 #pragma unroll
-                for (int m = 0; m < 4; ++m) v = fma(col[32 * m], as[lane + 32 * m], v);
+                for (int m = 0; m < 4; ++m) v = fma(cur[c][m], as[lane + 32 * m], v);
                 acc[c] = v;
+            }
+            if (k - 1 > i) {
+                const double* p = Lcol + (size_t)(k - 1) * TB;
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) cur[c][m] = __ldcs(p + (size_t)c * a.ld + 32 * m);
             }
         }
 #pragma unroll
@@ -100,9 +142,10 @@ __global__ void __launch_bounds__(256) trsv_backward_kernel(TrsvArgs a) {
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) ts[16 * warp + c] = a.rhs[(size_t)i * TB + 16 * warp + c] - v;
         }
+        cp_async_wait<0>();
         __syncthreads();
         // a_i[c] = sum_r Dinv_i[r][c] t[r]
-        const double* D = a.Dinv + (size_t)i * TB * TB + (size_t)(16 * warp) * TB + lane;
+        const double* D = sD + (size_t)(16 * warp) * TB + lane;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
             const double* col = D + (size_t)c * TB;
@@ -122,14 +165,22 @@ __global__ void __launch_bounds__(256) trsv_backward_kernel(TrsvArgs a) {
 // scratch: [0]=counter [2]=abort [4..4+nb) ready.  rhs and out may not alias.
 cudaError_t launch_trsv(int backward, const double* L, size_t ld, int nb, const double* Dinv, const double* rhs,
                         double* out, int* scratch, int num_sms, cudaStream_t st) {
+    static int attr_done = 0;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(trsv_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(trsv_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = 1;
+    }
     cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(int) * (4 + (size_t)nb), st);
     if (e != cudaSuccess) return e;
     TrsvArgs a;
     a.L = L; a.ld = ld; a.nb = nb; a.Dinv = Dinv; a.rhs = rhs; a.out = out;
     a.counter = scratch; a.abort = scratch + 2; a.ready = scratch + 4;
-    const int grid = nb < 2 * num_sms ? nb : 2 * num_sms;
-    if (backward) trsv_backward_kernel<<<grid, 256, 0, st>>>(a);
-    else trsv_forward_kernel<<<grid, 256, 0, st>>>(a);
+    const int grid = nb < num_sms ? nb : num_sms;
+    if (backward) trsv_backward_kernel<<<grid, 256, TRSV_SMEM, st>>>(a);
+    else trsv_forward_kernel<<<grid, 256, TRSV_SMEM, st>>>(a);
     return cudaGetLastError();
 }
 

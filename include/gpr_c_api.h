@@ -108,6 +108,9 @@ int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double
 int gpr_selftest_gemm(const double* hA, const double* hB, int b_kmajor, double* hC, int m_tiles, int n_tiles, int k);
 int gpr_selftest_leaf(double* h_tile_inout, double* h_inv_out, int* info);
 int gpr_selftest_factor(double* hA_inout, int n_tiles, double* h_linv_or_null, int serial, long long* pivot);
+/* Timeline of the tile-task Cholesky: 4 ns stamps per task (n_tiles(n_tiles+1)/2 tasks, column-major
+ * task order); leaf_cycles[2] = SM cycles of the in-CTA 128x128 Cholesky and triangular inverse. */
+int gpr_selftest_factor_trace(int n_tiles, long long* h_trace, long long* leaf_cycles_or_null);
 /* Raw pipe probes (CUDA-event timed): which = 0 FP64 tensor (DMMA.8x8x4), 1 FP64 FMA; TFLOP/s. */
 int gpr_selftest_peak(int which, int ctas_per_sm, double* tflops);
 
