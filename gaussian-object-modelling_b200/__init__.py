@@ -40,14 +40,14 @@ class KernelT(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "cov_ms", "chol_ms", "solve_ms", "normals_ms", "fit_total_ms", "linv_ms",
-        "predict_mean_ms", "predict_var_ms", "predict_total_ms", "h2d_ms", "d2h_ms")]
+        "predict_mean_ms", "predict_var_ms", "predict_total_ms", "h2d_ms", "d2h_ms", "append_ms")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class ModelState(C.Structure):
-    _fields_ = [("n", C.c_size_t), ("padded_n", C.c_size_t), ("kernel", KernelT), ("R", C.c_double),
+    _fields_ = [("n", C.c_size_t), ("padded_n", C.c_size_t), ("ld", C.c_size_t), ("kernel", KernelT), ("R", C.c_double),
                 ("xyz", C.c_void_p), ("alpha", C.c_void_p), ("linv", C.c_void_p)]
 
 
@@ -86,6 +86,7 @@ def lib():
         L.gpr_predict_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
         L.gpr_model_prepare_variance.argtypes = [vp, vp]
         L.gpr_append.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, sz]
+        L.gpr_model_reserve.argtypes = [vp, vp, sz]
         L.gpr_model_state_get.argtypes = [vp, vp, ci, C.POINTER(ModelState)]
         L.gpr_model_create_replica.argtypes = [vp, sz, KernelT, cd, ci, C.POINTER(vp)]
         L.gpr_selftest_gemm.argtypes = [_dp, _dp, ci, _dp, ci, ci, ci]
@@ -102,6 +103,7 @@ C_ABI_SYMBOLS = [
     "gpr_ctx_create", "gpr_ctx_destroy", "gpr_ctx_num_devices", "gpr_last_error", "gpr_last_pivot",
     "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_get",
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
+    "gpr_model_reserve",
     "gpr_model_state_get", "gpr_model_create_replica", "gpr_selftest_gemm", "gpr_selftest_leaf",
     "gpr_selftest_factor", "gpr_selftest_peak", "gpr_selftest_factor_trace",
 ]
@@ -254,6 +256,10 @@ class GPRegressor:
             raise GPRegressionException("Empty model pointer")
         x, y, z, label, sigma2 = map(_arr, (x, y, z, label, sigma2))
         _check(lib().gpr_append(self.ctx._h, model._h, _p(x), _p(y), _p(z), _p(label), _p(sigma2), len(x)))
+
+    def reserve(self, model, capacity):
+        """Pre-allocate room for `capacity` points (incremental appends then never reallocate)."""
+        _check(lib().gpr_model_reserve(self.ctx._h, model._h, int(capacity)))
 
     def prepare_variance(self, model):
         _check(lib().gpr_model_prepare_variance(self.ctx._h, model._h))

@@ -1,0 +1,344 @@
+// gpr_append.cu — K5: incremental append of k <= 32 training points to a fitted model (rank-k row append of
+// the Cholesky factor AND of its inverse), instead of the reference's full refit.
+//
+// Replaces GPRegressor::update<>() (/root/reference/include/gp_regression/gp_regressor.hpp:367-479), which
+// grows Kpp by conservativeResize (:442-452) and then calls LDLT::compute on the whole matrix again
+// (:457-459).  The only incremental precedent in the reference is the row append of its unused second
+// library (include/gp/GaussianProcess.h:340-374).
+//
+// With K' = [[K, P], [P^T, C]], L = chol(K), X = L^-1 (kept resident for the variance path):
+//     B   = X P                      (n x k)   new rows of L are B^T
+//     S   = C - B^T B                (k x k)   Schur complement
+//     L22 = chol(S),  W = L22^-1
+//     L'  = [[L, 0], [B^T, L22]]
+//     X'  = [[X, 0], [-W (B^T X), W]]
+// The two n^2*k products read the triangle of X once each (4 n^2 bytes): they are HBM/L2-bandwidth
+// bound skinny products, done with FP64 FMAs on 32x32 register-tiled output blocks (the 128x128 DMMA tile
+// engine would waste 3/4 of its flops on a 32-wide operand and serialise on 64 long tasks).
+// Every reduction has a fixed order: the append is bit-reproducible.
+#include "gpr_mma.cuh"
+#include "gpr_leaf.cuh"
+#include "gpr_kernels.h"
+
+namespace gpr {
+
+constexpr int AK = 32;      // slab width: new points handled per pass
+constexpr int KC = 64;      // k extent of one shared-memory chunk of the skinny products
+constexpr int APITCH = 65;  // pitch of the k-contiguous A chunk (odd: conflict-free column reads)
+
+// ---------------------------------------------------------------------------------------------
+// (1) cross-covariance of the new points against the old ones, and among themselves.
+//     Pn[c*32 + a] = k(|p_c - new_a|)  (c < n0, a < k; 0 for a >= k)
+//     S0[a*32 + b] = k(|new_a - new_b|) + [a==b] sigma2_a   (identity for a or b >= k)
+// Same arithmetic as cov_build_kernel (dist_exact / kern_value_exact): an appended model has bit-identical
+// covariance entries to a refitted one.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) append_panel_kernel(const double* x, const double* y, const double* z,
+                                                           const double* sigma2, int n0, int k, double* Pn, double* S0,
+                                                           KernParams kp) {
+    __shared__ double nx[AK], ny[AK], nz[AK];
+    if (threadIdx.x < AK) {
+        const bool real = threadIdx.x < k;
+        nx[threadIdx.x] = real ? x[n0 + threadIdx.x] : 0.0;
+        ny[threadIdx.x] = real ? y[n0 + threadIdx.x] : 0.0;
+        nz[threadIdx.x] = real ? z[n0 + threadIdx.x] : 0.0;
+    }
+    __syncthreads();
+    const int idx = blockIdx.x * 256 + threadIdx.x;          // (c, a) with a fastest
+    const int c = idx >> 5, a = idx & 31;
+    if (c < n0) {
+        double v = 0.0;
+        if (a < k) v = kern_value_exact(kp, dist_exact(x[c], y[c], z[c], nx[a], ny[a], nz[a]));
+        Pn[idx] = v;
+    }
+    if (blockIdx.x == 0) {
+        for (int e = threadIdx.x; e < AK * AK; e += 256) {
+            const int a2 = e >> 5, b2 = e & 31;
+            double v = (a2 == b2) ? 1.0 : 0.0;
+            if (a2 < k && b2 < k) {
+                v = kern_value_exact(kp, dist_exact(nx[a2], ny[a2], nz[a2], nx[b2], ny[b2], nz[b2]));
+                if (a2 == b2) v = __dadd_rn(v, sigma2[n0 + a2]);       // gp_regressor.hpp:449-452
+            }
+            S0[e] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2)/(5) skinny triangular products against X = L^-1 (column-major, leading dimension ld, lower part).
+//   MODE 0:  OUT[r][a] = sum_{c <= r} X[r][c] * Bm[c][a]          (B = X * Pn)        block rows r0 = 32*blockIdx.x
+//   MODE 1:  OUT[c][b] = sum_{r >= c, r < n0} X[r][c] * Bm[r][b]   (G = X^T * B)       block columns c0 = 32*blockIdx.x
+// OUT and Bm are n0 x 32 row-major.  One CTA = one 32x32 output block; 256 threads = 4 k-phases x (8 x 8)
+// threads with a 4x4 register tile each (rows tm + 8i, columns 4tn + j); the k-phases are summed in a
+// fixed order at the end.  Chunks of 64 k are double-buffered through registers.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restrict__ X, size_t ld, int n0,
+                                                         const double* __restrict__ Bm, double* __restrict__ OUT) {
+    __shared__ __align__(16) double As[4 * AK * AK];      // MODE 0: [k][m] pitch 32;  MODE 1: [m][k] pitch 65; then the k-phase sums
+    __shared__ __align__(16) double Bs[KC * AK];          // [k][a]
+    const int tid = threadIdx.x;
+    // heavy blocks first: MODE 0 rows near n0 have the longest k range, MODE 1 columns near 0
+    const int nblk = (n0 + AK - 1) / AK;
+    const int blk = MODE == 0 ? (nblk - 1 - blockIdx.x) : blockIdx.x;
+    const int m0 = blk * AK;
+    const int kbeg = MODE == 0 ? 0 : m0;
+    const int kend = MODE == 0 ? min(m0 + AK, n0) : n0;
+    const int kg = tid >> 6, t64 = tid & 63, tm = t64 & 7, tn = t64 >> 3;
+
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    double ra[8], rb[8];
+    auto load_chunk = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int idx = tid + 256 * j;
+            int mm, kk;
+            if (MODE == 0) { kk = idx >> 5; mm = idx & 31; } else { mm = idx >> 6; kk = idx & 63; }
+            const int kglob = k0 + kk, mglob = m0 + mm;
+            double v = 0.0;
+            if (kglob < kend && mglob < n0) {
+                if (MODE == 0) { if (kglob <= mglob) v = __ldg(X + (size_t)kglob * ld + mglob); }
+                else { if (kglob >= mglob) v = __ldg(X + (size_t)mglob * ld + kglob); }
+            }
+            ra[j] = v;
+            const int kb = k0 + (idx >> 5);
+            rb[j] = kb < kend ? __ldg(Bm + (size_t)kb * AK + (idx & 31)) : 0.0;
+        }
+    };
+    auto store_chunk = [&]() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int idx = tid + 256 * j;
+            if (MODE == 0) As[idx] = ra[j];                       // [k][m], pitch 32
+            else As[(idx >> 6) * APITCH + (idx & 63)] = ra[j];    // [m][k], pitch 65
+            Bs[idx] = rb[j];
+        }
+    };
+
+    load_chunk(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += KC) {
+        __syncthreads();
+        store_chunk();
+        __syncthreads();
+        if (k0 + KC < kend) load_chunk(k0 + KC);
+#pragma unroll 4
+        for (int kk = kg; kk < KC; kk += 4) {
+            double a[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = MODE == 0 ? As[kk * AK + tm + 8 * i] : As[(tm + 8 * i) * APITCH + kk];
+            const double2 b01 = *reinterpret_cast<const double2*>(Bs + kk * AK + 4 * tn);
+            const double2 b23 = *reinterpret_cast<const double2*>(Bs + kk * AK + 4 * tn + 2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][0] = fma(a[i], b01.x, acc[i][0]); acc[i][1] = fma(a[i], b01.y, acc[i][1]);
+                acc[i][2] = fma(a[i], b23.x, acc[i][2]); acc[i][3] = fma(a[i], b23.y, acc[i][3]);
+            }
+        }
+    }
+    // sum the four k-phases in a fixed order through shared memory (As is reused)
+    __syncthreads();
+    double* red = As;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[kg * 1024 + (tm + 8 * i) * AK + 4 * tn + j] = acc[i][j];
+    __syncthreads();
+    for (int e = tid; e < AK * AK; e += 256) {
+        const int mm = e >> 5;
+        if (m0 + mm < n0) OUT[(size_t)(m0 + mm) * AK + (e & 31)] = ((red[e] + red[1024 + e]) + red[2048 + e]) + red[3072 + e];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (3) partial Gram matrices of B: part[blk][a*32 + b] = sum_{r in block} B[r][a] B[r][b], 256 rows per CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int GRAM_ROWS = 256;
+__global__ void __launch_bounds__(256) append_gram_kernel(const double* __restrict__ B, int n0, double* __restrict__ part) {
+    __shared__ double Bs[64 * AK];
+    const int tid = threadIdx.x, a = tid & 31, b0 = (tid >> 5) * 4;
+    const int r0 = blockIdx.x * GRAM_ROWS;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int rc = 0; rc < GRAM_ROWS; rc += 64) {
+        __syncthreads();
+        for (int e = tid; e < 64 * AK; e += 256) {
+            const int r = r0 + rc + (e >> 5);
+            Bs[e] = r < n0 ? B[(size_t)r * AK + (e & 31)] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+            const double va = Bs[r * AK + a];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fma(va, Bs[r * AK + b0 + j], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part[(size_t)blockIdx.x * AK * AK + a * AK + b0 + j] = acc[j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// (4) S = S0 - sum_blk part[blk] (fixed order);  L22 = chol(S), W = L22^-1 with the 128x128 shared-memory
+// leaves of the tile Cholesky (S is embedded in an identity tile).  out22: [0,1024) L22, [1024,2048) W, both
+// row-major [a*32 + b].  *flag = 0, or 1 + global index of the first non-positive pivot (sticky over the slabs
+// of one append: once set, the later kernels of the append do nothing).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) append_leaf_kernel(const double* S0, const double* part, int nparts,
+                                                                  double* out22, int* flag, int n0) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_fail;
+    __shared__ double s_inv[TB];
+    double* T = smem;
+    const int tid = threadIdx.x;
+    if (*flag != 0) return;                  // an earlier slab of this append failed: the flag is sticky
+    if (tid == 0) s_fail = 1 << 20;
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+        const int r = idx & (TB - 1), c = idx >> 7;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < AK && c < AK) {
+            double s = 0.0;
+            for (int p = 0; p < nparts; ++p) s += part[(size_t)p * AK * AK + r * AK + c];
+            v = S0[r * AK + c] - s;
+        }
+        T[c * PM + r] = v;
+    }
+    __syncthreads();
+    potrf128_smem(T, s_inv, &s_fail);
+    __syncthreads();
+    if (s_fail < TB) {
+        if (tid == 0) *flag = n0 + s_fail + 1;
+        return;
+    }
+    for (int e = tid; e < AK * AK; e += NTHREADS) {
+        const int a = e >> 5, b = e & 31;
+        out22[e] = a >= b ? T[b * PM + a] : 0.0;
+    }
+    __syncthreads();
+    trinv128_smem(T, s_inv, smem + R0_DBL);
+    __syncthreads();
+    for (int e = tid; e < AK * AK; e += NTHREADS) {
+        const int a = e >> 5, b = e & 31;
+        out22[AK * AK + e] = a >= b ? T[b * PM + a] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (6) scatter the new rows into L and X (nothing is written when the slab failed):
+//   L[n0+a][c] = B[c][a],  X[n0+a][c] = -sum_{b<=a} W[a][b] G[c][b]   (c < n0)
+//   L[n0+a][n0+b] = L22[a][b],  X[n0+a][n0+b] = W[a][b]                (b <= a; zero above the diagonal)
+// then refresh the inverse diagonal tiles: Dinv_t = X_tt for the tiles the new rows touch.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) append_scatter_kernel(const double* __restrict__ B, const double* __restrict__ G,
+                                                             const double* __restrict__ out22, const int* flag, int n0,
+                                                             int k, double* L, double* X, size_t ld) {
+    if (*flag != 0) return;
+    __shared__ double W[AK * AK];
+    for (int e = threadIdx.x; e < AK * AK; e += 256) W[e] = out22[AK * AK + e];
+    __syncthreads();
+    const int idx = blockIdx.x * 256 + threadIdx.x;       // (c, a), a fastest: 32 lanes write 256 contiguous bytes
+    const int c = idx >> 5, a = idx & 31;
+    if (a >= k) return;
+    if (c < n0) {
+        L[(size_t)c * ld + n0 + a] = B[(size_t)c * AK + a];
+        double s = 0.0;
+        for (int b = 0; b <= a; ++b) s = fma(W[a * AK + b], G[(size_t)c * AK + b], s);
+        X[(size_t)c * ld + n0 + a] = -s;
+    } else if (c < n0 + k) {
+        const int b = c - n0;
+        L[(size_t)c * ld + n0 + a] = a >= b ? out22[a * AK + b] : 0.0;
+        X[(size_t)c * ld + n0 + a] = a >= b ? W[a * AK + b] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256) dinv_from_x_kernel(const double* __restrict__ X, size_t ld, int tile0, double* Dinv,
+                                                          const int* flag) {
+    if (flag && *flag != 0) return;
+    const int t = tile0 + blockIdx.x;
+    const double* src = X + (size_t)t * TB * ld + (size_t)t * TB;
+    double* dst = Dinv + (size_t)t * TB * TB;
+    for (int idx = threadIdx.x; idx < TB * TB; idx += 256) {
+        const int r = idx & (TB - 1), c = idx >> 7;
+        dst[idx] = r >= c ? src[(size_t)c * ld + r] : 0.0;
+    }
+}
+
+// Rows [r0, r1) of L and X become identity rows (padding state): zero for columns < row, 1 on the diagonal,
+// and the part of later rows' columns [r0, r1) is zeroed as well (rows >= r1 up to row_end).
+__global__ void __launch_bounds__(256) identity_rows_kernel(double* L, double* X, size_t ld, int r0, int r1, int row_end) {
+    const int c = blockIdx.x;                 // column
+    for (int r = r0 + threadIdx.x; r < row_end; r += 256) {
+        if (r < c) continue;                  // upper part is never read
+        if (r < r1 || (c >= r0 && c < r1)) {
+            const double v = (r == c) ? 1.0 : 0.0;
+            L[(size_t)c * ld + r] = v;
+            if (X) X[(size_t)c * ld + r] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+size_t append_workspace_doubles(size_t cap) {
+    // Pn, B, G (cap x 32 each) + gram partials + S0 (1024) + L22|W (2048) + flag (as one double slot)
+    const size_t parts = (cap + GRAM_ROWS - 1) / GRAM_ROWS;
+    return 3 * cap * AK + parts * AK * AK + 3 * AK * AK + 8;
+}
+
+cudaError_t launch_append_slab(const double* xyz, size_t ld, const double* sigma2, int n0, int k, double* L, double* X,
+                               double* Dinv, double* ws, size_t cap, const KernParams& kp, int reset_flag,
+                               cudaStream_t st) {
+    static int attr_done = 0;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(append_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = 1;
+    }
+    const size_t parts_cap = (cap + GRAM_ROWS - 1) / GRAM_ROWS;
+    double* Pn = ws;
+    double* B = Pn + cap * AK;
+    double* G = B + cap * AK;
+    double* part = G + cap * AK;
+    double* S0 = part + parts_cap * AK * AK;
+    double* out22 = S0 + AK * AK;
+    int* flag = reinterpret_cast<int*>(out22 + 2 * AK * AK);
+    if (reset_flag) {
+        cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+    }
+    const int nblk = (n0 + AK - 1) / AK;
+    const int nparts = (n0 + GRAM_ROWS - 1) / GRAM_ROWS;
+    append_panel_kernel<<<(n0 * AK + 255) / 256 > 0 ? (n0 * AK + 255) / 256 : 1, 256, 0, st>>>(
+        xyz, xyz + ld, xyz + 2 * ld, sigma2, n0, k, Pn, S0, kp);
+    skinny_tri_kernel<0><<<nblk, 256, 0, st>>>(X, ld, n0, Pn, B);
+    append_gram_kernel<<<nparts, 256, 0, st>>>(B, n0, part);
+    append_leaf_kernel<<<1, NTHREADS, TILE_SMEM_BYTES, st>>>(S0, part, nparts, out22, flag, n0);
+    skinny_tri_kernel<1><<<nblk, 256, 0, st>>>(X, ld, n0, B, G);
+    append_scatter_kernel<<<((n0 + k) * AK + 255) / 256, 256, 0, st>>>(B, G, out22, flag, n0, k, L, X, ld);
+    const int t0 = n0 / TB, t1 = (n0 + k - 1) / TB;
+    dinv_from_x_kernel<<<t1 - t0 + 1, 256, 0, st>>>(X, ld, t0, Dinv, flag);
+    return cudaGetLastError();
+}
+
+const int* append_flag_ptr(const double* ws, size_t cap) {
+    const size_t parts_cap = (cap + GRAM_ROWS - 1) / GRAM_ROWS;
+    return reinterpret_cast<const int*>(ws + 3 * cap * AK + parts_cap * AK * AK + 3 * AK * AK);
+}
+
+cudaError_t launch_identity_rows(double* L, double* X, size_t ld, int r0, int r1, int row_end, cudaStream_t st) {
+    if (r1 <= r0 || row_end <= r0) return cudaSuccess;
+    identity_rows_kernel<<<row_end, 256, 0, st>>>(L, X, ld, r0, r1, row_end);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dinv_from_x(const double* X, size_t ld, int tile0, int ntiles, double* Dinv, cudaStream_t st) {
+    if (ntiles <= 0) return cudaSuccess;
+    dinv_from_x_kernel<<<ntiles, 256, 0, st>>>(X, ld, tile0, Dinv, nullptr);
+    return cudaGetLastError();
+}
+
+}  // namespace gpr

@@ -101,8 +101,10 @@ struct ModelDev {            // what predict needs, per device
 
 struct gpr_model {
     gpr_ctx* ctx = nullptr;
-    size_t n = 0, N = 0;
+    size_t n = 0, N = 0;       // real points; active padded size 128*ceil(n/128)
+    size_t cap = 0;            // leading dimension of every per-point buffer and of L / L^-1 (>= N, multiple of 128)
     int nb = 0;
+    double* aws = nullptr; size_t aws_dbl = 0;   // append workspace (primary device)
     gpr_kernel_t kernel{};
     KernParams kp{};
     double R = 0.0, k0 = 0.0;
@@ -111,7 +113,8 @@ struct gpr_model {
     double* label = nullptr; double* s2 = nullptr; double* zfwd = nullptr;
     double* L = nullptr; double* Dinv = nullptr; int* scratch = nullptr;
     std::vector<ModelDev> devs;
-    std::vector<double> hx, hy, hz, hlabel, hs2, h_alpha, h_normals;
+    std::vector<double> hx, hy, hz, hlabel, hs2, h_alpha, h_normals;   // h_normals: n_normals x 3 column-major
+    size_t n_normals = 0;
     std::mutex mu;
 };
 
@@ -130,7 +133,8 @@ static void free_factor(gpr_model* m) {
     if (m->devs.empty()) return;
     cudaSetDevice(m->devs[0].dev);
     cudaFree(m->label); cudaFree(m->s2); cudaFree(m->zfwd); cudaFree(m->L); cudaFree(m->Dinv); cudaFree(m->scratch);
-    m->label = m->s2 = m->zfwd = m->L = m->Dinv = nullptr; m->scratch = nullptr;
+    cudaFree(m->aws);
+    m->label = m->s2 = m->zfwd = m->L = m->Dinv = m->aws = nullptr; m->scratch = nullptr; m->aws_dbl = 0;
     for (auto& d : m->devs) {
         cudaSetDevice(d.dev);
         cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.linv);
@@ -152,7 +156,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     const size_t n = m->hx.size();
     const size_t N = (n + TB - 1) / TB * TB;
     const int nb = (int)(N / TB);
-    m->n = n; m->N = N; m->nb = nb;
+    m->n = n; m->N = N; m->nb = nb; m->cap = N;
     m->devs.assign(ctx->devs.size(), ModelDev());
     for (size_t i = 0; i < ctx->devs.size(); ++i) m->devs[i].dev = ctx->devs[i]->dev;
     ModelDev& md = m->devs[0];
@@ -209,6 +213,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     m->h_alpha.resize(n);
     CU(cudaMemcpyAsync(m->h_alpha.data(), md.alpha, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     m->h_normals.clear();
+    m->n_normals = 0;
     if (m->with_normals) {
         // create<true>(): N_i = normalize(sum_j alpha_j k~(D_ij)(p_i - p_j))  (gp_regressor.hpp:166-181)
         rc = ws_reserve(&ws->io, &ws->io_cap, 14 * N);
@@ -218,6 +223,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
                           (int)n, f, g, N, nullptr, 0, m->kp, n <= 4096, st));
         CU(launch_normalize_rows(g, N, (int)n, st));
         m->h_normals.resize(3 * n);
+        m->n_normals = n;
         for (int c = 0; c < 3; ++c)
             CU(cudaMemcpyAsync(m->h_normals.data() + c * n, g + c * N, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
@@ -247,13 +253,14 @@ static int ensure_linv_primary(gpr_model* m) {
     if (m->replica) return fail(GPR_ERR_INVALID, "replica model was created without L^-1");
     DeviceCtx* dc = m->ctx->devs[0];
     CU(cudaSetDevice(dc->dev));
-    if (!md.linv) CU(cudaMalloc((void**)&md.linv, m->N * m->N * sizeof(double)));
+    if (!md.linv) CU(cudaMalloc((void**)&md.linv, m->cap * m->cap * sizeof(double)));
     Workspace* ws = nullptr;
     int rc = ws_acquire(dc, &ws);
     if (rc) return rc;
     struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
     CU(cudaEventRecord(ws->ev[0], ws->st));
-    CU(launch_linv(m->L, md.linv, m->N, m->nb, m->Dinv, m->scratch, dc->num_sms, ws->st));
+    CU(launch_linv(m->L, md.linv, m->cap, m->nb, m->Dinv, m->scratch, dc->num_sms, ws->st));
+    if (m->cap > m->N) CU(launch_identity_rows(md.linv, nullptr, m->cap, (int)m->N, (int)m->cap, (int)m->cap, ws->st));
     CU(cudaEventRecord(ws->ev[1], ws->st));
     int flags[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(flags, m->scratch, sizeof(flags), cudaMemcpyDeviceToHost, ws->st));
@@ -274,15 +281,15 @@ static int ensure_on_device(gpr_model* m, size_t di, bool need_linv) {
     ModelDev& dst = m->devs[di];
     CU(cudaSetDevice(dst.dev));
     if (!dst.have) {
-        CU(cudaMalloc((void**)&dst.xyz, 3 * m->N * sizeof(double)));
-        CU(cudaMalloc((void**)&dst.alpha, m->N * sizeof(double)));
-        CU(cudaMemcpyPeer(dst.xyz, dst.dev, src.xyz, src.dev, 3 * m->N * sizeof(double)));
-        CU(cudaMemcpyPeer(dst.alpha, dst.dev, src.alpha, src.dev, m->N * sizeof(double)));
+        if (!dst.xyz) CU(cudaMalloc((void**)&dst.xyz, 3 * m->cap * sizeof(double)));
+        if (!dst.alpha) CU(cudaMalloc((void**)&dst.alpha, m->cap * sizeof(double)));
+        CU(cudaMemcpyPeer(dst.xyz, dst.dev, src.xyz, src.dev, 3 * m->cap * sizeof(double)));
+        CU(cudaMemcpyPeer(dst.alpha, dst.dev, src.alpha, src.dev, m->cap * sizeof(double)));
         dst.have = true;
     }
     if (need_linv && !dst.have_linv) {
-        if (!dst.linv) CU(cudaMalloc((void**)&dst.linv, m->N * m->N * sizeof(double)));
-        CU(cudaMemcpyPeer(dst.linv, dst.dev, src.linv, src.dev, m->N * m->N * sizeof(double)));
+        if (!dst.linv) CU(cudaMalloc((void**)&dst.linv, m->cap * m->cap * sizeof(double)));
+        CU(cudaMemcpyPeer(dst.linv, dst.dev, src.linv, src.dev, m->cap * m->cap * sizeof(double)));
         dst.have_linv = true;
     }
     return GPR_OK;
@@ -313,7 +320,7 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
     if (rc) return rc;
     struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
     cudaStream_t st = ws->st;
-    const size_t N = m->N;
+    const size_t N = m->N, ld = m->cap;
     const int n = (int)m->n;
     const bool small_var = want_var && io.q <= 8;
     size_t batch = io.q;
@@ -352,12 +359,12 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         CU(cudaEventRecord(ws->ev[1], st));
         const size_t pld = small_var ? (size_t)TB : (bq + TB - 1) / TB * TB;
         const bool warp_mode = small_var || (!want_var && bq <= (size_t)64 * dc->num_sms);
-        CU(launch_predict(md.xyz, md.xyz + N, md.xyz + 2 * N, md.alpha, n, (int)N, qx, qy, qz, (int)bq, f, g, gld,
+        CU(launch_predict(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, n, (int)N, qx, qy, qz, (int)bq, f, g, gld,
                           want_var ? ws->panel : nullptr, pld, m->kp, warp_mode, st));
         CU(cudaEventRecord(ws->ev[2], st));
         if (want_var) {
-            if (small_var) CU(launch_variance_small(md.linv, N, (int)N, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
-            else CU(launch_variance(md.linv, N, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+            if (small_var) CU(launch_variance_small(md.linv, ld, (int)N, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+            else CU(launch_variance(md.linv, ld, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
         }
         CU(cudaEventRecord(ws->ev[3], st));
         if (want_t && !io.device_ptrs) CU(launch_tangent_basis(g, gld, (int)bq, dtx, dty, st));
@@ -487,8 +494,13 @@ int gpr_model_get(const gpr_model* m, double* alpha, double* R, double* normals)
     }
     if (R) *R = m->R;
     if (normals) {
-        if (m->h_normals.size() != 3 * m->n) return fail(GPR_ERR_INVALID, "model was fitted without normals");
-        memcpy(normals, m->h_normals.data(), 3 * m->n * sizeof(double));
+        // Normals exist for the points of the last create<true>(); rows appended by update() stay zero
+        // (the reference does not refresh them either, gp_regressor.hpp:462-477).
+        if (m->n_normals == 0 || m->h_normals.size() != 3 * m->n_normals) return fail(GPR_ERR_INVALID, "model was fitted without normals");
+        for (int c = 0; c < 3; ++c) {
+            memcpy(normals + c * m->n, m->h_normals.data() + c * m->n_normals, m->n_normals * sizeof(double));
+            for (size_t i = m->n_normals; i < m->n; ++i) normals[c * m->n + i] = 0.0;
+        }
     }
     return GPR_OK;
 }
@@ -497,7 +509,7 @@ int gpr_model_get_factor(const gpr_model* m, double* L) {
     if (!m || !L) return fail(GPR_ERR_INVALID, "null pointer");
     if (!m->L) return fail(GPR_ERR_INVALID, "model holds no factor (replica)");
     CU(cudaSetDevice(m->devs[0].dev));
-    CU(cudaMemcpy2D(L, m->n * sizeof(double), m->L, m->N * sizeof(double), m->n * sizeof(double), m->n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy2D(L, m->n * sizeof(double), m->L, m->cap * sizeof(double), m->n * sizeof(double), m->n, cudaMemcpyDeviceToHost));
     for (size_t c = 0; c < m->n; ++c)
         for (size_t r = 0; r < c; ++r) L[c * m->n + r] = 0.0;
     return GPR_OK;
@@ -566,13 +578,62 @@ int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m) {
     return GPR_OK;
 }
 
-int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
-               const double* sigma2, size_t k) {
-    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
-    if (!m) return fail(GPR_ERR_INVALID, "Empty model pointer");
-    if (!x || !y || !z || !label || k == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
-    if (m->replica) return fail(GPR_ERR_INVALID, "cannot append to a replica model");
-    std::lock_guard<std::mutex> lk(m->mu);
+// Reallocate every per-model buffer of the primary device with leading dimension newcap (multiple of 128,
+// >= m->N), keeping the fitted state; rows [N, newcap) of L and L^-1 become identity padding.
+static int grow_capacity(gpr_model* m, size_t newcap, cudaStream_t st) {
+    if (newcap <= m->cap) return GPR_OK;
+    ModelDev& md = m->devs[0];
+    const size_t N = m->N, oc = m->cap;
+    const int nbc = (int)(newcap / TB);
+    double *xyz = nullptr, *alpha = nullptr, *label = nullptr, *s2 = nullptr, *zfwd = nullptr, *L = nullptr, *Dinv = nullptr, *X = nullptr;
+    int* scratch = nullptr;
+    auto drop = [&]() { cudaFree(xyz); cudaFree(alpha); cudaFree(label); cudaFree(s2); cudaFree(zfwd); cudaFree(L); cudaFree(Dinv); cudaFree(X); cudaFree(scratch); };
+#define GROW_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { drop(); return fail(e__ == cudaErrorMemoryAllocation ? GPR_ERR_OOM : GPR_ERR_CUDA, std::string("grow_capacity: ") + cudaGetErrorString(e__)); } } while (0)
+    GROW_TRY(cudaMalloc((void**)&xyz, 3 * newcap * sizeof(double)));
+    GROW_TRY(cudaMalloc((void**)&alpha, newcap * sizeof(double)));
+    GROW_TRY(cudaMalloc((void**)&label, newcap * sizeof(double)));
+    GROW_TRY(cudaMalloc((void**)&s2, newcap * sizeof(double)));
+    GROW_TRY(cudaMalloc((void**)&zfwd, newcap * sizeof(double)));
+    GROW_TRY(cudaMalloc((void**)&L, newcap * newcap * sizeof(double)));
+    GROW_TRY(cudaMalloc((void**)&Dinv, (size_t)nbc * TB * TB * sizeof(double)));
+    GROW_TRY(cudaMalloc((void**)&scratch, (8 + (size_t)nbc * nbc) * sizeof(int)));
+    if (md.have_linv) GROW_TRY(cudaMalloc((void**)&X, newcap * newcap * sizeof(double)));
+    GROW_TRY(cudaMemsetAsync(xyz, 0, 3 * newcap * sizeof(double), st));
+    GROW_TRY(cudaMemsetAsync(alpha, 0, newcap * sizeof(double), st));
+    GROW_TRY(cudaMemsetAsync(label, 0, newcap * sizeof(double), st));
+    GROW_TRY(cudaMemsetAsync(s2, 0, newcap * sizeof(double), st));
+    GROW_TRY(cudaMemsetAsync(zfwd, 0, newcap * sizeof(double), st));
+    for (int c = 0; c < 3; ++c)
+        GROW_TRY(cudaMemcpyAsync(xyz + c * newcap, md.xyz + c * oc, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    GROW_TRY(cudaMemcpyAsync(alpha, md.alpha, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    GROW_TRY(cudaMemcpyAsync(label, m->label, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    GROW_TRY(cudaMemcpyAsync(s2, m->s2, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    GROW_TRY(cudaMemcpy2DAsync(L, newcap * sizeof(double), m->L, oc * sizeof(double), N * sizeof(double), N, cudaMemcpyDeviceToDevice, st));
+    if (X) GROW_TRY(cudaMemcpy2DAsync(X, newcap * sizeof(double), md.linv, oc * sizeof(double), N * sizeof(double), N, cudaMemcpyDeviceToDevice, st));
+    GROW_TRY(cudaMemcpyAsync(Dinv, m->Dinv, (size_t)m->nb * TB * TB * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    GROW_TRY(launch_identity_rows(L, X, newcap, (int)N, (int)newcap, (int)newcap, st));
+    // identity inverse diagonal tiles for the new tile rows (L^-1 of an identity tile)
+    GROW_TRY(launch_dinv_from_x(L, newcap, m->nb, nbc - m->nb, Dinv, st));
+    GROW_TRY(cudaStreamSynchronize(st));
+#undef GROW_TRY
+    cudaFree(md.xyz); cudaFree(md.alpha); cudaFree(m->label); cudaFree(m->s2); cudaFree(m->zfwd); cudaFree(m->L);
+    cudaFree(m->Dinv); cudaFree(m->scratch); cudaFree(md.linv); cudaFree(m->aws);
+    md.xyz = xyz; md.alpha = alpha; m->label = label; m->s2 = s2; m->zfwd = zfwd; m->L = L; m->Dinv = Dinv;
+    m->scratch = scratch; md.linv = X; m->aws = nullptr; m->aws_dbl = 0;
+    m->cap = newcap;
+    // replicas on the other devices have the old layout: drop them, they are re-copied on demand
+    for (size_t di = 1; di < m->devs.size(); ++di) {
+        ModelDev& d = m->devs[di];
+        cudaSetDevice(d.dev);
+        cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.linv);
+        d.xyz = d.alpha = d.linv = nullptr; d.have = d.have_linv = false;
+    }
+    cudaSetDevice(md.dev);
+    return GPR_OK;
+}
+
+static void host_append(gpr_model* m, const double* x, const double* y, const double* z, const double* label,
+                        const double* sigma2, size_t k) {
     const size_t p = m->hx.size();
     m->hx.insert(m->hx.end(), x, x + k); m->hy.insert(m->hy.end(), y, y + k); m->hz.insert(m->hz.end(), z, z + k);
     m->hlabel.insert(m->hlabel.end(), label, label + k);
@@ -582,19 +643,139 @@ int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, con
         if (sigma2) m->hs2.insert(m->hs2.end(), sigma2, sigma2 + k); else m->hs2.resize(p + k, 0.0);
         m->has_s2 = true;
     }
+}
+
+// Incremental path of gpr_append (gpr_append.cu).  Caller holds m->mu.
+static int append_incremental(gpr_model* m, const double* x, const double* y, const double* z, const double* label,
+                              const double* sigma2, size_t k) {
+    gpr_ctx* ctx = m->ctx;
+    DeviceCtx* dc = ctx->devs[0];
+    CU(cudaSetDevice(dc->dev));
+    int rc = ensure_linv_primary(m);
+    if (rc) return rc;
+    Workspace* ws = nullptr;
+    rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    cudaStream_t st = ws->st;
+    const size_t n0 = m->n, n1 = n0 + k;
+    const size_t N1 = (n1 + TB - 1) / TB * TB;
+    if (N1 > m->cap) {
+        size_t want = std::max(N1, (m->cap * 5 / 4 + TB - 1) / TB * TB);
+        rc = grow_capacity(m, want, st);
+        if (rc) return rc;
+    }
+    ModelDev& md = m->devs[0];
+    const size_t ld = m->cap;
+    const size_t need = append_workspace_doubles(ld);
+    if (m->aws_dbl < need) {
+        cudaFree(m->aws); m->aws = nullptr; m->aws_dbl = 0;
+        CU(cudaMalloc((void**)&m->aws, need * sizeof(double)));
+        m->aws_dbl = need;
+    }
+    CU(cudaEventRecord(ws->ev[0], st));
+    CU(cudaMemcpyAsync(md.xyz + n0, x, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(md.xyz + ld + n0, y, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(md.xyz + 2 * ld + n0, z, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->label + n0, label, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (sigma2) CU(cudaMemcpyAsync(m->s2 + n0, sigma2, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(m->s2 + n0, 0, k * sizeof(double), st));
+    CU(cudaEventRecord(ws->ev[1], st));
+    for (size_t o = 0; o < k; o += 32) {
+        const int kk = (int)std::min<size_t>(32, k - o);
+        CU(launch_append_slab(md.xyz, ld, m->s2, (int)(n0 + o), kk, m->L, md.linv, m->Dinv, m->aws, ld, m->kp, o == 0, st));
+    }
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, append_flag_ptr(m->aws, ld), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flag != 0) {
+        // roll back: the rows of the slabs that were committed before the failing one become padding again
+        CU(launch_identity_rows(m->L, md.linv, ld, (int)n0, (int)n1, (int)N1, st));
+        CU(launch_dinv_from_x(md.linv, ld, (int)(n0 / TB), (int)(N1 / TB - n0 / TB), m->Dinv, st));
+        for (int c = 0; c < 3; ++c) CU(cudaMemsetAsync(md.xyz + c * ld + n0, 0, k * sizeof(double), st));
+        CU(cudaMemsetAsync(m->label + n0, 0, k * sizeof(double), st));
+        CU(cudaMemsetAsync(m->s2 + n0, 0, k * sizeof(double), st));
+        CU(cudaStreamSynchronize(st));
+        g_pivot = flag;
+        char b[256];
+        snprintf(b, sizeof b, "covariance matrix is not positive definite after the append: pivot %d of %zu is <= 0", flag, n1);
+        return fail(GPR_ERR_NOT_SPD, b);
+    }
+    const int nb1 = (int)(N1 / TB);
+    CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
+    CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
+    CU(cudaEventRecord(ws->ev[2], st));
+    m->h_alpha.resize(n1);
+    CU(cudaMemcpyAsync(m->h_alpha.data(), md.alpha, n1 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    int flags[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(flags, m->scratch, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flags[2] != 0) return fail(GPR_ERR_CUDA, "triangular solve kernel aborted (dependency wait timed out)");
+    host_append(m, x, y, z, label, sigma2, k);
+    m->n = n1; m->N = N1; m->nb = nb1;
+    for (size_t di = 1; di < m->devs.size(); ++di) { m->devs[di].have = false; m->devs[di].have_linv = false; }
+    std::lock_guard<std::mutex> lk(ctx->tmu);
+    ctx->timings.h2d_ms = ev_ms(ws->ev[0], ws->ev[1]);
+    ctx->timings.append_ms = ev_ms(ws->ev[1], ws->ev[2]);
+    return GPR_OK;
+}
+
+int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
+               const double* sigma2, size_t k) {
+    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
+    if (!m) return fail(GPR_ERR_INVALID, "Empty model pointer");
+    if (!x || !y || !z || !label || k == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
+    if (m->replica) return fail(GPR_ERR_INVALID, "cannot append to a replica model");
+    std::lock_guard<std::mutex> lk(m->mu);
+    const char* force = getenv("GPR_APPEND_REFIT");
+    const bool refit = (force && atoi(force) != 0) || k > 256 || 8 * k > m->n;
+    if (!refit) return append_incremental(m, x, y, z, label, sigma2, k);
+    // Large batches: append on the host and refit, like the reference (gp_regressor.hpp:442-459).
+    const size_t p = m->hx.size();
+    const bool had_s2 = m->has_s2;
+    host_append(m, x, y, z, label, sigma2, k);
     const bool normals = m->with_normals;
     m->with_normals = false;                 // :462-477: normals are not refreshed by update()
     std::vector<double> keep = m->h_normals;
+    const size_t keep_n = m->n_normals;
     int rc = fit_from_host(m, true);
+    { std::lock_guard<std::mutex> tl(ctx->tmu); ctx->timings.append_ms = 0.0; }   // no incremental update ran
     m->with_normals = normals;
-    m->h_normals = keep;
+    m->h_normals = keep; m->n_normals = keep_n;
+    if (rc) {
+        // leave the model as it was: drop the appended points and refit the old set
+        const int code = rc; const std::string msg = g_err; const long long piv = g_pivot;
+        m->hx.resize(p); m->hy.resize(p); m->hz.resize(p); m->hlabel.resize(p);
+        if (had_s2) m->hs2.resize(p); else { m->hs2.clear(); m->has_s2 = false; }
+        m->with_normals = false;
+        fit_from_host(m, true);
+        m->with_normals = normals; m->h_normals = keep; m->n_normals = keep_n;
+        g_err = msg; g_pivot = piv;
+        return code;
+    }
+    return rc;
+}
+
+int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity) {
+    if (!ctx || !m) return fail(GPR_ERR_INVALID, "Empty model pointer");
+    if (m->replica) return fail(GPR_ERR_INVALID, "cannot reserve on a replica model");
+    std::lock_guard<std::mutex> lk(m->mu);
+    const size_t want = (capacity + TB - 1) / TB * TB;
+    if (want <= m->cap) return GPR_OK;
+    DeviceCtx* dc = ctx->devs[0];
+    CU(cudaSetDevice(dc->dev));
+    Workspace* ws = nullptr;
+    int rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    rc = grow_capacity(m, want, ws->st);
+    ws_release(dc, ws);
     return rc;
 }
 
 int gpr_model_state_get(gpr_ctx* ctx, gpr_model* m, int with_linv, gpr_model_state* out) {
     if (!ctx || !m || !out) return fail(GPR_ERR_INVALID, "null pointer");
     if (with_linv) { int rc = ensure_on_device(m, 0, true); if (rc) return rc; }
-    out->n = m->n; out->padded_n = m->N; out->kernel = m->kernel; out->R = m->R;
+    out->n = m->n; out->padded_n = m->N; out->ld = m->cap; out->kernel = m->kernel; out->R = m->R;
     out->xyz = m->devs[0].xyz; out->alpha = m->devs[0].alpha;
     out->linv = m->devs[0].have_linv ? m->devs[0].linv : nullptr;
     return GPR_OK;
@@ -605,7 +786,7 @@ int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double
     gpr_model* m = new gpr_model();
     m->ctx = ctx; m->kernel = kernel; m->kp = make_kp(kernel); m->k0 = kernel_at_zero(m->kp); m->R = R;
     m->replica = true;
-    m->n = n; m->N = (n + TB - 1) / TB * TB; m->nb = (int)(m->N / TB);
+    m->n = n; m->N = (n + TB - 1) / TB * TB; m->nb = (int)(m->N / TB); m->cap = m->N;
     m->devs.assign(ctx->devs.size(), ModelDev());
     for (size_t i = 0; i < ctx->devs.size(); ++i) m->devs[i].dev = ctx->devs[i]->dev;
     ModelDev& md = m->devs[0];

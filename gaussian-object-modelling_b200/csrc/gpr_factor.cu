@@ -7,7 +7,8 @@
 // reported (never NaN), see SURVEY F2.
 //
 // Algorithm (left-looking by 128x128 tiles, dependency flags in global memory):
-//   task (i,j), i >= j, claimed from an atomic counter in column-major order:
+//   task (i,j), i >= j, claimed from an atomic counter in column order (diagonal tasks one column ahead,
+//   see chol_task_decode):
 //     acc  = sum_{k<j} L_ik L_jk^T                 DMMA mainloop; waits on ready[i][k], ready[j][k]
 //     T    = K_ij - acc                            -> shared memory
 //     i==j : L_jj = chol(T) in shared memory (warp-level 16x16 diagonal blocks, DMMA trailing
@@ -39,46 +40,75 @@ struct CholArgs {
     long long* trace; // optional: 4 globaltimer stamps per task (claim, accumulated, solved, published)
 };
 
+// Task order.  Column j contributes, in this order, (j+1,j), (j+1,j+1), (j+2,j), ..., (nb-1,j); task 0 is
+// (0,0).  The diagonal task of column j+1 is therefore claimed one whole column ahead of the tasks
+// that need its result (L_{j+1,j+1}^-1): its in-CTA Cholesky + inverse, the only serial piece of the
+// algorithm, overlaps the accumulation of the column-j tasks instead of stalling every task of column
+// j+1 behind it.  Dependencies of (i,j): (i,k),(j,k) for k<j (earlier columns), (j,j) (second task of
+// column j-1), and for a diagonal task (j,j-1), which is the task just before it — all smaller indices.
+__host__ __device__ __forceinline__ void chol_task_decode(int task, int nb, int& i, int& j) {
+    if (task == 0) { i = 0; j = 0; return; }
+    task -= 1;
+    j = 0;
+    while (task >= nb - j) { task -= nb - j; ++j; }
+    if (task == 0) { i = j + 1; }
+    else if (task == 1) { i = j + 1; j = j + 1; }
+    else { i = j + task; }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ int s_task, s_abort, s_fail, s_upto;
+    __shared__ int s_task, s_abort, s_fail, s_upto, s_i, s_j;
     __shared__ double s_inv[TB];
     const int tid = threadIdx.x;
-    const TileCoord tc;
+    // The tile coordinates live in shared memory and are re-read (volatile) by each phase of a task, so that
+    // nothing but the accumulators, the fragments and the copy addresses is live across the DMMA loop: with
+    // them held in registers the loop ran out of registers, ptxas rotated the accumulators and the address
+    // updates of the asynchronous copies stalled on the previous copies (long-scoreboard stalls, ~8 %).
+#define GPR_SH(x) (*(volatile int*)&(x))
     for (;;) {
         if (tid == 0) {
-            s_task = a.task_begin + atomicAdd(a.counter, 1);
+            const int t = a.task_begin + atomicAdd(a.counter, 1);
+            int ti = 0, tj = 0;
+            if (t < a.task_end) chol_task_decode(t, a.nb, ti, tj);
+            s_task = t; s_i = ti; s_j = tj;
             s_abort = ld_volatile(a.abort) != 0;
             s_fail = 1 << 20;
             s_upto = 1 << 30;
+            if (a.trace && t < a.task_end) a.trace[4 * (size_t)t + 0] = globaltimer_ns();
         }
         __syncthreads();
-        int task = s_task;
-        if (task >= a.task_end || s_abort) return;
-        const int task_id = task;
-        int j = 0;
-        while (task >= a.nb - j) { task -= a.nb - j; ++j; }
-        const int i = j + task;
-        if (a.trace && tid == 0) a.trace[4 * (size_t)task_id + 0] = globaltimer_ns();
+        if (GPR_SH(s_task) >= a.task_end || s_abort) return;
 
         Acc acc;
         acc_zero(acc);
-        const double* Li = a.A + (size_t)i * TB;     // row panel i, k = 0
-        const double* Lj = a.A + (size_t)j * TB;
-        // One bulk look at the readiness flags of both row panels: the k-blocks [0, upto) are complete
-        // (almost always all but the last one or two), so the mainloop only polls beyond that prefix
-        // instead of paying an L2 round trip in front of a barrier at every 128-wide block.
-        const int* fi = a.ready + (size_t)i * a.nb;
-        const int* fj = a.ready + (size_t)j * a.nb;
-        const int upto = ready_prefix(j, [&](int t) { return ld_acquire(fi + t) != 0 && ld_acquire(fj + t) != 0; }, &s_upto);
-        auto waitf = [&](int kb) -> bool {
-            if (tid != 0 || kb < upto) return true;
-            if (!spin_wait(fi + kb, a.abort)) return false;
-            if (i != j && !spin_wait(fj + kb, a.abort)) return false;
-            return true;
-        };
-        if (!tile_mainloop<STREAM_M, STREAM_M>(acc, Li, a.ld, Lj, a.ld, 8 * j, smem, &s_abort, waitf)) return;
+        {
+            // One bulk look at the readiness flags of both row panels: the k-blocks [0, upto) are complete
+            // (almost always all but the last one or two).  They are accumulated by the wait-free mainloop
+            // (the same instantiation as the variance kernel).
+            const int i = GPR_SH(s_i), j = GPR_SH(s_j);
+            const int* fi = a.ready + (size_t)i * a.nb;
+            const int* fj = a.ready + (size_t)j * a.nb;
+            const int upto = ready_prefix(j, [&](int t) { return ld_acquire(fi + t) != 0 && ld_acquire(fj + t) != 0; }, &s_upto);
+            if (!tile_mainloop<STREAM_M, STREAM_M>(acc, a.A + (size_t)i * TB, a.ld, a.A + (size_t)j * TB, a.ld, 8 * upto, smem,
+                                                   &s_abort, NoWait())) return;
+        }
+        // the few blocks beyond the prefix are awaited and accumulated one 128-wide block at a time
+        for (int kb = GPR_SH(s_upto); kb < GPR_SH(s_j); ++kb) {
+            const int i = GPR_SH(s_i), j = GPR_SH(s_j);
+            if (tid == 0) {
+                if (!spin_wait(a.ready + (size_t)i * a.nb + kb, a.abort) ||
+                    (i != j && !spin_wait(a.ready + (size_t)j * a.nb + kb, a.abort))) s_abort = 1;
+            }
+            __syncthreads();
+            if (s_abort) return;
+            const size_t off = (size_t)kb * TB * a.ld;
+            if (!tile_mainloop<STREAM_M, STREAM_M>(acc, a.A + (size_t)i * TB + off, a.ld, a.A + (size_t)j * TB + off, a.ld, 8,
+                                                   smem, &s_abort, NoWait())) return;
+        }
 
+        const int i = GPR_SH(s_i), j = GPR_SH(s_j), task_id = GPR_SH(s_task);
+        const TileCoord tc;
         if (a.trace && tid == 0) a.trace[4 * (size_t)task_id + 1] = globaltimer_ns();
         double* T = smem;   // region 0, column-major pitch PM
         double* Gij = a.A + (size_t)j * TB * a.ld + (size_t)i * TB;
@@ -168,11 +198,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) linv_tiles_kernel(LinvArgs a) {
             // j operand: X[k, j-tile cols] K-major, element (c,k) at X[(j*128+c)*ld + k], k from j*128
             const double* Xj = a.X + (size_t)j * TB * a.ld + (size_t)j * TB;
             const int upto = ready_prefix(d, [&](int t) { return ld_acquire(a.ready + (size_t)(j + t) * a.nb + j) != 0; }, &s_upto);
-            auto waitf = [&](int kb) -> bool {
-                if (tid != 0 || kb < upto) return true;
-                return spin_wait(a.ready + (size_t)(j + kb) * a.nb + j, a.abort);
-            };
-            if (!tile_mainloop<STREAM_M, STREAM_K>(acc, Li, a.ld, Xj, a.ld, 8 * d, smem, &s_abort, waitf)) return;
+            if (!tile_mainloop<STREAM_M, STREAM_K>(acc, Li, a.ld, Xj, a.ld, 8 * upto, smem, &s_abort, NoWait())) return;
+            for (int kb = upto; kb < d; ++kb) {
+                if (tid == 0 && !spin_wait(a.ready + (size_t)(j + kb) * a.nb + j, a.abort)) s_abort = 1;
+                __syncthreads();
+                if (s_abort) return;
+                if (!tile_mainloop<STREAM_M, STREAM_K>(acc, Li + (size_t)kb * TB * a.ld, a.ld, Xj + (size_t)kb * TB, a.ld, 8, smem,
+                                                       &s_abort, NoWait())) return;
+            }
             double* W = smem;   // region 0, column-major pitch PM: W[k][c] at c*PM + k
             store_tile<true, 1>(acc, W, PM, tc);
             __syncthreads();
@@ -222,20 +255,24 @@ cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scr
         chol_tiles_kernel<<<grid, NTHREADS, TILE_SMEM_BYTES, st>>>(a);
         return cudaGetLastError();
     }
-    // Debug mode: one launch for each diagonal task and one for the rest of its column, so that no
-    // task ever waits on a flag inside a launch.
-    int t0 = 0;
-    for (int j = 0; j < nb; ++j) {
-        a.task_begin = t0; a.task_end = t0 + 1;
+    // Debug mode: tasks are launched in dependency levels (never more than one level per launch), so
+    // that no task ever waits on a flag inside a launch: (0,0); then per column j: (j+1,j) | (j+1,j+1) |
+    // the rest of column j.
+    auto run = [&](int t0, int t1) {
+        if (t1 <= t0) return;
+        a.task_begin = t0; a.task_end = t1;
         cudaMemsetAsync(a.counter, 0, sizeof(int), st);
-        chol_tiles_kernel<<<1, NTHREADS, TILE_SMEM_BYTES, st>>>(a);
-        int rest = nb - j - 1;
-        if (rest > 0) {
-            a.task_begin = t0 + 1; a.task_end = t0 + 1 + rest;
-            cudaMemsetAsync(a.counter, 0, sizeof(int), st);
-            chol_tiles_kernel<<<rest < num_sms ? rest : num_sms, NTHREADS, TILE_SMEM_BYTES, st>>>(a);
-        }
-        t0 += nb - j;
+        const int cnt = t1 - t0;
+        chol_tiles_kernel<<<cnt < num_sms ? cnt : num_sms, NTHREADS, TILE_SMEM_BYTES, st>>>(a);
+    };
+    run(0, 1);
+    int t0 = 1;
+    for (int j = 0; j + 1 < nb; ++j) {
+        const int len = nb - j;          // tasks contributed by column j
+        run(t0, t0 + 1);
+        run(t0 + 1, t0 + 2);
+        run(t0 + 2, t0 + len);
+        t0 += len;
     }
     return cudaGetLastError();
 }

@@ -30,6 +30,14 @@ cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* pa
                             double* partial, double k0, double* var, cudaStream_t st);
 cudaError_t launch_variance_small(const double* X, size_t ld, int N, const double* panel, size_t panel_ld, int q,
                                   double* part, double k0, double* var, cudaStream_t st);
+// K5 (gpr_append.cu): one slab of k <= 32 appended points at rows [n0, n0+k); ws: append_workspace_doubles(cap).
+size_t append_workspace_doubles(size_t cap);
+cudaError_t launch_append_slab(const double* xyz, size_t ld, const double* sigma2, int n0, int k, double* L, double* X,
+                               double* Dinv, double* ws, size_t cap, const KernParams& kp, int reset_flag,
+                               cudaStream_t st);
+const int* append_flag_ptr(const double* ws, size_t cap);
+cudaError_t launch_identity_rows(double* L, double* X_or_null, size_t ld, int r0, int r1, int row_end, cudaStream_t st);
+cudaError_t launch_dinv_from_x(const double* X, size_t ld, int tile0, int ntiles, double* Dinv, cudaStream_t st);
 // Engine self-test (gpr_selftest.cu): C = A * B^T on one 128x128 tile per CTA.
 cudaError_t launch_gemm_selftest(const double* A, size_t lda, const double* B, size_t ldb, int b_kmajor, double* C,
                                  size_t ldc, int mt, int nt, int k, cudaStream_t st);

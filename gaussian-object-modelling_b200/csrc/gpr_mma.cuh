@@ -115,34 +115,59 @@ __device__ __forceinline__ void compute_ks(Acc& acc, const double* __restrict__ 
     }
 }
 
-// Per-thread addressing of the asynchronous stage copies, computed once per tile.  One k16 stage of an
-// operand is 1024 chunks of 16 bytes, 4 per thread:
-//   M-major source: element (m,k) at src[m + k*ld] -> stage[k*PM + m]; thread owns k = tid>>6 (+4c), m = 2(tid&63)
-//   K-major source: element (m,k) at src[k + m*ld] -> stage[m*PK + k]; thread owns m = tid>>3 (+32c), k = 2(tid&7)
+// Per-thread addressing of the asynchronous stage copies.  One k16 stage of an operand is 1024 chunks of
+// 16 bytes, 4 per thread, and the stages are issued strictly in order (kk = 0, 1, 2, ...), so the source
+// address is a RUNNING pointer that advances by one stage per issue — no multiplications and no fresh
+// address registers inside the DMMA loop (recomputing src + kk*stride for every chunk cost ~30 integer
+// instructions per stage and made the address updates wait on the copies still reading those registers):
+//   M-major source: element (m,k) at src[m + k*ld] -> stage[k*PM + m]; thread owns column k = tid>>4 and
+//                   rows m = 2(tid&15) + 32c: its 4 chunks are 256 bytes apart in global AND shared memory
+//                   (compile-time immediates on one address register each).
+//   K-major source: element (m,k) at src[k + m*ld] -> stage[m*PK + k]; thread owns m = tid>>3 (+32c),
+//                   k = 2(tid&7): 4 running pointers (rows are ld apart).
+template <bool KMAJOR>
 struct StageCopy {
-    const double* src;     // this thread's first chunk at k16 stage 0
-    size_t chunk_stride;   // source elements between the thread's consecutive chunks
-    size_t stage_stride;   // source elements between consecutive k16 stages
-    int dst;               // offset of the first chunk inside a stage buffer
-    int dst_stride;        // stage-buffer elements between consecutive chunks
-    template <bool KMAJOR>
+    const double* p[KMAJOR ? 4 : 1];   // source of this thread's chunk(s) in the NEXT stage to be issued
+    size_t stage_stride;               // source elements between consecutive k16 stages
+    int dst;                           // offset of the first chunk inside a stage buffer
     __device__ __forceinline__ void init(const double* base, size_t ld) {
         const int tid = threadIdx.x;
         if (!KMAJOR) {
-            src = base + (size_t)(tid >> 6) * ld + 2 * (tid & 63);
-            chunk_stride = 4 * ld; stage_stride = (size_t)KT * ld;
-            dst = (tid >> 6) * PM + 2 * (tid & 63); dst_stride = 4 * PM;
+            p[0] = base + (size_t)(tid >> 4) * ld + 2 * (tid & 15);
+            stage_stride = (size_t)KT * ld;
+            dst = (tid >> 4) * PM + 2 * (tid & 15);
         } else {
-            src = base + (size_t)(tid >> 3) * ld + 2 * (tid & 7);
-            chunk_stride = 32 * ld; stage_stride = KT;
-            dst = (tid >> 3) * PK + 2 * (tid & 7); dst_stride = 32 * PK;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) p[c] = base + (size_t)((tid >> 3) + 32 * c) * ld + 2 * (tid & 7);
+            stage_stride = KT;
+            dst = (tid >> 3) * PK + 2 * (tid & 7);
         }
     }
-    __device__ __forceinline__ void issue(double* stage, int kk) const {
-        const double* g = src + (size_t)kk * stage_stride;
-        double* d = stage + dst;
+    // Copies the next TWO stages into s0 and s1.  All address arithmetic is done before the first copy is
+    // issued, into the registers read by the copies of the PREVIOUS pair (issued microseconds ago): a
+    // pointer update placed right after the copies that read the pointer stalls on their scoreboard.
+    __device__ __forceinline__ void issue_pair(double* s0, double* s1) {
+        if (!KMAJOR) {
+            const double* g0 = p[0];
+            const double* g1 = g0 + stage_stride;
+            p[0] = g1 + stage_stride;
+            double* d0 = s0 + dst;
+            double* d1 = s1 + dst;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) cp_async16(d + c * dst_stride, g + c * chunk_stride);
+            for (int c = 0; c < 4; ++c) cp_async16(d0 + 32 * c, g0 + 32 * c);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async16(d1 + 32 * c, g1 + 32 * c);
+        } else {
+            const double* g[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { g[c] = p[c]; p[c] = g[c] + 2 * KT; }
+            double* d0 = s0 + dst;
+            double* d1 = s1 + dst;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async16(d0 + c * 32 * PK, g[c]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async16(d1 + c * 32 * PK, g[c] + KT);
+        }
     }
 };
 
@@ -169,17 +194,15 @@ __device__ __forceinline__ bool tile_mainloop(Acc& acc, const double* Ag, size_t
     double* istage = JRES ? r1 : r0;     // i stages move to region 1 when j is resident in region 0
     double* jstage = r1;
     const TileCoord tc;
-    StageCopy ci, cj;
-    if (IS) ci.template init<false>(Ag, lda);
-    if (JS) cj.template init<JK>(Bg, ldb);
+    StageCopy<false> ci;
+    StageCopy<JK> cj;
+    if (IS) ci.init(Ag, lda);
+    if (JS) cj.init(Bg, ldb);
 
     auto issue_pair = [&](int kk) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int s = (kk + h) & (STAGES - 1);
-            if (IS) ci.issue(istage + s * STAGE_I, kk + h);
-            if (JS) cj.issue(jstage + s * STAGE_J, kk + h);
-        }
+        const int s0 = kk & (STAGES - 1), s1 = (kk + 1) & (STAGES - 1);
+        if (IS) ci.issue_pair(istage + s0 * STAGE_I, istage + s1 * STAGE_I);
+        if (JS) cj.issue_pair(jstage + s0 * STAGE_J, jstage + s1 * STAGE_J);
         cp_async_commit();
     };
     auto a_of = [&](int kk) -> const double* {
@@ -240,23 +263,24 @@ __device__ __forceinline__ void store_tile(const Acc& acc, double* dst, size_t l
 }
 
 // dst_smem (column-major, pitch PM) = G - acc, where G is a column-major global tile (read through L2).
+// Two passes: the accumulators are first parked in shared memory (negated), then the tile is read with
+// coalesced 16-byte loads and added in place.  (Subtracting in registers, in fragment layout, makes ptxas
+// hoist all 64 global loads next to the 128 accumulator registers: 255 registers and spilled copy
+// strides that were reloaded inside every DMMA loop of the kernel.)  Ends with a __syncthreads().
 template <bool JK>
 __device__ __forceinline__ void residual_to_smem(const Acc& acc, const double* G, size_t ld, double* dst,
                                                  const TileCoord& tc) {
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-        const int c = tc.col<JK>(mt);
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int r = tc.row(p, 0);
-            const double2* gp = reinterpret_cast<const double2*>(G + (size_t)c * ld + r);
-            double2 lo = __ldcg(gp), hi = __ldcg(gp + 1);
-            lo.x -= GPR_ACC(acc, mt, p, 0); lo.y -= GPR_ACC(acc, mt, p, 1);
-            hi.x -= GPR_ACC(acc, mt, p, 2); hi.y -= GPR_ACC(acc, mt, p, 3);
-            double2* d = reinterpret_cast<double2*>(dst + c * PM + r);
-            d[0] = lo; d[1] = hi;
-        }
+    store_tile<JK, -1>(acc, dst, PM, tc);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TB * TB / 2; idx += NTHREADS) {
+        const int r2 = idx & 63, c = idx >> 6;
+        const double2 g = __ldcg(reinterpret_cast<const double2*>(G + (size_t)c * ld) + r2);
+        double2* d = reinterpret_cast<double2*>(dst + c * PM) + r2;
+        double2 v = *d;
+        v.x += g.x; v.y += g.y;
+        *d = v;
     }
+    __syncthreads();
 }
 
 }  // namespace gpr

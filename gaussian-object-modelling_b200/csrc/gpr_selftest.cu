@@ -105,7 +105,29 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
     if (s == 123.456) out[0] = s;
 }
 
-// which: 0 DMMA, 1 DFMA.  Returns achieved TFLOP/s (2 flop per multiply-add) in *tflops.
+// Both pipes at once: per iteration 16 DMMA (128 FMA per thread) interleaved with 16*REP independent DFMA
+// per thread.  Shows whether DMMA and DFMA are served by the same FP64 datapath (rates do not add) or not.
+template <int REP>
+__global__ void __launch_bounds__(256) dmix_peak_kernel(double* out, int iters) {
+    double c[16][2], f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; f[i] = i; }
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            dmma(c[i][0], c[i][1], a, b);
+#pragma unroll
+            for (int r = 0; r < REP; ++r) f[(i * REP + r) & 15] = fma(f[(i * REP + r) & 15], a, b);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1] + f[i];
+    if (s == 123.456) out[0] = s;
+}
+
+// which: 0 DMMA, 1 DFMA, 2 / 3: 16 DMMA (128 FMA per thread) mixed with 32 / 128 DFMA per thread.  Returns achieved TFLOP/s (2 flop per multiply-add) in *tflops.
 cudaError_t run_peak_probe(int which, int ctas_per_sm, double* tflops) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -114,20 +136,23 @@ cudaError_t run_peak_probe(int which, int ctas_per_sm, double* tflops) {
     if (e != cudaSuccess) return e;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    const int iters = which == 0 ? 4000 : 20000;
+    const int iters = which == 1 ? 20000 : 4000;
     const int grid = sms * ctas_per_sm;
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(a);
         if (which == 0) dmma_peak_kernel<<<grid, 256>>>(d, iters);
-        else dfma_peak_kernel<<<grid, 256>>>(d, iters);
+        else if (which == 1) dfma_peak_kernel<<<grid, 256>>>(d, iters);
+        else if (which == 2) dmix_peak_kernel<2><<<grid, 256>>>(d, iters);
+        else dmix_peak_kernel<8><<<grid, 256>>>(d, iters);
         cudaEventRecord(b);
         e = cudaEventSynchronize(b);
         if (e != cudaSuccess) return e;
         float ms; cudaEventElapsedTime(&ms, a, b);
         if (rep > 0 && ms < best) best = ms;
     }
-    const double per_thread_fma = which == 0 ? 16.0 * 8 * 8 * 4 / 32.0 : 16.0;   // DMMA: 256 FMA per warp instr
+    const double dmma_fma = 16.0 * 8 * 8 * 4 / 32.0;                              // DMMA: 256 FMA per warp instr
+    const double per_thread_fma = which == 0 ? dmma_fma : which == 1 ? 16.0 : which == 2 ? dmma_fma + 32.0 : dmma_fma + 128.0;
     const double flops = 2.0 * per_thread_fma * iters * 256.0 * grid;
     *tflops = flops / (best * 1e-3) / 1e12;
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);

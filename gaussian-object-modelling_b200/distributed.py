@@ -40,6 +40,8 @@ def broadcast_model(reg, model, n, R, with_linv, rank, device, src=0):
         model = reg.create_replica(n, R, with_linv)
     st = model.state(with_linv=with_linv)
     N = st.padded_n
+    if st.ld != N:
+        raise ValueError("model has spare capacity (ld %d != padded n %d): broadcast a freshly fitted model" % (st.ld, N))
     nbytes = 0
     for ptr, cnt in ((st.xyz, 3 * N), (st.alpha, N)) + (((st.linv, N * N),) if with_linv else ()):
         t = as_tensor(ptr, cnt, device)

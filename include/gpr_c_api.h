@@ -44,6 +44,7 @@ typedef struct {
     double linv_ms;                 /* one-time L^-1 for the variance path */
     double predict_mean_ms, predict_var_ms, predict_total_ms;
     double h2d_ms, d2h_ms;
+    double append_ms;               /* last gpr_append: device time of the incremental update incl. the alpha re-solve */
 } gpr_timings;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -84,9 +85,16 @@ int gpr_predict_device(gpr_ctx* ctx, gpr_model* m, const double* d_qx, const dou
 int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m);
 
 /* ---- update: GPRegressor::update<withNormals>  (gp_regressor.hpp:367-479) --------------------- */
-/* Appends k points; R and the normals are not refreshed, as in the reference (:454-455, :462-477). */
+/* Appends k points; R and the normals are not refreshed, as in the reference (:454-455, :462-477).
+ * The reference re-factorises from scratch (:457-459).  Here small batches (k <= 256 and 8k <= n) take the
+ * incremental path: the new rows of the Cholesky factor and of its inverse are appended (slabs of 32
+ * points, two bandwidth-bound products against L^-1 each) and alpha is re-solved; larger batches refit.
+ * On GPR_ERR_NOT_SPD the model is left as it was before the call.  GPR_APPEND_REFIT=1 forces the refit. */
 int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
                const double* sigma2_or_null, size_t k);
+/* Pre-allocates room for `capacity` points so that later appends do not reallocate (growth is otherwise
+ * geometric, x1.25).  Invalidates pointers returned earlier by gpr_model_state_get. */
+int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity);
 
 /* ---- replication across processes (one process per GPU, launched by bench.py) ----------------- */
 /* The fitted state that predict needs, as raw device pointers on the primary device, so that the
@@ -95,6 +103,8 @@ int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, con
  * until the variance path was prepared). */
 typedef struct {
     size_t n, padded_n;
+    size_t ld;                   /* leading dimension of xyz (x | y | z at multiples of ld), alpha and linv;
+                                    == padded_n unless the model grew through gpr_append / gpr_model_reserve */
     gpr_kernel_t kernel;
     double R;
     double* xyz; double* alpha; double* linv;
@@ -111,7 +121,8 @@ int gpr_selftest_factor(double* hA_inout, int n_tiles, double* h_linv_or_null, i
 /* Timeline of the tile-task Cholesky: 4 ns stamps per task (n_tiles(n_tiles+1)/2 tasks, column-major
  * task order); leaf_cycles[2] = SM cycles of the in-CTA 128x128 Cholesky and triangular inverse. */
 int gpr_selftest_factor_trace(int n_tiles, long long* h_trace, long long* leaf_cycles_or_null);
-/* Raw pipe probes (CUDA-event timed): which = 0 FP64 tensor (DMMA.8x8x4), 1 FP64 FMA; TFLOP/s. */
+/* Raw pipe probes (CUDA-event timed): which = 0 FP64 tensor (DMMA.8x8x4), 1 FP64 FMA, 2 / 3 both pipes
+ * mixed (16 DMMA with 32 / 128 DFMA per thread); total TFLOP/s. */
 int gpr_selftest_peak(int which, int ctas_per_sm, double* tflops);
 
 #ifdef __cplusplus

@@ -270,3 +270,98 @@ def test_cxx_dropin_headers_end_to_end(gpr, orc, tmp_path):
     assert abs(rows["single"][0] - g["f"][0]) <= 1e-9 and abs(rows["single"][1] - g["v"][0]) <= 1e-7 * np.abs(g["v"]).max()
     assert relerr(rows["alpha_updated"], g["alpha_updated"]) <= TOL_ALPHA
     assert relerr(rows["f_updated"], g["f_updated"][:q]) <= TOL_MEAN and rows["R_updated"][0] == rows["R"][0]
+
+
+# ---- K5: incremental append (rank-k row append of L and L^-1) vs refit, SURVEY row a13 / config 4 -------------
+def _append_case(gpr, n=900, seed=5):
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(n + 200, seed=seed)
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(len(P))
+    P, y, s2 = P[perm], y[perm], s2[perm]
+    return W, P, y, s2
+
+
+@pytest.mark.parametrize("batches", [(32,), (7, 1, 50), (32, 32, 32, 32, 32)])
+def test_incremental_append_matches_refit_and_oracle(gpr, orc, ctx, batches, monkeypatch):
+    """n = 900 base (tile padding 124) so that the appended rows cross a 128-tile boundary and grow the
+    capacity; slabs of 32 and ragged slabs.  The incremental model must agree with a from-scratch fit of the
+    same points (alpha to cond*eps, factor to 1e-11) and with the oracle's update() (a refit, like the
+    reference, gp_regressor.hpp:442-459), and later variance queries must use the appended L^-1 rows."""
+    W, P, y, s2 = _append_case(gpr)
+    n0 = 900
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    m = reg.create(P[:n0, 0], P[:n0, 1], P[:n0, 2], y[:n0], s2[:n0])
+    o = orc.Oracle(P[:n0, 0], P[:n0, 1], P[:n0, 2], y[:n0], s2[:n0], "thin_plate", W.SYNTH_R, 0.0, factor="llt")
+    a = n0
+    for k in batches:
+        reg.update(m, P[a:a + k, 0], P[a:a + k, 1], P[a:a + k, 2], y[a:a + k], s2[a:a + k])
+        o.update(P[a:a + k, 0], P[a:a + k, 1], P[a:a + k, 2], y[a:a + k], s2[a:a + k])
+        a += k
+        assert ctx.timings()["append_ms"] > 0.0            # the incremental path ran (a refit leaves it at 0)
+    assert m.n == a
+    fresh = reg.create(P[:a, 0], P[:a, 1], P[:a, 2], y[:a], s2[:a])
+    assert relerr(m.factor(), fresh.factor()) <= 1e-11
+    assert relerr(m.alpha, fresh.alpha) <= TOL_ALPHA and relerr(m.alpha, o.alpha) <= TOL_ALPHA
+    Q = W.grid_slab(12, 0, 12)[::5]
+    f, v, g = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True)
+    f2, v2, g2 = reg.evaluate(fresh, Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True)
+    fo, vo, go = o.predict(Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True, threads=4)
+    assert relerr(f, f2) <= TOL_MEAN and relerr(f, fo) <= TOL_MEAN and relerr(g, go) <= TOL_MEAN
+    assert np.abs(v - v2).max() <= TOL_VAR * np.abs(vo).max() and np.abs(v - vo).max() <= TOL_VAR * np.abs(vo).max()
+    f1, v1 = reg.evaluate(m, Q[:3, 0], Q[:3, 1], Q[:3, 2], var=True)          # q <= 8: matrix-vector path on L^-1
+    assert np.abs(v1 - vo[:3]).max() <= TOL_VAR * np.abs(vo).max()
+
+
+def test_incremental_append_equals_forced_refit(gpr, ctx, monkeypatch):
+    W, P, y, s2 = _append_case(gpr, seed=6)
+    n0, k = 700, 40
+    reg = gpr.GPRegressor("gaussian", 1.0, 1.0, ctx=ctx)
+    sl = lambda a, b: (P[a:b, 0], P[a:b, 1], P[a:b, 2], y[a:b], s2[a:b])
+    m1 = reg.create(*sl(0, n0))
+    reg.update(m1, *sl(n0, n0 + k))
+    monkeypatch.setenv("GPR_APPEND_REFIT", "1")
+    m2 = reg.create(*sl(0, n0))
+    reg.update(m2, *sl(n0, n0 + k))
+    assert relerr(m1.alpha, m2.alpha) <= TOL_ALPHA and relerr(m1.factor(), m2.factor()) <= 1e-11
+
+
+def test_incremental_append_is_bit_reproducible_and_reserve(gpr, ctx):
+    W, P, y, s2 = _append_case(gpr, seed=7)
+    n0 = 640
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    outs = []
+    for rep in range(2):
+        m = reg.create(P[:n0, 0], P[:n0, 1], P[:n0, 2], y[:n0], s2[:n0])
+        if rep == 1:
+            reg.reserve(m, 2048)                       # pre-allocated capacity must not change a single bit
+        for a in range(n0, n0 + 96, 32):
+            reg.update(m, P[a:a + 32, 0], P[a:a + 32, 1], P[a:a + 32, 2], y[a:a + 32], s2[a:a + 32])
+        Q = W.grid_slab(8, 0, 8)
+        f, v = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+        outs.append((m.alpha.copy(), m.factor(), f, v))
+    for x0, x1 in zip(*outs):
+        assert np.array_equal(x0, x1)
+
+
+def test_incremental_append_failure_leaves_model_intact(gpr, ctx):
+    """A point farther than R from the cloud makes the thin-plate matrix indefinite: NOT_SPD with
+    the global pivot index — found in the SECOND slab, after the first was already committed on the device —
+    and the model answers exactly as before the call."""
+    W, P, y, s2 = _append_case(gpr, seed=8)
+    n0 = 500
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    m = reg.create(P[:n0, 0], P[:n0, 1], P[:n0, 2], y[:n0], s2[:n0])
+    Q = W.grid_slab(6, 0, 6)
+    before = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    alpha0, L0 = m.alpha.copy(), m.factor()
+    bad = np.vstack([P[n0:n0 + 41], [[3 * W.SYNTH_R, 0.0, 0.0]], P[n0 + 41:n0 + 45]])
+    with pytest.raises(gpr.GPRegressionException) as e:
+        reg.update(m, bad[:, 0], bad[:, 1], bad[:, 2], np.zeros(len(bad)), np.full(len(bad), 0.1))
+    assert e.value.code == gpr.GPR_ERR_NOT_SPD and e.value.pivot == n0 + 42
+    assert m.n == n0 and np.array_equal(m.alpha, alpha0) and np.array_equal(m.factor(), L0)
+    after = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    assert np.array_equal(before[0], after[0]) and np.array_equal(before[1], after[1])
+    reg.update(m, P[n0:n0 + 16, 0], P[n0:n0 + 16, 1], P[n0:n0 + 16, 2], y[n0:n0 + 16], s2[n0:n0 + 16])   # still usable
+    fresh = reg.create(P[:n0 + 16, 0], P[:n0 + 16, 1], P[:n0 + 16, 2], y[:n0 + 16], s2[:n0 + 16])
+    assert m.n == n0 + 16 and relerr(m.alpha, fresh.alpha) <= TOL_ALPHA
