@@ -77,31 +77,58 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_run(steps, warmup, sample_q, threads_note=True):
-    """The CPU arm: the reference's mathematics with OpenBLAS LAPACK on all host cores (oracle.blas_*,
-    the "port" flavour of BASELINE.md §5 — the reference itself cannot be built here: Eigen is absent)."""
+def cpu_reference_run(steps, warmup, sample_q=None):
+    """The CPU arm, timed on this box's host cores.
+
+    kind "reference": the reference's OWN evaluate(gp, query, f, v) (gp_regressor.hpp:282-324, compiled from
+    /root/reference into oracle/_ref/libgpr_ref.so against the Eigen-API shim), driven the way the node drives it:
+    one query per call from as many concurrent std::threads as there are cores (src/gp_node.cpp:1027-1038, :1074).
+    Its model is installed from an OpenBLAS dpotrf factor, because the reference's unblocked single-threaded
+    LDLT::compute takes tens of minutes at n = 16384 (that fit time is reported, not part of `value`).
+    kind "port" (only when oracle/_ref is absent): the same mathematics with OpenBLAS dpotrf/dtrsm on all cores."""
     import oracle
     import gpr_b200
     W = gpr_b200.workloads
     P, y, s2 = W.synthetic_cloud(N_TRAIN, seed=0)
-    cores = os.cpu_count()
+    cores = os.cpu_count() or 1
     t0 = time.perf_counter()
     model = oracle.blas_fit(P, y, s2, "thin_plate", W.SYNTH_R, 0.0)
     fit_s = time.perf_counter() - t0
+    use_ref = oracle.have_reference()
+    if sample_q is None:
+        sample_q = 8 * cores if use_ref else 1024
+    ref = None
+    if use_ref:
+        ref = oracle.Reference("thin_plate", W.SYNTH_R, 0.0)
+        ref.adopt(P[:, 0], P[:, 1], P[:, 2], y, s2, model["alpha"], model["L"], 4.0)
     rng = np.random.default_rng(0)
-    times = []
+    times, port_times = [], []
     for s in range(warmup + steps):
         z = int(rng.integers(0, GRID_RES))
-        Q = W.grid_slab(GRID_RES, z, z + 1)[:sample_q]
+        Q = W.grid_slab(GRID_RES, z, z + 1)
+        Qs = Q[:sample_q]
         t0 = time.perf_counter()
-        oracle.blas_predict(model, Q, var=True)
+        if use_ref:
+            f, v = ref.evaluate_mt(Qs[:, 0], Qs[:, 1], Qs[:, 2], var=True, threads=cores, per_call=1)
+        else:
+            f, v = oracle.blas_predict(model, Qs, var=True)
+        dt = time.perf_counter() - t0
         if s >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
+        assert np.isfinite(f).all() and float(v.min()) > 0.0
+    # the BLAS port on a 1024-query sample, for context next to the reference's own code
+    t0 = time.perf_counter()
+    oracle.blas_predict(model, W.grid_slab(GRID_RES, 7, 8)[:1024], var=True)
+    port_qps = 1024 / (time.perf_counter() - t0)
     dt = sum(times)
-    return {"value": sample_q * len(times) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d steps x %d queries of the same grid (mean+variance, dtrsm) after one dpotrf fit of n=%d "
-                      "(fit %.1f s, not in value)" % (len(times), sample_q, N_TRAIN, fit_s),
-            "fit_s": fit_s, "ms_per_step": 1e3 * dt / len(times)}
+    kind = "reference" if use_ref else "port"
+    what = ("the reference's own evaluate(f, v), 1 query per call from %d concurrent threads" % cores) if use_ref else \
+           "OpenBLAS port (dtrsm)"
+    return {"value": sample_q * len(times) / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d steps x %d queries of the same grid (mean+variance), %s; model from one OpenBLAS dpotrf fit of "
+                      "n=%d (%.1f s, not in value)" % (len(times), sample_q, what, N_TRAIN, fit_s),
+            "fit_s": fit_s, "ms_per_step": 1e3 * dt / len(times), "sample_q": sample_q,
+            "port_blas_dtrsm_points_per_s": port_qps}
 
 
 def main():
@@ -122,13 +149,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        res = cpu_reference_run(args.steps, args.warmup, sample_q=1024)
+        res = cpu_reference_run(args.steps, args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config({"sample_queries_per_step": 1024}),
-                "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
-                "fit_ms": 1e3 * res["fit_s"],
+                "config": workload_config({"sample_queries_per_step": res["sample_q"]}),
+                "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+                "fit_ms": 1e3 * res["fit_s"], "port_blas_dtrsm_points_per_s": res["port_blas_dtrsm_points_per_s"],
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -286,9 +313,9 @@ def main():
                              "mean_panel_kernel_ms_per_step": mean_ms / args.steps}}
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
-            res = cpu_reference_run(2, 1, sample_q=1024)
-            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-            line["cpu_baseline"]["fit_s"] = res["fit_s"]
+            res = cpu_reference_run(2, 1)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "fit_s",
+                                                        "port_blas_dtrsm_points_per_s")}
         print(json.dumps(line))
     if world > 1:
         dist.barrier(device_ids=[local_rank])

@@ -150,6 +150,8 @@ class Reference:
         L.ref_get.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.ref_evaluate.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.ref_update.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_int]
+        L.ref_adopt.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, C.c_double]
+        L.ref_evaluate_mt.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]
         L.ref_error_message.argtypes = [C.c_int]
         L.ref_error_message.restype = C.c_char_p
         self._L = L
@@ -202,6 +204,23 @@ class Reference:
         if mode >= 4:
             out += [np.ascontiguousarray(Tx), np.ascontiguousarray(Ty)]
         return tuple(out)
+
+    def adopt(self, x, y, z, label, sigma2, alpha, Lc, R):
+        """Timing support (bench.py --impl reference): install a model whose factor was computed elsewhere
+        (Lc: n x n lower Cholesky factor) so that the reference's own evaluate() can run at sizes where its
+        unblocked LDLT::compute would take tens of minutes."""
+        x, y, z, label, sigma2, alpha = map(_f64, (x, y, z, label, sigma2, alpha))
+        Lc = np.asfortranarray(Lc, dtype=np.float64)
+        self._check(self._L.ref_adopt(self._h, _p(x), _p(y), _p(z), _p(label), _p(sigma2), len(x), _p(alpha), _p(Lc), float(R)))
+        return self
+
+    def evaluate_mt(self, qx, qy, qz, var=True, threads=1, per_call=1):
+        """The reference's evaluate() from `threads` concurrent threads, `per_call` queries per call."""
+        qx, qy, qz = map(_f64, (qx, qy, qz))
+        q = len(qx)
+        f, v = np.zeros(q), np.zeros(q)
+        self._check(self._L.ref_evaluate_mt(self._h, _p(qx), _p(qy), _p(qz), q, 2 if var else 1, int(threads), int(per_call), _p(f), _p(v)))
+        return f, (v if var else None)
 
     def update(self, x, y, z, label, sigma2):
         x, y, z, label, sigma2 = map(_f64, (x, y, z, label, sigma2))

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 #include <cstring>
+#include <thread>
+#include <algorithm>
 
 #include <gp_regression/gp_regressors.h>   // -> /root/reference/include (reference, unmodified)
 
@@ -108,6 +110,62 @@ int ref_update(void* p, const double* x, const double* y, const double* z, const
         else if (h->kind == 1) h->ga->update<false>(d, h->model);
         else h->la->update<false>(d, h->model);
     });
+}
+
+// Timing support for bench.py --impl reference (NOT used by any parity test): builds the reference's Model
+// from an externally computed Cholesky factor (the reference's own LDLT::compute is unblocked and
+// single-threaded: tens of minutes at n = 16384), so that the reference's UNMODIFIED evaluate() can be
+// timed at the bench size.  Fields filled: P, Y, S2, alpha, R, cholesker (gp_regressor.hpp:71-87).
+int ref_adopt(void* p, const double* x, const double* y, const double* z, const double* label,
+              const double* sigma2_or_null, int n, const double* alpha, const double* Lc, double R) {
+    Handle* h = (Handle*)p;
+    return guarded(h, [&] {
+        auto m = std::make_shared<Model>();
+        m->P.resize(n, 3);
+        m->Y.resize(n);
+        m->alpha.resize(n);
+        if (sigma2_or_null) m->S2.resize(n);
+        for (int i = 0; i < n; ++i) {
+            m->P(i, 0) = x[i]; m->P(i, 1) = y[i]; m->P(i, 2) = z[i];
+            m->Y(i) = label[i]; m->alpha(i) = alpha[i];
+            if (sigma2_or_null) m->S2(i) = sigma2_or_null[i];
+        }
+        m->R = R;
+        m->cholesker.adoptCholesky(Lc, n);
+        h->model = m;
+    });
+}
+
+// The reference's evaluate() called concurrently from `threads` std::threads on one shared const Model, each
+// on its own contiguous chunk of the queries with `per_call` queries per call — the way the node drives it
+// (one thread per grid point, q = 1 per call, src/gp_node.cpp:1027-1038, :1074).  mode 1: f; 2: f, v.
+int ref_evaluate_mt(void* p, const double* qx, const double* qy, const double* qz, int q, int mode, int threads,
+                    int per_call, double* f, double* v) {
+    Handle* h = (Handle*)p;
+    if (threads < 1) threads = 1;
+    if (per_call < 1) per_call = 1;
+    std::vector<std::string> errs((size_t)threads);
+    std::vector<std::thread> pool;
+    Model::ConstPtr gp = h->model;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t] {
+            const int a = (int)((long long)q * t / threads), b = (int)((long long)q * (t + 1) / threads);
+            try {
+                for (int s = a; s < b; s += per_call) {
+                    const int c = std::min(per_call, b - s);
+                    Data::Ptr d = make_data(qx + s, qy + s, qz + s, nullptr, nullptr, c);
+                    std::vector<double> ff, vv;
+                    auto run = [&](auto& reg) { if (mode == 1) reg.evaluate(gp, d, ff); else reg.evaluate(gp, d, ff, vv); };
+                    if (h->kind == 0) run(*h->tp); else if (h->kind == 1) run(*h->ga); else run(*h->la);
+                    std::memcpy(f + s, ff.data(), sizeof(double) * c);
+                    if (mode >= 2) std::memcpy(v + s, vv.data(), sizeof(double) * c);
+                }
+            } catch (const std::exception& e) { errs[(size_t)t] = e.what(); }
+        });
+    }
+    for (auto& th : pool) th.join();
+    for (auto& e : errs) if (!e.empty()) { h->err = e; return 1; }
+    return 0;
 }
 
 // Exercise the reference's argument checks (gp_regressor.hpp:197,224,230,284,290,334,340,373,563-572).
