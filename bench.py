@@ -124,7 +124,8 @@ def cpu_reference_run(steps, warmup, sample_q=None):
     kind = "reference" if use_ref else "port"
     what = ("the reference's own evaluate(f, v), 1 query per call from %d concurrent threads" % cores) if use_ref else \
            "OpenBLAS port (dtrsm)"
-    return {"value": sample_q * len(times) / dt, "unit": UNIT, "cores": cores, "kind": kind,
+    return {"last_queries": Qs, "last_f": f, "last_v": v, "alpha": model["alpha"],
+            "value": sample_q * len(times) / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": "%d steps x %d queries of the same grid (mean+variance), %s; model from one OpenBLAS dpotrf fit of "
                       "n=%d (%.1f s, not in value)" % (len(times), sample_q, what, N_TRAIN, fit_s),
             "fit_s": fit_s, "ms_per_step": 1e3 * dt / len(times), "sample_q": sample_q,
@@ -289,6 +290,11 @@ def main():
         flops_per_launch = float(N_TRAIN) ** 2 * batch                # n^2 * q per variance batch
         achieved = flops_per_launch / (var_ms / launches_var * 1e-3) / 1e12
         dmma_peak = g.selftest_peak(0, 4)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "var_tiles_traffic.json")
+        if os.path.exists(tpath):          # dram__bytes_read+write of one launch, from the committed ncu --set full capture
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         a64 = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
         for _ in range(2):
             a64 @ a64
@@ -306,7 +312,8 @@ def main():
                 "clocks": clocks,
                 "roofline": {"kernel": "var_tiles_kernel (variance product X*K*^T + column norms)", "bound": "tensor",
                              "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
-                             "traffic": None,
+                             "traffic": traffic, "traffic_source": traffic_src,
+                             "algorithmic_operand_bytes": 8.0 * N_TRAIN * (N_TRAIN + 128) / 2 + 8.0 * N_TRAIN * batch,
                              "peak_source": "FP64: measured in this run, raw DMMA.8x8x4 issue rate (gpr_selftest_peak); "
                                             "MEASURED_PEAKS.json has no FP64 entry. cuBLAS DGEMM 8192^3 in this run: %.1f TF/s" % dgemm,
                              "cublas_dgemm_tflops": dgemm, "share_of_step": var_ms / elapsed_ms,
@@ -316,6 +323,17 @@ def main():
             res = cpu_reference_run(2, 1)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "fit_s",
                                                         "port_blas_dtrsm_points_per_s")}
+            # parity at the full bench size, on the CPU arm's last sample: our alpha against the OpenBLAS
+            # Cholesky solve, our mean / variance against what the reference's evaluate() returned
+            Qs = res["last_queries"]
+            fg, vg = reg.evaluate(model, Qs[:, 0], Qs[:, 1], Qs[:, 2], var=True)
+            rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+            big = np.abs(res["last_f"]) > 1e-9
+            line["parity_full_size"] = {"against": res["kind"], "queries": int(len(Qs)),
+                                        "alpha_rel_inf_vs_dpotrs": rel(model.alpha, res["alpha"]),
+                                        "mean_rel_inf": rel(fg, res["last_f"]), "var_rel_inf": rel(vg, res["last_v"]),
+                                        "sign_mismatches": int((np.sign(fg) != np.sign(res["last_f"]))[big].sum()),
+                                        "tolerance": {"alpha": "max(1e-9, 50*cond*eps)", "mean": 1e-9, "var": 1e-7}}
         print(json.dumps(line))
     if world > 1:
         dist.barrier(device_ids=[local_rank])

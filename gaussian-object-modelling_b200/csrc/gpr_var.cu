@@ -10,7 +10,8 @@
 // L2, and its epilogue reduces the squared column norms so V itself is never written.
 //   algorithmic work: n^2 * q flop (one multiply-add per entry of the triangular factor per query).
 // Per-tile partial sums are written to a [row tile][query] scratch and summed in a fixed order by a
-// second small kernel, so the variance is bit-reproducible (no floating-point atomics).
+// second small kernel, so the variance is bit-reproducible (no floating-point atomics) and independent of
+// how the queries are batched or sharded.
 #include "gpr_mma.cuh"
 #include "gpr_kernels.h"
 
@@ -21,38 +22,57 @@ struct VarArgs {
     const double* panel; size_t panel_ld;     // K*: element (query, k) at panel[k*panel_ld + query]
     int nqt;                                  // query tiles in this batch (panel_ld / 128)
     double* partial;                          // nb x panel_ld
+    int gq, qgroups;                          // query tiles per co-scheduled group, number of such groups
 };
 
+constexpr int VAR_GI = 4;                     // row-tile pairs per co-scheduled group
+
+// Task = (pair p, query tile qt): the CTA computes row tile nb-1-p and then row tile p of V = X K*^T for
+// its 128 queries.  The k ranges of the two rows add up to nb+1 blocks for EVERY task, so all CTAs of
+// the grid run in lockstep from the first wave to the last, and the block order makes the ~148 CTAs
+// that are resident together a (VAR_GI pairs) x (gq query tiles) rectangle: each X row tile is streamed
+// by gq CTAs at the same time and each K* tile by VAR_GI CTAs at (nearly) the same time, i.e. once from
+// HBM and then from L2.  (With one row tile per CTA and a whole row of query tiles resident together,
+// every K* tile was fetched from HBM again for each of the nb row tiles: 161 GB of DRAM reads per batch
+// for 3.6 GB of operands, ncu profile r1b.)
 __global__ void __launch_bounds__(NTHREADS, 1) var_tiles_kernel(VarArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_abort;
     __shared__ double sred[8][32];
-    const int b = blockIdx.x;
-    const int it = a.nb - 1 - b / a.nqt;      // heavy row tiles (long k range) are scheduled first
-    const int qt = b % a.nqt;
+    const int per_group = VAR_GI * a.gq;
+    const int g = blockIdx.x / per_group, w = blockIdx.x % per_group;
+    const int pg = g / a.qgroups, qg = g % a.qgroups;
+    const int p = pg * VAR_GI + w % VAR_GI;
+    const int qt = qg * a.gq + w / VAR_GI;
+    if (2 * p >= a.nb || qt >= a.nqt) return;          // pairs p < ceil(nb/2)
     if (threadIdx.x == 0) s_abort = 0;
     const TileCoord tc;
-    Acc acc;
-    acc_zero(acc);
-    tile_mainloop<STREAM_M, STREAM_M>(acc, a.X + (size_t)it * TB, a.ld, a.panel + (size_t)qt * TB, a.panel_ld,
-                                      8 * (it + 1), smem, &s_abort, NoWait());
-    // column sums of squares over this tile's 128 rows
+    for (int h = 0; h < 2; ++h) {
+        const int it = h == 0 ? a.nb - 1 - p : p;
+        if (h == 1 && it == a.nb - 1 - p) break;        // odd nb: the middle row tile is its own pair
+        Acc acc;
+        acc_zero(acc);
+        tile_mainloop<STREAM_M, STREAM_M>(acc, a.X + (size_t)it * TB, a.ld, a.panel + (size_t)qt * TB, a.panel_ld,
+                                          8 * (it + 1), smem, &s_abort, NoWait());
+        // column sums of squares over this tile's 128 rows
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-        double s = 0.0;
+        for (int mt = 0; mt < 4; ++mt) {
+            double s = 0.0;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            s = fma(acc[mt][nt][0], acc[mt][nt][0], s);
-            s = fma(acc[mt][nt][1], acc[mt][nt][1], s);
+            for (int nt = 0; nt < 8; ++nt) {
+                s = fma(acc[mt][nt][0], acc[mt][nt][0], s);
+                s = fma(acc[mt][nt][1], acc[mt][nt][1], s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (tc.t == 0) sred[tc.warp][tc.col<false>(mt) - tc.j0] = s;
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (tc.t == 0) sred[tc.warp][tc.col<false>(mt) - tc.j0] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < TB) {
-        const int c = threadIdx.x, wj = c >> 5, lc = c & 31;
-        a.partial[(size_t)it * a.panel_ld + (size_t)qt * TB + c] = sred[2 * wj][lc] + sred[2 * wj + 1][lc];
+        __syncthreads();
+        if (threadIdx.x < TB) {
+            const int c = threadIdx.x, wj = c >> 5, lc = c & 31;
+            a.partial[(size_t)it * a.panel_ld + (size_t)qt * TB + c] = sred[2 * wj][lc] + sred[2 * wj + 1][lc];
+        }
+        __syncthreads();
     }
 }
 
@@ -77,7 +97,15 @@ cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* pa
     VarArgs a;
     a.X = X; a.ld = ld; a.nb = nb; a.panel = panel; a.panel_ld = panel_ld;
     a.nqt = (int)(panel_ld / TB); a.partial = partial;
-    var_tiles_kernel<<<(unsigned)(a.nqt * nb), NTHREADS, TILE_SMEM_BYTES, st>>>(a);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    a.gq = sms / VAR_GI > 0 ? sms / VAR_GI : 1;
+    if (a.gq > a.nqt) a.gq = a.nqt;
+    a.qgroups = (a.nqt + a.gq - 1) / a.gq;
+    const int npairs = (nb + 1) / 2;
+    const int pgroups = (npairs + VAR_GI - 1) / VAR_GI;
+    var_tiles_kernel<<<(unsigned)(pgroups * a.qgroups * VAR_GI * a.gq), NTHREADS, TILE_SMEM_BYTES, st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     var_finalize_kernel<<<(q + 255) / 256, 256, 0, st>>>(partial, panel_ld, nb, q, k0, var);
