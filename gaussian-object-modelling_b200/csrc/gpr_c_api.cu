@@ -45,6 +45,7 @@ struct Workspace {
     double* io = nullptr; size_t io_cap = 0;          // 14 * io_cap doubles: q(3) f var grad(3) tx(3) ty(3)
     double* panel = nullptr; size_t panel_dbl = 0;
     double* partial = nullptr; size_t partial_dbl = 0;
+    double* mpart = nullptr; size_t mpart_dbl = 0;     // per-chunk partial sums of the split mean kernel
 };
 
 struct DeviceCtx {
@@ -219,8 +220,10 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
         rc = ws_reserve(&ws->io, &ws->io_cap, 14 * N);
         if (rc) return rc;
         double* f = ws->io; double* g = ws->io + N;
+        const int nsplit = n <= 4096 ? 1 : predict_split((int)n, (int)N, dc->num_sms);
+        if (nsplit > 1) { rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, predict_part_doubles((int)n, (int)N)); if (rc) return rc; }
         CU(launch_predict(md.xyz, md.xyz + N, md.xyz + 2 * N, md.alpha, (int)n, (int)N, md.xyz, md.xyz + N, md.xyz + 2 * N,
-                          (int)n, f, g, N, nullptr, 0, m->kp, n <= 4096, st));
+                          (int)n, f, g, N, nullptr, 0, m->kp, n <= 4096, ws->mpart, nsplit, st));
         CU(launch_normalize_rows(g, N, (int)n, st));
         m->h_normals.resize(3 * n);
         m->n_normals = n;
@@ -359,8 +362,13 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         CU(cudaEventRecord(ws->ev[1], st));
         const size_t pld = small_var ? (size_t)TB : (bq + TB - 1) / TB * TB;
         const bool warp_mode = small_var || (!want_var && bq <= (size_t)64 * dc->num_sms);
+        int nsplit = 1;
+        if (!warp_mode) {
+            nsplit = predict_split((int)(want_var ? pld : bq), (int)N, dc->num_sms);
+            if (nsplit > 1) { rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, predict_part_doubles((int)bq, (int)N)); if (rc) return rc; }
+        }
         CU(launch_predict(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, n, (int)N, qx, qy, qz, (int)bq, f, g, gld,
-                          want_var ? ws->panel : nullptr, pld, m->kp, warp_mode, st));
+                          want_var ? ws->panel : nullptr, pld, m->kp, warp_mode, ws->mpart, nsplit, st));
         CU(cudaEventRecord(ws->ev[2], st));
         if (want_var) {
             if (small_var) CU(launch_variance_small(md.linv, ld, (int)N, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
@@ -441,7 +449,7 @@ int gpr_ctx_destroy(gpr_ctx* ctx) {
     for (DeviceCtx* dc : ctx->devs) {
         cudaSetDevice(dc->dev);
         for (Workspace* ws : dc->free_ws) {
-            cudaFree(ws->io); cudaFree(ws->panel); cudaFree(ws->partial);
+            cudaFree(ws->io); cudaFree(ws->panel); cudaFree(ws->partial); cudaFree(ws->mpart);
             for (auto& e : ws->ev) cudaEventDestroy(e);
             cudaStreamDestroy(ws->st);
             delete ws;

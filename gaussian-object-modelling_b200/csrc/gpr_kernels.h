@@ -18,11 +18,14 @@ cudaError_t launch_linv(const double* L, double* X, size_t ld, int nb, const dou
 // K3 (gpr_solve.cu).  scratch: at least 4 + nb ints.
 cudaError_t launch_trsv(int backward, const double* L, size_t ld, int nb, const double* Dinv, const double* rhs,
                         double* out, int* scratch, int num_sms, cudaStream_t st);
-// K4 (gpr_predict.cu)
+// K4 (gpr_predict.cu).  part/split: optional split of the training points over CTAs for the thread-per-query
+// kernel (split from predict_split, part of predict_part_doubles(q, N) doubles); bit-identical results either way.
+int predict_split(int q_span, int N, int num_sms);
+size_t predict_part_doubles(int q_span, int N);
 cudaError_t launch_predict(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
                            const double* qx, const double* qy, const double* qz, int q, double* f, double* grad,
                            size_t grad_ld, double* panel, size_t panel_ld, const KernParams& kp, int warp_mode,
-                           cudaStream_t st);
+                           double* part, int split, cudaStream_t st);
 cudaError_t launch_tangent_basis(const double* grad, size_t ld, int q, double* Tx, double* Ty, cudaStream_t st);
 cudaError_t launch_normalize_rows(double* g, size_t ld, int q, cudaStream_t st);
 // K3' (gpr_var.cu)

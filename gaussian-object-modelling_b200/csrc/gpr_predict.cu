@@ -31,12 +31,19 @@ struct PredictArgs {
     size_t grad_ld;
     double* panel;         // N x panel_ld: element (query, k) at panel[k*panel_ld + query], or null
     size_t panel_ld;       // >= q rounded up to 128; padded queries and padded k are written as 0
+    double* part;          // split mode: per-chunk partial sums, [chunk][4][part_ld] (f, gx, gy, gz)
+    size_t part_ld;
+    int chunks_per_cta;    // training chunks (of PCHUNK points) handled by one CTA along blockIdx.y
     KernParams kp;
 };
 
 constexpr int PCHUNK = 1024;   // training points staged per shared-memory chunk
 
-template <int KIND, bool GRAD, bool PANEL>
+// Summation order (the same whatever the launch geometry, so that splitting the query set or the training
+// set over CTAs never changes a bit): within a chunk of 1024 training points sequentially from zero, then
+// the chunk sums sequentially in chunk order.  SPLIT: the chunk sums go to `part` and are added up by
+// predict_reduce_kernel; otherwise the CTA walks all chunks and adds them up itself.
+template <int KIND, bool GRAD, bool PANEL, bool SPLIT>
 __global__ void __launch_bounds__(256) predict_thread_kernel(PredictArgs a) {
     __shared__ double4 sp[PCHUNK];   // x, y, z, alpha
     const int qi = blockIdx.x * 256 + threadIdx.x;
@@ -44,7 +51,11 @@ __global__ void __launch_bounds__(256) predict_thread_kernel(PredictArgs a) {
     const bool in_panel = PANEL && (size_t)qi < a.panel_ld;
     const double qx = real ? a.qx[qi] : 0.0, qy = real ? a.qy[qi] : 0.0, qz = real ? a.qz[qi] : 0.0;
     double f = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
-    for (int base = 0; base < a.N; base += PCHUNK) {
+    const int nchunks = (a.N + PCHUNK - 1) / PCHUNK;
+    const int c0 = SPLIT ? blockIdx.y * a.chunks_per_cta : 0;
+    const int c1 = SPLIT ? min(nchunks, c0 + a.chunks_per_cta) : nchunks;
+    for (int ch = c0; ch < c1; ++ch) {
+        const int base = ch * PCHUNK;
         __syncthreads();
         for (int k = threadIdx.x; k < PCHUNK; k += 256) {
             const int j = base + k;
@@ -54,26 +65,51 @@ __global__ void __launch_bounds__(256) predict_thread_kernel(PredictArgs a) {
         }
         __syncthreads();
         const int lim = min(PCHUNK, a.N - base);
+        double cf = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
 #pragma unroll 4
         for (int k = 0; k < lim; ++k) {
             const double4 p = sp[k];
             const double dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
             const double d = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
             const double kv = kern_value<KIND>(a.kp, d);
-            f = fma(kv, p.w, f);
+            cf = fma(kv, p.w, cf);
             if (GRAD) {
                 const double w = p.w * kern_diff<KIND>(a.kp, d, kv);
-                gx = fma(w, dx, gx); gy = fma(w, dy, gy); gz = fma(w, dz, gz);
+                cx = fma(w, dx, cx); cy = fma(w, dy, cy); cz = fma(w, dz, cz);
             }
             if (PANEL) {
                 if (in_panel) a.panel[(size_t)(base + k) * a.panel_ld + qi] = (real && base + k < a.n) ? kv : 0.0;
             }
         }
+        if (SPLIT) {
+            if (real) {
+                double* pp = a.part + (size_t)ch * 4 * a.part_ld + qi;
+                pp[0] = cf;
+                if (GRAD) { pp[a.part_ld] = cx; pp[2 * a.part_ld] = cy; pp[3 * a.part_ld] = cz; }
+            }
+        } else {
+            f += cf;
+            if (GRAD) { gx += cx; gy += cy; gz += cz; }
+        }
     }
-    if (real) {
+    if (!SPLIT && real) {
         a.f[qi] = f;
         if (GRAD) { a.grad[qi] = gx; a.grad[a.grad_ld + qi] = gy; a.grad[2 * a.grad_ld + qi] = gz; }
     }
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(256) predict_reduce_kernel(PredictArgs a, int nchunks) {
+    const int qi = blockIdx.x * 256 + threadIdx.x;
+    if (qi >= a.q) return;
+    double f = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const double* pp = a.part + (size_t)ch * 4 * a.part_ld + qi;
+        f += pp[0];
+        if (GRAD) { gx += pp[a.part_ld]; gy += pp[2 * a.part_ld]; gz += pp[3 * a.part_ld]; }
+    }
+    a.f[qi] = f;
+    if (GRAD) { a.grad[qi] = gx; a.grad[a.grad_ld + qi] = gy; a.grad[2 * a.grad_ld + qi] = gz; }
 }
 
 template <int KIND, bool GRAD, bool PANEL>
@@ -111,8 +147,21 @@ __global__ void __launch_bounds__(256) predict_warp_kernel(PredictArgs a) {
     }
 }
 
+template <int KIND, bool GRAD, bool PANEL>
+static void launch_thread(const PredictArgs& a, int split, cudaStream_t st) {
+    const size_t span = PANEL ? a.panel_ld : (size_t)a.q;
+    const int qblocks = (int)((span + 255) / 256);
+    if (split > 1) {
+        dim3 grid(qblocks, split);
+        predict_thread_kernel<KIND, GRAD, PANEL, true><<<grid, 256, 0, st>>>(a);
+        predict_reduce_kernel<GRAD><<<(a.q + 255) / 256, 256, 0, st>>>(a, (a.N + PCHUNK - 1) / PCHUNK);
+    } else {
+        predict_thread_kernel<KIND, GRAD, PANEL, false><<<qblocks, 256, 0, st>>>(a);
+    }
+}
+
 template <int KIND>
-static cudaError_t launch_kind(const PredictArgs& a, bool warp_mode, cudaStream_t st) {
+static cudaError_t launch_kind(const PredictArgs& a, bool warp_mode, int split, cudaStream_t st) {
     const bool grad = a.grad != nullptr, panel = a.panel != nullptr;
     if (warp_mode) {
         const int grid = (a.q + 7) / 8;
@@ -121,29 +170,45 @@ static cudaError_t launch_kind(const PredictArgs& a, bool warp_mode, cudaStream_
         else if (panel) predict_warp_kernel<KIND, false, true><<<grid, 256, 0, st>>>(a);
         else predict_warp_kernel<KIND, false, false><<<grid, 256, 0, st>>>(a);
     } else {
-        const size_t span = panel ? a.panel_ld : (size_t)a.q;
-        const int grid = (int)((span + 255) / 256);
-        if (grad && panel) predict_thread_kernel<KIND, true, true><<<grid, 256, 0, st>>>(a);
-        else if (grad) predict_thread_kernel<KIND, true, false><<<grid, 256, 0, st>>>(a);
-        else if (panel) predict_thread_kernel<KIND, false, true><<<grid, 256, 0, st>>>(a);
-        else predict_thread_kernel<KIND, false, false><<<grid, 256, 0, st>>>(a);
+        if (grad && panel) launch_thread<KIND, true, true>(a, split, st);
+        else if (grad) launch_thread<KIND, true, false>(a, split, st);
+        else if (panel) launch_thread<KIND, false, true>(a, split, st);
+        else launch_thread<KIND, false, false>(a, split, st);
     }
     return cudaGetLastError();
+}
+
+// Number of CTAs along the training-point axis for the thread-per-query kernel: 1 when the queries alone
+// fill the GPU, otherwise enough to reach ~4 CTAs per SM.
+int predict_split(int q_span, int N, int num_sms) {
+    const int qblocks = (q_span + 255) / 256;
+    const int nchunks = (N + PCHUNK - 1) / PCHUNK;
+    if (qblocks >= 2 * num_sms || nchunks < 2) return 1;
+    int s = (4 * num_sms + qblocks - 1) / qblocks;
+    return s > nchunks ? nchunks : s;
+}
+size_t predict_part_doubles(int q_span, int N) {
+    return (size_t)((N + PCHUNK - 1) / PCHUNK) * 4 * (size_t)((q_span + 255) / 256 * 256);
 }
 
 cudaError_t launch_predict(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
                            const double* qx, const double* qy, const double* qz, int q, double* f, double* grad,
                            size_t grad_ld, double* panel, size_t panel_ld, const KernParams& kp, int warp_mode,
-                           cudaStream_t st) {
+                           double* part, int split, cudaStream_t st) {
     if (q <= 0) return cudaSuccess;
     PredictArgs a;
     a.px = px; a.py = py; a.pz = pz; a.alpha = alpha; a.n = n; a.N = N;
     a.qx = qx; a.qy = qy; a.qz = qz; a.q = q; a.f = f; a.grad = grad; a.grad_ld = grad_ld;
     a.panel = panel; a.panel_ld = panel_ld; a.kp = kp;
+    if (!part) split = 1;
+    const int nchunks = (N + PCHUNK - 1) / PCHUNK;
+    a.part = part; a.part_ld = (size_t)((q + 255) / 256 * 256);
+    a.chunks_per_cta = split > 1 ? (nchunks + split - 1) / split : nchunks;
+    if (split > 1) split = (nchunks + a.chunks_per_cta - 1) / a.chunks_per_cta;
     switch (kp.kind) {
-        case 0: return launch_kind<0>(a, warp_mode != 0, st);
-        case 1: return launch_kind<1>(a, warp_mode != 0, st);
-        default: return launch_kind<2>(a, warp_mode != 0, st);
+        case 0: return launch_kind<0>(a, warp_mode != 0, split, st);
+        case 1: return launch_kind<1>(a, warp_mode != 0, split, st);
+        default: return launch_kind<2>(a, warp_mode != 0, split, st);
     }
 }
 
