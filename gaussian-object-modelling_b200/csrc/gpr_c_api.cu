@@ -46,6 +46,8 @@ struct Workspace {
     double* panel = nullptr; size_t panel_dbl = 0;
     double* partial = nullptr; size_t partial_dbl = 0;
     double* mpart = nullptr; size_t mpart_dbl = 0;     // per-chunk partial sums of the split mean kernel
+    double* hio = nullptr; double* hio_dev = nullptr;  // pinned host buffer mapped into the device (q <= 8 path)
+    double* small = nullptr; size_t small_dbl = 0; size_t small_N = 0;   // scratch + tickets of the fused small-batch kernel
 };
 
 struct DeviceCtx {
@@ -325,6 +327,45 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
     cudaStream_t st = ws->st;
     const size_t N = m->N, ld = m->cap;
     const int n = (int)m->n;
+    if (!io.device_ptrs && io.q <= 8) {
+        // The reference's callers: one query per call.  One fused launch, I/O through mapped pinned memory.
+        if (!ws->hio) {
+            CU(cudaHostAlloc((void**)&ws->hio, SMALL_HIO_DOUBLES * sizeof(double), cudaHostAllocMapped));
+            CU(cudaHostGetDevicePointer((void**)&ws->hio_dev, ws->hio, 0));
+        }
+        const size_t need = predict_small_scratch_doubles((int)N);
+        if (ws->small_dbl < need || ws->small_N != N) {
+            rc = ws_reserve(&ws->small, &ws->small_dbl, need);
+            if (rc) return rc;
+            CU(cudaMemsetAsync(ws->small, 0, ws->small_dbl * sizeof(double), st));   // the layout (tickets) depends on N
+            ws->small_N = N;
+        }
+        const int q = (int)io.q;
+        for (int i = 0; i < q; ++i) {
+            ws->hio[i] = io.qx[io.offset + i]; ws->hio[8 + i] = io.qy[io.offset + i]; ws->hio[16 + i] = io.qz[io.offset + i];
+        }
+        CU(cudaEventRecord(ws->ev[0], st));
+        CU(launch_predict_small(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, n, (int)N, want_var ? md.linv : nullptr, ld,
+                                ws->hio_dev, ws->small, q, want_var, want_grad, want_t, m->k0, m->kp, st));
+        CU(cudaEventRecord(ws->ev[1], st));
+        CU(cudaStreamSynchronize(st));
+        const double* out = ws->hio + 24;
+        for (int i = 0; i < q; ++i) {
+            const size_t gi = io.offset + i;
+            io.f[gi] = out[i];
+            if (want_var) io.var[gi] = out[8 + i];
+            for (int c = 0; c < 3; ++c) {
+                if (want_grad) io.grad[c * io.out_ld + gi] = out[16 + 8 * c + i];
+                if (want_t) { io.tx[c * io.out_ld + gi] = out[40 + 8 * c + i]; io.ty[c * io.out_ld + gi] = out[64 + 8 * c + i]; }
+            }
+        }
+        const float t = ev_ms(ws->ev[0], ws->ev[1]);
+        if (mean_ms) *mean_ms = want_var ? 0.0 : t;
+        if (var_ms) *var_ms = want_var ? t : 0.0;
+        if (h2d_ms) *h2d_ms = 0.0;
+        if (d2h_ms) *d2h_ms = 0.0;
+        return GPR_OK;
+    }
     const bool small_var = want_var && io.q <= 8;
     size_t batch = io.q;
     if (want_var && !small_var) batch = std::min(io.q, ctx->query_tile ? ctx->query_tile : (size_t)TB * dc->num_sms);
@@ -449,7 +490,8 @@ int gpr_ctx_destroy(gpr_ctx* ctx) {
     for (DeviceCtx* dc : ctx->devs) {
         cudaSetDevice(dc->dev);
         for (Workspace* ws : dc->free_ws) {
-            cudaFree(ws->io); cudaFree(ws->panel); cudaFree(ws->partial); cudaFree(ws->mpart);
+            cudaFree(ws->io); cudaFree(ws->panel); cudaFree(ws->partial); cudaFree(ws->mpart); cudaFree(ws->small);
+            if (ws->hio) cudaFreeHost(ws->hio);
             for (auto& e : ws->ev) cudaEventDestroy(e);
             cudaStreamDestroy(ws->st);
             delete ws;

@@ -26,6 +26,13 @@ cudaError_t launch_predict(const double* px, const double* py, const double* pz,
                            const double* qx, const double* qy, const double* qz, int q, double* f, double* grad,
                            size_t grad_ld, double* panel, size_t panel_ld, const KernParams& kp, int warp_mode,
                            double* part, int split, cudaStream_t st);
+// Fused q <= 8 path: one launch, queries and results in a mapped pinned host buffer (112 doubles, layout in
+// gpr_predict.cu).  scratch: predict_small_scratch_doubles(N) doubles, zeroed once at allocation.
+constexpr int SMALL_HIO_DOUBLES = 112;
+size_t predict_small_scratch_doubles(int N);
+cudaError_t launch_predict_small(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
+                                 const double* X, size_t ld, double* hio, double* scratch, int q, int want_var,
+                                 int want_grad, int want_t, double k0, const KernParams& kp, cudaStream_t st);
 cudaError_t launch_tangent_basis(const double* grad, size_t ld, int q, double* Tx, double* Ty, cudaStream_t st);
 cudaError_t launch_normalize_rows(double* g, size_t ld, int q, cudaStream_t st);
 // K3' (gpr_var.cu)

@@ -38,6 +38,7 @@ struct PredictArgs {
 };
 
 constexpr int PCHUNK = 1024;   // training points staged per shared-memory chunk
+constexpr int SMALL_MS = 8;    // at most this many mean blocks in the small-batch kernel
 
 // Summation order (the same whatever the launch geometry, so that splitting the query set or the training
 // set over CTAs never changes a bit): within a chunk of 1024 training points sequentially from zero, then
@@ -216,10 +217,7 @@ cudaError_t launch_predict(const double* px, const double* py, const double* pz,
 // computeTangentBasis for every row of the gradient (gp_regressor.hpp:29-44, :204-211).
 // grad, N?, Tx, Ty are q x 3 column-major with leading dimension ld.
 // ---------------------------------------------------------------------------------------------
-__global__ void tangent_basis_kernel(const double* grad, size_t ld, int q, double* Tx, double* Ty) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q) return;
-    double g0 = grad[i], g1 = grad[ld + i], g2 = grad[2 * ld + i];
+__device__ __forceinline__ void tangent_basis_dev(double g0, double g1, double g2, double (&T)[3], double (&U)[3]) {
     double nrm = sqrt(g0 * g0 + g1 * g1 + g2 * g2);
     double n0 = g0, n1 = g1, n2 = g2;
     if (nrm > 0.0) { n0 = g0 / nrm; n1 = g1 / nrm; n2 = g2 / nrm; }                  // :31
@@ -235,8 +233,16 @@ __global__ void tangent_basis_kernel(const double* grad, size_t ld, int q, doubl
     double u0 = n1 * t2 - n2 * t1, u1 = n2 * t0 - n0 * t2, u2 = n0 * t1 - n1 * t0;   // :35 / :41
     double un = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
     if (un > 0.0) { u0 /= un; u1 /= un; u2 /= un; }                                  // :36 / :42
-    Tx[i] = t0; Tx[ld + i] = t1; Tx[2 * ld + i] = t2;
-    Ty[i] = u0; Ty[ld + i] = u1; Ty[2 * ld + i] = u2;
+    T[0] = t0; T[1] = t1; T[2] = t2; U[0] = u0; U[1] = u1; U[2] = u2;
+}
+
+__global__ void tangent_basis_kernel(const double* grad, size_t ld, int q, double* Tx, double* Ty) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    double T[3], U[3];
+    tangent_basis_dev(grad[i], grad[ld + i], grad[2 * ld + i], T, U);
+    Tx[i] = T[0]; Tx[ld + i] = T[1]; Tx[2 * ld + i] = T[2];
+    Ty[i] = U[0]; Ty[ld + i] = U[1]; Ty[2 * ld + i] = U[2];
 }
 
 cudaError_t launch_tangent_basis(const double* grad, size_t ld, int q, double* Tx, double* Ty, cudaStream_t st) {
@@ -257,6 +263,248 @@ __global__ void normalize_rows_kernel(double* g, size_t ld, int q) {
 cudaError_t launch_normalize_rows(double* g, size_t ld, int q, cudaStream_t st) {
     if (q <= 0) return cudaSuccess;
     normalize_rows_kernel<<<(q + 255) / 256, 256, 0, st>>>(g, ld, q);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused small-batch predict (q <= 8): the call pattern of every real caller of the reference — ONE query
+// per evaluate() from hundreds of host threads (src/gp_node.cpp:1027-1038, :1074; include/atlas/
+// atlas_variance.hpp:78, :201; include/atlas/atlas.hpp:225, :259).  One launch, no device-side staging:
+//   * queries are read from, and all results written to, a pinned host buffer mapped into the device
+//     address space (hio): no cudaMemcpy in the call;
+//   * variance blocks: v = X k* as a matrix-vector product over the triangle of X = L^-1 (bandwidth bound,
+//     4 n^2 bytes); k* is evaluated on the fly per 256-point chunk into shared memory (never stored);
+//   * mean blocks: f and the un-normalised gradient over a slice of the training points;
+//   * the last block to finish (atomic ticket) reduces the partial results in a fixed order, applies
+//     computeTangentBasis if asked, writes the outputs and re-arms the ticket.
+// hio layout (doubles): [0,8) qx [8,16) qy [16,24) qz | [24,32) f [32,40) var [40,64) grad (c*8+i)
+//                       [64,88) tx [88,112) ty
+// ---------------------------------------------------------------------------------------------
+struct SmallArgs {
+    const double* px; const double* py; const double* pz; const double* alpha;
+    int n, N;
+    const double* X; size_t ld;     // L^-1 (null when no variance is wanted)
+    double* hio;                    // mapped pinned host buffer, SMALL_HIO_DOUBLES doubles
+    unsigned int* ticket;           // global ticket
+    unsigned int* rowticket;        // one per 64-row block
+    double* fpart;                  // SMALL_MS * 8 * 4 (mean / gradient partial sums)
+    double* rowpart;                // (N/64) * 8: squared norm of each 64-row block of v
+    double* part;                   // vs * N * 8 (partial dot products per k-split)
+    int q, want_var, want_grad, want_t;
+    int vs, kspan;                  // k-splits and their extent (multiple of 256)
+    int nvar_blocks, nmean_blocks;
+    double k0;
+    KernParams kp;
+};
+
+template <int KIND, int Q>
+__global__ void __launch_bounds__(256) predict_small_kernel(SmallArgs a) {
+    __shared__ double ks[256][Q];
+    __shared__ double red[256 * (Q > 1 ? Q : 1)];
+    __shared__ double sq[3][8];
+    __shared__ unsigned int s_last;
+    const int tid = threadIdx.x;
+    if (tid < 24) sq[tid >> 3][tid & 7] = (tid & 7) < a.q ? a.hio[tid] : 0.0;
+    __syncthreads();
+    bool to_global = false;          // does this block take a global ticket?
+    if ((int)blockIdx.x < a.nvar_blocks) {
+        // ---- variance block: 64 rows x one k-split; thread = (row rl, k-phase kq) ----
+        const int bx = blockIdx.x / a.vs, by = blockIdx.x % a.vs;
+        const int rl = tid & 63, kq = tid >> 6;
+        const int r = bx * 64 + rl;
+        const int kbeg = by * a.kspan;
+        const int kend = min(min(kbeg + a.kspan, a.N), bx * 64 + 64);
+        if (kbeg >= kend) return;                                    // above the diagonal: nothing to do
+        const int nsplit = (min(a.N, bx * 64 + 64) + a.kspan - 1) / a.kspan;   // non-empty splits of this row block
+        double acc[Q];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) acc[i] = 0.0;
+        for (int c0 = kbeg; c0 < kend; c0 += 256) {
+            __syncthreads();
+            {
+                const int c = c0 + tid;
+                const bool real = c < a.n;
+                const double x = real ? a.px[c] : 0.0, y = real ? a.py[c] : 0.0, z = real ? a.pz[c] : 0.0;
+#pragma unroll
+                for (int i = 0; i < Q; ++i) {
+                    const double dx = sq[0][i] - x, dy = sq[1][i] - y, dz = sq[2][i] - z;
+                    const double d = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
+                    ks[tid][i] = real ? kern_value<KIND>(a.kp, d) : 0.0;
+                }
+            }
+            __syncthreads();
+            // this thread's 64 k values of the chunk, 16 loads in flight at a time
+            const int kl0 = 64 * kq;
+            const double* xr = a.X + (size_t)(c0 + kl0) * a.ld + r;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double xv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int c = c0 + kl0 + 16 * b + u;
+                    xv[u] = (c <= r && c < kend) ? __ldcs(xr + (size_t)(16 * b + u) * a.ld) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+#pragma unroll
+                    for (int i = 0; i < Q; ++i) acc[i] = fma(xv[u], ks[kl0 + 16 * b + u][i], acc[i]);
+                }
+            }
+        }
+        // sum the four k-phases in a fixed order
+        __syncthreads();
+        double* r4 = &ks[0][0];                      // reuse: [kq][rl][i], 4*64*Q doubles = 256*Q
+#pragma unroll
+        for (int i = 0; i < Q; ++i) r4[(kq * 64 + rl) * Q + i] = acc[i];
+        __syncthreads();
+        if (kq == 0) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i)
+                a.part[((size_t)by * a.N + r) * 8 + i] = ((r4[rl * Q + i] + r4[(64 + rl) * Q + i]) + r4[(128 + rl) * Q + i]) + r4[(192 + rl) * Q + i];
+        }
+        // row-block ticket: the last of the nsplit blocks squares and sums the 64 rows
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(a.rowticket + bx, 1u) == (unsigned)(nsplit - 1) ? 1u : 0u;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (tid < 64) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) {
+                double v = 0.0;
+                for (int y = 0; y < nsplit; ++y) v += __ldcg(a.part + ((size_t)y * a.N + bx * 64 + tid) * 8 + i);
+                red[tid * Q + i] = v * v;
+            }
+        }
+        __syncthreads();
+        if (tid < Q) {
+            double ssum = 0.0;
+            for (int rr = 0; rr < 64; ++rr) ssum += red[rr * Q + tid];
+            a.rowpart[(size_t)bx * 8 + tid] = ssum;
+        }
+        if (tid == 0) a.rowticket[bx] = 0u;
+        to_global = true;
+    } else {
+        // ---- mean block: f and gradient over a slice of the training points ----
+        const int mb = blockIdx.x - a.nvar_blocks;
+        const int span = (a.n + a.nmean_blocks - 1) / a.nmean_blocks;
+        const int j0 = mb * span, j1 = min(a.n, j0 + span);
+        for (int i = 0; i < a.q; ++i) {
+            double f = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+            for (int j = j0 + tid; j < j1; j += 256) {
+                const double al = a.alpha[j];
+                const double dx = sq[0][i] - a.px[j], dy = sq[1][i] - a.py[j], dz = sq[2][i] - a.pz[j];
+                const double d = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
+                const double kv = kern_value<KIND>(a.kp, d);
+                f = fma(kv, al, f);
+                const double w = al * kern_diff<KIND>(a.kp, d, kv);
+                gx = fma(w, dx, gx); gy = fma(w, dy, gy); gz = fma(w, dz, gz);
+            }
+            double vals[4] = {f, gx, gy, gz};
+            for (int c = 0; c < (a.want_grad ? 4 : 1); ++c) {
+                // fixed-order tree: warp shuffles, then the 8 warp sums
+                double v = vals[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                __syncthreads();
+                if ((tid & 31) == 0) red[tid >> 5] = v;
+                __syncthreads();
+                if (tid == 0) {
+                    double t = 0.0;
+                    for (int w8 = 0; w8 < 8; ++w8) t += red[w8];
+                    a.fpart[(mb * 8 + i) * 4 + c] = t;
+                }
+            }
+        }
+        to_global = true;
+    }
+    if (!to_global) return;
+    // ---- global ticket: one per non-empty row block + one per mean block; the last one finishes ----
+    __threadfence();
+    __syncthreads();
+    const unsigned total = (unsigned)(a.want_var ? (a.N + 63) / 64 : 0) + (unsigned)a.nmean_blocks;
+    if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == total - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double* out = a.hio + 24;
+    const int nrb = (a.N + 63) / 64;
+    for (int i = 0; i < a.q; ++i) {
+        if (a.want_var) {
+            // squared norm = sum over the row blocks, fixed order: strided partial sums, then a tree
+            double sacc = 0.0;
+            for (int b = tid; b < nrb; b += 256) sacc += __ldcg(a.rowpart + (size_t)b * 8 + i);
+            __syncthreads();
+            red[tid] = sacc;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (tid < o) red[tid] += red[tid + o];
+                __syncthreads();
+            }
+            if (tid == 0) out[8 + i] = a.k0 - red[0];
+        }
+        if (tid == 0) {
+            double v[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int c = 0; c < (a.want_grad ? 4 : 1); ++c)
+                for (int mb = 0; mb < a.nmean_blocks; ++mb) v[c] += __ldcg(a.fpart + (mb * 8 + i) * 4 + c);
+            out[i] = v[0];
+            if (a.want_grad) {
+                out[16 + i] = v[1]; out[16 + 8 + i] = v[2]; out[16 + 16 + i] = v[3];
+                if (a.want_t) {
+                    double T[3], U[3];
+                    tangent_basis_dev(v[1], v[2], v[3], T, U);
+                    for (int c = 0; c < 3; ++c) { out[40 + c * 8 + i] = T[c]; out[64 + c * 8 + i] = U[c]; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { __threadfence_system(); *a.ticket = 0u; }
+}
+
+template <int KIND>
+static void launch_small_q(const SmallArgs& a, int grid, cudaStream_t st) {
+    if (a.q <= 1) predict_small_kernel<KIND, 1><<<grid, 256, 0, st>>>(a);
+    else if (a.q <= 2) predict_small_kernel<KIND, 2><<<grid, 256, 0, st>>>(a);
+    else if (a.q <= 4) predict_small_kernel<KIND, 4><<<grid, 256, 0, st>>>(a);
+    else predict_small_kernel<KIND, 8><<<grid, 256, 0, st>>>(a);
+}
+
+static int small_vs(int N) { int v = (N + 1023) / 1024; return v < 1 ? 1 : (v > 16 ? 16 : v); }
+
+// ticket (2) | fpart | row tickets (one unsigned per 64 rows) | rowpart | part
+size_t predict_small_scratch_doubles(int N) {
+    const size_t nrb = (size_t)(N + 63) / 64;
+    return 2 + SMALL_MS * 8 * 4 + (nrb + 1) / 2 + nrb * 8 + (size_t)small_vs(N) * N * 8;
+}
+
+// scratch: predict_small_scratch_doubles(N) doubles, zero-initialised when allocated AND whenever N changes (the
+// tickets inside it are re-armed by the kernel itself).  hio: device pointer of the mapped host buffer.
+cudaError_t launch_predict_small(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
+                                 const double* X, size_t ld, double* hio, double* scratch, int q, int want_var,
+                                 int want_grad, int want_t, double k0, const KernParams& kp, cudaStream_t st) {
+    if (q <= 0 || q > 8) return cudaErrorInvalidValue;
+    SmallArgs a;
+    a.px = px; a.py = py; a.pz = pz; a.alpha = alpha; a.n = n; a.N = N; a.X = X; a.ld = ld; a.hio = hio;
+    const size_t nrb = (size_t)(N + 63) / 64;
+    a.ticket = reinterpret_cast<unsigned int*>(scratch);
+    a.fpart = scratch + 2;
+    a.rowticket = reinterpret_cast<unsigned int*>(a.fpart + SMALL_MS * 8 * 4);
+    a.rowpart = a.fpart + SMALL_MS * 8 * 4 + (nrb + 1) / 2;
+    a.part = a.rowpart + nrb * 8;
+    a.q = q; a.want_var = want_var && X != nullptr; a.want_grad = want_grad; a.want_t = want_t; a.k0 = k0; a.kp = kp;
+    a.vs = small_vs(N);
+    a.kspan = ((N + a.vs - 1) / a.vs + 255) / 256 * 256;
+    a.nvar_blocks = a.want_var ? (int)nrb * a.vs : 0;
+    a.nmean_blocks = (n + 2047) / 2048 < SMALL_MS ? (n + 2047) / 2048 : SMALL_MS;
+    if (a.nmean_blocks < 1) a.nmean_blocks = 1;
+    const int grid = a.nvar_blocks + a.nmean_blocks;
+    switch (kp.kind) {
+        case 0: launch_small_q<0>(a, grid, st); break;
+        case 1: launch_small_q<1>(a, grid, st); break;
+        default: launch_small_q<2>(a, grid, st); break;
+    }
     return cudaGetLastError();
 }
 

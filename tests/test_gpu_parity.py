@@ -79,6 +79,41 @@ def test_single_query_calls_match_batched(gpr, ctx):
     for q in (2, 3, 5, 8, 9, 130):
         f, v = reg.evaluate(m, Q[:q, 0], Q[:q, 1], Q[:q, 2], var=True)
         assert relerr(f, g["f"][:q]) <= TOL_MEAN and np.abs(v - g["v"][:q]).max() <= TOL_VAR * np.abs(g["v"]).max()
+    # the fused q <= 8 kernel: every overload, against the reference fixture (mean-only, +grad, +tangent basis)
+    for q in (1, 4, 7):
+        s = slice(40, 40 + q)
+        f1 = reg.evaluate(m, Q[s, 0], Q[s, 1], Q[s, 2])
+        f4, v4, g4, tx, ty = reg.evaluate(m, Q[s, 0], Q[s, 1], Q[s, 2], var=True, tangent=True)
+        scale = np.abs(g["f"]).max()
+        assert np.abs(f1 - g["f"][s]).max() <= TOL_MEAN * scale and np.abs(f4 - g["f"][s]).max() <= TOL_MEAN * scale
+        assert np.abs(v4 - g["v"][s]).max() <= TOL_VAR * np.abs(g["v"]).max()
+        assert np.abs(g4 - g["grad"][s]).max() <= TOL_MEAN * np.abs(g["grad"]).max()
+        assert np.abs(tx - g["Tx"][s]).max() <= 1e-8 and np.abs(ty - g["Ty"][s]).max() <= 1e-8
+
+
+def test_single_query_path_at_scale_and_after_append(gpr, orc, ctx):
+    """q <= 8 on a model with several k-splits and row blocks (n = 3000), before and after an incremental
+    append that grows the capacity (the fused kernel's scratch and ticket must survive the growth)."""
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(3100, seed=9)
+    rng = np.random.default_rng(9)
+    perm = rng.permutation(len(P)); P, y, s2 = P[perm], y[perm], s2[perm]
+    n0 = 3000
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    m = reg.create(P[:n0, 0], P[:n0, 1], P[:n0, 2], y[:n0], s2[:n0])
+    Q = W.grid_slab(10, 2, 3)
+    for stage in range(2):
+        n = m.n
+        o = orc.Oracle(P[:n, 0], P[:n, 1], P[:n, 2], y[:n], s2[:n], "thin_plate", W.SYNTH_R, 0.0, factor="llt")
+        fo, vo, go = o.predict(Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True, threads=4)
+        for a, q in ((0, 1), (1, 2), (3, 8), (11, 5)):
+            f, v, gr = reg.evaluate(m, Q[a:a + q, 0], Q[a:a + q, 1], Q[a:a + q, 2], var=True, grad=True)
+            assert np.abs(f - fo[a:a + q]).max() <= TOL_MEAN * np.abs(fo).max()
+            assert np.abs(v - vo[a:a + q]).max() <= TOL_VAR * np.abs(vo).max()
+            assert np.abs(gr - go[a:a + q]).max() <= TOL_MEAN * np.abs(go).max()
+        if stage == 0:
+            reg.update(m, P[n0:n0 + 90, 0], P[n0:n0 + 90, 1], P[n0:n0 + 90, 2], y[n0:n0 + 90], s2[n0:n0 + 90])
+            assert m.n == n0 + 90
 
 
 def test_update_matches_reference_fixture(gpr, ctx):

@@ -52,10 +52,17 @@ def config1(ctx):
     for i in range(200):
         reg.evaluate(m, Q[i:i + 1, 0], Q[i:i + 1, 1], Q[i:i + 1, 2], var=True)
     single_us = 1e6 * (time.perf_counter() - t0) / 200
+    ref_single_us = None
+    if oracle.have_reference():      # the reference's own evaluate(), same call pattern, one host thread
+        ref = oracle.Reference("thin_plate", R, 0.0).fit(P[:, 0], P[:, 1], P[:, 2], y, s2)
+        t0 = time.perf_counter()
+        for i in range(200):
+            ref.evaluate(Q[i:i + 1, 0], Q[i:i + 1, 1], Q[i:i + 1, 2], 2)
+        ref_single_us = 1e6 * (time.perf_counter() - t0) / 200
     return {"config": 1, "workload": "mugD.pcd (262 pts) + 15 external, ThinPlate(R=%.4f = max pairwise distance), 29^3 grid mean+var" % R,
             "n": len(P), "queries": len(Q), "gpu_fit_ms_device": best[3], "gpu_fit_ms_wall": 1e3 * best[1],
             "gpu_predict_ms_device": best[4], "gpu_predict_ms_wall": 1e3 * best[2], "gpu_queries_per_s_wall": len(Q) / best[2],
-            "gpu_single_query_call_us": single_us,
+            "gpu_single_query_call_us": single_us, "reference_cpu_single_query_call_us": ref_single_us,
             "cpu_oracle_ldlt_fit_ms": 1e3 * cpu_fit, "cpu_oracle_predict_ms_%d_threads" % os.cpu_count(): 1e3 * cpu_ev,
             "alpha_rel": rel(m.alpha, o.alpha), "mean_rel": rel(f, fo), "var_rel": rel(v, vo),
             "sign_mismatches": int((np.sign(f) != np.sign(fo))[np.abs(fo) > 1e-9].sum())}
