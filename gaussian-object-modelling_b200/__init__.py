@@ -80,6 +80,8 @@ def lib():
         L.gpr_model_destroy.argtypes = [vp]
         L.gpr_model_size.argtypes = [vp]
         L.gpr_model_size.restype = sz
+        L.gpr_model_tail_size.argtypes = [vp]
+        L.gpr_model_tail_size.restype = sz
         L.gpr_model_get.argtypes = [vp, _dp, _dp, _dp]
         L.gpr_model_get_factor.argtypes = [vp, _dp]
         L.gpr_predict.argtypes = [vp, vp, _dp, _dp, _dp, sz, _dp, _dp, _dp, _dp, _dp]
@@ -101,7 +103,7 @@ def lib():
 # Every symbol include/gpr_c_api.h declares (checked by the CPU test-suite without a GPU).
 C_ABI_SYMBOLS = [
     "gpr_ctx_create", "gpr_ctx_destroy", "gpr_ctx_num_devices", "gpr_last_error", "gpr_last_pivot",
-    "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_get",
+    "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_tail_size", "gpr_model_get",
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
     "gpr_model_reserve",
     "gpr_model_state_get", "gpr_model_create_replica", "gpr_selftest_gemm", "gpr_selftest_leaf",
@@ -173,6 +175,11 @@ class Model:
     @property
     def n(self):
         return lib().gpr_model_size(self._h)
+
+    @property
+    def n_tail(self):
+        """Points eliminated as the dense indefinite pivot block (0 for an SPD covariance matrix)."""
+        return lib().gpr_model_tail_size(self._h)
 
     def get(self):
         n = self.n

@@ -34,14 +34,14 @@ constexpr int APITCH = 65;  // pitch of the k-contiguous A chunk (odd: conflict-
 // covariance entries to a refitted one.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) append_panel_kernel(const double* x, const double* y, const double* z,
-                                                           const double* sigma2, int n0, int k, double* Pn, double* S0,
-                                                           KernParams kp) {
+                                                           const double* sigma2, int n0, int t0, int k, double* Pn,
+                                                           double* S0, KernParams kp) {
     __shared__ double nx[AK], ny[AK], nz[AK];
     if (threadIdx.x < AK) {
         const bool real = threadIdx.x < k;
-        nx[threadIdx.x] = real ? x[n0 + threadIdx.x] : 0.0;
-        ny[threadIdx.x] = real ? y[n0 + threadIdx.x] : 0.0;
-        nz[threadIdx.x] = real ? z[n0 + threadIdx.x] : 0.0;
+        nx[threadIdx.x] = real ? x[t0 + threadIdx.x] : 0.0;     // the new points sit at [t0, t0 + k)
+        ny[threadIdx.x] = real ? y[t0 + threadIdx.x] : 0.0;
+        nz[threadIdx.x] = real ? z[t0 + threadIdx.x] : 0.0;
     }
     __syncthreads();
     const int idx = blockIdx.x * 256 + threadIdx.x;          // (c, a) with a fastest
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) append_panel_kernel(const double* x, cons
             double v = (a2 == b2) ? 1.0 : 0.0;
             if (a2 < k && b2 < k) {
                 v = kern_value_exact(kp, dist_exact(nx[a2], ny[a2], nz[a2], nx[b2], ny[b2], nz[b2]));
-                if (a2 == b2) v = __dadd_rn(v, sigma2[n0 + a2]);       // gp_regressor.hpp:449-452
+                if (a2 == b2) v = __dadd_rn(v, sigma2[t0 + a2]);       // gp_regressor.hpp:449-452
             }
             S0[e] = v;
         }
@@ -68,12 +68,13 @@ __global__ void __launch_bounds__(256) append_panel_kernel(const double* x, cons
 // (2)/(5) skinny triangular products against X = L^-1 (column-major, leading dimension ld, lower part).
 //   MODE 0:  OUT[r][a] = sum_{c <= r} X[r][c] * Bm[c][a]          (B = X * Pn)        block rows r0 = 32*blockIdx.x
 //   MODE 1:  OUT[c][b] = sum_{r >= c, r < n0} X[r][c] * Bm[r][b]   (G = X^T * B)       block columns c0 = 32*blockIdx.x
+//   MODE 2:  OUT[m][a] = sum_{k < kdim} A[k*ld + m] * Bm[k][a]     (plain skinny product, no triangle; rows m < n0)
 // OUT and Bm are n0 x 32 row-major.  One CTA = one 32x32 output block; 256 threads = 4 k-phases x (8 x 8)
 // threads with a 4x4 register tile each (rows tm + 8i, columns 4tn + j); the k-phases are summed in a
 // fixed order at the end.  Chunks of 64 k are double-buffered through registers.
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restrict__ X, size_t ld, int n0,
+__global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restrict__ X, size_t ld, int n0, int kdim,
                                                          const double* __restrict__ Bm, double* __restrict__ OUT) {
     __shared__ __align__(16) double As[4 * AK * AK];      // MODE 0: [k][m] pitch 32;  MODE 1: [m][k] pitch 65; then the k-phase sums
     __shared__ __align__(16) double Bs[KC * AK];          // [k][a]
@@ -82,8 +83,8 @@ __global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restric
     const int nblk = (n0 + AK - 1) / AK;
     const int blk = MODE == 0 ? (nblk - 1 - blockIdx.x) : blockIdx.x;
     const int m0 = blk * AK;
-    const int kbeg = MODE == 0 ? 0 : m0;
-    const int kend = MODE == 0 ? min(m0 + AK, n0) : n0;
+    const int kbeg = MODE == 1 ? m0 : 0;
+    const int kend = MODE == 0 ? min(m0 + AK, n0) : (MODE == 1 ? n0 : kdim);
     const int kg = tid >> 6, t64 = tid & 63, tm = t64 & 7, tn = t64 >> 3;
 
     double acc[4][4];
@@ -98,12 +99,13 @@ __global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restric
         for (int j = 0; j < 8; ++j) {
             const int idx = tid + 256 * j;
             int mm, kk;
-            if (MODE == 0) { kk = idx >> 5; mm = idx & 31; } else { mm = idx >> 6; kk = idx & 63; }
+            if (MODE != 1) { kk = idx >> 5; mm = idx & 31; } else { mm = idx >> 6; kk = idx & 63; }
             const int kglob = k0 + kk, mglob = m0 + mm;
             double v = 0.0;
             if (kglob < kend && mglob < n0) {
                 if (MODE == 0) { if (kglob <= mglob) v = __ldg(X + (size_t)kglob * ld + mglob); }
-                else { if (kglob >= mglob) v = __ldg(X + (size_t)mglob * ld + kglob); }
+                else if (MODE == 1) { if (kglob >= mglob) v = __ldg(X + (size_t)mglob * ld + kglob); }
+                else v = __ldg(X + (size_t)kglob * ld + mglob);
             }
             ra[j] = v;
             const int kb = k0 + (idx >> 5);
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restric
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int idx = tid + 256 * j;
-            if (MODE == 0) As[idx] = ra[j];                       // [k][m], pitch 32
+            if (MODE != 1) As[idx] = ra[j];                       // [k][m], pitch 32
             else As[(idx >> 6) * APITCH + (idx & 63)] = ra[j];    // [m][k], pitch 65
             Bs[idx] = rb[j];
         }
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restric
         for (int kk = kg; kk < KC; kk += 4) {
             double a[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = MODE == 0 ? As[kk * AK + tm + 8 * i] : As[(tm + 8 * i) * APITCH + kk];
+            for (int i = 0; i < 4; ++i) a[i] = MODE != 1 ? As[kk * AK + tm + 8 * i] : As[(tm + 8 * i) * APITCH + kk];
             const double2 b01 = *reinterpret_cast<const double2*>(Bs + kk * AK + 4 * tn);
             const double2 b23 = *reinterpret_cast<const double2*>(Bs + kk * AK + 4 * tn + 2);
 #pragma unroll
@@ -313,14 +315,33 @@ cudaError_t launch_append_slab(const double* xyz, size_t ld, const double* sigma
     const int nblk = (n0 + AK - 1) / AK;
     const int nparts = (n0 + GRAM_ROWS - 1) / GRAM_ROWS;
     append_panel_kernel<<<(n0 * AK + 255) / 256 > 0 ? (n0 * AK + 255) / 256 : 1, 256, 0, st>>>(
-        xyz, xyz + ld, xyz + 2 * ld, sigma2, n0, k, Pn, S0, kp);
-    skinny_tri_kernel<0><<<nblk, 256, 0, st>>>(X, ld, n0, Pn, B);
+        xyz, xyz + ld, xyz + 2 * ld, sigma2, n0, n0, k, Pn, S0, kp);
+    skinny_tri_kernel<0><<<nblk, 256, 0, st>>>(X, ld, n0, n0, Pn, B);
     append_gram_kernel<<<nparts, 256, 0, st>>>(B, n0, part);
     append_leaf_kernel<<<1, NTHREADS, TILE_SMEM_BYTES, st>>>(S0, part, nparts, out22, flag, n0);
-    skinny_tri_kernel<1><<<nblk, 256, 0, st>>>(X, ld, n0, B, G);
+    skinny_tri_kernel<1><<<nblk, 256, 0, st>>>(X, ld, n0, n0, B, G);
     append_scatter_kernel<<<((n0 + k) * AK + 255) / 256, 256, 0, st>>>(B, G, out22, flag, n0, k, L, X, ld);
     const int t0 = n0 / TB, t1 = (n0 + k - 1) / TB;
     dinv_from_x_kernel<<<t1 - t0 + 1, 256, 0, st>>>(X, ld, t0, Dinv, flag);
+    return cudaGetLastError();
+}
+
+// Generic launcher of the skinny products (used by the indefinite-tail path, gpr_tail.cu).
+cudaError_t launch_skinny(int mode, const double* A, size_t ld, int rows, int kdim, const double* Bm, double* OUT,
+                          cudaStream_t st) {
+    const int nblk = (rows + AK - 1) / AK;
+    if (nblk <= 0) return cudaSuccess;
+    if (mode == 0) skinny_tri_kernel<0><<<nblk, 256, 0, st>>>(A, ld, rows, rows, Bm, OUT);
+    else if (mode == 1) skinny_tri_kernel<1><<<nblk, 256, 0, st>>>(A, ld, rows, rows, Bm, OUT);
+    else skinny_tri_kernel<2><<<nblk, 256, 0, st>>>(A, ld, rows, kdim, Bm, OUT);
+    return cudaGetLastError();
+}
+
+// Pn[c*32 + a] = k(|p_c - p_{t0+a}|) for c < n0, a < k (and the k x k block S0 of the new points themselves).
+cudaError_t launch_append_panel(const double* xyz, size_t ld, const double* sigma2, int n0, int t0, int k, double* Pn,
+                                double* S0, const KernParams& kp, cudaStream_t st) {
+    const int blocks = (n0 * AK + 255) / 256 > 0 ? (n0 * AK + 255) / 256 : 1;
+    append_panel_kernel<<<blocks, 256, 0, st>>>(xyz, xyz + ld, xyz + 2 * ld, sigma2, n0, t0, k, Pn, S0, kp);
     return cudaGetLastError();
 }
 

@@ -46,6 +46,7 @@ struct Workspace {
     double* panel = nullptr; size_t panel_dbl = 0;
     double* partial = nullptr; size_t partial_dbl = 0;
     double* mpart = nullptr; size_t mpart_dbl = 0;     // per-chunk partial sums of the split mean kernel
+    double* tailw = nullptr; size_t tailw_dbl = 0;     // W = Z^T k_1 of the indefinite-tail correction
     double* hio = nullptr; double* hio_dev = nullptr;  // pinned host buffer mapped into the device (q <= 8 path)
     double* small = nullptr; size_t small_dbl = 0; size_t small_N = 0;   // scratch + tickets of the fused small-batch kernel
 };
@@ -99,7 +100,9 @@ struct ModelDev {            // what predict needs, per device
     double* xyz = nullptr;   // 3N: x | y | z
     double* alpha = nullptr; // N
     double* linv = nullptr;  // N x N, lower tiles
-    bool have = false, have_linv = false;
+    double* tZ = nullptr;    // indefinite tail (gpr_tail.cu): Z = A^-1 P in 32-column slabs, S^-1
+    double* tSinv = nullptr;
+    bool have = false, have_linv = false, have_tail = false;
 };
 
 struct gpr_model {
@@ -108,6 +111,11 @@ struct gpr_model {
     size_t cap = 0;            // leading dimension of every per-point buffer and of L / L^-1 (>= N, multiple of 128)
     int nb = 0;
     double* aws = nullptr; size_t aws_dbl = 0;   // append workspace (primary device)
+    // Indefinite tail (gpr_tail.cu): the last n_tail points are eliminated as one dense pivot block; L / L^-1
+    // / nb then describe the leading n_spd = n - n_tail points only.  n_tail == 0 for SPD matrices.
+    size_t n_spd = 0, n_tail = 0;
+    int mp = 0;                                  // n_tail rounded up to a multiple of 32
+    double* tB = nullptr; double* tmisc = nullptr;   // B = X P (slabs); C | S | t | a2 | gram partials | panel tmp
     gpr_kernel_t kernel{};
     KernParams kp{};
     double R = 0.0, k0 = 0.0;
@@ -136,14 +144,43 @@ static void free_factor(gpr_model* m) {
     if (m->devs.empty()) return;
     cudaSetDevice(m->devs[0].dev);
     cudaFree(m->label); cudaFree(m->s2); cudaFree(m->zfwd); cudaFree(m->L); cudaFree(m->Dinv); cudaFree(m->scratch);
-    cudaFree(m->aws);
-    m->label = m->s2 = m->zfwd = m->L = m->Dinv = m->aws = nullptr; m->scratch = nullptr; m->aws_dbl = 0;
+    cudaFree(m->aws); cudaFree(m->tB); cudaFree(m->tmisc);
+    m->label = m->s2 = m->zfwd = m->L = m->Dinv = m->aws = m->tB = m->tmisc = nullptr; m->scratch = nullptr; m->aws_dbl = 0;
+    m->n_tail = 0; m->mp = 0;
     for (auto& d : m->devs) {
         cudaSetDevice(d.dev);
-        cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.linv);
-        d.xyz = d.alpha = d.linv = nullptr; d.have = d.have_linv = false;
+        cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.linv); cudaFree(d.tZ); cudaFree(d.tSinv);
+        d.xyz = d.alpha = d.linv = d.tZ = d.tSinv = nullptr; d.have = d.have_linv = d.have_tail = false;
     }
 }
+
+// Inverse of the symmetric (possibly indefinite) mp x mp matrix S by Gauss-Jordan elimination with partial
+// pivoting, on the host (mp <= 256).  Returns false if S is numerically singular.
+static bool invert_small(std::vector<double>& S, int mp, std::vector<double>& inv) {
+    inv.assign((size_t)mp * mp, 0.0);
+    for (int i = 0; i < mp; ++i) inv[(size_t)i * mp + i] = 1.0;
+    double scale = 0.0;
+    for (double v : S) scale = std::max(scale, std::fabs(v));
+    for (int c = 0; c < mp; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < mp; ++r) if (std::fabs(S[(size_t)r * mp + c]) > std::fabs(S[(size_t)piv * mp + c])) piv = r;
+        if (!(std::fabs(S[(size_t)piv * mp + c]) > 1e-14 * scale)) return false;
+        if (piv != c) for (int k = 0; k < mp; ++k) { std::swap(S[(size_t)c * mp + k], S[(size_t)piv * mp + k]); std::swap(inv[(size_t)c * mp + k], inv[(size_t)piv * mp + k]); }
+        const double d = 1.0 / S[(size_t)c * mp + c];
+        for (int k = 0; k < mp; ++k) { S[(size_t)c * mp + k] *= d; inv[(size_t)c * mp + k] *= d; }
+        for (int r = 0; r < mp; ++r) {
+            if (r == c) continue;
+            const double f = S[(size_t)r * mp + c];
+            if (f == 0.0) continue;
+            for (int k = 0; k < mp; ++k) { S[(size_t)r * mp + k] -= f * S[(size_t)c * mp + k]; inv[(size_t)r * mp + k] -= f * inv[(size_t)c * mp + k]; }
+        }
+    }
+    for (int a = 0; a < mp; ++a)                       // symmetrise
+        for (int b = 0; b < a; ++b) { const double v = 0.5 * (inv[(size_t)a * mp + b] + inv[(size_t)b * mp + a]); inv[(size_t)a * mp + b] = inv[(size_t)b * mp + a] = v; }
+    return true;
+}
+
+constexpr size_t MAX_TAIL = 256;
 
 // ------------------------------------------------------------------------------------------------
 // fit
@@ -159,7 +196,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     const size_t n = m->hx.size();
     const size_t N = (n + TB - 1) / TB * TB;
     const int nb = (int)(N / TB);
-    m->n = n; m->N = N; m->nb = nb; m->cap = N;
+    m->n = n; m->N = N; m->nb = nb; m->cap = N; m->n_spd = n; m->n_tail = 0; m->mp = 0;
     m->devs.assign(ctx->devs.size(), ModelDev());
     for (size_t i = 0; i < ctx->devs.size(); ++i) m->devs[i].dev = ctx->devs[i]->dev;
     ModelDev& md = m->devs[0];
@@ -197,21 +234,82 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     CU(cudaMemcpyAsync(&Rbits_host, rbits, sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(ws->ev[2], st));
     CU(launch_cholesky(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st));
-    CU(cudaEventRecord(ws->ev[3], st));
     int info[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (info[1] != 0) {
-        g_pivot = info[1];
-        char b[256];
-        snprintf(b, sizeof b, "covariance matrix is not positive definite: pivot %d of %zu is <= 0 "
-                 "(thin-plate R must be >= the largest pairwise distance, %.6g here)", info[1], n, Rbits_host);
-        return fail(GPR_ERR_NOT_SPD, b);
+        const size_t p = (size_t)info[1] - 1;
+        const char* no_tail = getenv("GPR_NO_TAIL");
+        if (p >= 1 && n - p <= MAX_TAIL && !(no_tail && atoi(no_tail) != 0)) {
+            // Indefinite matrix whose offending points are the last few (the node's external sphere points,
+            // SURVEY F2): keep the Cholesky factor of the leading p points, eliminate the rest as one dense
+            // pivot block (gpr_tail.cu).  The leading block is rebuilt with the tail rows as identity padding.
+            m->n_spd = p; m->n_tail = n - p; m->nb = (int)((p + TB - 1) / TB);
+            CU(launch_cov_build(md.xyz, md.xyz + N, md.xyz + 2 * N, m->s2, (int)p, m->nb, 0, m->L, N, rbits + 1, m->kp, st));
+            CU(launch_cholesky(m->L, N, m->nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st));
+            CU(cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        if (info[1] != 0) {
+            g_pivot = info[1];
+            char b[256];
+            snprintf(b, sizeof b, "covariance matrix is not positive definite: pivot %d of %zu is <= 0 "
+                     "(thin-plate R must be >= the largest pairwise distance, %.6g here)", info[1], n, Rbits_host);
+            return fail(GPR_ERR_NOT_SPD, b);
+        }
     }
     if (info[2] != 0) return fail(GPR_ERR_CUDA, "cholesky kernel aborted (dependency wait timed out)");
     if (!keep_R) m->R = Rbits_host;
-    CU(launch_trsv(0, m->L, N, nb, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
-    CU(launch_trsv(1, m->L, N, nb, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
+    CU(cudaEventRecord(ws->ev[3], st));
+    if (m->n_tail == 0) {
+        CU(launch_trsv(0, m->L, N, nb, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
+        CU(launch_trsv(1, m->L, N, nb, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
+    } else {
+        const size_t p = m->n_spd, mt = m->n_tail;
+        const int nslab = (int)((mt + 31) / 32), mp = 32 * nslab;
+        m->mp = mp;
+        const size_t part_dbl = tail_gram_part_doubles((int)p, mp);
+        // tmisc: C | S | t | a2 | gram partials | panel tmp (N x 32) | rhs (N) | S0 dummy (1024)
+        const size_t misc = 2 * (size_t)mp * mp + 2 * mp + part_dbl + 32 * N + N + 1024;
+        CU(cudaMalloc((void**)&m->tB, (size_t)nslab * N * 32 * sizeof(double)));
+        CU(cudaMalloc((void**)&md.tZ, (size_t)nslab * N * 32 * sizeof(double)));
+        CU(cudaMalloc((void**)&md.tSinv, (size_t)mp * mp * sizeof(double)));
+        CU(cudaMalloc((void**)&m->tmisc, misc * sizeof(double)));
+        if (!md.linv) CU(cudaMalloc((void**)&md.linv, N * N * sizeof(double)));
+        double* tC = m->tmisc; double* tS = tC + (size_t)mp * mp; double* tt = tS + (size_t)mp * mp; double* ta2 = tt + mp;
+        double* tpart = ta2 + mp; double* tPn = tpart + part_dbl; double* trhs = tPn + 32 * N; double* tS0 = trhs + N;
+        // alpha_1 part 1: z_f = X y_1, z_1 = A^-1 y_1 (the tail labels must not enter the leading solve)
+        CU(cudaMemsetAsync(trhs, 0, N * sizeof(double), st));
+        CU(cudaMemcpyAsync(trhs, m->label, p * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CU(launch_trsv(0, m->L, N, m->nb, m->Dinv, trhs, m->zfwd, m->scratch, dc->num_sms, st));
+        CU(launch_trsv(1, m->L, N, m->nb, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
+        // X = L^-1 of the leading block, then B = X P and Z = X^T B slab by slab
+        CU(launch_linv(m->L, md.linv, N, m->nb, m->Dinv, m->scratch, dc->num_sms, st));
+        for (int s = 0; s < nslab; ++s) {
+            const int kk = (int)std::min<size_t>(32, mt - 32 * (size_t)s);
+            double* Bs = m->tB + (size_t)s * N * 32;
+            double* Zs = md.tZ + (size_t)s * N * 32;
+            CU(launch_append_panel(md.xyz, N, m->s2, (int)p, (int)(p + 32 * (size_t)s), kk, tPn, tS0, m->kp, st));
+            CU(launch_skinny(0, md.linv, N, (int)p, (int)p, tPn, Bs, st));
+            CU(launch_skinny(1, md.linv, N, (int)p, (int)p, Bs, Zs, st));
+        }
+        CU(launch_tail_cc(md.xyz, N, m->s2, (int)p, (int)mt, mp, tC, m->kp, st));
+        CU(launch_tail_schur(m->tB, N, (int)p, mp, tC, tpart, tS, st));
+        std::vector<double> hS((size_t)mp * mp), hSinv;
+        CU(cudaMemcpyAsync(hS.data(), tS, hS.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        int lflags[4] = {0, 0, 0, 0};
+        CU(cudaMemcpyAsync(lflags, m->scratch, sizeof(lflags), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (lflags[2] != 0) return fail(GPR_ERR_CUDA, "L^-1 kernel aborted (dependency wait timed out)");
+        if (!invert_small(hS, mp, hSinv)) {
+            g_pivot = (long long)p + 1;
+            return fail(GPR_ERR_NOT_SPD, "covariance matrix is singular: the Schur complement of the trailing pivot block cannot be inverted");
+        }
+        CU(cudaMemcpyAsync(md.tSinv, hSinv.data(), hSinv.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(launch_tail_alpha(m->tB, md.tZ, N, (int)p, (int)mt, mp, m->zfwd, m->label, md.tSinv, tt, ta2, md.alpha, st));
+        CU(cudaStreamSynchronize(st));      // hSinv must outlive the copy
+        md.have_linv = true; md.have_tail = true;
+    }
     CU(cudaEventRecord(ws->ev[4], st));
     m->h_alpha.resize(n);
     CU(cudaMemcpyAsync(m->h_alpha.data(), md.alpha, n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -225,7 +323,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
         const int nsplit = n <= 4096 ? 1 : predict_split((int)n, (int)N, dc->num_sms);
         if (nsplit > 1) { rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, predict_part_doubles((int)n, (int)N)); if (rc) return rc; }
         CU(launch_predict(md.xyz, md.xyz + N, md.xyz + 2 * N, md.alpha, (int)n, (int)N, md.xyz, md.xyz + N, md.xyz + 2 * N,
-                          (int)n, f, g, N, nullptr, 0, m->kp, n <= 4096, ws->mpart, nsplit, st));
+                          (int)n, f, g, N, nullptr, 0, (int)n, m->kp, n <= 4096, ws->mpart, nsplit, st));
         CU(launch_normalize_rows(g, N, (int)n, st));
         m->h_normals.resize(3 * n);
         m->n_normals = n;
@@ -297,6 +395,14 @@ static int ensure_on_device(gpr_model* m, size_t di, bool need_linv) {
         CU(cudaMemcpyPeer(dst.linv, dst.dev, src.linv, src.dev, m->cap * m->cap * sizeof(double)));
         dst.have_linv = true;
     }
+    if (need_linv && m->n_tail > 0 && !dst.have_tail) {
+        const size_t zb = (size_t)(m->mp / 32) * m->cap * 32 * sizeof(double), sb = (size_t)m->mp * m->mp * sizeof(double);
+        if (!dst.tZ) CU(cudaMalloc((void**)&dst.tZ, zb));
+        if (!dst.tSinv) CU(cudaMalloc((void**)&dst.tSinv, sb));
+        CU(cudaMemcpyPeer(dst.tZ, dst.dev, src.tZ, src.dev, zb));
+        CU(cudaMemcpyPeer(dst.tSinv, dst.dev, src.tSinv, src.dev, sb));
+        dst.have_tail = true;
+    }
     return GPR_OK;
 }
 
@@ -327,7 +433,7 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
     cudaStream_t st = ws->st;
     const size_t N = m->N, ld = m->cap;
     const int n = (int)m->n;
-    if (!io.device_ptrs && io.q <= 8) {
+    if (!io.device_ptrs && io.q <= 8 && m->n_tail == 0) {
         // The reference's callers: one query per call.  One fused launch, I/O through mapped pinned memory.
         if (!ws->hio) {
             CU(cudaHostAlloc((void**)&ws->hio, SMALL_HIO_DOUBLES * sizeof(double), cudaHostAllocMapped));
@@ -409,11 +515,22 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
             if (nsplit > 1) { rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, predict_part_doubles((int)bq, (int)N)); if (rc) return rc; }
         }
         CU(launch_predict(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, n, (int)N, qx, qy, qz, (int)bq, f, g, gld,
-                          want_var ? ws->panel : nullptr, pld, m->kp, warp_mode, ws->mpart, nsplit, st));
+                          want_var ? ws->panel : nullptr, pld, (int)m->n_spd, m->kp, warp_mode, ws->mpart, nsplit, st));
         CU(cudaEventRecord(ws->ev[2], st));
         if (want_var) {
-            if (small_var) CU(launch_variance_small(md.linv, ld, (int)N, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+            if (small_var) CU(launch_variance_small(md.linv, ld, m->nb * TB, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
             else CU(launch_variance(md.linv, ld, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+            if (m->n_tail > 0) {
+                // indefinite tail: var -= w^T S^-1 w,  w = k_2 - Z^T k_1  (gpr_tail.cu)
+                const int nslab = m->mp / 32;
+                rc = ws_reserve(&ws->tailw, &ws->tailw_dbl, (size_t)nslab * pld * 32);
+                if (rc) return rc;
+                for (int s = 0; s < nslab; ++s)
+                    CU(launch_skinny(2, ws->panel, pld, (int)bq, (int)m->n_spd, md.tZ + (size_t)s * ld * 32,
+                                     ws->tailw + (size_t)s * pld * 32, st));
+                CU(launch_tail_var(qx, qy, qz, (int)bq, md.xyz, ld, (int)m->n_spd, (int)m->n_tail, m->mp, ws->tailw, pld,
+                                   md.tSinv, v, m->kp, st));
+            }
         }
         CU(cudaEventRecord(ws->ev[3], st));
         if (want_t && !io.device_ptrs) CU(launch_tangent_basis(g, gld, (int)bq, dtx, dty, st));
@@ -490,7 +607,7 @@ int gpr_ctx_destroy(gpr_ctx* ctx) {
     for (DeviceCtx* dc : ctx->devs) {
         cudaSetDevice(dc->dev);
         for (Workspace* ws : dc->free_ws) {
-            cudaFree(ws->io); cudaFree(ws->panel); cudaFree(ws->partial); cudaFree(ws->mpart); cudaFree(ws->small);
+            cudaFree(ws->io); cudaFree(ws->panel); cudaFree(ws->partial); cudaFree(ws->mpart); cudaFree(ws->small); cudaFree(ws->tailw);
             if (ws->hio) cudaFreeHost(ws->hio);
             for (auto& e : ws->ev) cudaEventDestroy(e);
             cudaStreamDestroy(ws->st);
@@ -535,6 +652,7 @@ int gpr_model_destroy(gpr_model* m) {
 }
 
 size_t gpr_model_size(const gpr_model* m) { return m ? m->n : 0; }
+size_t gpr_model_tail_size(const gpr_model* m) { return m ? m->n_tail : 0; }
 
 int gpr_model_get(const gpr_model* m, double* alpha, double* R, double* normals) {
     if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
@@ -762,7 +880,7 @@ static int append_incremental(gpr_model* m, const double* x, const double* y, co
     CU(cudaStreamSynchronize(st));
     if (flags[2] != 0) return fail(GPR_ERR_CUDA, "triangular solve kernel aborted (dependency wait timed out)");
     host_append(m, x, y, z, label, sigma2, k);
-    m->n = n1; m->N = N1; m->nb = nb1;
+    m->n = n1; m->n_spd = n1; m->N = N1; m->nb = nb1;
     for (size_t di = 1; di < m->devs.size(); ++di) { m->devs[di].have = false; m->devs[di].have_linv = false; }
     std::lock_guard<std::mutex> lk(ctx->tmu);
     ctx->timings.h2d_ms = ev_ms(ws->ev[0], ws->ev[1]);
@@ -778,7 +896,7 @@ int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, con
     if (m->replica) return fail(GPR_ERR_INVALID, "cannot append to a replica model");
     std::lock_guard<std::mutex> lk(m->mu);
     const char* force = getenv("GPR_APPEND_REFIT");
-    const bool refit = (force && atoi(force) != 0) || k > 256 || 8 * k > m->n;
+    const bool refit = (force && atoi(force) != 0) || k > 256 || 8 * k > m->n || m->n_tail > 0;
     if (!refit) return append_incremental(m, x, y, z, label, sigma2, k);
     // Large batches: append on the host and refit, like the reference (gp_regressor.hpp:442-459).
     const size_t p = m->hx.size();
@@ -812,6 +930,7 @@ int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity) {
     std::lock_guard<std::mutex> lk(m->mu);
     const size_t want = (capacity + TB - 1) / TB * TB;
     if (want <= m->cap) return GPR_OK;
+    if (m->n_tail > 0) return fail(GPR_ERR_INVALID, "reserve is not supported on a model with an indefinite tail block");
     DeviceCtx* dc = ctx->devs[0];
     CU(cudaSetDevice(dc->dev));
     Workspace* ws = nullptr;
@@ -824,6 +943,7 @@ int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity) {
 
 int gpr_model_state_get(gpr_ctx* ctx, gpr_model* m, int with_linv, gpr_model_state* out) {
     if (!ctx || !m || !out) return fail(GPR_ERR_INVALID, "null pointer");
+    if (m->n_tail > 0) return fail(GPR_ERR_INVALID, "a model with an indefinite tail block cannot be replicated across processes yet");
     if (with_linv) { int rc = ensure_on_device(m, 0, true); if (rc) return rc; }
     out->n = m->n; out->padded_n = m->N; out->ld = m->cap; out->kernel = m->kernel; out->R = m->R;
     out->xyz = m->devs[0].xyz; out->alpha = m->devs[0].alpha;
@@ -836,7 +956,7 @@ int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double
     gpr_model* m = new gpr_model();
     m->ctx = ctx; m->kernel = kernel; m->kp = make_kp(kernel); m->k0 = kernel_at_zero(m->kp); m->R = R;
     m->replica = true;
-    m->n = n; m->N = (n + TB - 1) / TB * TB; m->nb = (int)(m->N / TB); m->cap = m->N;
+    m->n = n; m->n_spd = n; m->N = (n + TB - 1) / TB * TB; m->nb = (int)(m->N / TB); m->cap = m->N;
     m->devs.assign(ctx->devs.size(), ModelDev());
     for (size_t i = 0; i < ctx->devs.size(); ++i) m->devs[i].dev = ctx->devs[i]->dev;
     ModelDev& md = m->devs[0];

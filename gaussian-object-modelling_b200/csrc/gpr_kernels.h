@@ -24,8 +24,8 @@ int predict_split(int q_span, int N, int num_sms);
 size_t predict_part_doubles(int q_span, int N);
 cudaError_t launch_predict(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
                            const double* qx, const double* qy, const double* qz, int q, double* f, double* grad,
-                           size_t grad_ld, double* panel, size_t panel_ld, const KernParams& kp, int warp_mode,
-                           double* part, int split, cudaStream_t st);
+                           size_t grad_ld, double* panel, size_t panel_ld, int n_panel, const KernParams& kp,
+                           int warp_mode, double* part, int split, cudaStream_t st);
 // Fused q <= 8 path: one launch, queries and results in a mapped pinned host buffer (112 doubles, layout in
 // gpr_predict.cu).  scratch: predict_small_scratch_doubles(N) doubles, zeroed once at allocation.
 constexpr int SMALL_HIO_DOUBLES = 112;
@@ -48,6 +48,22 @@ cudaError_t launch_append_slab(const double* xyz, size_t ld, const double* sigma
 const int* append_flag_ptr(const double* ws, size_t cap);
 cudaError_t launch_identity_rows(double* L, double* X_or_null, size_t ld, int r0, int r1, int row_end, cudaStream_t st);
 cudaError_t launch_dinv_from_x(const double* X, size_t ld, int tile0, int ntiles, double* Dinv, cudaStream_t st);
+cudaError_t launch_skinny(int mode, const double* A, size_t ld, int rows, int kdim, const double* Bm, double* OUT,
+                          cudaStream_t st);
+cudaError_t launch_append_panel(const double* xyz, size_t ld, const double* sigma2, int n0, int t0, int k, double* Pn,
+                                double* S0, const KernParams& kp, cudaStream_t st);
+// Indefinite tail (gpr_tail.cu)
+cudaError_t launch_tail_cc(const double* xyz, size_t ld, const double* sigma2, int p, int m, int mp, double* C,
+                           const KernParams& kp, cudaStream_t st);
+size_t tail_gram_part_doubles(int p, int mp);
+cudaError_t launch_tail_schur(const double* B, size_t ldr, int p, int mp, const double* C, double* part, double* S,
+                              cudaStream_t st);
+cudaError_t launch_tail_alpha(const double* B, const double* Z, size_t ldr, int p, int m, int mp, const double* zf,
+                              const double* label, const double* Sinv, double* t, double* a2, double* alpha,
+                              cudaStream_t st);
+cudaError_t launch_tail_var(const double* qx, const double* qy, const double* qz, int q, const double* xyz, size_t ld,
+                            int p, int m, int mp, const double* W, size_t ldq, const double* Sinv, double* var,
+                            const KernParams& kp, cudaStream_t st);
 // Engine self-test (gpr_selftest.cu): C = A * B^T on one 128x128 tile per CTA.
 cudaError_t launch_gemm_selftest(const double* A, size_t lda, const double* B, size_t ldb, int b_kmajor, double* C,
                                  size_t ldc, int mt, int nt, int k, cudaStream_t st);

@@ -31,6 +31,7 @@ struct PredictArgs {
     size_t grad_ld;
     double* panel;         // N x panel_ld: element (query, k) at panel[k*panel_ld + query], or null
     size_t panel_ld;       // >= q rounded up to 128; padded queries and padded k are written as 0
+    int n_panel;           // training points whose k* goes into the panel (the rest is written as 0)
     double* part;          // split mode: per-chunk partial sums, [chunk][4][part_ld] (f, gx, gy, gz)
     size_t part_ld;
     int chunks_per_cta;    // training chunks (of PCHUNK points) handled by one CTA along blockIdx.y
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(256) predict_thread_kernel(PredictArgs a) {
                 cx = fma(w, dx, cx); cy = fma(w, dy, cy); cz = fma(w, dz, cz);
             }
             if (PANEL) {
-                if (in_panel) a.panel[(size_t)(base + k) * a.panel_ld + qi] = (real && base + k < a.n) ? kv : 0.0;
+                if (in_panel) a.panel[(size_t)(base + k) * a.panel_ld + qi] = (real && base + k < a.n_panel) ? kv : 0.0;
             }
         }
         if (SPLIT) {
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) predict_warp_kernel(PredictArgs a) {
             const double w = al * kern_diff<KIND>(a.kp, d, kv);
             gx = fma(w, dx, gx); gy = fma(w, dy, gy); gz = fma(w, dz, gz);
         }
-        if (PANEL) a.panel[(size_t)j * a.panel_ld + qi] = j < a.n ? kv : 0.0;
+        if (PANEL) a.panel[(size_t)j * a.panel_ld + qi] = j < a.n_panel ? kv : 0.0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -194,13 +195,13 @@ size_t predict_part_doubles(int q_span, int N) {
 
 cudaError_t launch_predict(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
                            const double* qx, const double* qy, const double* qz, int q, double* f, double* grad,
-                           size_t grad_ld, double* panel, size_t panel_ld, const KernParams& kp, int warp_mode,
-                           double* part, int split, cudaStream_t st) {
+                           size_t grad_ld, double* panel, size_t panel_ld, int n_panel, const KernParams& kp,
+                           int warp_mode, double* part, int split, cudaStream_t st) {
     if (q <= 0) return cudaSuccess;
     PredictArgs a;
     a.px = px; a.py = py; a.pz = pz; a.alpha = alpha; a.n = n; a.N = N;
     a.qx = qx; a.qy = qy; a.qz = qz; a.q = q; a.f = f; a.grad = grad; a.grad_ld = grad_ld;
-    a.panel = panel; a.panel_ld = panel_ld; a.kp = kp;
+    a.panel = panel; a.panel_ld = panel_ld; a.n_panel = n_panel < n ? n_panel : n; a.kp = kp;
     if (!part) split = 1;
     const int nchunks = (N + PCHUNK - 1) / PCHUNK;
     a.part = part; a.part_ld = (size_t)((q + 255) / 256 * 256);

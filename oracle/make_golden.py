@@ -47,6 +47,16 @@ def run_case(tag, P, y, s2, kind, p0, p1, Q, normals, upd=None):
     print(tag, "n=%d q=%d R=%.6f |alpha|max=%.3e" % (len(P), len(Q), ref.R, np.abs(got["alpha"]).max()))
 
 
+def node_cases():
+    """The ROS node's REAL operating point: ThinPlate(2.0) (src/gp_node.cpp:919) with the 15 external
+    points at r = 2 (:16, :821-849).  K is indefinite (3 negative eigenvalues); the reference's pivoted LDLT
+    handles it, a plain Cholesky cannot."""
+    grid = W.node_grid()
+    for name, step in (("mugD", 97), ("jug", 131)):
+        P, y, s2 = W.node_training_set(W.read_pcd_xyz(os.path.join(REF, name + ".pcd")))
+        run_case("ref_%s_thinplate_R2_node" % name, P, y, s2, "thin_plate", 2.0, 0.0, grid[::step], normals=True)
+
+
 def main():
     oracle.build()
     grid = W.node_grid()
@@ -61,6 +71,7 @@ def main():
     P, y, s2 = W.node_training_set(cloud("jug"))
     run_case("ref_jug_gaussian", P, y, s2, "gaussian", 1.0, 1.0, P[::5], normals=True)
     run_case("ref_jug_laplace", P, y, s2, "laplace", 1.0, 1.0, grid[::211], normals=False)
+    node_cases()
     # the reference's argument checks
     msgs = [oracle.Reference().error_message(i) for i in range(4)]
     np.savez(os.path.join(GOLD, "ref_error_messages.npz"), messages=np.array(msgs))
@@ -68,4 +79,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "node":
+        oracle.build()
+        node_cases()
+    else:
+        main()

@@ -128,14 +128,61 @@ def test_update_matches_reference_fixture(gpr, ctx):
     assert relerr(reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2]), g["f_updated"]) <= TOL_MEAN
 
 
-def test_not_spd_is_reported_never_nan(gpr, ctx):
-    """Appendix B.7: the node's ThinPlate(2.0) setting is indefinite; pivot = first external point."""
+def test_not_spd_is_reported_never_nan(gpr, ctx, monkeypatch):
+    """Appendix B.7: the node's ThinPlate(2.0) setting is indefinite; pivot = first external point.  With the
+    trailing-block elimination switched off (GPR_NO_TAIL=1) that is an error, never NaN; an indefinite matrix
+    whose offending points come early (more than 256 points after the failing pivot) is an error in any case."""
     g = load_golden("ref_mugD_thinplate")
     P = g["P"]
     reg = gpr.GPRegressor("thin_plate", 2.0, ctx=ctx)
+    monkeypatch.setenv("GPR_NO_TAIL", "1")
     with pytest.raises(gpr.GPRegressionException) as e:
         reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"])
     assert e.value.code == gpr.GPR_ERR_NOT_SPD and e.value.pivot == 263
+    monkeypatch.delenv("GPR_NO_TAIL")
+    W = gpr.workloads
+    Ps, ys, ss = W.synthetic_cloud(1024, seed=3)
+    far = np.vstack([[[9.0, 0.0, 0.0]], Ps])                     # the far point is FIRST: pivot 2 fails, 1023 points remain
+    reg2 = gpr.GPRegressor("thin_plate", 2.0, ctx=ctx)
+    with pytest.raises(gpr.GPRegressionException) as e:
+        reg2.create(far[:, 0], far[:, 1], far[:, 2], np.concatenate([[1.0], ys]), np.concatenate([[0.1], ss]))
+    assert e.value.code == gpr.GPR_ERR_NOT_SPD
+
+
+@pytest.mark.parametrize("case", ["ref_mugD_thinplate_R2_node", "ref_jug_thinplate_R2_node"])
+def test_node_configuration_indefinite_matrix(gpr, ctx, case):
+    """the ROS node's REAL setting — ThinPlate(2.0), 15 external points at r = 2 — gives an
+    indefinite K (3 negative eigenvalues).  The reference's pivoted LDLT handles it; here the 15 trailing points
+    are eliminated as one dense pivot block (block L D L^T, csrc/gpr_tail.cu).  Parity against the reference's
+    own outputs for that setting: all four evaluate overloads, training normals, q = 1 calls."""
+    g = load_golden(case)
+    P, Q = g["P"], g["Q"]
+    reg = _reg(gpr, ctx, g)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"], with_normals=True)
+    assert m.n_tail == 15 and m.n == len(P)
+    got = m.get()
+    assert abs(got["R"] - g["R"]) <= 1e-15 * g["R"]
+    assert relerr(got["alpha"], g["alpha"]) <= TOL_ALPHA
+    assert np.abs(got["normals"] - g["normals"]).max() <= 1e-8
+    f1 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2])
+    f4, v4, g4, tx, ty = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, tangent=True)
+    for f in (f1, f4):
+        assert relerr(f, g["f"]) <= TOL_MEAN and _signs_agree(f, g["f"])
+    assert np.abs(v4 - g["v"]).max() <= TOL_VAR * np.abs(g["v"]).max()
+    assert relerr(g4, g["grad"]) <= TOL_MEAN
+    assert np.abs(tx - g["Tx"]).max() <= 1e-8 and np.abs(ty - g["Ty"]).max() <= 1e-8
+    for i in (0, 5, 100):                                        # the node's call pattern: one query per call
+        f, v = reg.evaluate(m, Q[i:i + 1, 0], Q[i:i + 1, 1], Q[i:i + 1, 2], var=True)
+        assert abs(f[0] - g["f"][i]) <= TOL_MEAN * np.abs(g["f"]).max()
+        assert abs(v[0] - g["v"][i]) <= TOL_VAR * np.abs(g["v"]).max()
+    # a big batch (thread-per-query + tile variance path) agrees with the small-batch path
+    big = np.vstack([Q] * 40)
+    fb, vb = reg.evaluate(m, big[:, 0], big[:, 1], big[:, 2], var=True)
+    assert relerr(fb[:len(Q)], g["f"]) <= TOL_MEAN and np.abs(vb[:len(Q)] - g["v"]).max() <= TOL_VAR * np.abs(g["v"]).max()
+    assert np.array_equal(fb[:len(Q)], fb[-len(Q):]) and np.array_equal(vb[:len(Q)], vb[-len(Q):])
+    # update() on such a model refits (the tail is re-detected) and stays consistent with a fresh fit
+    reg.update(m, [0.3, 0.0], [0.1, 0.5], [-0.2, 0.4], [0.0, 0.0], [0.05, 0.05])
+    assert m.n == len(P) + 2 and m.n_tail == 17
 
 
 def test_closed_form_posteriors(gpr, ctx):

@@ -18,7 +18,10 @@ def _fit(orc, g, **kw):
     return orc.Oracle(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"], g["kind"], g["p0"], g["p1"], **kw)
 
 
-@pytest.mark.parametrize("case", CASES)
+NODE_CASES = ["ref_mugD_thinplate_R2_node", "ref_jug_thinplate_R2_node"]      # indefinite K
+
+
+@pytest.mark.parametrize("case", CASES + NODE_CASES)
 def test_oracle_reproduces_reference_fixture_exactly(orc, case):
     """Expansion-form distance + pivoted LDLT + no FMA contraction = the reference's arithmetic:
     every output must agree to the last bits (1e-13 relative leaves room for libm's exp only)."""
@@ -183,3 +186,35 @@ def test_blas_flavour_matches(orc):
     f, v = orc.blas_predict(m, g["Q"])
     assert relerr(m["alpha"], g["alpha"]) <= 1e-10 and relerr(f, g["f"]) <= 1e-11
     assert np.abs(v - g["v"]).max() <= 1e-9 * np.abs(g["v"]).max()
+
+
+@pytest.mark.parametrize("case", NODE_CASES)
+def test_node_configuration_is_indefinite_and_block_elimination_matches(orc, case):
+    """The node's ThinPlate(2.0) + external sphere (src/gp_node.cpp:919, :821-849): K has negative eigenvalues, the
+    reference's pivoted LDLT solves it anyway.  The block elimination used on the GPU (leading SPD block by Cholesky,
+    the trailing 15 points as one dense pivot block, csrc/gpr_tail.cu) is restated here in numpy and must reproduce
+    the reference's alpha / mean / variance to cond*eps."""
+    g = load_golden(case)
+    P, y, s2, Q = g["P"], g["y"], g["s2"], g["Q"]
+    R = g["p0"]
+    kern = lambda d: 2 * d ** 3 - 3 * R * d ** 2 + R ** 3
+    dist = lambda A, B: np.sqrt(((A[:, None, :] - B[None, :, :]) ** 2).sum(-1))
+    K = kern(dist(P, P)) + np.diag(s2)
+    assert (np.linalg.eigvalsh(K) < 0).sum() == 3
+    p = len(P) - 15
+    L = np.linalg.cholesky(K[:p, :p])                       # the leading block (object points) is SPD
+    X = np.linalg.inv(L)
+    B = X @ K[:p, p:]
+    S = K[p:, p:] - B.T @ B
+    assert (np.linalg.eigvalsh(S) < 0).sum() == 3           # all the indefiniteness sits in the Schur complement
+    Z = X.T @ B
+    Sinv = np.linalg.inv(S)
+    a2 = Sinv @ (y[p:] - B.T @ (X @ y[:p]))
+    a1 = X.T @ (X @ y[:p]) - Z @ a2
+    alpha = np.concatenate([a1, a2])
+    assert relerr(alpha, g["alpha"]) <= 1e-10
+    Kq = kern(dist(Q, P))
+    f = Kq @ alpha
+    w = Kq[:, p:] - Kq[:, :p] @ Z
+    v = R ** 3 - ((Kq[:, :p] @ X.T) ** 2).sum(1) - np.einsum("qa,ab,qb->q", w, Sinv, w)
+    assert relerr(f, g["f"]) <= 1e-10 and np.abs(v - g["v"]).max() <= 1e-9 * np.abs(g["v"]).max()
