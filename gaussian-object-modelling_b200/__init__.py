@@ -86,6 +86,7 @@ def lib():
         L.gpr_model_get_factor.argtypes = [vp, _dp]
         L.gpr_predict.argtypes = [vp, vp, _dp, _dp, _dp, sz, _dp, _dp, _dp, _dp, _dp]
         L.gpr_predict_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
+        L.gpr_sample_isosurface.argtypes = [vp, vp, cd, cd, cd, cd, sz, _dp, _dp, _dp, _dp, _dp, C.POINTER(sz)]
         L.gpr_model_prepare_variance.argtypes = [vp, vp]
         L.gpr_append.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, sz]
         L.gpr_model_reserve.argtypes = [vp, vp, sz]
@@ -105,7 +106,7 @@ C_ABI_SYMBOLS = [
     "gpr_ctx_create", "gpr_ctx_destroy", "gpr_ctx_num_devices", "gpr_last_error", "gpr_last_pivot",
     "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_tail_size", "gpr_model_get",
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
-    "gpr_model_reserve",
+    "gpr_model_reserve", "gpr_sample_isosurface",
     "gpr_model_state_get", "gpr_model_create_replica", "gpr_selftest_gemm", "gpr_selftest_leaf",
     "gpr_selftest_factor", "gpr_selftest_peak", "gpr_selftest_factor_trace",
 ]
@@ -267,6 +268,24 @@ class GPRegressor:
     def reserve(self, model, capacity):
         """Pre-allocate room for `capacity` points (incremental appends then never reallocate)."""
         _check(lib().gpr_model_reserve(self.ctx._h, model._h, int(capacity)))
+
+    def sample_isosurface(self, model, lo=-1.01, hi=1.01, step=0.07, tol=0.01, var=True, capacity=None):
+        """Batched counterpart of the node's fakeDeterministicSampling (src/gp_node.cpp:998-1100): lattice points
+        with |f| <= tol, as (points (k,3), f, var).  Defaults are the node's (scale 1.01, sample_res 0.07, 0.01)."""
+        cnt = C.c_size_t()
+        auto = capacity is None
+        if auto:
+            na, a = 0, lo
+            while a <= hi:
+                na, a = na + 1, a + step
+            capacity = min(na ** 3, 1 << 22)
+        xs, ys, zs, f = (np.zeros(capacity) for _ in range(4))
+        v = np.zeros(capacity) if var else None
+        _check(lib().gpr_sample_isosurface(self.ctx._h, model._h, lo, hi, step, tol, capacity, _p(xs), _p(ys), _p(zs), _p(f), _p(v), C.byref(cnt)))
+        if auto and cnt.value > capacity:          # more survivors than room: once more with the exact size
+            return self.sample_isosurface(model, lo, hi, step, tol, var, cnt.value)
+        k = min(cnt.value, capacity)
+        return np.stack([xs[:k], ys[:k], zs[:k]], axis=1), f[:k], (None if v is None else v[:k])
 
     def prepare_variance(self, model):
         _check(lib().gpr_model_prepare_variance(self.ctx._h, model._h))

@@ -737,6 +737,103 @@ int gpr_predict_device(gpr_ctx* ctx, gpr_model* m, const double* d_qx, const dou
     return GPR_OK;
 }
 
+int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, double step, double tol, size_t capacity,
+                          double* x, double* y, double* z, double* f, double* var, size_t* count) {
+    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
+    if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
+    if (!count || !(step > 0.0) || !(hi >= lo) || !(tol >= 0.0)) return fail(GPR_ERR_INVALID, "bad lattice or null count");
+    // the lattice axis, accumulated exactly like the node's loops: for (x = -scale; x <= scale; x += pass)
+    std::vector<double> axis;
+    for (double a = lo; a <= hi; a += step) {
+        axis.push_back(a);
+        if (axis.size() > 4096) return fail(GPR_ERR_INVALID, "lattice has more than 4096 points per axis");
+    }
+    const size_t na = axis.size();
+    const unsigned long long total = (unsigned long long)na * na * na;
+    int rc = ensure_on_device(m, 0, false);
+    if (rc) return rc;
+    DeviceCtx* dc = ctx->devs[0];
+    CU(cudaSetDevice(dc->dev));
+    ModelDev& md = m->devs[0];
+    Workspace* ws = nullptr;
+    rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    std::vector<std::pair<unsigned long long, double>> hits;
+    {
+        struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+        cudaStream_t st = ws->st;
+        const size_t chunk = (size_t)std::min<unsigned long long>(total, 1ull << 21);
+        // io: q (3) | f (1) | selected f (1) | selected index (1, as 8-byte integers) | axis | counter
+        rc = ws_reserve(&ws->io, &ws->io_cap, 14 * std::max(chunk + na + 8, (size_t)TB));
+        if (rc) return rc;
+        const size_t cap = ws->io_cap / 14;
+        double* dq = ws->io; double* df = dq + 3 * cap; double* dself = df + cap;
+        unsigned long long* dselidx = reinterpret_cast<unsigned long long*>(dself + cap);
+        double* daxis = dself + 2 * cap;
+        unsigned int* dcounter = reinterpret_cast<unsigned int*>(daxis + na);
+        CU(cudaMemcpyAsync(daxis, axis.data(), na * sizeof(double), cudaMemcpyHostToDevice, st));
+        const size_t N = m->N, ld = m->cap;
+        std::vector<unsigned long long> hidx;
+        std::vector<double> hf;
+        CU(cudaEventRecord(ws->ev[0], st));
+        for (unsigned long long g0 = 0; g0 < total; g0 += chunk) {
+            const int cnt = (int)std::min<unsigned long long>(chunk, total - g0);
+            CU(cudaMemsetAsync(dcounter, 0, sizeof(unsigned int), st));
+            CU(launch_grid_fill(daxis, (int)na, g0, cnt, dq, dq + cap, dq + 2 * cap, st));
+            const bool warp_mode = (size_t)cnt <= (size_t)64 * dc->num_sms;
+            int nsplit = 1;
+            if (!warp_mode) {
+                nsplit = predict_split(cnt, (int)N, dc->num_sms);
+                if (nsplit > 1) { rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, predict_part_doubles(cnt, (int)N)); if (rc) return rc; }
+            }
+            CU(launch_predict(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, (int)m->n, (int)N, dq, dq + cap, dq + 2 * cap, cnt,
+                              df, nullptr, 0, nullptr, 0, (int)m->n_spd, m->kp, warp_mode, ws->mpart, nsplit, st));
+            CU(launch_grid_select(df, g0, cnt, tol, dcounter, dselidx, dself, st));
+            unsigned int found = 0;
+            CU(cudaMemcpyAsync(&found, dcounter, sizeof(found), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (found) {
+                hidx.resize(found); hf.resize(found);
+                CU(cudaMemcpyAsync(hidx.data(), dselidx, found * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(hf.data(), dself, found * sizeof(double), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                for (unsigned int i = 0; i < found; ++i) hits.emplace_back(hidx[i], hf[i]);
+            }
+        }
+        CU(cudaEventRecord(ws->ev[1], st));
+        CU(cudaStreamSynchronize(st));
+        std::lock_guard<std::mutex> lk(ctx->tmu);
+        ctx->timings.predict_mean_ms = ev_ms(ws->ev[0], ws->ev[1]);
+    }
+    std::sort(hits.begin(), hits.end());                 // lattice order: deterministic output
+    *count = hits.size();
+    const size_t keep = std::min(hits.size(), capacity);
+    if (keep == 0 || (!x && !y && !z && !f && !var)) return GPR_OK;
+    std::vector<double> sx(keep), sy(keep), sz(keep), sf(keep);
+    for (size_t i = 0; i < keep; ++i) {
+        const unsigned long long g = hits[i].first;
+        sx[i] = axis[(size_t)(g / ((unsigned long long)na * na))];
+        sy[i] = axis[(size_t)((g / na) % na)];
+        sz[i] = axis[(size_t)(g % na)];
+        sf[i] = hits[i].second;
+    }
+    if (var) {
+        // the expensive part (n^2 flop per point) only for the survivors, through the regular predict path
+        std::vector<double> f2(keep);
+        const double mean_ms = ctx->timings.predict_mean_ms;
+        rc = gpr_predict(ctx, m, sx.data(), sy.data(), sz.data(), keep, f2.data(), var, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> lk(ctx->tmu);
+        ctx->timings.predict_mean_ms += mean_ms;
+        ctx->timings.predict_total_ms += mean_ms;
+    }
+    if (x) memcpy(x, sx.data(), keep * sizeof(double));
+    if (y) memcpy(y, sy.data(), keep * sizeof(double));
+    if (z) memcpy(z, sz.data(), keep * sizeof(double));
+    if (f) memcpy(f, sf.data(), keep * sizeof(double));
+    return GPR_OK;
+}
+
 int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m) {
     if (!ctx || !m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
     for (size_t di = 0; di < ctx->devs.size(); ++di) {

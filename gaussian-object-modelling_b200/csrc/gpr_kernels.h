@@ -33,6 +33,11 @@ size_t predict_small_scratch_doubles(int N);
 cudaError_t launch_predict_small(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
                                  const double* X, size_t ld, double* hio, double* scratch, int q, int want_var,
                                  int want_grad, int want_t, double k0, const KernParams& kp, cudaStream_t st);
+// Lattice generation + |f| <= tol compaction for the batched iso-surface sampler.
+cudaError_t launch_grid_fill(const double* axis, int na, unsigned long long g0, int count, double* qx, double* qy,
+                             double* qz, cudaStream_t st);
+cudaError_t launch_grid_select(const double* f, unsigned long long g0, int count, double tol, unsigned int* counter,
+                               unsigned long long* sel_idx, double* sel_f, cudaStream_t st);
 cudaError_t launch_tangent_basis(const double* grad, size_t ld, int q, double* Tx, double* Ty, cudaStream_t st);
 cudaError_t launch_normalize_rows(double* g, size_t ld, int q, cudaStream_t st);
 // K3' (gpr_var.cu)

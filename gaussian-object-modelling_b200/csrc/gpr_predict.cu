@@ -509,4 +509,47 @@ cudaError_t launch_predict_small(const double* px, const double* py, const doubl
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched iso-surface sampling: the node's fakeDeterministicSampling / samplePoint
+// (src/gp_node.cpp:998-1100) walks a lattice with one thread and one evaluate(q = 1) per lattice point and
+// keeps the points with |f| <= 0.01.  Here the lattice is generated on the device chunk by chunk, the fused
+// mean kernel evaluates it, and the survivors are compacted on the device; the variance (n^2 flop per
+// point) is then computed for the survivors only.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grid_fill_kernel(const double* __restrict__ axis, int na, unsigned long long g0,
+                                                        int count, double* qx, double* qy, double* qz) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= count) return;
+    const unsigned long long g = g0 + i;              // x-major, then y, then z (the node's loop nest)
+    const int iz = (int)(g % na), iy = (int)((g / na) % na), ix = (int)(g / ((unsigned long long)na * na));
+    qx[i] = axis[ix]; qy[i] = axis[iy]; qz[i] = axis[iz];
+}
+
+__global__ void __launch_bounds__(256) grid_select_kernel(const double* __restrict__ f, unsigned long long g0, int count,
+                                                          double tol, unsigned int* counter, unsigned long long* sel_idx,
+                                                          double* sel_f) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= count) return;
+    const double v = f[i];
+    if (fabs(v) <= tol) {                              // src/gp_node.cpp:1075
+        const unsigned int pos = atomicAdd(counter, 1u);
+        sel_idx[pos] = g0 + i;
+        sel_f[pos] = v;
+    }
+}
+
+cudaError_t launch_grid_fill(const double* axis, int na, unsigned long long g0, int count, double* qx, double* qy,
+                             double* qz, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    grid_fill_kernel<<<(count + 255) / 256, 256, 0, st>>>(axis, na, g0, count, qx, qy, qz);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_select(const double* f, unsigned long long g0, int count, double tol, unsigned int* counter,
+                               unsigned long long* sel_idx, double* sel_f, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    grid_select_kernel<<<(count + 255) / 256, 256, 0, st>>>(f, g0, count, tol, counter, sel_idx, sel_f);
+    return cudaGetLastError();
+}
+
 }  // namespace gpr

@@ -176,6 +176,27 @@ public:
         refreshHostMirror(*new_data, *gp, false, p);
     }
 
+    // Extension (no counterpart in the reference's regressor): the node's fakeDeterministicSampling /
+    // samplePoint loop (src/gp_node.cpp:998-1100 — one thread and one evaluate(q = 1) per lattice point of
+    // [-scale, scale]^3 with spacing `pass`, keep |f| <= tol, variance as intensity) as ONE batched call.
+    // points / f / v receive the kept lattice points in lattice order.
+    void sampleIsoSurface(Model::ConstPtr gp, double scale, double pass, double tol, Data& points,
+                          std::vector<double>& f, std::vector<double>& v) {
+        if (!gp) throw GPRegressionException("Empty Model pointer");
+        if (!gp->device) throw GPRegressionException("Model was not created by this regressor");
+        size_t count = 0;
+        int rc = gpr_sample_isosurface(detail::context(), detail::handle(*gp), -scale, scale, pass, tol, 0, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, &count);
+        if (rc != GPR_OK) detail::raise(rc);
+        points.clear();
+        points.coord_x.assign(count, 0.0); points.coord_y.assign(count, 0.0); points.coord_z.assign(count, 0.0);
+        f.assign(count, 0.0); v.assign(count, 0.0);
+        if (count == 0) return;
+        rc = gpr_sample_isosurface(detail::context(), detail::handle(*gp), -scale, scale, pass, tol, count,
+                                   points.coord_x.data(), points.coord_y.data(), points.coord_z.data(), f.data(), v.data(), &count);
+        if (rc != GPR_OK) detail::raise(rc);
+    }
+
 private:
     // :563-572
     void assertData(Data::ConstPtr data) const {

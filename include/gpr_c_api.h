@@ -87,6 +87,16 @@ int gpr_predict(gpr_ctx* ctx, gpr_model* m, const double* qx, const double* qy, 
  * Runs on an internal stream and returns after it has drained. */
 int gpr_predict_device(gpr_ctx* ctx, gpr_model* m, const double* d_qx, const double* d_qy, const double* d_qz,
                        size_t q, double* d_f, double* d_var_or_null, double* d_grad_or_null);
+/* Batched iso-surface sampling — the step right above the path in the reference's node
+ * (fakeDeterministicSampling / samplePoint, src/gp_node.cpp:998-1100: one std::thread and one
+ * evaluate(q = 1) per lattice point, keep the point if |f| <= 0.01, its variance is the intensity).
+ * Lattice: every axis takes the values lo, lo+step, ... <= hi accumulated like the node's loops
+ * (x outermost, z innermost).  The mean is evaluated for the whole lattice on the device; the variance
+ * only for the points that are kept.  Outputs (host, each `capacity` doubles or NULL) are in lattice order;
+ * *count receives the number of lattice points with |f| <= tol (it may exceed capacity: then only the first
+ * `capacity` are written). */
+int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, double step, double tol, size_t capacity,
+                          double* x, double* y, double* z, double* f, double* var_or_null, size_t* count);
 /* Builds L^-1 now (otherwise built by the first call that asks for a variance). */
 int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m);
 

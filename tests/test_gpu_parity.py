@@ -447,3 +447,37 @@ def test_incremental_append_failure_leaves_model_intact(gpr, ctx):
     reg.update(m, P[n0:n0 + 16, 0], P[n0:n0 + 16, 1], P[n0:n0 + 16, 2], y[n0:n0 + 16], s2[n0:n0 + 16])   # still usable
     fresh = reg.create(P[:n0 + 16, 0], P[:n0 + 16, 1], P[:n0 + 16, 2], y[:n0 + 16], s2[:n0 + 16])
     assert m.n == n0 + 16 and relerr(m.alpha, fresh.alpha) <= TOL_ALPHA
+
+
+def test_batched_isosurface_sampler_matches_point_by_point(gpr, ctx):
+    """the node's fakeDeterministicSampling (src/gp_node.cpp:998-1100) as ONE call: same lattice
+    (x outermost, accumulated axis values), same |f| <= 0.01 criterion, variance as the kept points' intensity.
+    Checked against evaluating the whole lattice through evaluate() and filtering on the host."""
+    g = load_golden("ref_mugD_thinplate_R2_node")           # the node's own setting (indefinite K, tail block)
+    P = g["P"]
+    W = gpr.workloads
+    reg = _reg(gpr, ctx, g)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"])
+    Q = W.node_grid()                                         # 29^3, same loop nest
+    f, v = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    keep = np.abs(f) <= 0.01
+    pts, fs, vs = reg.sample_isosurface(m)
+    assert 0 < keep.sum() < len(Q) // 4
+    edge = np.abs(np.abs(f) - 0.01) < 1e-12                   # lattice points sitting on the threshold may flip
+    assert len(pts) >= (keep & ~edge).sum() and len(pts) <= (keep | edge).sum()
+    if not edge.any():
+        assert np.array_equal(pts, Q[keep])
+        assert np.abs(fs - f[keep]).max() <= TOL_MEAN * np.abs(f).max()
+        assert np.abs(vs - v[keep]).max() <= TOL_VAR * np.abs(v).max()
+    pts2, fs2, _ = reg.sample_isosurface(m, var=False, capacity=5)      # truncated output, mean only
+    assert len(pts2) == 5 and np.array_equal(pts2, pts[:5]) and np.array_equal(fs2, fs[:5])
+    # a finer lattice on a bigger SPD model: several device chunks
+    Ps, ys, ss = W.synthetic_cloud(1500, seed=11)
+    reg2 = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    m2 = reg2.create(Ps[:, 0], Ps[:, 1], Ps[:, 2], ys, ss)
+    pts3, fs3, vs3 = reg2.sample_isosurface(m2, lo=-1.2, hi=1.2, step=2.4 / 149, tol=0.002)
+    assert len(pts3) > 100 and np.abs(fs3).max() <= 0.002 and vs3.min() > 0.0
+    r = np.linalg.norm(pts3, axis=1)
+    assert 0.8 < r.min() and r.max() < 1.2                    # the zero level set hugs the unit sphere of the cloud
+    f3, v3 = reg2.evaluate(m2, pts3[:, 0], pts3[:, 1], pts3[:, 2], var=True)
+    assert np.abs(f3 - fs3).max() <= 1e-9 and np.array_equal(v3, vs3)
