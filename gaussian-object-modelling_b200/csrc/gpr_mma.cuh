@@ -175,66 +175,72 @@ struct StageCopy {
 //   IMODE in {STREAM_M, RES_M}; JMODE in {STREAM_M, STREAM_K, RES_M, RES_K}.
 //   Streamed operands: Ag/Bg point at (tile row 0, k = 0) of the operand; lda/ldb are its leading
 //   dimensions.  Resident operands: Ag/Bg are shared-memory tiles with pitch PM.
-//   waitf(kb) is called by ALL threads before the loads of k16-step 8*kb are issued (it may spin on a
-//   readiness flag in thread 0); it returns false to abandon the tile.  It must not contain a barrier.
-// The k16 stages are processed in pairs: one barrier per 32 k, the copies of the next pair are issued
+// The k16 stages are processed in pairs: one barrier per 32 k, the copies of a later pair are issued
 // in the middle of the current pair's DMMA stream (so their address arithmetic and the barrier do not
-// sit in front of a block of tensor instructions), four stage buffers = two pairs in flight.
-// Returns false if abandoned.  Ends with all async copies drained and a __syncthreads().
+// sit in front of a block of tensor instructions).
+//   * both operands streamed M-major (Cholesky accumulation, variance product): SIX stage buffers carved
+//     out of the whole shared-memory block = three pairs in flight; a pair is awaited two iterations
+//     (~9 us of DMMA work) after it was issued (cp.async.wait_group 1).  With two pairs in flight 3.3 % of
+//     the warp samples sat on the copy scoreboard at the top of the loop (ncu r1e).
+//   * otherwise (an operand resident in region 0): four stage buffers in region 1 = two pairs in flight.
+// All dependency waits of the callers happen OUTSIDE this loop (s_abort / the wait functor are kept in the
+// signature for the callers' convenience and are not used).  Always returns true.  Ends with all async
+// copies drained and a __syncthreads().
 template <int IMODE, int JMODE, class WaitF>
 __device__ __forceinline__ bool tile_mainloop(Acc& acc, const double* Ag, size_t lda, const double* Bg, size_t ldb,
-                                              int nk16, double* smem, int* s_abort, WaitF waitf) {
+                                              int nk16, double* smem, int* /*s_abort*/, WaitF /*waitf*/) {
     constexpr bool IS = (IMODE == STREAM_M);
     constexpr bool JS = (JMODE == STREAM_M || JMODE == STREAM_K);
     constexpr bool JK = (JMODE == STREAM_K || JMODE == RES_K);
     constexpr bool JRES = !JS;
+    constexpr bool SS = IS && JS && !JK;                 // both streamed M-major
+    constexpr int NST = SS ? 6 : STAGES;                 // stage buffers per operand
+    constexpr int LA = NST / 2 - 1;                      // pairs issued ahead of the one being computed
+    constexpr int SJ = SS ? STAGE_I : STAGE_J;           // doubles per j stage
     constexpr int PB = JS ? (JK ? PK : PM) : PM;
+    static_assert(!SS || 2 * 6 * STAGE_I <= R0_DBL + R1_DBL, "six M-major stage pairs must fit the block");
     double* r0 = smem;
     double* r1 = smem + R0_DBL;
-    double* istage = JRES ? r1 : r0;     // i stages move to region 1 when j is resident in region 0
-    double* jstage = r1;
+    double* istage = SS ? smem : (JRES ? r1 : r0);       // i stages move to region 1 when j is resident in region 0
+    double* jstage = SS ? smem + 6 * STAGE_I : r1;
     const TileCoord tc;
     StageCopy<false> ci;
     StageCopy<JK> cj;
     if (IS) ci.init(Ag, lda);
     if (JS) cj.init(Bg, ldb);
 
-    auto issue_pair = [&](int kk) {
-        const int s0 = kk & (STAGES - 1), s1 = (kk + 1) & (STAGES - 1);
-        if (IS) ci.issue_pair(istage + s0 * STAGE_I, istage + s1 * STAGE_I);
-        if (JS) cj.issue_pair(jstage + s0 * STAGE_J, jstage + s1 * STAGE_J);
-        cp_async_commit();
+    // stage index of k16 step kk is kk % NST; ld_s / cp_s walk it without a division
+    int ld_s = 0, cp_s = 0;
+    auto issue_pair = [&](bool real) {
+        if (real) {
+            if (IS) ci.issue_pair(istage + ld_s * STAGE_I, istage + (ld_s + 1) * STAGE_I);
+            if (JS) cj.issue_pair(jstage + ld_s * SJ, jstage + (ld_s + 1) * SJ);
+            ld_s = (ld_s + 2 == NST) ? 0 : ld_s + 2;
+        }
+        cp_async_commit();                               // an (empty) group per iteration keeps the accounting uniform
     };
-    auto a_of = [&](int kk) -> const double* {
-        return IS ? (istage + (kk & (STAGES - 1)) * STAGE_I) : (Ag + (size_t)kk * KT * PM);
+    auto a_of = [&](int kk, int h) -> const double* {
+        return IS ? (istage + (cp_s + h) * STAGE_I) : (Ag + (size_t)(kk + h) * KT * PM);
     };
-    auto b_of = [&](int kk) -> const double* {
-        return JS ? (jstage + (kk & (STAGES - 1)) * STAGE_J) : (JK ? (Bg + kk * KT) : (Bg + (size_t)kk * KT * PM));
+    auto b_of = [&](int kk, int h) -> const double* {
+        return JS ? (jstage + (cp_s + h) * SJ) : (JK ? (Bg + (kk + h) * KT) : (Bg + (size_t)(kk + h) * KT * PM));
     };
 
-    bool ok = true;
-    if (nk16 > 0) {
-        if (!waitf(0)) *s_abort = 1;
-    }
-    __syncthreads();
-    if (*s_abort) return false;
-    if (nk16 > 0) issue_pair(0);
+    __syncthreads();                                     // the previous user of the shared-memory block is done
+#pragma unroll
+    for (int p = 0; p < LA; ++p) issue_pair(2 * p < nk16);
     for (int kk = 0; kk < nk16; kk += 2) {
-        cp_async_wait<0>();
-        const int nxt = kk + 2;
-        if (nxt < nk16 && (nxt & 7) == 0) {
-            if (!waitf(nxt >> 3)) *s_abort = 1;
-        }
-        __syncthreads();
-        if (*s_abort) { ok = false; break; }
-        compute_ks<JK, 0, 2>(acc, a_of(kk), PM, b_of(kk), PB, tc);
-        if (nxt < nk16) issue_pair(nxt);
-        compute_ks<JK, 2, 4>(acc, a_of(kk), PM, b_of(kk), PB, tc);
-        compute_ks<JK, 0, 4>(acc, a_of(kk + 1), PM, b_of(kk + 1), PB, tc);
+        cp_async_wait<LA - 1>();                         // pair kk has landed (for this thread) ...
+        __syncthreads();                                 // ... and for everybody; pair kk-2 is consumed by all
+        compute_ks<JK, 0, 2>(acc, a_of(kk, 0), PM, b_of(kk, 0), PB, tc);
+        issue_pair(kk + 2 * LA < nk16);
+        compute_ks<JK, 2, 4>(acc, a_of(kk, 0), PM, b_of(kk, 0), PB, tc);
+        compute_ks<JK, 0, 4>(acc, a_of(kk, 1), PM, b_of(kk, 1), PB, tc);
+        cp_s = (cp_s + 2 == NST) ? 0 : cp_s + 2;
     }
     cp_async_wait<0>();
     __syncthreads();
-    return ok;
+    return true;
 }
 
 struct NoWait {
