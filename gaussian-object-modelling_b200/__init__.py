@@ -87,6 +87,7 @@ def lib():
         L.gpr_predict.argtypes = [vp, vp, _dp, _dp, _dp, sz, _dp, _dp, _dp, _dp, _dp]
         L.gpr_predict_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
         L.gpr_sample_isosurface.argtypes = [vp, vp, cd, cd, cd, cd, sz, _dp, _dp, _dp, _dp, _dp, C.POINTER(sz)]
+        L.gpr_project.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, _dp, sz, cd, cd, C.c_uint, cd, _dp, _dp, _dp, C.POINTER(ci)]
         L.gpr_model_prepare_variance.argtypes = [vp, vp]
         L.gpr_append.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, sz]
         L.gpr_model_reserve.argtypes = [vp, vp, sz]
@@ -106,7 +107,7 @@ C_ABI_SYMBOLS = [
     "gpr_ctx_create", "gpr_ctx_destroy", "gpr_ctx_num_devices", "gpr_last_error", "gpr_last_pivot",
     "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_tail_size", "gpr_model_get",
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
-    "gpr_model_reserve", "gpr_sample_isosurface",
+    "gpr_model_reserve", "gpr_sample_isosurface", "gpr_project",
     "gpr_model_state_get", "gpr_model_create_replica", "gpr_selftest_gemm", "gpr_selftest_leaf",
     "gpr_selftest_factor", "gpr_selftest_peak", "gpr_selftest_factor_trace",
 ]
@@ -286,6 +287,20 @@ class GPRegressor:
             return self.sample_isosurface(model, lo, hi, step, tol, var, cnt.value)
         k = min(cnt.value, capacity)
         return np.stack([xs[:k], ys[:k], zs[:k]], axis=1), f[:k], (None if v is None else v[:k])
+
+    def project(self, model, points, normals, f_tol=1e-2, improve_tol=1e-7, max_iter=500, step_mul=0.001):
+        """Batched AtlasBase::project (include/atlas/atlas.hpp:201-276, same defaults): gradient-descent projection of
+        every row of `points` (k,3) onto f = 0, starting with the un-normalised gradients `normals` (k,3).
+        Returns (projected (k,3), status (k,) ints: iterations used, or -max_iter)."""
+        pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 3).T)
+        nrm = np.ascontiguousarray(np.asarray(normals, dtype=np.float64).reshape(-1, 3).T)
+        k = pts.shape[1]
+        out = np.zeros((3, k))
+        st = np.zeros(k, dtype=np.int32)
+        _check(lib().gpr_project(self.ctx._h, model._h, _p(pts[0]), _p(pts[1]), _p(pts[2]), _p(nrm[0]), _p(nrm[1]), _p(nrm[2]), k,
+                                 f_tol, improve_tol, int(max_iter), step_mul, _p(out[0]), _p(out[1]), _p(out[2]),
+                                 st.ctypes.data_as(C.POINTER(C.c_int))))
+        return np.ascontiguousarray(out.T), st
 
     def prepare_variance(self, model):
         _check(lib().gpr_model_prepare_variance(self.ctx._h, model._h))

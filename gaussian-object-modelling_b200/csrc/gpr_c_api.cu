@@ -6,6 +6,7 @@
 #include "gpr_mma.cuh"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -831,6 +832,52 @@ int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, doub
     if (y) memcpy(y, sy.data(), keep * sizeof(double));
     if (z) memcpy(z, sz.data(), keep * sizeof(double));
     if (f) memcpy(f, sf.data(), keep * sizeof(double));
+    return GPR_OK;
+}
+
+int gpr_project(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* nx,
+                const double* ny, const double* nz, size_t count, double f_tol, double improve_tol, unsigned max_iter,
+                double step_mul, double* ox, double* oy, double* oz, int* status) {
+    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
+    if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
+    if (!x || !y || !z || !nx || !ny || !nz || !ox || !oy || !oz || count == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
+    if (count > (size_t)1 << 24 || max_iter > (unsigned)1 << 24) return fail(GPR_ERR_INVALID, "too many points or iterations");
+    int rc = ensure_on_device(m, 0, false);
+    if (rc) return rc;
+    DeviceCtx* dc = ctx->devs[0];
+    CU(cudaSetDevice(dc->dev));
+    ModelDev& md = m->devs[0];
+    Workspace* ws = nullptr;
+    rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    cudaStream_t st = ws->st;
+    rc = ws_reserve(&ws->io, &ws->io_cap, 14 * std::max(count, (size_t)TB));
+    if (rc) return rc;
+    const size_t cap = ws->io_cap / 14, ld = m->cap;
+    double* din = ws->io;                  // x|y|z|nx|ny|nz
+    double* dout = din + 6 * cap;          // x|y|z
+    int* dstat = reinterpret_cast<int*>(dout + 3 * cap);
+    const double* src[6] = {x, y, z, nx, ny, nz};
+    for (int c = 0; c < 6; ++c) CU(cudaMemcpyAsync(din + c * cap, src[c], count * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(ws->ev[0], st));
+    CU(launch_project(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, (int)m->n, din, cap, (int)count, f_tol, improve_tol,
+                      (int)max_iter, step_mul, dout, dstat, m->kp, st));
+    CU(cudaEventRecord(ws->ev[1], st));
+    std::vector<int> hstat(count);
+    CU(cudaMemcpyAsync(ox, dout, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(oy, dout + cap, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(oz, dout + 2 * cap, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hstat.data(), dstat, count * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    {
+        std::lock_guard<std::mutex> lk(ctx->tmu);
+        ctx->timings.predict_mean_ms = ev_ms(ws->ev[0], ws->ev[1]);
+        ctx->timings.predict_total_ms = ctx->timings.predict_mean_ms;
+    }
+    bool bad = false;
+    for (size_t i = 0; i < count; ++i) { if (status) status[i] = hstat[i]; bad = bad || hstat[i] == INT_MIN; }
+    if (bad) return fail(GPR_ERR_INVALID, "f is nan or inf");       // include/atlas/atlas.hpp:230
     return GPR_OK;
 }
 

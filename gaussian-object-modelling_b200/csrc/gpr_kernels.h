@@ -38,6 +38,10 @@ cudaError_t launch_grid_fill(const double* axis, int na, unsigned long long g0, 
                              double* qz, cudaStream_t st);
 cudaError_t launch_grid_select(const double* f, unsigned long long g0, int count, double tol, unsigned int* counter,
                                unsigned long long* sel_idx, double* sel_f, cudaStream_t st);
+// Batched gradient-descent projection onto f = 0 (AtlasBase::project), one CTA per point.
+cudaError_t launch_project(const double* px, const double* py, const double* pz, const double* alpha, int n,
+                           const double* xyz_in, size_t ld, int count, double f_tol, double improve_tol, int max_iter,
+                           double step_mul, double* out, int* status, const KernParams& kp, cudaStream_t st);
 cudaError_t launch_tangent_basis(const double* grad, size_t ld, int q, double* Tx, double* Ty, cudaStream_t st);
 cudaError_t launch_normalize_rows(double* g, size_t ld, int q, cudaStream_t st);
 // K3' (gpr_var.cu)

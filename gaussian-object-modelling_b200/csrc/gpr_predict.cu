@@ -16,6 +16,7 @@
 //   * thread-per-query : training points broadcast from shared memory, n sequential terms per thread;
 //   * warp-per-query   : lanes stride over the training points, warp-shuffle reduction — for the
 //                        small batches (down to q = 1) that the reference's callers issue.
+#include <climits>
 #include "gpr_common.cuh"
 #include "gpr_kernels.h"
 
@@ -549,6 +550,101 @@ cudaError_t launch_grid_select(const double* f, unsigned long long g0, int count
                                unsigned long long* sel_idx, double* sel_f, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     grid_select_kernel<<<(count + 255) / 256, 256, 0, st>>>(f, g0, count, tol, counter, sel_idx, sel_f);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched projection onto the iso-surface f = 0: AtlasBase::project
+// (include/atlas/atlas.hpp:201-276) is a fixed-step gradient descent that calls evaluate(q = 1) twice per
+// iteration, up to 500 iterations, for ONE point.  Here one CTA owns one point and runs the whole iteration
+// on the device (f and the un-normalised gradient over all training points per iteration, block-reduced in
+// a fixed order); any number of points are projected by one launch.  Same update rule and the same three
+// stopping criteria; the variance the reference also computes in every iteration is only printed there and
+// is not computed here.
+// status: > 0 iterations used when a criterion was met (f_tol or improve_tol), -(max_iter) when the iteration
+// budget ran out, INT_MIN if f became NaN/Inf (the reference throws "f is nan or inf").
+// ---------------------------------------------------------------------------------------------
+struct ProjectArgs {
+    const double* px; const double* py; const double* pz; const double* alpha; int n;
+    const double* x; const double* y; const double* z;       // start points
+    const double* nx; const double* ny; const double* nz;    // initial (un-normalised) gradients
+    int count;
+    double f_tol, improve_tol, step_mul; int max_iter;
+    double* ox; double* oy; double* oz; int* status;
+    KernParams kp;
+};
+
+template <int KIND>
+__device__ __forceinline__ void block_eval(const ProjectArgs& a, double qx, double qy, double qz, double (&out)[4],
+                                           double (*red)[4]) {
+    double f = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+    for (int j = threadIdx.x; j < a.n; j += 256) {
+        const double al = a.alpha[j];
+        const double dx = qx - a.px[j], dy = qy - a.py[j], dz = qz - a.pz[j];
+        const double d = sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
+        const double kv = kern_value<KIND>(a.kp, d);
+        f = fma(kv, al, f);
+        const double w = al * kern_diff<KIND>(a.kp, d, kv);
+        gx = fma(w, dx, gx); gy = fma(w, dy, gy); gz = fma(w, dz, gz);
+    }
+    double v[4] = {f, gx, gy, gz};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+        for (int c = 0; c < 4; ++c) red[threadIdx.x >> 5][c] = v[c];
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double t = 0.0;
+        for (int w8 = 0; w8 < 8; ++w8) t += red[w8][c];
+        out[c] = t;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) project_kernel(ProjectArgs a) {
+    __shared__ double red[8][4];
+    const int b = blockIdx.x;
+    if (b >= a.count) return;
+    double cx = a.x[b], cy = a.y[b], cz = a.z[b];
+    double gx = a.nx[b], gy = a.ny[b], gz = a.nz[b];
+    double e[4];
+    block_eval<KIND>(a, cx, cy, cz, e, red);                     // atlas.hpp:225
+    double f_cur = e[0];
+    int status = -a.max_iter;
+    for (int iter = 0; iter < a.max_iter; ++iter) {
+        if (isnan(f_cur) || isinf(f_cur)) { status = INT_MIN; break; }                 // :227-231
+        if (fabs(f_cur) < a.f_tol) { status = iter + 1; break; }                        // :236-241
+        const double sx = a.step_mul * f_cur * gx, sy = a.step_mul * f_cur * gy, sz = a.step_mul * f_cur * gz;   // :245
+        const double ns2 = sx * sx + sy * sy + sz * sz;
+        if (ns2 <= 1e4 && ns2 > 1e-12) { cx -= sx; cy -= sy; cz -= sz; }                // :246-251 (isMuchSmallerThan / isZero)
+        block_eval<KIND>(a, cx, cy, cz, e, red);                                        // :259
+        const double ng2 = e[1] * e[1] + e[2] * e[2] + e[3] * e[3];
+        if (ng2 <= 1e4 && ng2 > 1e-10) { gx = e[1]; gy = e[2]; gz = e[3]; }            // :260-265
+        if (fabs(e[0] - f_cur) < a.improve_tol) { status = iter + 1; break; }           // :266-271
+        f_cur = e[0];
+    }
+    if (threadIdx.x == 0) { a.ox[b] = cx; a.oy[b] = cy; a.oz[b] = cz; a.status[b] = status; }
+}
+
+cudaError_t launch_project(const double* px, const double* py, const double* pz, const double* alpha, int n,
+                           const double* xyz_in /*x|y|z|nx|ny|nz, each `ld` apart*/, size_t ld, int count, double f_tol,
+                           double improve_tol, int max_iter, double step_mul, double* out /*x|y|z, ld apart*/,
+                           int* status, const KernParams& kp, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    ProjectArgs a;
+    a.px = px; a.py = py; a.pz = pz; a.alpha = alpha; a.n = n;
+    a.x = xyz_in; a.y = xyz_in + ld; a.z = xyz_in + 2 * ld; a.nx = xyz_in + 3 * ld; a.ny = xyz_in + 4 * ld; a.nz = xyz_in + 5 * ld;
+    a.count = count; a.f_tol = f_tol; a.improve_tol = improve_tol; a.step_mul = step_mul; a.max_iter = max_iter;
+    a.ox = out; a.oy = out + ld; a.oz = out + 2 * ld; a.status = status; a.kp = kp;
+    switch (kp.kind) {
+        case 0: project_kernel<0><<<count, 256, 0, st>>>(a); break;
+        case 1: project_kernel<1><<<count, 256, 0, st>>>(a); break;
+        default: project_kernel<2><<<count, 256, 0, st>>>(a); break;
+    }
     return cudaGetLastError();
 }
 

@@ -97,6 +97,16 @@ int gpr_predict_device(gpr_ctx* ctx, gpr_model* m, const double* d_qx, const dou
  * `capacity` are written). */
 int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, double step, double tol, size_t capacity,
                           double* x, double* y, double* z, double* f, double* var_or_null, size_t* count);
+/* Batched projection onto the iso-surface f = 0 — AtlasBase::project (include/atlas/atlas.hpp:201-276: fixed-step
+ * gradient descent, two evaluate(q = 1) calls per iteration, up to max_iter = 500 iterations per point).
+ * Same update rule (x -= step_mul * f(x) * g, g = last accepted un-normalised gradient, first one given by the
+ * caller) and the same stopping criteria (|f| < f_tol, |f_new - f_old| < improve_tol, max_iter); the whole
+ * iteration of every point runs on the device in ONE launch.  x..nz: count host doubles each; ox, oy, oz: count
+ * each; status (count ints or NULL): iterations used when a tolerance was met, -max_iter when the budget ran
+ * out.  Returns GPR_ERR_INVALID "f is nan or inf" if that happened for any point (the reference throws). */
+int gpr_project(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* nx,
+                const double* ny, const double* nz, size_t count, double f_tol, double improve_tol, unsigned max_iter,
+                double step_mul, double* ox, double* oy, double* oz, int* status_or_null);
 /* Builds L^-1 now (otherwise built by the first call that asks for a variance). */
 int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m);
 

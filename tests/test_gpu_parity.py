@@ -481,3 +481,46 @@ def test_batched_isosurface_sampler_matches_point_by_point(gpr, ctx):
     assert 0.8 < r.min() and r.max() < 1.2                    # the zero level set hugs the unit sphere of the cloud
     f3, v3 = reg2.evaluate(m2, pts3[:, 0], pts3[:, 1], pts3[:, 2], var=True)
     assert np.abs(f3 - fs3).max() <= 1e-9 and np.array_equal(v3, vs3)
+
+
+def _reference_project(reg, m, p, g, f_tol, improve_tol, max_iter, step_mul):
+    """include/atlas/atlas.hpp:201-276 transcribed, driving the q = 1 evaluate calls the way AtlasBase does."""
+    cur, g = np.array(p, dtype=np.float64), np.array(g, dtype=np.float64)
+    for it in range(max_iter):
+        f_cur = reg.evaluate(m, cur[:1], cur[1:2], cur[2:3])[0]
+        if abs(f_cur) < f_tol:
+            return cur, it + 1
+        step = step_mul * f_cur * g
+        if 1e-6 < np.linalg.norm(step) <= 100.0:
+            cur = cur - step
+        f_new, _, N = reg.evaluate(m, cur[:1], cur[1:2], cur[2:3], var=True, grad=True)
+        if 1e-5 < np.linalg.norm(N[0]) <= 100.0:
+            g = N[0]
+        if abs(f_new[0] - f_cur) < improve_tol:
+            return cur, it + 1
+    return cur, -max_iter
+
+
+def test_batched_projection_matches_the_atlas_loop(gpr, ctx):
+    """SURVEY §8(f).3: AtlasBase::project for many points in one launch, against the reference's loop transcribed
+    over single-query evaluate calls (same update rule, same three stopping criteria)."""
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(1200, seed=12)
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+    rng = np.random.default_rng(12)
+    d = rng.standard_normal((6, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    start = d * rng.uniform(0.85, 1.25, size=(6, 1))                   # inside and outside the unit-sphere surface
+    _, _, g0 = reg.evaluate(m, start[:, 0], start[:, 1], start[:, 2], var=True, grad=True)
+    kw = dict(f_tol=1e-3, improve_tol=1e-9, max_iter=80, step_mul=0.2)
+    out, st = reg.project(m, start, g0, **kw)
+    for i in range(len(start)):
+        ref_out, ref_it = _reference_project(reg, m, start[i], g0[i], **kw)
+        assert st[i] == ref_it
+        assert np.abs(out[i] - ref_out).max() <= 1e-9
+    f_end = reg.evaluate(m, out[:, 0], out[:, 1], out[:, 2])
+    assert (st > 0).all() and np.abs(f_end).max() < 1e-3               # all converged onto the surface
+    assert np.abs(np.linalg.norm(out, axis=1) - 1.0).max() < 0.1
+    # budget exhaustion is reported, not hidden (the reference prints and returns the last iterate)
+    out2, st2 = reg.project(m, start[:2], g0[:2], f_tol=1e-12, improve_tol=0.0, max_iter=5, step_mul=0.2)
+    assert (st2 == -5).all()
