@@ -65,6 +65,7 @@ struct gpr_ctx {
     std::mutex tmu;
     size_t query_tile = 0;     // queries per variance batch (multiple of 128)
     int chol_serial = 0;
+    int refine_steps = 1;      // iterative-refinement steps of alpha after the triangular solves
 };
 
 static int ws_acquire(DeviceCtx* dc, Workspace** out) {
@@ -265,6 +266,17 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     if (m->n_tail == 0) {
         CU(launch_trsv(0, m->L, N, nb, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
         CU(launch_trsv(1, m->L, N, nb, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
+        // iterative refinement with a double-double residual (gpr_solve.cu); GPR_REFINE=0 switches it off
+        for (int it = 0; it < ctx->refine_steps; ++it) {
+            rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, residual_scratch_doubles((int)N) + 2 * N);
+            if (rc) return rc;
+            double* rr = ws->mpart + residual_scratch_doubles((int)N);
+            double* dd = rr + N;
+            CU(launch_residual(md.xyz, N, m->s2, m->label, md.alpha, (int)n, (int)N, ws->mpart, rr, m->kp, st));
+            CU(launch_trsv(0, m->L, N, nb, m->Dinv, rr, m->zfwd, m->scratch, dc->num_sms, st));
+            CU(launch_trsv(1, m->L, N, nb, m->Dinv, m->zfwd, dd, m->scratch, dc->num_sms, st));
+            CU(launch_axpy1(md.alpha, dd, (int)n, st));
+        }
     } else {
         const size_t p = m->n_spd, mt = m->n_tail;
         const int nslab = (int)((mt + 31) / 32), mp = 32 * nslab;
@@ -599,6 +611,7 @@ int gpr_ctx_create(const int* devices, int ndev, gpr_ctx** out) {
         if (v > 0) ctx->query_tile = (size_t)(v + TB - 1) / TB * TB;
     }
     if (const char* s = getenv("GPR_CHOL_SERIAL")) ctx->chol_serial = atoi(s);
+    if (const char* s = getenv("GPR_REFINE")) ctx->refine_steps = std::max(0, std::min(4, atoi(s)));
     *out = ctx;
     return GPR_OK;
 }
@@ -1016,6 +1029,16 @@ static int append_incremental(gpr_model* m, const double* x, const double* y, co
     const int nb1 = (int)(N1 / TB);
     CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
     CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
+    for (int it = 0; it < ctx->refine_steps; ++it) {          // same refinement as after a fit (gpr_solve.cu)
+        rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, residual_scratch_doubles((int)N1) + 2 * N1);
+        if (rc) return rc;
+        double* rr = ws->mpart + residual_scratch_doubles((int)N1);
+        double* dd = rr + N1;
+        CU(launch_residual(md.xyz, ld, m->s2, m->label, md.alpha, (int)n1, (int)N1, ws->mpart, rr, m->kp, st));
+        CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, rr, m->zfwd, m->scratch, dc->num_sms, st));
+        CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, dd, m->scratch, dc->num_sms, st));
+        CU(launch_axpy1(md.alpha, dd, (int)n1, st));
+    }
     CU(cudaEventRecord(ws->ev[2], st));
     m->h_alpha.resize(n1);
     CU(cudaMemcpyAsync(m->h_alpha.data(), md.alpha, n1 * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -18,6 +18,11 @@ cudaError_t launch_linv(const double* L, double* X, size_t ld, int nb, const dou
 // K3 (gpr_solve.cu).  scratch: at least 4 + nb ints.
 cudaError_t launch_trsv(int backward, const double* L, size_t ld, int nb, const double* Dinv, const double* rhs,
                         double* out, int* scratch, int num_sms, cudaStream_t st);
+// Iterative refinement of alpha (gpr_solve.cu): r = y - K alpha in double-double; part: residual_scratch_doubles(N).
+size_t residual_scratch_doubles(int N);
+cudaError_t launch_residual(const double* xyz, size_t ld, const double* sigma2, const double* label, const double* alpha,
+                            int n, int N, double* part, double* r, const KernParams& kp, cudaStream_t st);
+cudaError_t launch_axpy1(double* a, const double* d, int n, cudaStream_t st);
 // K4 (gpr_predict.cu).  part/split: optional split of the training points over CTAs for the thread-per-query
 // kernel (split from predict_split, part of predict_part_doubles(q, N) doubles); bit-identical results either way.
 int predict_split(int q_span, int N, int num_sms);

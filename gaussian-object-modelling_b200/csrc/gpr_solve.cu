@@ -184,4 +184,94 @@ cudaError_t launch_trsv(int backward, const double* L, size_t ld, int nb, const 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Iterative refinement of alpha (one step after the two triangular solves): r = y - K alpha with K
+// re-evaluated entry by entry exactly as cov_build_kernel computed it (the factorisation overwrote K) and
+// the products accumulated in double-double (TwoProd by FMA + TwoSum), then L L^T delta = r, alpha += delta.
+// The tile Cholesky multiplies by explicit inverses of the 128x128 diagonal blocks (TRSM / TRSV as GEMM /
+// GEMV), which costs about one digit of alpha compared with substitution; one refinement step with an
+// accurate residual gives it back (tools/accuracy_report.py, profiles/accuracy_*.json).
+//   grid (row blocks of 256, chunks of 1024 columns); partial sums [chunk][2][N] reduced in chunk order.
+// ---------------------------------------------------------------------------------------------
+constexpr int RCH = 1024;
+
+// (s, c) += a * b in double-double: explicit round-to-nearest intrinsics so that nvcc cannot contract the
+// product into the following addition (that would destroy the error-free transformations).
+__device__ __forceinline__ void dd_add(double& s, double& c, double ph) {
+    const double t = __dadd_rn(s, ph);
+    const double bb = __dsub_rn(t, s);
+    const double e = __dadd_rn(__dsub_rn(s, __dsub_rn(t, bb)), __dsub_rn(ph, bb));      // TwoSum error
+    s = t;
+    c = __dadd_rn(c, e);
+}
+__device__ __forceinline__ void dd_add_prod(double& s, double& c, double a, double b) {
+    const double ph = __dmul_rn(a, b);
+    const double pl = __fma_rn(a, b, -ph);            // exact low part of the product
+    dd_add(s, c, ph);
+    c = __dadd_rn(c, pl);
+}
+
+__global__ void __launch_bounds__(256) residual_partial_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                               const double* __restrict__ z, const double* __restrict__ alpha,
+                                                               int n, int N, double* __restrict__ part, KernParams kp) {
+    __shared__ double4 sp[RCH];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int base = blockIdx.y * RCH;
+    for (int k = threadIdx.x; k < RCH; k += 256) {
+        const int j = base + k;
+        sp[k] = j < n ? make_double4(x[j], y[j], z[j], alpha[j]) : make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+    __syncthreads();
+    if (i >= n) return;
+    const double xi = x[i], yi = y[i], zi = z[i];
+    double s = 0.0, c = 0.0;
+    const int lim = min(RCH, n - base);
+#pragma unroll 2
+    for (int k = 0; k < lim; ++k) {
+        const double4 p = sp[k];
+        // dist_exact is bit-symmetric in its two points ((-dx)^2 == dx^2), so this is the very entry K_ij that
+        // cov_build_kernel wrote and the factorisation read
+        dd_add_prod(s, c, kern_value_exact(kp, dist_exact(xi, yi, zi, p.x, p.y, p.z)), p.w);
+    }
+    part[((size_t)blockIdx.y * 2) * N + i] = s;
+    part[((size_t)blockIdx.y * 2 + 1) * N + i] = c;
+}
+
+__global__ void __launch_bounds__(256) residual_finish_kernel(const double* __restrict__ part, int nchunks, int n, int N,
+                                                              const double* __restrict__ label, const double* __restrict__ sigma2,
+                                                              const double* __restrict__ alpha, double* __restrict__ r) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    if (i >= n) { r[i] = 0.0; return; }
+    double s = 0.0, c = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        dd_add(s, c, part[((size_t)ch * 2) * N + i]);
+        c = __dadd_rn(c, part[((size_t)ch * 2 + 1) * N + i]);
+    }
+    dd_add_prod(s, c, sigma2[i], alpha[i]);           // the diagonal noise term (gp_regressor.hpp:154-155)
+    r[i] = __dsub_rn(__dsub_rn(label[i], s), c);
+}
+
+__global__ void __launch_bounds__(256) axpy1_kernel(double* __restrict__ a, const double* __restrict__ d, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) a[i] += d[i];
+}
+
+size_t residual_scratch_doubles(int N) { return (size_t)2 * ((N + RCH - 1) / RCH) * N; }
+
+cudaError_t launch_residual(const double* xyz, size_t ld, const double* sigma2, const double* label, const double* alpha,
+                            int n, int N, double* part, double* r, const KernParams& kp, cudaStream_t st) {
+    const int nchunks = (n + RCH - 1) / RCH;
+    dim3 grid((n + 255) / 256, nchunks);
+    residual_partial_kernel<<<grid, 256, 0, st>>>(xyz, xyz + ld, xyz + 2 * ld, alpha, n, N, part, kp);
+    residual_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, nchunks, n, N, label, sigma2, alpha, r);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_axpy1(double* a, const double* d, int n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    axpy1_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, d, n);
+    return cudaGetLastError();
+}
+
 }  // namespace gpr

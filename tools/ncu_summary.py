@@ -8,7 +8,10 @@ import sys
 rep, out = sys.argv[1], sys.argv[2]
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
 q = int(sys.argv[4]) if len(sys.argv) > 4 else 148 * 128
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+if rep.endswith(".csv"):          # already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv > x_raw.csv
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}
@@ -48,7 +51,7 @@ for r in rows[2:]:
             cells.append("%s %s" % (v, u) if u and u not in ("%", "register/thread") else v)
         else:
             cells.append("-")
-    key = next((k for k in alg if k in short), None)
+    key = next((k for k in alg if k in short), None) if len(sys.argv) <= 5 else None
     work = ach = "-"
     if key:
         kind, amount = alg[key]
