@@ -63,6 +63,12 @@ static int run(std::ifstream& in, std::ofstream& out, std::shared_ptr<Cov> kerne
     std::vector<double> ff, vv;
     reg->evaluate(cgp, one, ff, vv);
     out << "single " << ff[0] << ' ' << vv[0] << "\n";
+    {   // extension: the node's per-point sampling loop (src/gp_node.cpp:998-1100) as one batched call
+        Data iso; std::vector<double> fi, vi;
+        reg->sampleIsoSurface(cgp, 1.01, 0.07, 0.01, iso, fi, vi);
+        double vsum = 0; for (double x : vi) vsum += x;
+        out << "iso " << iso.coord_x.size() << ' ' << vsum << "\n";
+    }
     if (k > 0) {
         reg->template update<false>(extra, gp);
         out << "alpha_updated"; for (int i = 0; i < n + k; ++i) out << ' ' << gp->alpha(i); out << "\n";

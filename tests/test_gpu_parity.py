@@ -352,6 +352,11 @@ def test_cxx_dropin_headers_end_to_end(gpr, orc, tmp_path):
     assert abs(rows["single"][0] - g["f"][0]) <= 1e-9 and abs(rows["single"][1] - g["v"][0]) <= 1e-7 * np.abs(g["v"]).max()
     assert relerr(rows["alpha_updated"], g["alpha_updated"]) <= TOL_ALPHA
     assert relerr(rows["f_updated"], g["f_updated"][:q]) <= TOL_MEAN and rows["R_updated"][0] == rows["R"][0]
+    # the batched sampler through the C++ header agrees with the Python mirror of the same C-ABI call
+    reg = gpr.GPRegressor("thin_plate", g["R"])
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"])
+    pts, fs, vs = reg.sample_isosurface(m)
+    assert int(rows["iso"][0]) == len(pts) and abs(rows["iso"][1] - vs.sum()) <= 1e-9 * max(1.0, abs(vs.sum()))
 
 
 # ---- K5: incremental append (rank-k row append of L and L^-1) vs refit, SURVEY row a13 / config 4 -------------
