@@ -37,7 +37,9 @@ constexpr int STAGE_I = KT * PM;           // doubles per i-operand stage (M-maj
 constexpr int STAGE_J = TB * PK;           // doubles per j-operand stage (max of both layouts: 2560 >= 2112)
 constexpr int R0_DBL = TB * PM;            // region 0: resident tile / i stages   (16896 doubles)
 constexpr int R1_DBL = STAGES * STAGE_J;   // region 1: j stages (or i stages when j is resident)
-constexpr size_t TILE_SMEM_BYTES = (size_t)(R0_DBL + R1_DBL) * sizeof(double);   // 217,088 B
+constexpr int SS_STAGES = 6;               // stage buffers per operand when BOTH operands are streamed
+constexpr int SS_DBL = SS_STAGES * (STAGE_I + STAGE_J);                              // 28,032 doubles
+constexpr size_t TILE_SMEM_BYTES = (size_t)(SS_DBL > R0_DBL + R1_DBL ? SS_DBL : R0_DBL + R1_DBL) * sizeof(double);   // 224,256 B
 
 static_assert(STAGES * STAGE_I <= R0_DBL, "i stages must fit region 0");
 static_assert(STAGES * STAGE_I <= R1_DBL, "i stages must fit region 1");
@@ -178,7 +180,7 @@ struct StageCopy {
 // The k16 stages are processed in pairs: one barrier per 32 k, the copies of a later pair are issued
 // in the middle of the current pair's DMMA stream (so their address arithmetic and the barrier do not
 // sit in front of a block of tensor instructions).
-//   * both operands streamed M-major (Cholesky accumulation, variance product): SIX stage buffers carved
+//   * both operands streamed (Cholesky accumulation, variance product, L^-1 accumulation): SIX stage buffers carved
 //     out of the whole shared-memory block = three pairs in flight; a pair is awaited two iterations
 //     (~9 us of DMMA work) after it was issued (cp.async.wait_group 1).  With two pairs in flight 3.3 % of
 //     the warp samples sat on the copy scoreboard at the top of the loop (ncu r1e).
@@ -193,16 +195,16 @@ __device__ __forceinline__ bool tile_mainloop(Acc& acc, const double* Ag, size_t
     constexpr bool JS = (JMODE == STREAM_M || JMODE == STREAM_K);
     constexpr bool JK = (JMODE == STREAM_K || JMODE == RES_K);
     constexpr bool JRES = !JS;
-    constexpr bool SS = IS && JS && !JK;                 // both streamed M-major
-    constexpr int NST = SS ? 6 : STAGES;                 // stage buffers per operand
+    constexpr bool SS = IS && JS;                        // both operands streamed
+    constexpr int NST = SS ? SS_STAGES : STAGES;         // stage buffers per operand
     constexpr int LA = NST / 2 - 1;                      // pairs issued ahead of the one being computed
-    constexpr int SJ = SS ? STAGE_I : STAGE_J;           // doubles per j stage
+    constexpr int SJ = (SS && !JK) ? STAGE_I : STAGE_J;  // doubles per j stage
     constexpr int PB = JS ? (JK ? PK : PM) : PM;
-    static_assert(!SS || 2 * 6 * STAGE_I <= R0_DBL + R1_DBL, "six M-major stage pairs must fit the block");
+    static_assert((size_t)SS_STAGES * (STAGE_I + STAGE_J) * sizeof(double) <= TILE_SMEM_BYTES, "six stage pairs must fit the block");
     double* r0 = smem;
     double* r1 = smem + R0_DBL;
     double* istage = SS ? smem : (JRES ? r1 : r0);       // i stages move to region 1 when j is resident in region 0
-    double* jstage = SS ? smem + 6 * STAGE_I : r1;
+    double* jstage = SS ? smem + SS_STAGES * STAGE_I : r1;
     const TileCoord tc;
     StageCopy<false> ci;
     StageCopy<JK> cj;
