@@ -328,7 +328,9 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": workload_config({"queries_per_step_per_gpu": step_q,
                                                                                "parallelism": "query-sharded x%d" % world}),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * step_q, "d2h_bytes_per_step": 16 * step_q},
-                "gpu_launches": 3 * BATCHES_PER_STEP * args.steps,
+                # per variance batch: predict_thread_kernel (mean + K* panel), predict_reduce_kernel, var_tiles_kernel,
+                # var_finalize_kernel (profiles/ncu_launches_bench_*.csv lists them)
+                "gpu_launches": 4 * BATCHES_PER_STEP * args.steps,
                 "clocks": clocks,
                 "roofline": {"kernel": "var_tiles_kernel (variance product X*K*^T + column norms)", "bound": "tensor",
                              "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,

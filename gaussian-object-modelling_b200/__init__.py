@@ -88,6 +88,8 @@ def lib():
         L.gpr_predict_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
         L.gpr_sample_isosurface.argtypes = [vp, vp, cd, cd, cd, cd, sz, _dp, _dp, _dp, _dp, _dp, C.POINTER(sz)]
         L.gpr_project.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, _dp, sz, cd, cd, C.c_uint, cd, _dp, _dp, _dp, C.POINTER(ci)]
+        L.gpr_model_save.argtypes = [vp, vp, C.c_char_p, ci]
+        L.gpr_model_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
         L.gpr_model_prepare_variance.argtypes = [vp, vp]
         L.gpr_append.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, sz]
         L.gpr_model_reserve.argtypes = [vp, vp, sz]
@@ -107,7 +109,7 @@ C_ABI_SYMBOLS = [
     "gpr_ctx_create", "gpr_ctx_destroy", "gpr_ctx_num_devices", "gpr_last_error", "gpr_last_pivot",
     "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_tail_size", "gpr_model_get",
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
-    "gpr_model_reserve", "gpr_sample_isosurface", "gpr_project",
+    "gpr_model_reserve", "gpr_sample_isosurface", "gpr_project", "gpr_model_save", "gpr_model_load",
     "gpr_model_state_get", "gpr_model_create_replica", "gpr_selftest_gemm", "gpr_selftest_leaf",
     "gpr_selftest_factor", "gpr_selftest_peak", "gpr_selftest_factor_trace",
 ]
@@ -301,6 +303,14 @@ class GPRegressor:
                                  f_tol, improve_tol, int(max_iter), step_mul, _p(out[0]), _p(out[1]), _p(out[2]),
                                  st.ctypes.data_as(C.POINTER(C.c_int))))
         return np.ascontiguousarray(out.T), st
+
+    def save(self, model, path, with_factor=True):
+        _check(lib().gpr_model_save(self.ctx._h, model._h, str(path).encode(), int(with_factor)))
+
+    def load(self, path, with_normals=False):
+        h = C.c_void_p()
+        _check(lib().gpr_model_load(self.ctx._h, str(path).encode(), C.byref(h)))
+        return Model(self.ctx, h, with_normals)
 
     def prepare_variance(self, model):
         _check(lib().gpr_model_prepare_variance(self.ctx._h, model._h))

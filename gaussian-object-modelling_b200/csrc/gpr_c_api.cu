@@ -894,6 +894,137 @@ int gpr_project(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, co
     return GPR_OK;
 }
 
+// ---- model export / import (SURVEY §5 "checkpoint / resume", §8(f).4) ---------------------------------------
+// File: header | x y z label [sigma2] alpha [normals] | [lower triangle of L by columns, n(n+1)/2 doubles].
+struct SaveHeader {
+    char magic[8];               // "GPRB200\0"
+    unsigned int version, kind;
+    double p0, p1, R;
+    unsigned long long n, n_normals, n_tail;
+    unsigned int has_s2, with_normals, has_factor, reserved;
+};
+
+int gpr_model_save(gpr_ctx* ctx, gpr_model* m, const char* path, int with_factor) {
+    if (!ctx || !m || !path) return fail(GPR_ERR_INVALID, "null pointer");
+    if (m->replica) return fail(GPR_ERR_INVALID, "cannot save a replica model");
+    std::lock_guard<std::mutex> lk(m->mu);
+    FILE* fh = fopen(path, "wb");
+    if (!fh) return fail(GPR_ERR_INVALID, std::string("cannot open ") + path + " for writing");
+    struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{fh};
+    SaveHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "GPRB200", 8);
+    h.version = 1; h.kind = (unsigned)m->kernel.kind; h.p0 = m->kernel.p0; h.p1 = m->kernel.p1; h.R = m->R;
+    h.n = m->n; h.n_normals = m->n_normals; h.n_tail = m->n_tail;
+    h.has_s2 = m->has_s2; h.with_normals = m->with_normals;
+    h.has_factor = (with_factor && m->n_tail == 0) ? 1 : 0;          // a tail model is refitted on load
+    bool ok = fwrite(&h, sizeof h, 1, fh) == 1;
+    auto put = [&](const std::vector<double>& v) { if (!v.empty()) ok = ok && fwrite(v.data(), sizeof(double), v.size(), fh) == v.size(); };
+    put(m->hx); put(m->hy); put(m->hz); put(m->hlabel);
+    if (m->has_s2) put(m->hs2);
+    put(m->h_alpha);
+    put(m->h_normals);
+    if (h.has_factor) {
+        CU(cudaSetDevice(m->devs[0].dev));
+        const size_t n = m->n;
+        std::vector<double> blk(n * TB), packed;
+        for (size_t c0 = 0; c0 < n; c0 += TB) {
+            const size_t cols = std::min<size_t>(TB, n - c0);
+            CU(cudaMemcpy2D(blk.data(), n * sizeof(double), m->L + c0 * m->cap, m->cap * sizeof(double), n * sizeof(double), cols,
+                            cudaMemcpyDeviceToHost));
+            packed.clear();
+            for (size_t c = 0; c < cols; ++c) packed.insert(packed.end(), blk.begin() + c * n + (c0 + c), blk.begin() + (c + 1) * n);
+            ok = ok && fwrite(packed.data(), sizeof(double), packed.size(), fh) == packed.size();
+        }
+    }
+    if (!ok) return fail(GPR_ERR_INVALID, std::string("short write to ") + path);
+    return GPR_OK;
+}
+
+int gpr_model_load(gpr_ctx* ctx, const char* path, gpr_model** out) {
+    if (!ctx || !path || !out) return fail(GPR_ERR_INVALID, "null pointer");
+    FILE* fh = fopen(path, "rb");
+    if (!fh) return fail(GPR_ERR_INVALID, std::string("cannot open ") + path);
+    struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{fh};
+    SaveHeader h;
+    if (fread(&h, sizeof h, 1, fh) != 1 || memcmp(h.magic, "GPRB200", 8) != 0 || h.version != 1 || h.kind > 2 || h.n == 0)
+        return fail(GPR_ERR_INVALID, std::string(path) + " is not a GPRB200 model file");
+    gpr_model* m = new gpr_model();
+    auto bail = [&](int rc) { free_factor(m); delete m; return rc; };
+    m->ctx = ctx; m->kernel = gpr_kernel_t{(int)h.kind, h.p0, h.p1}; m->kp = make_kp(m->kernel); m->k0 = kernel_at_zero(m->kp);
+    m->has_s2 = h.has_s2 != 0; m->with_normals = h.with_normals != 0;
+    const size_t n = (size_t)h.n;
+    bool ok = true;
+    auto get = [&](std::vector<double>& v, size_t cnt) { v.resize(cnt); if (cnt) ok = ok && fread(v.data(), sizeof(double), cnt, fh) == cnt; };
+    std::vector<double> alpha, normals;
+    get(m->hx, n); get(m->hy, n); get(m->hz, n); get(m->hlabel, n);
+    if (m->has_s2) get(m->hs2, n);
+    get(alpha, n);
+    get(normals, 3 * (size_t)h.n_normals);
+    if (!ok) return bail(fail(GPR_ERR_INVALID, std::string(path) + " is truncated"));
+    if (!h.has_factor) {
+        // no factor in the file (or an indefinite-tail model): refit from the stored training set
+        const bool wn = m->with_normals;
+        m->with_normals = false;
+        int rc = fit_from_host(m, false);
+        m->with_normals = wn;
+        if (rc) return bail(rc);
+        m->R = h.R; m->h_normals = normals; m->n_normals = (size_t)h.n_normals;
+        *out = m;
+        return GPR_OK;
+    }
+    DeviceCtx* dc = ctx->devs[0];
+    if (cudaSetDevice(dc->dev) != cudaSuccess) return bail(fail(GPR_ERR_CUDA, "cudaSetDevice failed"));
+    const size_t N = (n + TB - 1) / TB * TB;
+    const int nb = (int)(N / TB);
+    m->n = n; m->N = N; m->nb = nb; m->cap = N; m->n_spd = n; m->n_tail = 0; m->mp = 0; m->R = h.R;
+    m->devs.assign(ctx->devs.size(), ModelDev());
+    for (size_t i = 0; i < ctx->devs.size(); ++i) m->devs[i].dev = ctx->devs[i]->dev;
+    ModelDev& md = m->devs[0];
+#define LOAD_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(fail(e__ == cudaErrorMemoryAllocation ? GPR_ERR_OOM : GPR_ERR_CUDA, std::string("gpr_model_load: ") + cudaGetErrorString(e__))); } while (0)
+    LOAD_TRY(cudaMalloc((void**)&md.xyz, 3 * N * sizeof(double)));
+    LOAD_TRY(cudaMalloc((void**)&md.alpha, N * sizeof(double)));
+    LOAD_TRY(cudaMalloc((void**)&m->label, N * sizeof(double)));
+    LOAD_TRY(cudaMalloc((void**)&m->s2, N * sizeof(double)));
+    LOAD_TRY(cudaMalloc((void**)&m->zfwd, N * sizeof(double)));
+    LOAD_TRY(cudaMalloc((void**)&m->L, N * N * sizeof(double)));
+    LOAD_TRY(cudaMalloc((void**)&m->Dinv, (size_t)nb * TB * TB * sizeof(double)));
+    LOAD_TRY(cudaMalloc((void**)&m->scratch, (8 + (size_t)nb * nb) * sizeof(int)));
+    LOAD_TRY(cudaMemset(md.xyz, 0, 3 * N * sizeof(double)));
+    LOAD_TRY(cudaMemset(md.alpha, 0, N * sizeof(double)));
+    LOAD_TRY(cudaMemset(m->label, 0, N * sizeof(double)));
+    LOAD_TRY(cudaMemset(m->s2, 0, N * sizeof(double)));
+    LOAD_TRY(cudaMemcpy(md.xyz, m->hx.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    LOAD_TRY(cudaMemcpy(md.xyz + N, m->hy.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    LOAD_TRY(cudaMemcpy(md.xyz + 2 * N, m->hz.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    LOAD_TRY(cudaMemcpy(m->label, m->hlabel.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    if (m->has_s2) LOAD_TRY(cudaMemcpy(m->s2, m->hs2.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    LOAD_TRY(cudaMemcpy(md.alpha, alpha.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    // the factor: 128 columns at a time, padded rows / columns are identity
+    std::vector<double> blk(N * TB), packed;
+    for (size_t c0 = 0; c0 < N; c0 += TB) {
+        std::fill(blk.begin(), blk.end(), 0.0);
+        for (size_t c = 0; c < TB; ++c) {
+            const size_t gc = c0 + c;
+            if (gc < n) {
+                packed.resize(n - gc);
+                if (fread(packed.data(), sizeof(double), n - gc, fh) != n - gc) return bail(fail(GPR_ERR_INVALID, std::string(path) + " is truncated"));
+                std::copy(packed.begin(), packed.end(), blk.begin() + c * N + gc);
+            } else {
+                blk[c * N + gc] = 1.0;
+            }
+        }
+        LOAD_TRY(cudaMemcpy(m->L + c0 * N, blk.data(), N * TB * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    LOAD_TRY(launch_dinv_from_l(m->L, N, nb, m->Dinv, 0));
+    LOAD_TRY(cudaDeviceSynchronize());
+#undef LOAD_TRY
+    m->h_alpha = alpha; m->h_normals = normals; m->n_normals = (size_t)h.n_normals;
+    md.have = true;
+    *out = m;
+    return GPR_OK;
+}
+
 int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m) {
     if (!ctx || !m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
     for (size_t di = 0; di < ctx->devs.size(); ++di) {

@@ -223,12 +223,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) linv_tiles_kernel(LinvArgs a) {
     }
 }
 
+// Dinv_t = L_tt^-1 for every diagonal tile of an already factorised matrix (model import): one CTA per tile.
+__global__ void __launch_bounds__(NTHREADS, 1) dinv_from_l_kernel(const double* L, size_t ld, double* Dinv) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double s_inv[TB];
+    const int t = blockIdx.x;
+    const double* src = L + (size_t)t * TB * ld + (size_t)t * TB;
+    for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) {
+        const int r = idx & (TB - 1), c = idx >> 7;
+        smem[c * PM + r] = r >= c ? src[(size_t)c * ld + r] : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < TB) s_inv[threadIdx.x] = 1.0 / smem[threadIdx.x * PM + threadIdx.x];
+    __syncthreads();
+    trinv128_smem(smem, s_inv, smem + R0_DBL);
+    __syncthreads();
+    store_lower_tile(smem, Dinv + (size_t)t * TB * TB, TB);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------------------------
 static int g_tile_attr_done = 0;
 static cudaError_t ensure_attrs() {
     if (g_tile_attr_done) return cudaSuccess;
+    {
+        cudaError_t e0 = cudaFuncSetAttribute(dinv_from_l_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES);
+        if (e0 != cudaSuccess) return e0;
+    }
     cudaError_t e = cudaFuncSetAttribute(chol_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(linv_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES);
@@ -274,6 +296,14 @@ cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scr
         run(t0 + 2, t0 + len);
         t0 += len;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dinv_from_l(const double* L, size_t ld, int nb, double* Dinv, cudaStream_t st) {
+    cudaError_t e = ensure_attrs();
+    if (e != cudaSuccess) return e;
+    if (nb <= 0) return cudaSuccess;
+    dinv_from_l_kernel<<<nb, NTHREADS, TILE_SMEM_BYTES, st>>>(L, ld, Dinv);
     return cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@ cudaError_t launch_cov_build(const double* x, const double* y, const double* z, 
 // K2 (gpr_factor.cu).  scratch: at least 4 + nb*nb ints.
 cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, int serial,
                             cudaStream_t st, long long* trace = nullptr);
+cudaError_t launch_dinv_from_l(const double* L, size_t ld, int nb, double* Dinv, cudaStream_t st);
 cudaError_t launch_linv(const double* L, double* X, size_t ld, int nb, const double* Dinv, int* scratch, int num_sms,
                         cudaStream_t st);
 // K3 (gpr_solve.cu).  scratch: at least 4 + nb ints.

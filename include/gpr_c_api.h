@@ -122,6 +122,14 @@ int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, con
  * geometric, x1.25).  Invalidates pointers returned earlier by gpr_model_state_get. */
 int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity);
 
+/* ---- export / import (the reference has no persistence for the GP) ----------------- */
+/* Writes the training set, kernel, R, alpha, normals and — if with_factor != 0 and the matrix was positive
+ * definite — the lower Cholesky factor (n(n+1)/2 doubles) to a binary file.  gpr_model_load restores the model
+ * on ctx's primary device: with a stored factor without refactorising (only the 128x128 diagonal inverses are
+ * rebuilt; L^-1 is rebuilt on the first variance request), otherwise by refitting the stored training set. */
+int gpr_model_save(gpr_ctx* ctx, gpr_model* m, const char* path, int with_factor);
+int gpr_model_load(gpr_ctx* ctx, const char* path, gpr_model** out);
+
 /* ---- replication across processes (one process per GPU, launched by bench.py) ----------------- */
 /* The fitted state that predict needs, as raw device pointers on the primary device, so that the
  * launcher can broadcast it with NCCL into a model created by gpr_model_create_replica on another rank.

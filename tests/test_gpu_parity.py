@@ -529,3 +529,44 @@ def test_batched_projection_matches_the_atlas_loop(gpr, ctx):
     # budget exhaustion is reported, not hidden (the reference prints and returns the last iterate)
     out2, st2 = reg.project(m, start[:2], g0[:2], f_tol=1e-12, improve_tol=0.0, max_iter=5, step_mul=0.2)
     assert (st2 == -5).all()
+
+
+def test_model_save_and_load_round_trip(gpr, ctx, tmp_path):
+    """Export / import: with the stored factor the loaded model answers without refactorising
+    (same alpha and factor bits); without it (and for an indefinite-tail model) it is refitted from the stored
+    training set."""
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(700, seed=13)
+    reg = gpr.GPRegressor("gaussian", 1.3, 0.9, ctx=ctx)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2, with_normals=True)
+    Q = W.grid_slab(10, 3, 5)
+    ref = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True)
+    one = reg.evaluate(m, Q[:1, 0], Q[:1, 1], Q[:1, 2], var=True)
+    for with_factor in (True, False):
+        path = tmp_path / ("model_%d.bin" % with_factor)
+        reg.save(m, path, with_factor)
+        assert os.path.getsize(path) > (700 * 701 // 2 * 8 if with_factor else 0)
+        other = gpr.GPRegressor("thin_plate", 1.0, ctx=ctx)             # the kernel comes from the file
+        m2 = other.load(path, with_normals=True)
+        assert m2.n == m.n and m2.R == m.R and np.array_equal(m2.alpha, m.alpha)
+        assert np.array_equal(m2.get()["normals"], m.get()["normals"])
+        got = other.evaluate(m2, Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True)
+        # mean and gradient depend on alpha only: identical bits.  The variance goes through L^-1, rebuilt from the
+        # loaded factor with re-derived diagonal-block inverses (1/L_ii instead of the fit's rsqrt): last bits may differ.
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2])
+        assert np.abs(got[1] - ref[1]).max() <= 1e-11 * np.abs(ref[1]).max()
+        got1 = other.evaluate(m2, Q[:1, 0], Q[:1, 1], Q[:1, 2], var=True)
+        assert np.array_equal(got1[0], one[0]) and abs(got1[1][0] - one[1][0]) <= 1e-11 * np.abs(ref[1]).max()
+        if with_factor:
+            assert np.array_equal(m2.factor(), m.factor())
+            other.update(m2, P[:5, 0] * 0.5, P[:5, 1] * 0.5, P[:5, 2] * 0.5, y[:5], s2[:5])     # a loaded model can be appended to
+            assert m2.n == m.n + 5
+    g = load_golden("ref_mugD_thinplate_R2_node")                         # indefinite tail: refit on load
+    Pn = g["P"]
+    regn = _reg(gpr, ctx, g)
+    mn = regn.create(Pn[:, 0], Pn[:, 1], Pn[:, 2], g["y"], g["s2"])
+    regn.save(mn, tmp_path / "node.bin")
+    mn2 = regn.load(tmp_path / "node.bin")
+    assert mn2.n_tail == 15 and np.array_equal(mn2.alpha, mn.alpha)
+    with pytest.raises(gpr.GPRegressionException):
+        regn.load(tmp_path / "missing.bin")
