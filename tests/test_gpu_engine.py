@@ -78,4 +78,4 @@ def test_tile_cholesky_rejects_indefinite(gpr):
 
 def test_fp64_pipe_probes(gpr):
     dmma, dfma = gpr.selftest_peak(0, 4), gpr.selftest_peak(1, 4)
-    assert 20.0 < dmma < 60.0 and 20.0 < dfma < 60.0       # B200: ~37 TF/s on either FP64 pipe
+    assert 10.0 < dmma < 80.0 and 10.0 < dfma < 80.0       # B200: ~37 / ~34 TF/s; wide bounds: a power-capped box must not fail a parity suite
