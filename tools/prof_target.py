@@ -1,6 +1,6 @@
 """Profiling target (GPU box): ONE fit at n=16384 (covariance build, tile Cholesky, two triangular solves),
 the one-time L^-1, and ONE mean+variance batch of 148*128 queries through the host-pointer C-ABI call.
-Run plain first, then under ncu (tools/profile_round.sh)."""
+Run plain first, then under ncu (tools/profile_ncu.sh)."""
 import os
 import sys
 import numpy as np
