@@ -116,6 +116,7 @@ struct gpr_model {
     // Indefinite tail (gpr_tail.cu): the last n_tail points are eliminated as one dense pivot block; L / L^-1
     // / nb then describe the leading n_spd = n - n_tail points only.  n_tail == 0 for SPD matrices.
     size_t n_spd = 0, n_tail = 0;
+    std::vector<size_t> perm;                    // internal index -> caller's index (empty = identity)
     int mp = 0;                                  // n_tail rounded up to a multiple of 32
     double* tB = nullptr; double* tmisc = nullptr;   // B = X P (slabs); C | S | t | a2 | gram partials | panel tmp
     gpr_kernel_t kernel{};
@@ -218,47 +219,144 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
     cudaStream_t st = ws->st;
 
+    // Internal point order.  Normally the caller's order (perm empty).  When the factorisation meets a
+    // non-positive pivot with too many points after it for the trailing-block elimination, the offending point
+    // is moved to the END of the internal order and the factorisation is retried: after at most MAX_TAIL moves
+    // the offending points form the trailing block that gpr_tail.cu eliminates.  Everything on the device is in
+    // internal order; alpha / normals are returned to the caller's order below.
+    m->perm.clear();
+    const char* no_tail_env = getenv("GPR_NO_TAIL");
+    const bool tail_allowed = !(no_tail_env && atoi(no_tail_env) != 0);
+    std::vector<double> gx, gy, gz, gl, gs;
+    auto upload = [&]() -> int {
+        const double *px = m->hx.data(), *py = m->hy.data(), *pz = m->hz.data(), *pl = m->hlabel.data();
+        const double* ps = m->has_s2 ? m->hs2.data() : nullptr;
+        if (!m->perm.empty()) {
+            gx.resize(n); gy.resize(n); gz.resize(n); gl.resize(n); if (ps) gs.resize(n);
+            for (size_t i = 0; i < n; ++i) {
+                const size_t s = m->perm[i];
+                gx[i] = px[s]; gy[i] = py[s]; gz[i] = pz[s]; gl[i] = pl[s]; if (ps) gs[i] = ps[s];
+            }
+            px = gx.data(); py = gy.data(); pz = gz.data(); pl = gl.data(); if (ps) ps = gs.data();
+        }
+        CU(cudaMemsetAsync(md.xyz, 0, 3 * N * sizeof(double), st));
+        CU(cudaMemsetAsync(m->label, 0, N * sizeof(double), st));
+        CU(cudaMemsetAsync(m->s2, 0, N * sizeof(double), st));
+        CU(cudaMemcpyAsync(md.xyz, px, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(md.xyz + N, py, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(md.xyz + 2 * N, pz, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m->label, pl, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (ps) CU(cudaMemcpyAsync(m->s2, ps, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        return GPR_OK;
+    };
     CU(cudaEventRecord(ws->ev[0], st));
-    CU(cudaMemsetAsync(md.xyz, 0, 3 * N * sizeof(double), st));
-    CU(cudaMemsetAsync(m->label, 0, N * sizeof(double), st));
-    CU(cudaMemsetAsync(m->s2, 0, N * sizeof(double), st));
-    CU(cudaMemcpyAsync(md.xyz, m->hx.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(md.xyz + N, m->hy.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(md.xyz + 2 * N, m->hz.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(m->label, m->hlabel.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (m->has_s2) CU(cudaMemcpyAsync(m->s2, m->hs2.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
-    // the max-distance accumulator lives in the last 8 bytes of the int scratch header
-    unsigned long long* rbits = reinterpret_cast<unsigned long long*>(m->zfwd);   // reused before zfwd is written
+    rc = upload();
+    if (rc) return rc;
+    // the max-distance accumulator borrows the first 8 bytes of zfwd (reused before zfwd is written)
+    unsigned long long* rbits = reinterpret_cast<unsigned long long*>(m->zfwd);
     CU(cudaMemsetAsync(rbits, 0, sizeof(unsigned long long), st));
     CU(cudaEventRecord(ws->ev[1], st));
-    CU(launch_cov_build(md.xyz, md.xyz + N, md.xyz + 2 * N, m->s2, (int)n, nb, 0, m->L, N, rbits, m->kp, st));
     double Rbits_host = 0.0;
-    CU(cudaMemcpyAsync(&Rbits_host, rbits, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(ws->ev[2], st));
-    CU(launch_cholesky(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st));
     int info[4] = {0, 0, 0, 0};
-    CU(cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (info[1] != 0) {
-        const size_t p = (size_t)info[1] - 1;
-        const char* no_tail = getenv("GPR_NO_TAIL");
-        if (p >= 1 && n - p <= MAX_TAIL && !(no_tail && atoi(no_tail) != 0)) {
-            // Indefinite matrix whose offending points are the last few (the node's external sphere points,
-            // SURVEY F2): keep the Cholesky factor of the leading p points, eliminate the rest as one dense
-            // pivot block (gpr_tail.cu).  The leading block is rebuilt with the tail rows as identity padding.
+    size_t moved = 0;
+    std::vector<int> counts;                 // conflict counts per point (caller's order), computed on the first failure
+    for (;;) {
+        CU(launch_cov_build(md.xyz, md.xyz + N, md.xyz + 2 * N, m->s2, (int)n, nb, 0, m->L, N, rbits, m->kp, st));
+        if (moved == 0) {
+            CU(cudaMemcpyAsync(&Rbits_host, rbits, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(ws->ev[2], st));
+        }
+        CU(launch_cholesky(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st));
+        CU(cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (info[1] == 0) break;                                   // positive definite
+        const size_t p = (size_t)info[1] - 1;                      // internal index of the failing pivot
+        // Offending points are moved ("evicted") to the end of the internal order; once the failing pivot lies
+        // inside the evicted region, that region is the trailing block that gpr_tail.cu eliminates.
+        bool go_tail = tail_allowed && moved > 0 && p >= n - moved;
+        if (!go_tail) {
+            if (!tail_allowed || p == 0 || moved >= MAX_TAIL) break;   // give up: reported below
+            if (m->perm.empty()) { m->perm.resize(n); for (size_t i = 0; i < n; ++i) m->perm[i] = i; }
+            // A pair (a, b) with K_ab^2 > K_aa K_bb cannot sit in one positive definite block (its 2x2 minor is
+            // indefinite).  counts[i] = number of such partners of point i in the whole set (device kernel): an
+            // outlier — for the thin-plate kernel a point farther than R from most others — has many.
+            if (counts.empty()) {
+                counts.resize(n);
+                int* dcounts = reinterpret_cast<int*>(m->scratch + 8);      // the flag area is free between factorisations
+                if ((size_t)nb * nb < n) { CU(cudaFree(m->scratch)); CU(cudaMalloc((void**)&m->scratch, (8 + std::max((size_t)nb * nb, n)) * sizeof(int))); dcounts = m->scratch + 8; }
+                CU(launch_conflict_counts(md.xyz, N, m->s2, (int)n, dcounts, m->kp, st));
+                CU(cudaMemcpyAsync(counts.data(), dcounts, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));                                // counts are in INTERNAL order == caller's order here
+            }
+            auto cnt_of = [&](size_t internal) { return counts[m->perm[internal]]; };
+            auto kval = [&](size_t a, size_t b2) {
+                const size_t ua = m->perm[a], ub = m->perm[b2];
+                const double dx = m->hx[ua] - m->hx[ub], dy = m->hy[ua] - m->hy[ub], dz = m->hz[ua] - m->hz[ub];
+                const double d = std::sqrt(dx * dx + dy * dy + dz * dz);
+                double k = m->kp.kind == 0 ? 2 * d * d * d - 3 * m->kp.p0 * d * d + m->kp.R3 : m->kp.amp * std::exp(-d * m->kp.inv);
+                if (a == b2 && m->has_s2) k += m->hs2[ua];
+                return k;
+            };
+            // the earlier point q that conflicts most with the failing pivot p; evict the one of the two with more conflicts
+            size_t evict = p, q = p;
+            double worst = 1.0;
+            const double kpp = kval(p, p);
+            for (size_t j = 0; j < p; ++j) {
+                const double k = kval(p, j), r = k * k / (kpp * kval(j, j));
+                if (r > worst) { worst = r; q = j; }
+            }
+            if (q != p && cnt_of(q) > cnt_of(p)) evict = q;
+            // evict it together with every point that is at least half as conflicted (the other outliers), most
+            // conflicted first, keeping the relative order of the rest
+            const int thr = std::max(1, cnt_of(evict) / 2);
+            std::vector<size_t> out;
+            for (size_t i = 0; i < n - moved; ++i) if (i == evict || counts[m->perm[i]] >= thr) out.push_back(i);
+            std::stable_sort(out.begin(), out.end(), [&](size_t a2, size_t b2) { return cnt_of(a2) > cnt_of(b2); });
+            if (out.size() > MAX_TAIL - moved) {
+                out.resize(MAX_TAIL - moved);
+                if (std::find(out.begin(), out.end(), evict) == out.end()) out.back() = evict;
+            }
+            std::vector<char> gone(n, 0);
+            for (size_t i : out) gone[i] = 1;
+            std::vector<size_t> np;
+            np.reserve(n);
+            for (size_t i = 0; i < n - moved; ++i) if (!gone[i]) np.push_back(m->perm[i]);
+            const size_t first_evicted = np.size();
+            std::sort(out.begin(), out.end());
+            for (size_t i : out) np.push_back(m->perm[i]);
+            for (size_t i = n - moved; i < n; ++i) np.push_back(m->perm[i]);
+            const bool unchanged = np == m->perm;
+            m->perm.swap(np);
+            moved += out.size();
+            // the evicted points were already a suffix and the failure was at its first point: no retry needed
+            go_tail = unchanged && p == first_evicted;
+            if (!go_tail) {
+                rc = upload();
+                if (rc) return rc;
+                continue;
+            }
+        }
+        {
+            // Indefinite matrix whose offending points are now the last few of the internal order (in the node's own
+            // ordering they are from the start: its external sphere points): keep the Cholesky factor of
+            // the leading p points, eliminate the rest as one dense pivot block (gpr_tail.cu).  The leading block
+            // is rebuilt with the tail rows as identity padding.
             m->n_spd = p; m->n_tail = n - p; m->nb = (int)((p + TB - 1) / TB);
             CU(launch_cov_build(md.xyz, md.xyz + N, md.xyz + 2 * N, m->s2, (int)p, m->nb, 0, m->L, N, rbits + 1, m->kp, st));
             CU(launch_cholesky(m->L, N, m->nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st));
             CU(cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            break;
         }
-        if (info[1] != 0) {
-            g_pivot = info[1];
-            char b[256];
-            snprintf(b, sizeof b, "covariance matrix is not positive definite: pivot %d of %zu is <= 0 "
-                     "(thin-plate R must be >= the largest pairwise distance, %.6g here)", info[1], n, Rbits_host);
-            return fail(GPR_ERR_NOT_SPD, b);
-        }
+    }
+    if (info[1] != 0) {
+        const size_t user_pivot = m->perm.empty() ? (size_t)info[1] : m->perm[(size_t)info[1] - 1] + 1;
+        g_pivot = (long long)user_pivot;
+        char b[256];
+        snprintf(b, sizeof b, "covariance matrix is not positive definite: pivot %zu of %zu is <= 0 "
+                 "(thin-plate R must be >= the largest pairwise distance, %.6g here)", user_pivot, n, Rbits_host);
+        m->perm.clear();
+        return fail(GPR_ERR_NOT_SPD, b);
     }
     if (info[2] != 0) return fail(GPR_ERR_CUDA, "cholesky kernel aborted (dependency wait timed out)");
     if (!keep_R) m->R = Rbits_host;
@@ -325,7 +423,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     }
     CU(cudaEventRecord(ws->ev[4], st));
     m->h_alpha.resize(n);
-    CU(cudaMemcpyAsync(m->h_alpha.data(), md.alpha, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(m->h_alpha.data(), md.alpha, n * sizeof(double), cudaMemcpyDeviceToHost, st));   // internal order; un-permuted below
     m->h_normals.clear();
     m->n_normals = 0;
     if (m->with_normals) {
@@ -345,6 +443,15 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     }
     CU(cudaEventRecord(ws->ev[5], st));
     CU(cudaStreamSynchronize(st));
+    if (!m->perm.empty()) {                      // back to the caller's point order
+        std::vector<double> tmp(m->h_alpha);
+        for (size_t i = 0; i < n; ++i) m->h_alpha[m->perm[i]] = tmp[i];
+        if (!m->h_normals.empty()) {
+            tmp = m->h_normals;
+            for (int c = 0; c < 3; ++c)
+                for (size_t i = 0; i < n; ++i) m->h_normals[c * n + m->perm[i]] = tmp[c * n + i];
+        }
+    }
     int abortflag[4] = {0, 0, 0, 0};
     CU(cudaMemcpy(abortflag, m->scratch, sizeof(abortflag), cudaMemcpyDeviceToHost));
     if (abortflag[2] != 0) return fail(GPR_ERR_CUDA, "triangular solve kernel aborted (dependency wait timed out)");

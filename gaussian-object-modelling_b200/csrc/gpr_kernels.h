@@ -68,6 +68,8 @@ cudaError_t launch_skinny(int mode, const double* A, size_t ld, int rows, int kd
 cudaError_t launch_append_panel(const double* xyz, size_t ld, const double* sigma2, int n0, int t0, int k, double* Pn,
                                 double* S0, const KernParams& kp, cudaStream_t st);
 // Indefinite tail (gpr_tail.cu)
+cudaError_t launch_conflict_counts(const double* xyz, size_t ld, const double* sigma2, int n, int* counts,
+                                   const KernParams& kp, cudaStream_t st);
 cudaError_t launch_tail_cc(const double* xyz, size_t ld, const double* sigma2, int p, int m, int mp, double* C,
                            const KernParams& kp, cudaStream_t st);
 size_t tail_gram_part_doubles(int p, int mp);

@@ -196,6 +196,43 @@ __global__ void __launch_bounds__(256) tail_var_kernel(const double* __restrict_
     if (real) var[qi] -= corr;
 }
 
+// counts[i] = #{ j != i : K_ij^2 > K_ii K_jj }: the number of points whose 2x2 minor with point i is indefinite —
+// no positive definite block can hold both.  For the thin-plate kernel these are the points farther than ~R
+// from i; an outlier conflicts with most of the set.  Used by the host to choose which points to move into the
+// trailing pivot block (gpr_c_api.cu).  Thread per point, the others staged in shared memory.
+__global__ void __launch_bounds__(256) conflict_count_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                             const double* __restrict__ z, const double* __restrict__ sigma2,
+                                                             int n, int* __restrict__ counts, KernParams kp) {
+    __shared__ double4 sp[256];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const bool real = i < n;
+    const double xi = real ? x[i] : 0.0, yi = real ? y[i] : 0.0, zi = real ? z[i] : 0.0;
+    const double k0 = kp.kind == 0 ? kp.R3 : kp.amp;
+    const double kii = k0 + (real ? sigma2[i] : 0.0);
+    int cnt = 0;
+    for (int base = 0; base < n; base += 256) {
+        __syncthreads();
+        const int j = base + threadIdx.x;
+        sp[threadIdx.x] = j < n ? make_double4(x[j], y[j], z[j], k0 + sigma2[j]) : make_double4(0.0, 0.0, 0.0, 0.0);
+        __syncthreads();
+        const int lim = min(256, n - base);
+        for (int k = 0; k < lim; ++k) {
+            if (base + k == i) continue;
+            const double4 q = sp[k];
+            const double kij = kern_value_exact(kp, dist_exact(xi, yi, zi, q.x, q.y, q.z));
+            if (kij * kij > kii * q.w) ++cnt;
+        }
+    }
+    if (real) counts[i] = cnt;
+}
+
+cudaError_t launch_conflict_counts(const double* xyz, size_t ld, const double* sigma2, int n, int* counts,
+                                   const KernParams& kp, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    conflict_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(xyz, xyz + ld, xyz + 2 * ld, sigma2, n, counts, kp);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------

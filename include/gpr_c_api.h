@@ -64,10 +64,11 @@ int gpr_fit(gpr_ctx* ctx, const double* x, const double* y, const double* z, con
 int gpr_model_destroy(gpr_model* m);
 size_t gpr_model_size(const gpr_model* m);                 /* n */
 /* Indefinite covariance (the node's ThinPlate(2.0) + external sphere setting): when the Cholesky
- * factorisation meets a non-positive pivot and at most 256 points remain, those trailing points are
- * eliminated as one dense pivot block (block L D L^T, csrc/gpr_tail.cu) and the fit succeeds; this returns
- * how many points are in that block (0 for a positive definite matrix).  GPR_NO_TAIL=1 disables it
- * (gpr_fit then returns GPR_ERR_NOT_SPD as for any other indefinite matrix). */
+ * factorisation meets a non-positive pivot, the offending points (at most 256; found by counting indefinite 2x2
+ * minors, wherever they sit in the training set) are moved to the end of an internal order and eliminated as
+ * one dense pivot block (block L D L^T, csrc/gpr_tail.cu), and the fit succeeds; this returns how many points
+ * are in that block (0 for a positive definite matrix).  Outputs stay in the caller's point order.
+ * GPR_NO_TAIL=1 disables it (gpr_fit then returns GPR_ERR_NOT_SPD as for any other indefinite matrix). */
 size_t gpr_model_tail_size(const gpr_model* m);
 /* Model fields the reference exposes (gp_regressor.hpp:71-87): alpha[n], R, N (n x 3 column-major,
  * only when fitted with normals).  Any output pointer may be NULL. */

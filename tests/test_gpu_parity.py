@@ -131,7 +131,7 @@ def test_update_matches_reference_fixture(gpr, ctx):
 def test_not_spd_is_reported_never_nan(gpr, ctx, monkeypatch):
     """Appendix B.7: the node's ThinPlate(2.0) setting is indefinite; pivot = first external point.  With the
     trailing-block elimination switched off (GPR_NO_TAIL=1) that is an error, never NaN; an indefinite matrix
-    whose offending points come early (more than 256 points after the failing pivot) is an error in any case."""
+    with more than 256 offending points is an error in any case."""
     g = load_golden("ref_mugD_thinplate")
     P = g["P"]
     reg = gpr.GPRegressor("thin_plate", 2.0, ctx=ctx)
@@ -142,11 +142,36 @@ def test_not_spd_is_reported_never_nan(gpr, ctx, monkeypatch):
     monkeypatch.delenv("GPR_NO_TAIL")
     W = gpr.workloads
     Ps, ys, ss = W.synthetic_cloud(1024, seed=3)
-    far = np.vstack([[[9.0, 0.0, 0.0]], Ps])                     # the far point is FIRST: pivot 2 fails, 1023 points remain
+    Ps, ys, ss = Ps[:768], ys[:768], ss[:768]                        # the unit-sphere part (scaled below: diameter 0.9 <= R)
+    rng = np.random.default_rng(3)
+    d = rng.standard_normal((300, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    far = np.vstack([d * 40.0, Ps * 0.45])                           # 300 mutually distant outliers FIRST, then a compact cloud
     reg2 = gpr.GPRegressor("thin_plate", 2.0, ctx=ctx)
-    with pytest.raises(gpr.GPRegressionException) as e:
-        reg2.create(far[:, 0], far[:, 1], far[:, 2], np.concatenate([[1.0], ys]), np.concatenate([[0.1], ss]))
-    assert e.value.code == gpr.GPR_ERR_NOT_SPD
+    with pytest.raises(gpr.GPRegressionException) as e:              # more than 256 offending points: an error in any case
+        reg2.create(far[:, 0], far[:, 1], far[:, 2], np.concatenate([np.ones(300), ys]), np.full(len(far), 0.1))
+    assert e.value.code == gpr.GPR_ERR_NOT_SPD and 1 <= e.value.pivot <= len(far)
+
+
+@pytest.mark.parametrize("order", ["externals_first", "shuffled"])
+def test_indefinite_matrix_with_offending_points_anywhere(gpr, ctx, order):
+    """The node's indefinite setting with the training set re-ordered: the 15 external points first, or all 277
+    points shuffled.  The offending points are moved to the end of the INTERNAL order (the caller never sees it:
+    alpha comes back in the caller's order) and eliminated as the trailing pivot block; results must equal the
+    reference's pivoted-LDLT outputs for the same set."""
+    g = load_golden("ref_mugD_thinplate_R2_node")
+    P, Q, n = g["P"], g["Q"], len(g["P"])
+    idx = np.concatenate([np.arange(n - 15, n), np.arange(n - 15)]) if order == "externals_first" else np.random.default_rng(4).permutation(n)
+    reg = _reg(gpr, ctx, g)
+    m = reg.create(P[idx, 0], P[idx, 1], P[idx, 2], g["y"][idx], g["s2"][idx], with_normals=True)
+    assert m.n_tail == 15 and m.n == n
+    got = m.get()
+    assert relerr(got["alpha"], g["alpha"][idx]) <= TOL_ALPHA
+    assert np.abs(got["normals"] - g["normals"][idx]).max() <= 1e-8
+    f, v, gr = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True)
+    assert relerr(f, g["f"]) <= TOL_MEAN and _signs_agree(f, g["f"])
+    assert np.abs(v - g["v"]).max() <= TOL_VAR * np.abs(g["v"]).max() and relerr(gr, g["grad"]) <= TOL_MEAN
+    f1, v1 = reg.evaluate(m, Q[:1, 0], Q[:1, 1], Q[:1, 2], var=True)
+    assert abs(f1[0] - g["f"][0]) <= TOL_MEAN * np.abs(g["f"]).max() and abs(v1[0] - g["v"][0]) <= TOL_VAR * np.abs(g["v"]).max()
 
 
 @pytest.mark.parametrize("case", ["ref_mugD_thinplate_R2_node", "ref_jug_thinplate_R2_node"])
@@ -180,9 +205,14 @@ def test_node_configuration_indefinite_matrix(gpr, ctx, case):
     fb, vb = reg.evaluate(m, big[:, 0], big[:, 1], big[:, 2], var=True)
     assert relerr(fb[:len(Q)], g["f"]) <= TOL_MEAN and np.abs(vb[:len(Q)] - g["v"]).max() <= TOL_VAR * np.abs(g["v"]).max()
     assert np.array_equal(fb[:len(Q)], fb[-len(Q):]) and np.array_equal(vb[:len(Q)], vb[-len(Q):])
-    # update() on such a model refits (the tail is re-detected) and stays consistent with a fresh fit
+    # update() on such a model refits: the two new surface points come AFTER the external points in the caller's
+    # order, yet only the 15 external points end up in the trailing block (they are moved behind the new points
+    # in the internal order); alpha comes back in the caller's order and agrees with a fresh fit of all 279
     reg.update(m, [0.3, 0.0], [0.1, 0.5], [-0.2, 0.4], [0.0, 0.0], [0.05, 0.05])
-    assert m.n == len(P) + 2 and m.n_tail == 17
+    assert m.n == len(P) + 2 and m.n_tail == 15
+    P2 = np.vstack([P, [[0.3, 0.1, -0.2], [0.0, 0.5, 0.4]]])
+    fresh = reg.create(P2[:, 0], P2[:, 1], P2[:, 2], np.concatenate([g["y"], [0.0, 0.0]]), np.concatenate([g["s2"], [0.05, 0.05]]))
+    assert fresh.n_tail == 15 and np.array_equal(fresh.alpha, m.alpha)
 
 
 def test_closed_form_posteriors(gpr, ctx):
