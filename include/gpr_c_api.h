@@ -74,7 +74,9 @@ size_t gpr_model_tail_size(const gpr_model* m);
  * only when fitted with normals).  Any output pointer may be NULL. */
 int gpr_model_get(const gpr_model* m, double* alpha, double* R, double* normals_or_null);
 /* Debug / parity access: the assembled covariance is not kept; the lower Cholesky factor is.
- * L: n x n column-major, strict upper triangle zeroed. */
+ * L: n x n column-major, strict upper triangle zeroed.  For a model with an indefinite tail block
+ * (gpr_model_tail_size() > 0) only the leading (n - tail) x (n - tail) block is a Cholesky factor, in the
+ * library's internal point order. */
 int gpr_model_get_factor(const gpr_model* m, double* L);
 
 /* ---- predict: the four GPRegressor::evaluate overloads (gp_regressor.hpp:194,:222,:282,:332) - */
