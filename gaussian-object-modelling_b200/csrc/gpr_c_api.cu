@@ -66,7 +66,58 @@ struct gpr_ctx {
     size_t query_tile = 0;     // queries per variance batch (multiple of 128)
     int chol_serial = 0;
     int refine_steps = 1;      // iterative-refinement steps of alpha after the triangular solves
+    // The n x n buffers (L, L^-1) of the most recently destroyed models, kept for the next fit of the same size
+    // (a refit per touch, src/gp_node.cpp:750-751, would otherwise pay cudaMalloc/cudaFree of gigabytes each time).
+    struct Big { void* p; size_t bytes; int dev; };
+    std::vector<Big> big_cache;
+    std::mutex cmu;
 };
+
+static std::mutex g_live_mu;
+static std::vector<gpr_ctx*> g_live_ctx;                 // contexts that have not been destroyed (a model may outlive its context)
+constexpr size_t BIG_MIN = (size_t)64 << 20, BIG_MAX_TOTAL = (size_t)9 << 30;
+
+static bool big_cache_off() { static const bool off = getenv("GPR_NO_CACHE") && atoi(getenv("GPR_NO_CACHE")) != 0; return off; }
+
+static void* big_take(gpr_ctx* ctx, int dev, size_t bytes) {
+    if (big_cache_off()) return nullptr;
+    std::lock_guard<std::mutex> lk(ctx->cmu);
+    for (size_t i = 0; i < ctx->big_cache.size(); ++i)
+        if (ctx->big_cache[i].dev == dev && ctx->big_cache[i].bytes == bytes) {
+            void* p = ctx->big_cache[i].p;
+            ctx->big_cache.erase(ctx->big_cache.begin() + (std::ptrdiff_t)i);
+            return p;
+        }
+    return nullptr;
+}
+// cudaMalloc through the cache.  The buffer is NOT cleared.
+static cudaError_t big_alloc(gpr_ctx* ctx, int dev, void** p, size_t bytes) {
+    *p = bytes >= BIG_MIN ? big_take(ctx, dev, bytes) : nullptr;
+    return *p ? cudaSuccess : cudaMalloc(p, bytes);
+}
+// Returns the buffer to the cache of its context (if that context is still alive and the cache has room), else frees it.
+// The caller guarantees that no work is pending on the buffer.  Current device must be `dev`.
+static void big_free(gpr_ctx* ctx, int dev, void* p, size_t bytes) {
+    if (!p) return;
+    if (!big_cache_off() && bytes >= BIG_MIN && bytes <= BIG_MAX_TOTAL / 2) {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        if (std::find(g_live_ctx.begin(), g_live_ctx.end(), ctx) != g_live_ctx.end()) {
+            std::lock_guard<std::mutex> lk2(ctx->cmu);
+            size_t total = bytes;
+            for (auto& b : ctx->big_cache) total += b.bytes;
+            while (!ctx->big_cache.empty() && (total > BIG_MAX_TOTAL || ctx->big_cache.size() >= 4)) {
+                total -= ctx->big_cache.front().bytes;
+                cudaSetDevice(ctx->big_cache.front().dev);
+                cudaFree(ctx->big_cache.front().p);
+                ctx->big_cache.erase(ctx->big_cache.begin());
+            }
+            cudaSetDevice(dev);
+            ctx->big_cache.push_back(gpr_ctx::Big{p, bytes, dev});
+            return;
+        }
+    }
+    cudaFree(p);
+}
 
 static int ws_acquire(DeviceCtx* dc, Workspace** out) {
     {
@@ -146,13 +197,15 @@ static double kernel_at_zero(const KernParams& kp) { return kp.kind == 0 ? kp.R3
 static void free_factor(gpr_model* m) {
     if (m->devs.empty()) return;
     cudaSetDevice(m->devs[0].dev);
-    cudaFree(m->label); cudaFree(m->s2); cudaFree(m->zfwd); cudaFree(m->L); cudaFree(m->Dinv); cudaFree(m->scratch);
+    cudaFree(m->label); cudaFree(m->s2); cudaFree(m->zfwd); cudaFree(m->Dinv); cudaFree(m->scratch);
+    big_free(m->ctx, m->devs[0].dev, m->L, m->cap * m->cap * sizeof(double));
     cudaFree(m->aws); cudaFree(m->tB); cudaFree(m->tmisc);
     m->label = m->s2 = m->zfwd = m->L = m->Dinv = m->aws = m->tB = m->tmisc = nullptr; m->scratch = nullptr; m->aws_dbl = 0;
     m->n_tail = 0; m->mp = 0;
     for (auto& d : m->devs) {
         cudaSetDevice(d.dev);
-        cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.linv); cudaFree(d.tZ); cudaFree(d.tSinv);
+        cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.tZ); cudaFree(d.tSinv);
+        big_free(m->ctx, d.dev, d.linv, m->cap * m->cap * sizeof(double));
         d.xyz = d.alpha = d.linv = d.tZ = d.tSinv = nullptr; d.have = d.have_linv = d.have_tail = false;
     }
 }
@@ -209,7 +262,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     CU(cudaMalloc((void**)&m->label, N * sizeof(double)));
     CU(cudaMalloc((void**)&m->s2, N * sizeof(double)));
     CU(cudaMalloc((void**)&m->zfwd, N * sizeof(double)));
-    CU(cudaMalloc((void**)&m->L, N * N * sizeof(double)));
+    CU(big_alloc(ctx, dc->dev, (void**)&m->L, N * N * sizeof(double)));
     CU(cudaMalloc((void**)&m->Dinv, (size_t)nb * TB * TB * sizeof(double)));
     CU(cudaMalloc((void**)&m->scratch, (8 + (size_t)nb * nb) * sizeof(int)));
 
@@ -386,7 +439,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
         CU(cudaMalloc((void**)&md.tZ, (size_t)nslab * N * 32 * sizeof(double)));
         CU(cudaMalloc((void**)&md.tSinv, (size_t)mp * mp * sizeof(double)));
         CU(cudaMalloc((void**)&m->tmisc, misc * sizeof(double)));
-        if (!md.linv) CU(cudaMalloc((void**)&md.linv, N * N * sizeof(double)));
+        if (!md.linv) CU(big_alloc(ctx, dc->dev, (void**)&md.linv, N * N * sizeof(double)));
         double* tC = m->tmisc; double* tS = tC + (size_t)mp * mp; double* tt = tS + (size_t)mp * mp; double* ta2 = tt + mp;
         double* tpart = ta2 + mp; double* tPn = tpart + part_dbl; double* trhs = tPn + 32 * N; double* tS0 = trhs + N;
         // alpha_1 part 1: z_f = X y_1, z_1 = A^-1 y_1 (the tail labels must not enter the leading solve)
@@ -476,7 +529,7 @@ static int ensure_linv_primary(gpr_model* m) {
     if (m->replica) return fail(GPR_ERR_INVALID, "replica model was created without L^-1");
     DeviceCtx* dc = m->ctx->devs[0];
     CU(cudaSetDevice(dc->dev));
-    if (!md.linv) CU(cudaMalloc((void**)&md.linv, m->cap * m->cap * sizeof(double)));
+    if (!md.linv) CU(big_alloc(m->ctx, dc->dev, (void**)&md.linv, m->cap * m->cap * sizeof(double)));
     Workspace* ws = nullptr;
     int rc = ws_acquire(dc, &ws);
     if (rc) return rc;
@@ -511,7 +564,7 @@ static int ensure_on_device(gpr_model* m, size_t di, bool need_linv) {
         dst.have = true;
     }
     if (need_linv && !dst.have_linv) {
-        if (!dst.linv) CU(cudaMalloc((void**)&dst.linv, m->cap * m->cap * sizeof(double)));
+        if (!dst.linv) CU(big_alloc(m->ctx, dst.dev, (void**)&dst.linv, m->cap * m->cap * sizeof(double)));
         CU(cudaMemcpyPeer(dst.linv, dst.dev, src.linv, src.dev, m->cap * m->cap * sizeof(double)));
         dst.have_linv = true;
     }
@@ -719,12 +772,19 @@ int gpr_ctx_create(const int* devices, int ndev, gpr_ctx** out) {
     }
     if (const char* s = getenv("GPR_CHOL_SERIAL")) ctx->chol_serial = atoi(s);
     if (const char* s = getenv("GPR_REFINE")) ctx->refine_steps = std::max(0, std::min(4, atoi(s)));
+    { std::lock_guard<std::mutex> lk(g_live_mu); g_live_ctx.push_back(ctx); }
     *out = ctx;
     return GPR_OK;
 }
 
 int gpr_ctx_destroy(gpr_ctx* ctx) {
     if (!ctx) return GPR_OK;
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live_ctx.erase(std::remove(g_live_ctx.begin(), g_live_ctx.end(), ctx), g_live_ctx.end());
+    }
+    for (auto& b : ctx->big_cache) { cudaSetDevice(b.dev); cudaFree(b.p); }
+    ctx->big_cache.clear();
     for (DeviceCtx* dc : ctx->devs) {
         cudaSetDevice(dc->dev);
         for (Workspace* ws : dc->free_ws) {
