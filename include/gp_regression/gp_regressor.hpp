@@ -197,6 +197,31 @@ public:
         if (rc != GPR_OK) detail::raise(rc);
     }
 
+    // Extension: AtlasBase::project (include/atlas/atlas.hpp:201-276, same defaults) for any number of points in one
+    // call.  in / normals / out: k x 3 (rows = points; normals = initial un-normalised gradients).  Returns, per
+    // point, the iterations used when a tolerance was met or -max_iter when the budget ran out.
+    std::vector<int> projectOnSurface(Model::ConstPtr gp, const Eigen::MatrixXd& in, const Eigen::MatrixXd& normals,
+                                      Eigen::MatrixXd& out, double f_tol = 1e-2, double improve_tol = 1e-7,
+                                      unsigned int max_iter = 500, double step_mul = 0.001) {
+        if (!gp) throw GPRegressionException("Empty Model pointer");
+        if (!gp->device) throw GPRegressionException("Model was not created by this regressor");
+        const size_t k = (size_t)in.rows();
+        if (k == 0 || in.cols() != 3 || normals.rows() != in.rows() || normals.cols() != 3)
+            throw GPRegressionException("All input data is empty!");
+        std::vector<double> buf(9 * k);
+        for (size_t i = 0; i < k; ++i)
+            for (int c = 0; c < 3; ++c) { buf[c * k + i] = in((Eigen::Index)i, c); buf[(3 + c) * k + i] = normals((Eigen::Index)i, c); }
+        std::vector<int> status(k);
+        const int rc = gpr_project(detail::context(), detail::handle(*gp), &buf[0], &buf[k], &buf[2 * k], &buf[3 * k], &buf[4 * k],
+                                   &buf[5 * k], k, f_tol, improve_tol, max_iter, step_mul, &buf[6 * k], &buf[7 * k], &buf[8 * k],
+                                   status.data());
+        if (rc != GPR_OK) detail::raise(rc);
+        out.resize((Eigen::Index)k, 3);
+        for (size_t i = 0; i < k; ++i)
+            for (int c = 0; c < 3; ++c) out((Eigen::Index)i, c) = buf[(6 + c) * k + i];
+        return status;
+    }
+
 private:
     // :563-572
     void assertData(Data::ConstPtr data) const {
