@@ -48,7 +48,8 @@ class Timings(C.Structure):
 
 class ModelState(C.Structure):
     _fields_ = [("n", C.c_size_t), ("padded_n", C.c_size_t), ("ld", C.c_size_t), ("kernel", KernelT), ("R", C.c_double),
-                ("xyz", C.c_void_p), ("alpha", C.c_void_p), ("linv", C.c_void_p)]
+                ("xyz", C.c_void_p), ("alpha", C.c_void_p), ("linv", C.c_void_p),
+                ("n_tail", C.c_size_t), ("tail_pad", C.c_size_t), ("tail_z", C.c_void_p), ("tail_sinv", C.c_void_p)]
 
 
 def build(force=False):
@@ -95,6 +96,7 @@ def lib():
         L.gpr_model_reserve.argtypes = [vp, vp, sz]
         L.gpr_model_state_get.argtypes = [vp, vp, ci, C.POINTER(ModelState)]
         L.gpr_model_create_replica.argtypes = [vp, sz, KernelT, cd, ci, C.POINTER(vp)]
+        L.gpr_model_create_replica_tail.argtypes = [vp, sz, sz, KernelT, cd, ci, C.POINTER(vp)]
         L.gpr_selftest_gemm.argtypes = [_dp, _dp, ci, _dp, ci, ci, ci]
         L.gpr_selftest_leaf.argtypes = [_dp, _dp, C.POINTER(ci)]
         L.gpr_selftest_factor.argtypes = [_dp, ci, _dp, ci, C.POINTER(C.c_longlong)]
@@ -110,7 +112,7 @@ C_ABI_SYMBOLS = [
     "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_tail_size", "gpr_model_get",
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
     "gpr_model_reserve", "gpr_sample_isosurface", "gpr_project", "gpr_model_save", "gpr_model_load",
-    "gpr_model_state_get", "gpr_model_create_replica", "gpr_selftest_gemm", "gpr_selftest_leaf",
+    "gpr_model_state_get", "gpr_model_create_replica", "gpr_model_create_replica_tail", "gpr_selftest_gemm", "gpr_selftest_leaf",
     "gpr_selftest_factor", "gpr_selftest_peak", "gpr_selftest_factor_trace",
 ]
 
@@ -319,9 +321,9 @@ class GPRegressor:
         """Device-pointer variant (ints from tensor.data_ptr()); no host copies."""
         _check(lib().gpr_predict_device(self.ctx._h, model._h, d_qx, d_qy, d_qz, q, d_f, d_var, d_grad))
 
-    def create_replica(self, n, R, with_linv):
+    def create_replica(self, n, R, with_linv, n_tail=0):
         h = C.c_void_p()
-        _check(lib().gpr_model_create_replica(self.ctx._h, n, self.kernel, float(R), int(with_linv), C.byref(h)))
+        _check(lib().gpr_model_create_replica_tail(self.ctx._h, n, n_tail, self.kernel, float(R), int(with_linv), C.byref(h)))
         return Model(self.ctx, h, False)
 
 

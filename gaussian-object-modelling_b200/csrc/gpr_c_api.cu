@@ -1408,16 +1408,26 @@ int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity) {
 
 int gpr_model_state_get(gpr_ctx* ctx, gpr_model* m, int with_linv, gpr_model_state* out) {
     if (!ctx || !m || !out) return fail(GPR_ERR_INVALID, "null pointer");
-    if (m->n_tail > 0) return fail(GPR_ERR_INVALID, "a model with an indefinite tail block cannot be replicated across processes yet");
     if (with_linv) { int rc = ensure_on_device(m, 0, true); if (rc) return rc; }
     out->n = m->n; out->padded_n = m->N; out->ld = m->cap; out->kernel = m->kernel; out->R = m->R;
     out->xyz = m->devs[0].xyz; out->alpha = m->devs[0].alpha;
     out->linv = m->devs[0].have_linv ? m->devs[0].linv : nullptr;
+    out->n_tail = m->n_tail; out->tail_pad = (size_t)m->mp;
+    out->tail_z = m->n_tail ? m->devs[0].tZ : nullptr;
+    out->tail_sinv = m->n_tail ? m->devs[0].tSinv : nullptr;
     return GPR_OK;
 }
 
+int gpr_model_create_replica_tail(gpr_ctx* ctx, size_t n, size_t n_tail, gpr_kernel_t kernel, double R, int with_linv,
+                                  gpr_model** out);
+
 int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double R, int with_linv, gpr_model** out) {
-    if (!ctx || !out || n == 0) return fail(GPR_ERR_INVALID, "null pointer or empty model");
+    return gpr_model_create_replica_tail(ctx, n, 0, kernel, R, with_linv, out);
+}
+
+int gpr_model_create_replica_tail(gpr_ctx* ctx, size_t n, size_t n_tail, gpr_kernel_t kernel, double R, int with_linv,
+                                  gpr_model** out) {
+    if (!ctx || !out || n == 0 || n_tail >= n || n_tail > MAX_TAIL) return fail(GPR_ERR_INVALID, "null pointer, empty model or bad tail size");
     gpr_model* m = new gpr_model();
     m->ctx = ctx; m->kernel = kernel; m->kp = make_kp(kernel); m->k0 = kernel_at_zero(m->kp); m->R = R;
     m->replica = true;
@@ -1435,6 +1445,15 @@ int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double
         if (cudaMalloc((void**)&md.linv, m->N * m->N * sizeof(double)) != cudaSuccess)
             return bail(fail(GPR_ERR_OOM, "out of device memory"));
         md.have_linv = true;
+    }
+    if (n_tail > 0) {
+        // the trailing pivot block of an indefinite matrix (gpr_tail.cu): L / L^-1 describe the leading n - n_tail points
+        m->n_spd = n - n_tail; m->n_tail = n_tail; m->nb = (int)((m->n_spd + TB - 1) / TB);
+        m->mp = 32 * (int)((n_tail + 31) / 32);
+        if (cudaMalloc((void**)&md.tZ, (size_t)(m->mp / 32) * m->cap * 32 * sizeof(double)) != cudaSuccess ||
+            cudaMalloc((void**)&md.tSinv, (size_t)m->mp * m->mp * sizeof(double)) != cudaSuccess)
+            return bail(fail(GPR_ERR_OOM, "out of device memory"));
+        md.have_tail = true;
     }
     *out = m;
     return GPR_OK;

@@ -33,17 +33,21 @@ def broadcast_model(reg, model, n, R, with_linv, rank, device, src=0):
     Returns (model, bytes_broadcast)."""
     import torch
     import torch.distributed as dist
-    meta = torch.tensor([float(n), float(R)], dtype=torch.float64, device=device)
+    n_tail = model.n_tail if rank == src else 0
+    meta = torch.tensor([float(n), float(R), float(n_tail)], dtype=torch.float64, device=device)
     dist.broadcast(meta, src=src)
-    n, R = int(meta[0].item()), float(meta[1].item())
+    n, R, n_tail = int(meta[0].item()), float(meta[1].item()), int(meta[2].item())
     if rank != src:
-        model = reg.create_replica(n, R, with_linv)
+        model = reg.create_replica(n, R, with_linv, n_tail)
     st = model.state(with_linv=with_linv)
     N = st.padded_n
     if st.ld != N:
         raise ValueError("model has spare capacity (ld %d != padded n %d): broadcast a freshly fitted model" % (st.ld, N))
     nbytes = 0
-    for ptr, cnt in ((st.xyz, 3 * N), (st.alpha, N)) + (((st.linv, N * N),) if with_linv else ()):
+    parts = ((st.xyz, 3 * N), (st.alpha, N)) + (((st.linv, N * N),) if with_linv else ())
+    if n_tail:                                  # indefinite tail block: Z = A^-1 P (slabs) and S^-1
+        parts += ((st.tail_z, (st.tail_pad // 32) * N * 32), (st.tail_sinv, st.tail_pad * st.tail_pad))
+    for ptr, cnt in parts:
         t = as_tensor(ptr, cnt, device)
         # NCCL counts are 32-bit element counts in some paths: broadcast the factor in 1 GiB pieces
         step = 1 << 27

@@ -145,11 +145,18 @@ typedef struct {
     gpr_kernel_t kernel;
     double R;
     double* xyz; double* alpha; double* linv;
+    /* indefinite tail block (0 / NULL for a positive definite matrix): tail_z is (tail_pad/32) slabs of ld x 32
+     * doubles, tail_sinv tail_pad x tail_pad; linv / the factor then describe the leading n - n_tail points */
+    size_t n_tail, tail_pad;
+    double* tail_z; double* tail_sinv;
 } gpr_model_state;
 int gpr_model_state_get(gpr_ctx* ctx, gpr_model* m, int with_linv, gpr_model_state* out);
 /* Allocates an un-fitted model of the given size on ctx's primary device; the caller fills the buffers
  * returned by gpr_model_state_get(replica, ...) (e.g. as the destination of a broadcast). */
 int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double R, int with_linv, gpr_model** out);
+/* Same for a model whose last n_tail points (internal order) form the indefinite tail block (gpr_model_tail_size). */
+int gpr_model_create_replica_tail(gpr_ctx* ctx, size_t n, size_t n_tail, gpr_kernel_t kernel, double R, int with_linv,
+                                  gpr_model** out);
 
 /* ---- self-tests of the tile engine (used by tests/, device pointers, one 128-tile granularity) -- */
 int gpr_selftest_gemm(const double* hA, const double* hB, int b_kmajor, double* hC, int m_tiles, int n_tiles, int k);

@@ -600,3 +600,14 @@ def test_model_save_and_load_round_trip(gpr, ctx, tmp_path):
     assert mn2.n_tail == 15 and np.array_equal(mn2.alpha, mn.alpha)
     with pytest.raises(gpr.GPRegressionException):
         regn.load(tmp_path / "missing.bin")
+
+
+def test_tail_block_is_replicated_across_processes(gpr):
+    """Two ranks under torchrun (needs 2 GPUs): the indefinite-tail model of the node's configuration is broadcast with
+    NCCL and both ranks reproduce the reference fixture on their query shards."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([os.sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", os.path.join(ROOT, "tools", "tail_replica_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "TAIL_REPLICA_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
