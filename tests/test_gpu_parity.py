@@ -353,6 +353,33 @@ def test_full_size_properties_config3(gpr, ctx):
     assert t["predict_var_ms"] > 0 and t["linv_ms"] > 0
 
 
+def test_full_size_properties_config5(gpr, ctx):
+    """BASELINE config 5 at full size (n = 65,536: K = 32 GiB factorised in place, + 32 GiB of L^-1): the solve's
+    residual on a row subset, single-query calls (fused kernel over the whole triangle of L^-1), one tile-variance
+    batch, and consistency between the two variance paths."""
+    import torch
+    free, total = torch.cuda.mem_get_info(0)
+    if free < 90 * (1 << 30):
+        pytest.skip("needs ~80 GB of free device memory")
+    W = gpr.workloads
+    n = 65536
+    P, y, s2 = W.synthetic_cloud(n, seed=0)
+    reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+    a = m.alpha
+    idx = np.arange(0, n, 1024)
+    d = np.sqrt(((P[idx, None, :] - P[None, :, :]) ** 2).sum(-1))
+    K = 2 * d ** 3 - 3 * W.SYNTH_R * d ** 2 + W.SYNTH_R ** 3
+    K[np.arange(len(idx)), idx] += s2[idx]
+    assert np.abs(K @ a - y[idx]).max() <= 1e-9
+    Q = W.grid_slab(512, 256, 257)[:2048]
+    f, v = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)                 # tile path (16 query tiles)
+    assert np.isfinite(f).all() and v.min() > 0.0 and v.max() < 1.0
+    f1, v1 = reg.evaluate(m, Q[:4, 0], Q[:4, 1], Q[:4, 2], var=True)            # fused small-batch kernel
+    assert np.abs(f1 - f[:4]).max() <= 1e-9 * np.abs(f).max() and np.abs(v1 - v[:4]).max() <= 1e-7 * v.max()
+    m.close()
+
+
 def test_cxx_dropin_headers_end_to_end(gpr, orc, tmp_path):
     """The reference-facing C++ API (include/gp_regression/*.h) compiled as C++11 and run on the GPU."""
     from test_host import _build_driver
