@@ -12,6 +12,7 @@
 // Per-tile partial sums are written to a [row tile][query] scratch and summed in a fixed order by a
 // second small kernel, so the variance is bit-reproducible (no floating-point atomics) and independent of
 // how the queries are batched or sharded.
+#include <cstdlib>
 #include "gpr_mma.cuh"
 #include "gpr_kernels.h"
 
@@ -22,10 +23,10 @@ struct VarArgs {
     const double* panel; size_t panel_ld;     // K*: element (query, k) at panel[k*panel_ld + query]
     int nqt;                                  // query tiles in this batch (panel_ld / 128)
     double* partial;                          // nb x panel_ld
-    int gq, qgroups;                          // query tiles per co-scheduled group, number of such groups
+    int gi, gq, qgroups;                      // row-tile pairs / query tiles per co-scheduled group, number of query groups
 };
 
-constexpr int VAR_GI = 4;                     // row-tile pairs per co-scheduled group
+constexpr int VAR_GI = 8;                     // row-tile pairs per co-scheduled group (GPR_VAR_GI overrides; sweep: tools/var_gi_sweep.sh)
 
 // Task = (pair p, query tile qt): the CTA computes row tile nb-1-p and then row tile p of V = X K*^T for
 // its 128 queries.  The k ranges of the two rows add up to nb+1 blocks for EVERY task, so all CTAs of
@@ -34,16 +35,17 @@ constexpr int VAR_GI = 4;                     // row-tile pairs per co-scheduled
 // by gq CTAs at the same time and each K* tile by VAR_GI CTAs at (nearly) the same time, i.e. once from
 // HBM and then from L2.  (With one row tile per CTA and a whole row of query tiles resident together,
 // every K* tile was fetched from HBM again for each of the nb row tiles: 161 GB of DRAM reads per batch
-// for 3.6 GB of operands, ncu profile r1b.)
+// for 3.6 GB of operands, ncu profile r1b.  Measured DRAM reads per batch at n = 16384: 4 x 37 -> 45.9 GB,
+// 8 x 18 -> 31.2 GB, 16 x 9 -> 35.1 GB, all at the same 35.8 TF/s.)
 __global__ void __launch_bounds__(NTHREADS, 1) var_tiles_kernel(VarArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_abort;
     __shared__ double sred[8][32];
-    const int per_group = VAR_GI * a.gq;
+    const int per_group = a.gi * a.gq;
     const int g = blockIdx.x / per_group, w = blockIdx.x % per_group;
     const int pg = g / a.qgroups, qg = g % a.qgroups;
-    const int p = pg * VAR_GI + w % VAR_GI;
-    const int qt = qg * a.gq + w / VAR_GI;
+    const int p = pg * a.gi + w % a.gi;
+    const int qt = qg * a.gq + w / a.gi;
     if (2 * p >= a.nb || qt >= a.nqt) return;          // pairs p < ceil(nb/2)
     if (threadIdx.x == 0) s_abort = 0;
     const TileCoord tc;
@@ -100,12 +102,14 @@ cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* pa
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    a.gq = sms / VAR_GI > 0 ? sms / VAR_GI : 1;
+    static const int gi_env = getenv("GPR_VAR_GI") ? atoi(getenv("GPR_VAR_GI")) : 0;
+    a.gi = gi_env >= 1 && gi_env <= 64 ? gi_env : VAR_GI;
+    a.gq = sms / a.gi > 0 ? sms / a.gi : 1;
     if (a.gq > a.nqt) a.gq = a.nqt;
     a.qgroups = (a.nqt + a.gq - 1) / a.gq;
     const int npairs = (nb + 1) / 2;
-    const int pgroups = (npairs + VAR_GI - 1) / VAR_GI;
-    var_tiles_kernel<<<(unsigned)(pgroups * a.qgroups * VAR_GI * a.gq), NTHREADS, TILE_SMEM_BYTES, st>>>(a);
+    const int pgroups = (npairs + a.gi - 1) / a.gi;
+    var_tiles_kernel<<<(unsigned)(pgroups * a.qgroups * a.gi * a.gq), NTHREADS, TILE_SMEM_BYTES, st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     var_finalize_kernel<<<(q + 255) / 256, 256, 0, st>>>(partial, panel_ld, nb, q, k0, var);
