@@ -606,18 +606,19 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
     cudaStream_t st = ws->st;
     const size_t N = m->N, ld = m->cap;
     const int n = (int)m->n;
-    if (!io.device_ptrs && io.q <= 8 && m->n_tail == 0) {
+    if (!io.device_ptrs && io.q <= 8) {
         // The reference's callers: one query per call.  One fused launch, I/O through mapped pinned memory.
         if (!ws->hio) {
             CU(cudaHostAlloc((void**)&ws->hio, SMALL_HIO_DOUBLES * sizeof(double), cudaHostAllocMapped));
             CU(cudaHostGetDevicePointer((void**)&ws->hio_dev, ws->hio, 0));
         }
-        const size_t need = predict_small_scratch_doubles((int)N);
-        if (ws->small_dbl < need || ws->small_N != N) {
+        const size_t Nv = (size_t)m->nb * TB;                   // padded rows of L^-1 (the leading block if there is a tail)
+        const size_t need = predict_small_scratch_doubles((int)Nv);
+        if (ws->small_dbl < need || ws->small_N != Nv) {
             rc = ws_reserve(&ws->small, &ws->small_dbl, need);
             if (rc) return rc;
-            CU(cudaMemsetAsync(ws->small, 0, ws->small_dbl * sizeof(double), st));   // the layout (tickets) depends on N
-            ws->small_N = N;
+            CU(cudaMemsetAsync(ws->small, 0, ws->small_dbl * sizeof(double), st));   // the layout (tickets) depends on Nv
+            ws->small_N = Nv;
         }
         const int q = (int)io.q;
         for (int i = 0; i < q; ++i) {
@@ -625,7 +626,8 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         }
         CU(cudaEventRecord(ws->ev[0], st));
         CU(launch_predict_small(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, n, (int)N, want_var ? md.linv : nullptr, ld,
-                                ws->hio_dev, ws->small, q, want_var, want_grad, want_t, m->k0, m->kp, st));
+                                ws->hio_dev, ws->small, q, want_var, want_grad, want_t, m->k0, m->kp, (int)m->n_spd, (int)Nv,
+                                m->mp, md.tZ, md.tSinv, st));
         CU(cudaEventRecord(ws->ev[1], st));
         CU(cudaStreamSynchronize(st));
         const double* out = ws->hio + 24;

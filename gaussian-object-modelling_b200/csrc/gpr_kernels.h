@@ -35,10 +35,11 @@ cudaError_t launch_predict(const double* px, const double* py, const double* pz,
 // Fused q <= 8 path: one launch, queries and results in a mapped pinned host buffer (112 doubles, layout in
 // gpr_predict.cu).  scratch: predict_small_scratch_doubles(N) doubles, zeroed once at allocation.
 constexpr int SMALL_HIO_DOUBLES = 112;
-size_t predict_small_scratch_doubles(int N);
+size_t predict_small_scratch_doubles(int Nv);
 cudaError_t launch_predict_small(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
                                  const double* X, size_t ld, double* hio, double* scratch, int q, int want_var,
-                                 int want_grad, int want_t, double k0, const KernParams& kp, cudaStream_t st);
+                                 int want_grad, int want_t, double k0, const KernParams& kp, int n_var, int Nv, int mp,
+                                 const double* tZ, const double* tSinv, cudaStream_t st);
 // Lattice generation + |f| <= tol compaction for the batched iso-surface sampler.
 cudaError_t launch_grid_fill(const double* axis, int na, unsigned long long g0, int count, double* qx, double* qy,
                              double* qz, cudaStream_t st);

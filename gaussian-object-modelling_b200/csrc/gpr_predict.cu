@@ -295,6 +295,11 @@ struct SmallArgs {
     int q, want_var, want_grad, want_t;
     int vs, kspan;                  // k-splits and their extent (multiple of 256)
     int nvar_blocks, nmean_blocks;
+    // indefinite tail block (gpr_tail.cu): X covers the leading n_var points / Nv padded rows; the last n_tail points
+    // enter through var -= w^T S^-1 w, w = k_2 - Z^T k_1.  n_tail == 0: n_var == n, Nv == N.
+    int n_var, Nv, n_tail, mp;
+    const double* tZ; const double* tSinv;
+    double* wpart;                  // SMALL_MS * 8 * 256: partial Z^T k_1 per mean block and query
     double k0;
     KernParams kp;
 };
@@ -315,9 +320,9 @@ __global__ void __launch_bounds__(256) predict_small_kernel(SmallArgs a) {
         const int rl = tid & 63, kq = tid >> 6;
         const int r = bx * 64 + rl;
         const int kbeg = by * a.kspan;
-        const int kend = min(min(kbeg + a.kspan, a.N), bx * 64 + 64);
+        const int kend = min(min(kbeg + a.kspan, a.Nv), bx * 64 + 64);
         if (kbeg >= kend) return;                                    // above the diagonal: nothing to do
-        const int nsplit = (min(a.N, bx * 64 + 64) + a.kspan - 1) / a.kspan;   // non-empty splits of this row block
+        const int nsplit = (min(a.Nv, bx * 64 + 64) + a.kspan - 1) / a.kspan;   // non-empty splits of this row block
         double acc[Q];
 #pragma unroll
         for (int i = 0; i < Q; ++i) acc[i] = 0.0;
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(256) predict_small_kernel(SmallArgs a) {
             __syncthreads();
             {
                 const int c = c0 + tid;
-                const bool real = c < a.n;
+                const bool real = c < a.n_var;
                 const double x = real ? a.px[c] : 0.0, y = real ? a.py[c] : 0.0, z = real ? a.pz[c] : 0.0;
 #pragma unroll
                 for (int i = 0; i < Q; ++i) {
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(256) predict_small_kernel(SmallArgs a) {
         if (kq == 0) {
 #pragma unroll
             for (int i = 0; i < Q; ++i)
-                a.part[((size_t)by * a.N + r) * 8 + i] = ((r4[rl * Q + i] + r4[(64 + rl) * Q + i]) + r4[(128 + rl) * Q + i]) + r4[(192 + rl) * Q + i];
+                a.part[((size_t)by * a.Nv + r) * 8 + i] = ((r4[rl * Q + i] + r4[(64 + rl) * Q + i]) + r4[(128 + rl) * Q + i]) + r4[(192 + rl) * Q + i];
         }
         // row-block ticket: the last of the nsplit blocks squares and sums the 64 rows
         __threadfence();
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(256) predict_small_kernel(SmallArgs a) {
 #pragma unroll
             for (int i = 0; i < Q; ++i) {
                 double v = 0.0;
-                for (int y = 0; y < nsplit; ++y) v += __ldcg(a.part + ((size_t)y * a.N + bx * 64 + tid) * 8 + i);
+                for (int y = 0; y < nsplit; ++y) v += __ldcg(a.part + ((size_t)y * a.Nv + bx * 64 + tid) * 8 + i);
                 red[tid * Q + i] = v * v;
             }
         }
@@ -403,6 +408,40 @@ __global__ void __launch_bounds__(256) predict_small_kernel(SmallArgs a) {
                 const double w = al * kern_diff<KIND>(a.kp, d, kv);
                 gx = fma(w, dx, gx); gy = fma(w, dy, gy); gz = fma(w, dz, gz);
             }
+            if (a.n_tail > 0 && a.want_var) {
+                // partial W = Z^T k_1 over this block's slice of the leading points: chunks of 256 kernel values in
+                // shared memory, thread = (tail column ta, row phase), phases summed in a fixed order
+                const int nph = 256 / a.mp, ta = tid % a.mp, ph = tid / a.mp;
+                const int jv1 = min(j1, a.n_var);
+                double wacc = 0.0;
+                for (int c0 = j0; c0 < jv1; c0 += 256) {
+                    __syncthreads();
+                    {
+                        const int j = c0 + tid;
+                        double kv = 0.0;
+                        if (j < jv1) {
+                            const double dx = sq[0][i] - a.px[j], dy = sq[1][i] - a.py[j], dz = sq[2][i] - a.pz[j];
+                            kv = kern_value<KIND>(a.kp, sqrt(fma(dz, dz, fma(dy, dy, dx * dx))));
+                        }
+                        ks[tid][0] = kv;
+                    }
+                    __syncthreads();
+                    if (ph < nph) {
+                        const int lim = min(256, jv1 - c0);
+                        const double* zc = a.tZ + ((size_t)(ta >> 5) * a.ld + c0) * 32 + (ta & 31);
+                        for (int jl = ph; jl < lim; jl += nph) wacc = fma(zc[(size_t)jl * 32], ks[jl][0], wacc);
+                    }
+                }
+                __syncthreads();
+                red[tid] = ph < nph ? wacc : 0.0;
+                __syncthreads();
+                if (tid < a.mp) {
+                    double t = 0.0;
+                    for (int p2 = 0; p2 < nph; ++p2) t += red[p2 * a.mp + tid];
+                    a.wpart[((size_t)mb * 8 + i) * 256 + tid] = t;
+                }
+                __syncthreads();
+            }
             double vals[4] = {f, gx, gy, gz};
             for (int c = 0; c < (a.want_grad ? 4 : 1); ++c) {
                 // fixed-order tree: warp shuffles, then the 8 warp sums
@@ -425,13 +464,13 @@ __global__ void __launch_bounds__(256) predict_small_kernel(SmallArgs a) {
     // ---- global ticket: one per non-empty row block + one per mean block; the last one finishes ----
     __threadfence();
     __syncthreads();
-    const unsigned total = (unsigned)(a.want_var ? (a.N + 63) / 64 : 0) + (unsigned)a.nmean_blocks;
+    const unsigned total = (unsigned)(a.want_var ? (a.Nv + 63) / 64 : 0) + (unsigned)a.nmean_blocks;
     if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == total - 1 ? 1u : 0u;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     double* out = a.hio + 24;
-    const int nrb = (a.N + 63) / 64;
+    const int nrb = (a.Nv + 63) / 64;
     for (int i = 0; i < a.q; ++i) {
         if (a.want_var) {
             // squared norm = sum over the row blocks, fixed order: strided partial sums, then a tree
@@ -444,7 +483,39 @@ __global__ void __launch_bounds__(256) predict_small_kernel(SmallArgs a) {
                 if (tid < o) red[tid] += red[tid + o];
                 __syncthreads();
             }
-            if (tid == 0) out[8 + i] = a.k0 - red[0];
+            double var = a.k0 - red[0];
+            if (a.n_tail > 0) {
+                // var -= w^T S^-1 w,  w = k_2 - Z^T k_1
+                double* wsm = &ks[0][0];
+                __syncthreads();
+                if (tid < a.mp) {
+                    double wv = 0.0;
+                    if (tid < a.n_tail) {
+                        double W = 0.0;
+                        for (int mb = 0; mb < a.nmean_blocks; ++mb) W += __ldcg(a.wpart + ((size_t)mb * 8 + i) * 256 + tid);
+                        const int j = a.n_var + tid;
+                        const double dx = sq[0][i] - a.px[j], dy = sq[1][i] - a.py[j], dz = sq[2][i] - a.pz[j];
+                        wv = kern_value<KIND>(a.kp, sqrt(fma(dz, dz, fma(dy, dy, dx * dx)))) - W;
+                    }
+                    wsm[tid] = wv;
+                }
+                __syncthreads();
+                double term = 0.0;
+                if (tid < a.n_tail) {
+                    double row = 0.0;
+                    for (int b = 0; b < a.n_tail; ++b) row = fma(a.tSinv[(size_t)tid * a.mp + b], wsm[b], row);
+                    term = wsm[tid] * row;
+                }
+                __syncthreads();
+                red[tid] = term;
+                __syncthreads();
+                for (int o = 128; o > 0; o >>= 1) {
+                    if (tid < o) red[tid] += red[tid + o];
+                    __syncthreads();
+                }
+                var -= red[0];
+            }
+            if (tid == 0) out[8 + i] = var;
         }
         if (tid == 0) {
             double v[4] = {0.0, 0.0, 0.0, 0.0};
@@ -475,29 +546,36 @@ static void launch_small_q(const SmallArgs& a, int grid, cudaStream_t st) {
 
 static int small_vs(int N) { int v = (N + 1023) / 1024; return v < 1 ? 1 : (v > 16 ? 16 : v); }
 
-// ticket (2) | fpart | row tickets (one unsigned per 64 rows) | rowpart | part
-size_t predict_small_scratch_doubles(int N) {
-    const size_t nrb = (size_t)(N + 63) / 64;
-    return 2 + SMALL_MS * 8 * 4 + (nrb + 1) / 2 + nrb * 8 + (size_t)small_vs(N) * N * 8;
+constexpr int SMALL_WPART = SMALL_MS * 8 * 256;
+
+// ticket (2) | fpart | wpart | row tickets (one unsigned per 64 rows) | rowpart | part
+size_t predict_small_scratch_doubles(int Nv) {
+    const size_t nrb = (size_t)(Nv + 63) / 64;
+    return 2 + SMALL_MS * 8 * 4 + SMALL_WPART + (nrb + 1) / 2 + nrb * 8 + (size_t)small_vs(Nv) * Nv * 8;
 }
 
-// scratch: predict_small_scratch_doubles(N) doubles, zero-initialised when allocated AND whenever N changes (the
+// scratch: predict_small_scratch_doubles(Nv) doubles, zero-initialised when allocated AND whenever Nv changes (the
 // tickets inside it are re-armed by the kernel itself).  hio: device pointer of the mapped host buffer.
+// n / N: all training points (mean, gradient); n_var / Nv: the points / padded rows covered by X = L^-1 (== n / N unless
+// the model has an indefinite tail block of n_tail = n - n_var points, described by tZ / tSinv / mp).
 cudaError_t launch_predict_small(const double* px, const double* py, const double* pz, const double* alpha, int n, int N,
                                  const double* X, size_t ld, double* hio, double* scratch, int q, int want_var,
-                                 int want_grad, int want_t, double k0, const KernParams& kp, cudaStream_t st) {
+                                 int want_grad, int want_t, double k0, const KernParams& kp, int n_var, int Nv, int mp,
+                                 const double* tZ, const double* tSinv, cudaStream_t st) {
     if (q <= 0 || q > 8) return cudaErrorInvalidValue;
     SmallArgs a;
     a.px = px; a.py = py; a.pz = pz; a.alpha = alpha; a.n = n; a.N = N; a.X = X; a.ld = ld; a.hio = hio;
-    const size_t nrb = (size_t)(N + 63) / 64;
+    a.n_var = n_var; a.Nv = Nv; a.n_tail = n - n_var; a.mp = mp > 0 ? mp : 32; a.tZ = tZ; a.tSinv = tSinv;
+    const size_t nrb = (size_t)(Nv + 63) / 64;
     a.ticket = reinterpret_cast<unsigned int*>(scratch);
     a.fpart = scratch + 2;
-    a.rowticket = reinterpret_cast<unsigned int*>(a.fpart + SMALL_MS * 8 * 4);
-    a.rowpart = a.fpart + SMALL_MS * 8 * 4 + (nrb + 1) / 2;
+    a.wpart = a.fpart + SMALL_MS * 8 * 4;
+    a.rowticket = reinterpret_cast<unsigned int*>(a.wpart + SMALL_WPART);
+    a.rowpart = a.wpart + SMALL_WPART + (nrb + 1) / 2;
     a.part = a.rowpart + nrb * 8;
     a.q = q; a.want_var = want_var && X != nullptr; a.want_grad = want_grad; a.want_t = want_t; a.k0 = k0; a.kp = kp;
-    a.vs = small_vs(N);
-    a.kspan = ((N + a.vs - 1) / a.vs + 255) / 256 * 256;
+    a.vs = small_vs(Nv);
+    a.kspan = ((Nv + a.vs - 1) / a.vs + 255) / 256 * 256;
     a.nvar_blocks = a.want_var ? (int)nrb * a.vs : 0;
     a.nmean_blocks = (n + 2047) / 2048 < SMALL_MS ? (n + 2047) / 2048 : SMALL_MS;
     if (a.nmean_blocks < 1) a.nmean_blocks = 1;
