@@ -139,3 +139,20 @@ def test_query_sharding_world_size_2_gloo(tmp_path, orc):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GLOO_OK" in outs[0]
+
+
+def test_standalone_cmake_build(tmp_path):
+    """the library builds standalone, without ROS / catkin (the reference is a catkin package): configure and
+    build CMakeLists.txt (nvcc cross-compiles sm_100a without a GPU), then run the drop-in driver's argument checks."""
+    import shutil
+    if shutil.which("cmake") is None or not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("cmake or nvcc not available")
+    b = str(tmp_path / "build")
+    cfg = subprocess.run(["cmake", "-S", ROOT, "-B", b, "-DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc"], capture_output=True, text=True)
+    assert cfg.returncode == 0, cfg.stdout[-2000:] + cfg.stderr[-2000:]
+    bld = subprocess.run(["cmake", "--build", b, "-j8"], capture_output=True, text=True)
+    assert bld.returncode == 0, bld.stdout[-2000:] + bld.stderr[-2000:]
+    out = subprocess.run([os.path.join(b, "dropin_driver"), "--errors"], capture_output=True, text=True)
+    assert out.returncode == 0 and "All input data is empty!" in out.stdout
+    syms = subprocess.run(["nm", "-D", "--defined-only", os.path.join(b, "libgpr_b200.so")], capture_output=True, text=True).stdout
+    assert " gpr_fit" in syms and " gpr_predict" in syms and " gpr_append" in syms
