@@ -268,17 +268,21 @@ __global__ void __launch_bounds__(256) dinv_from_x_kernel(const double* __restri
     }
 }
 
-// Rows [r0, r1) of L and X become identity rows (padding state): zero for columns < row, 1 on the diagonal,
-// and the part of later rows' columns [r0, r1) is zeroed as well (rows >= r1 up to row_end).
+// Rows AND columns [r0, r1) of L and X become those of the identity (padding state) for rows < row_end: 1 on the
+// diagonal, 0 elsewhere in the lower triangle — and 0 above the diagonal INSIDE the diagonal 128x128 tiles, which the
+// tile kernels read as whole tiles (the rest of the upper triangle is never read).
 __global__ void __launch_bounds__(256) identity_rows_kernel(double* L, double* X, size_t ld, int r0, int r1, int row_end) {
     const int c = blockIdx.x;                 // column
-    for (int r = r0 + threadIdx.x; r < row_end; r += 256) {
-        if (r < c) continue;                  // upper part is never read
-        if (r < r1 || (c >= r0 && c < r1)) {
-            const double v = (r == c) ? 1.0 : 0.0;
-            L[(size_t)c * ld + r] = v;
-            if (X) X[(size_t)c * ld + r] = v;
-        }
+    const bool c_new = c >= r0 && c < r1;
+    const int tile0 = c & ~(TB - 1);          // first row of column c's diagonal tile
+    for (int r = min(r0, tile0) + threadIdx.x; r < row_end; r += 256) {
+        if (r < tile0) continue;              // above the diagonal tile: never read
+        const bool r_new = r >= r0 && r < r1;
+        if (!(r_new || c_new)) continue;      // an entry of the old factor
+        if (r < c && r >= tile0 + TB) continue;
+        const double v = (r == c) ? 1.0 : 0.0;
+        L[(size_t)c * ld + r] = v;
+        if (X) X[(size_t)c * ld + r] = v;
     }
 }
 

@@ -36,6 +36,20 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         }                                                                                          \
     } while (0)
 
+// Debug aid: GPR_POISON=1 fills every fresh device allocation of this file with 0xFF bytes (NaN doubles, huge
+// ints), so that any read of memory the library has not written shows up as NaN in the parity tests instead of
+// depending on what cudaMalloc happens to return (a fresh process gets zeroed pages, a long-running one does not).
+static cudaError_t gpr_malloc_poison(void** p, size_t bytes) {
+    static const bool poison = getenv("GPR_POISON") && atoi(getenv("GPR_POISON")) != 0;
+    cudaError_t e = (cudaMalloc)(p, bytes);
+    if (e == cudaSuccess && poison && bytes) {
+        e = cudaMemset(*p, 0xFF, bytes);          // legacy stream: not ordered against the library's non-blocking streams
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    return e;
+}
+#define cudaMalloc(p, bytes) gpr_malloc_poison((void**)(p), (bytes))
+
 // ------------------------------------------------------------------------------------------------
 // context, workspaces
 // ------------------------------------------------------------------------------------------------
@@ -93,7 +107,13 @@ static void* big_take(gpr_ctx* ctx, int dev, size_t bytes) {
 // cudaMalloc through the cache.  The buffer is NOT cleared.
 static cudaError_t big_alloc(gpr_ctx* ctx, int dev, void** p, size_t bytes) {
     *p = bytes >= BIG_MIN ? big_take(ctx, dev, bytes) : nullptr;
-    return *p ? cudaSuccess : cudaMalloc(p, bytes);
+    if (*p) {
+        static const bool poison = getenv("GPR_POISON") && atoi(getenv("GPR_POISON")) != 0;
+        if (!poison) return cudaSuccess;
+        cudaError_t e = cudaMemset(*p, 0xFF, bytes);
+        return e == cudaSuccess ? cudaDeviceSynchronize() : e;
+    }
+    return cudaMalloc(p, bytes);
 }
 // Returns the buffer to the cache of its context (if that context is still alive and the cache has room), else frees it.
 // The caller guarantees that no work is pending on the buffer.  Current device must be `dev`.
@@ -295,6 +315,9 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
         CU(cudaMemsetAsync(md.xyz, 0, 3 * N * sizeof(double), st));
         CU(cudaMemsetAsync(m->label, 0, N * sizeof(double), st));
         CU(cudaMemsetAsync(m->s2, 0, N * sizeof(double), st));
+        // alpha of the padding points must be 0 (the thread-per-query kernel walks all N padded points); with an
+        // indefinite tail the solves only write the rows of the leading block and of the tail
+        CU(cudaMemsetAsync(md.alpha, 0, N * sizeof(double), st));
         CU(cudaMemcpyAsync(md.xyz, px, n * sizeof(double), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(md.xyz + N, py, n * sizeof(double), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(md.xyz + 2 * N, pz, n * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -359,6 +382,14 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
                 if (r > worst) { worst = r; q = j; }
             }
             if (q != p && cnt_of(q) > cnt_of(p)) evict = q;
+            if (cnt_of(evict) == 0) {
+                // No point is to blame (no indefinite 2x2 minor): the matrix is indefinite as a whole — e.g. a nearly
+                // noise-free thin-plate matrix, which is only conditionally positive definite.  Moving single points
+                // away would let the factorisation run on into tiny pivots; take everything from the failing pivot on
+                // as the trailing block if that is small enough, otherwise give up.
+                if (n - p <= MAX_TAIL) go_tail = true; else break;
+            }
+          if (!go_tail) {
             // evict it together with every point that is at least half as conflicted (the other outliers), most
             // conflicted first, keeping the relative order of the rest
             const int thr = std::max(1, cnt_of(evict) / 2);
@@ -388,6 +419,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
                 if (rc) return rc;
                 continue;
             }
+          }
         }
         {
             // Indefinite matrix whose offending points are now the last few of the internal order (in the node's own
@@ -975,6 +1007,11 @@ int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, doub
             unsigned int found = 0;
             CU(cudaMemcpyAsync(&found, dcounter, sizeof(found), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            if (found > (unsigned)cnt) {
+                char b[160];
+                snprintf(b, sizeof b, "iso-surface sampler: selection counter %u exceeds the chunk size %d", found, cnt);
+                return fail(GPR_ERR_CUDA, b);
+            }
             if (found) {
                 hidx.resize(found); hf.resize(found);
                 CU(cudaMemcpyAsync(hidx.data(), dselidx, found * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1397,7 +1434,7 @@ int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity) {
     std::lock_guard<std::mutex> lk(m->mu);
     const size_t want = (capacity + TB - 1) / TB * TB;
     if (want <= m->cap) return GPR_OK;
-    if (m->n_tail > 0) return fail(GPR_ERR_INVALID, "reserve is not supported on a model with an indefinite tail block");
+    if (m->n_tail > 0) return GPR_OK;        // updates of a model with an indefinite tail block refit: nothing to reserve
     DeviceCtx* dc = ctx->devs[0];
     CU(cudaSetDevice(dc->dev));
     Workspace* ws = nullptr;

@@ -122,7 +122,8 @@ int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m);
 int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
                const double* sigma2_or_null, size_t k);
 /* Pre-allocates room for `capacity` points so that later appends do not reallocate (growth is otherwise
- * geometric, x1.25).  Invalidates pointers returned earlier by gpr_model_state_get. */
+ * geometric, x1.25).  Invalidates pointers returned earlier by gpr_model_state_get.  No effect on a model with an
+ * indefinite tail block (its updates refit). */
 int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity);
 
 /* ---- export / import (the reference has no persistence for the GP) ----------------- */

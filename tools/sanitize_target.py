@@ -31,4 +31,8 @@ fq, vq = reg2.evaluate(mn, Q[:2, 0], Q[:2, 1], Q[:2, 2], var=True)
 reg3 = g.GPRegressor("gaussian", 1.0, 1.0, ctx=ctx)
 mg = reg3.create(P[:300, 0], P[:300, 1], P[:300, 2], y[:300], None)
 fg, vg, gg = reg3.evaluate(mg, Q[:200, 0], Q[:200, 1], Q[:200, 2], var=True, grad=True)
+for name, arr in (("f", f), ("v", v), ("grad", gr), ("tx", tx), ("f1", f1), ("v1", v1), ("f2", f2), ("v2", v2), ("fb", fb), ("vb", vb),
+                  ("iso_f", fs), ("iso_v", vs), ("fn", fn), ("vn", vn), ("fq", fq), ("vq", vq), ("fg", fg), ("vg", vg), ("gg", gg)):
+    assert np.isfinite(arr).all(), name
+assert (v > 0).all() and (vb > 0).all() and (v2 > 0).all() and (vg > -1e-12).all()
 print("ok", m.n, mn.n_tail, len(pts), float(np.abs(f).max()), float(v.min()), float(vn.min()), float(vg.min()))

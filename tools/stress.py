@@ -44,8 +44,12 @@ for case in range(cases):
         reg = g.GPRegressor(kind, p0, p1, ctx=ctx)
         m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2, with_normals=normals)
         o = oracle.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, kind, p0, p1, factor="llt", with_normals=normals)
+        indefinite = o.info != 0
+        if indefinite:      # e.g. a nearly noise-free thin-plate matrix with a slightly negative eigenvalue: the reference's
+            # pivoted LDLT solves it, and so does the GPU path (trailing pivot block); compare against the LDLT oracle
+            o = oracle.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, kind, p0, p1, factor="ldlt", with_normals=normals)
         K = o.get(K=True)["K"]
-        w = np.linalg.eigvalsh(K) if n <= 1500 else None
+        w = np.abs(np.linalg.eigvalsh(K))
         cond = float(w.max() / w.min())
         tol_a = max(1e-9, 50 * cond * 2.2e-16)
         tol_f = max(1e-9, 5 * cond * 2.2e-16)
@@ -60,7 +64,15 @@ for case in range(cases):
             sn = rng.uniform(0.02, 0.2, k) if s2 is not None else None
             if rng.random() < 0.3:
                 reg.reserve(m, m.n + 300)
-            reg.update(m, Pn[:, 0], Pn[:, 1], Pn[:, 2], yn, sn)
+            try:
+                reg.update(m, Pn[:, 0], Pn[:, 1], Pn[:, 2], yn, sn)
+            except g.GPRegressionException as e:
+                # documented limit: a matrix that is indefinite as a whole (no outlier points to blame) with more than 256
+                # points after the first non-positive pivot is reported as NOT_SPD — and the model must be left intact
+                if indefinite and e.code == g.GPR_ERR_NOT_SPD and m.n == o.n:
+                    steps.append("NOT_SPD(limit)")
+                    break
+                raise
             o.update(Pn[:, 0], Pn[:, 1], Pn[:, 2], yn, sn)
             steps.append(k)
             errs["alpha_after_append_%d" % len(steps)] = rel(m.alpha, o.alpha) / (2 * tol_a)
@@ -71,8 +83,15 @@ for case in range(cases):
             sub = slice(0, min(q, 400))
             fo, vo, go = o.predict(Q[sub, 0], Q[sub, 1], Q[sub, 2], var=True, grad=True, threads=8)
             k0 = abs(vo).max()
-            errs["q%d" % q] = max(rel(f[sub], fo) / tol_f, rel(f1[sub], fo) / tol_f, np.abs(v[sub] - vo).max() / (max(1e-7, 50 * cond * 2.2e-16) * max(k0, 1e-12)),
-                                  rel(gr[sub], go) / tol_f)
+            errs["q%d_mean" % q] = max(rel(f[sub], fo), rel(f1[sub], fo)) / tol_f
+            if errs["q%d_mean" % q] > 1.0 and os.environ.get("STRESS_DEBUG"):
+                fresh = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2) if not steps or steps == ["NOT_SPD(limit)"] else None
+                f2 = reg.evaluate(fresh, Q[:, 0], Q[:, 1], Q[:, 2]) if fresh is not None else f1
+                bad_i = np.argsort(-np.abs(f[sub] - fo))[:5]
+                print("   DEBUG q=%d: f-vs-oracle %.3e f1-vs-oracle %.3e fresh-model-vs-oracle %.3e | worst idx %s f %s fo %s n_tail %d/%d alpha-dev-vs-host ok" % (
+                    q, rel(f[sub], fo), rel(f1[sub], fo), rel(f2[sub], fo), bad_i, f[sub][bad_i], fo[bad_i], m.n_tail, fresh.n_tail if fresh is not None else -1), flush=True)
+            errs["q%d_var" % q] = np.abs(v[sub] - vo).max() / (max(1e-7, 50 * cond * 2.2e-16) * max(k0, 1e-12))
+            errs["q%d_grad" % q] = rel(gr[sub], go) / tol_f
             N, Tx, Ty = oracle.tangent_basis(gr[sub])
             errs["q%d_tangent" % q] = max(np.abs(tx[sub] - Tx).max(), np.abs(ty[sub] - Ty).max()) / 1e-8
             if not (np.isfinite(f).all() and np.isfinite(v).all() and np.isfinite(gr).all()):
@@ -81,8 +100,8 @@ for case in range(cases):
         status = "ok" if worst <= 1.0 else "VIOLATION"
         if worst > 1.0:
             bad.append((seed, {k: round(v, 2) for k, v in errs.items() if v > 1.0}))
-        print("case %3d seed %4d n=%4d %-10s noise=%d normals=%d appends=%s cond=%.1e worst=%.3f %s" % (
-            case, seed, n, kind, noise, normals, steps, cond, worst, status), flush=True)
+        print("case %3d seed %4d n=%4d %-10s noise=%d normals=%d appends=%s cond=%.1e tail=%d%s worst=%.3f %s" % (
+            case, seed, n, kind, noise, normals, steps, cond, m.n_tail, " (indefinite)" if indefinite else "", worst, status), flush=True)
     except Exception as e:     # noqa: BLE001
         bad.append((seed, repr(e)))
         print("case %3d seed %4d EXCEPTION %r" % (case, seed, e), flush=True)
