@@ -1364,23 +1364,37 @@ static int append_incremental(gpr_model* m, const double* x, const double* y, co
         return fail(GPR_ERR_NOT_SPD, b);
     }
     const int nb1 = (int)(N1 / TB);
-    CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
-    CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
-    for (int it = 0; it < ctx->refine_steps; ++it) {          // same refinement as after a fit (gpr_solve.cu)
-        rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, residual_scratch_doubles((int)N1) + 2 * N1);
-        if (rc) return rc;
-        double* rr = ws->mpart + residual_scratch_doubles((int)N1);
-        double* dd = rr + N1;
+    // alpha = X^T (X y) through the inverse factor that the append has just brought up to date (two bandwidth-bound
+    // passes, no dependency chain), then the same refinement as after a fit with the correction also through X.
+    // GPR_APPEND_TRSV=1 uses the triangular solves over L instead.
+    static const bool use_trsv = getenv("GPR_APPEND_TRSV") && atoi(getenv("GPR_APPEND_TRSV")) != 0;
+    const size_t sol_dbl = (size_t)(32 + 1) * m->cap;                  // sized by the capacity: no reallocation per call
+    rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, residual_scratch_doubles((int)m->cap) + 2 * m->cap + sol_dbl);
+    if (rc) return rc;
+    double* rr = ws->mpart + residual_scratch_doubles((int)N1);
+    double* dd = rr + N1;
+    double* sol = dd + N1;
+    if (use_trsv) {
+        CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
+        CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
+    } else {
+        CU(launch_solve_with_inverse(md.linv, ld, (int)n1, m->label, md.alpha, sol, st));
+    }
+    for (int it = 0; it < std::max(1, ctx->refine_steps); ++it) {      // at least one step: it also absorbs the explicit-inverse rounding
         CU(launch_residual(md.xyz, ld, m->s2, m->label, md.alpha, (int)n1, (int)N1, ws->mpart, rr, m->kp, st));
-        CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, rr, m->zfwd, m->scratch, dc->num_sms, st));
-        CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, dd, m->scratch, dc->num_sms, st));
+        if (use_trsv) {
+            CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, rr, m->zfwd, m->scratch, dc->num_sms, st));
+            CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, dd, m->scratch, dc->num_sms, st));
+        } else {
+            CU(launch_solve_with_inverse(md.linv, ld, (int)n1, rr, dd, sol, st));
+        }
         CU(launch_axpy1(md.alpha, dd, (int)n1, st));
     }
     CU(cudaEventRecord(ws->ev[2], st));
     m->h_alpha.resize(n1);
     CU(cudaMemcpyAsync(m->h_alpha.data(), md.alpha, n1 * sizeof(double), cudaMemcpyDeviceToHost, st));
     int flags[4] = {0, 0, 0, 0};
-    CU(cudaMemcpyAsync(flags, m->scratch, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    if (use_trsv) CU(cudaMemcpyAsync(flags, m->scratch, sizeof(flags), cudaMemcpyDeviceToHost, st));   // the control words belong to the last flag-chained kernel
     CU(cudaStreamSynchronize(st));
     if (flags[2] != 0) return fail(GPR_ERR_CUDA, "triangular solve kernel aborted (dependency wait timed out)");
     host_append(m, x, y, z, label, sigma2, k);

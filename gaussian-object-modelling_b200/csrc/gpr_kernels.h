@@ -24,6 +24,11 @@ size_t residual_scratch_doubles(int N);
 cudaError_t launch_residual(const double* xyz, size_t ld, const double* sigma2, const double* label, const double* alpha,
                             int n, int N, double* part, double* r, const KernParams& kp, cudaStream_t st);
 cudaError_t launch_axpy1(double* a, const double* d, int n, cudaStream_t st);
+// out = X^T (X in): K^-1 applied through the resident inverse factor (two bandwidth-bound triangular matrix-vector
+// products, no dependency chain); scratch: (tri_gemv_splits(n) + 1) * n doubles.
+int tri_gemv_splits(int n);
+cudaError_t launch_solve_with_inverse(const double* X, size_t ld, int n, const double* in, double* out, double* scratch,
+                                      cudaStream_t st);
 // K4 (gpr_predict.cu).  part/split: optional split of the training points over CTAs for the thread-per-query
 // kernel (split from predict_split, part of predict_part_doubles(q, N) doubles); bit-identical results either way.
 int predict_split(int q_span, int N, int num_sms);

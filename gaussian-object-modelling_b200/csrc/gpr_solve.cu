@@ -274,4 +274,92 @@ cudaError_t launch_axpy1(double* a, const double* d, int n, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// alpha = K^-1 y through the explicit inverse factor X = L^-1 (kept resident for the variance path):
+//     v = X y   (lower-triangular matrix-vector product),   alpha = X^T v
+// Two dependency-free, bandwidth-bound passes over the triangle of X (4 n^2 bytes each) instead of the two
+// flag-chained triangular solves over L (nb dependent steps each).  Used by the incremental append, where X is
+// up to date anyway; the refinement step that follows removes the extra rounding of the explicit inverse.
+//   lower: CTA = 64 rows x one k-split, thread = (row, k-phase), 16 loads in flight; splits summed in order.
+//   upper: one warp per column, lanes stride down the column (coalesced), fixed-order shuffle tree.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tri_gemv_lower_kernel(const double* __restrict__ X, size_t ld, int n, int kspan,
+                                                             const double* __restrict__ in, double* __restrict__ part) {
+    __shared__ double ys[256];
+    __shared__ double r4[4][64];
+    const int tid = threadIdx.x, rl = tid & 63, kq = tid >> 6;
+    const int bx = blockIdx.x, by = blockIdx.y;
+    const int r = bx * 64 + rl;
+    const int kbeg = by * kspan;
+    const int kend = min(min(kbeg + kspan, n), bx * 64 + 64);
+    double acc = 0.0;
+    for (int c0 = kbeg; c0 < kend; c0 += 256) {
+        __syncthreads();
+        ys[tid] = c0 + tid < kend ? in[c0 + tid] : 0.0;
+        __syncthreads();
+        const int kl0 = 64 * kq;
+        const double* xr = X + (size_t)(c0 + kl0) * ld + r;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            double xv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int c = c0 + kl0 + 16 * b + u;
+                xv[u] = (c <= r && c < kend && r < n) ? __ldcs(xr + (size_t)(16 * b + u) * ld) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc = fma(xv[u], ys[kl0 + 16 * b + u], acc);
+        }
+    }
+    r4[kq][rl] = acc;
+    __syncthreads();
+    if (kq == 0 && r < n) part[(size_t)by * n + r] = ((r4[0][rl] + r4[1][rl]) + r4[2][rl]) + r4[3][rl];
+}
+
+__global__ void __launch_bounds__(256) tri_gemv_lower_finish_kernel(const double* __restrict__ part, int n, int vs, int kspan,
+                                                                    double* __restrict__ out) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= n) return;
+    const int nsplit = (min(n, (r / 64) * 64 + 64) + kspan - 1) / kspan;      // splits that reach this row block
+    double s = 0.0;
+    for (int y = 0; y < nsplit && y < vs; ++y) s += part[(size_t)y * n + r];
+    out[r] = s;
+}
+
+__global__ void __launch_bounds__(256) tri_gemv_upper_kernel(const double* __restrict__ X, size_t ld, int n,
+                                                             const double* __restrict__ v, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);          // columns near 0 are the long ones: they come first
+    if (c >= n) return;
+    const double* col = X + (size_t)c * ld;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int r = c + lane;
+    for (; r + 96 < n; r += 128) {                               // 4 independent loads per lane in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(__ldcs(col + r + 32 * u), v[r + 32 * u], acc[u]);
+    }
+    for (; r < n; r += 32) acc[0] = fma(__ldcs(col + r), v[r], acc[0]);
+    double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[c] = s;
+}
+
+// out = X^T (X in) for the leading n x n block of X; scratch: (vs + 1) * n doubles with vs = tri_gemv_splits(n).
+int tri_gemv_splits(int n) { int v = (n + 1023) / 1024; return v < 1 ? 1 : (v > 32 ? 32 : v); }
+
+cudaError_t launch_solve_with_inverse(const double* X, size_t ld, int n, const double* in, double* out, double* scratch,
+                                      cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int vs = tri_gemv_splits(n);
+    const int kspan = ((n + vs - 1) / vs + 255) / 256 * 256;
+    double* part = scratch;
+    double* v = scratch + (size_t)vs * n;
+    dim3 grid((n + 63) / 64, vs);
+    tri_gemv_lower_kernel<<<grid, 256, 0, st>>>(X, ld, n, kspan, in, part);
+    tri_gemv_lower_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, n, vs, kspan, v);
+    tri_gemv_upper_kernel<<<(n + 7) / 8, 256, 0, st>>>(X, ld, n, v, out);
+    return cudaGetLastError();
+}
+
 }  // namespace gpr

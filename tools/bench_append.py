@@ -12,7 +12,7 @@ import gpr_b200 as g
 
 W = g.workloads
 n0 = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-batches, k = 64, 32
+batches, k = (int(sys.argv[2]) if len(sys.argv) > 2 else 64), 32
 ctx = g.Context()
 reg = g.GPRegressor("thin_plate", W.SYNTH_R, ctx=ctx)
 P, y, s2 = W.synthetic_cloud(n0, seed=0)
@@ -44,8 +44,9 @@ f1, v1 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
 f2, v2 = reg.evaluate(fresh, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
 rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
 n1 = n0 + batches * k
-# algorithmic bytes of one append: the triangle of L^-1 read twice (B = X P, G = X^T B) + the two alpha solves over L
-bytes_per = 2 * 4.0 * n1 * n1 + 2 * 4.0 * n1 * n1
+# algorithmic bytes of one append: the triangle of L^-1 (4 n^2 bytes) read twice for the new rows (B = X P, G = X^T B)
+# and four times for alpha (X y and X^T v, for the solve and for its refinement step)
+bytes_per = 6 * 4.0 * n1 * n1
 print(json.dumps({"workload": "config4: n=%d base + %d x %d appended points, ThinPlate(R=%.1f)" % (n0, batches, k, W.SYNTH_R),
                   "base_fit_ms": fit_ms, "base_linv_ms": linv_ms,
                   "append_ms_device_median": float(np.median(dev)), "append_ms_device_first": dev[0], "append_ms_device_last": dev[-1],
