@@ -13,8 +13,9 @@
 //     L'  = [[L, 0], [B^T, L22]]
 //     X'  = [[X, 0], [-W (B^T X), W]]
 // The two n^2*k products read the triangle of X once each (4 n^2 bytes): they are HBM/L2-bandwidth
-// bound skinny products, done with FP64 FMAs on 32x32 register-tiled output blocks (the 128x128 DMMA tile
-// engine would waste 3/4 of its flops on a 32-wide operand and serialise on 64 long tasks).
+// bound skinny products.  The 128x128 DMMA tile engine would waste 3/4 of its flops on a 32-wide operand and
+// serialise on 64 long tasks, so they have their own kernel: m8n8k4 DMMA fragments loaded straight from global
+// memory, split over k (skinny_dmma_kernel); an FMA variant on 32x32 register tiles serves the tail build.
 // Every reduction has a fixed order: the append is bit-reproducible.
 #include "gpr_mma.cuh"
 #include "gpr_leaf.cuh"
@@ -157,6 +158,107 @@ __global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// (2') The same two products on the FP64 tensor pipe, split over k (used by the append slab; the FMA kernel
+// above stays for the few calls of the indefinite-tail build).  A 32-wide operand fits the m8n8k4 DMMA shape
+// exactly (4 n-tiles), so no flops are wasted.
+//   CTA  = 128 rows x one k-span of SPAN columns, 8 warps, warp = 16 rows (two 8-row groups sharing the panel
+//          fragments) over the whole span;
+//   X    fragments straight from global memory into registers (8 rows x 4 k = sector-exact pieces), each register
+//          reloaded for the next 32-k chunk right after its last use: 16 loads per lane always in flight;
+//   panel chunk [32 k][32] through shared memory (cp.async, two stages, pitch 40: conflict-free fragment reads) -
+//          fragment loads from global memory would touch 4 lines each and saturate the L1 pipe (measured: 94 %);
+//   part[span][m][a] partial sums, then skinny_finish_kernel adds the spans of each row in ascending order.
+// ---------------------------------------------------------------------------------------------
+constexpr int SPAN = 1024;
+constexpr int SROWS = 128;      // rows per CTA
+constexpr int SKC = 32;         // k per shared-memory chunk of the panel
+constexpr int SPB = 40;         // panel pitch in shared memory
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) skinny_dmma_kernel(const double* __restrict__ X, size_t ld, int n0,
+                                                             const double* __restrict__ Bm, double* __restrict__ part) {
+    __shared__ __align__(16) double Bs[2][SKC * SPB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int nblk = (n0 + SROWS - 1) / SROWS;
+    const int blk = MODE == 0 ? (nblk - 1 - blockIdx.x) : blockIdx.x;      // heavy blocks first
+    const int span = blockIdx.y;
+    const int rbeg = blk * SROWS, rend = min(rbeg + SROWS, n0);
+    const int kbeg = max(MODE == 0 ? 0 : rbeg, span * SPAN);                // multiples of 32
+    const int kend = min(MODE == 0 ? rend : n0, (span + 1) * SPAN);
+    if (kbeg >= kend) return;
+    const int m0 = rbeg + 16 * warp + g;                                     // row of group 0; group 1 is m0 + 8
+
+    auto load_a = [&](int k, int m) -> double {
+        if (k >= kend || m >= n0) return 0.0;
+        if (MODE == 0) return k <= m ? __ldcs(X + (size_t)k * ld + m) : 0.0;
+        return k >= m ? __ldcs(X + (size_t)m * ld + k) : 0.0;
+    };
+    auto stage_b = [&](int kc, int st) {                                     // 32 x 32 doubles = 512 x 16 bytes
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int idx = tid + 256 * e, kk = idx >> 4, c2 = (idx & 15) * 2;
+            double* dst = &Bs[st][kk * SPB + c2];
+            if (kc + kk < kend) cp_async16(dst, Bm + (size_t)(kc + kk) * AK + c2);
+            else { dst[0] = 0.0; dst[1] = 0.0; }
+        }
+        cp_async_commit();
+    };
+
+    double acc[2][4][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[r][j][0] = 0.0; acc[r][j][1] = 0.0; }
+    double a[8][2];
+    stage_b(kbeg, 0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u][0] = load_a(kbeg + 4 * u + t, m0); a[u][1] = load_a(kbeg + 4 * u + t, m0 + 8); }
+    int st = 0;
+    for (int kc = kbeg; kc < kend; kc += SKC, st ^= 1) {
+        const bool more = kc + SKC < kend;
+        if (more) stage_b(kc + SKC, st ^ 1);
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+        const double* bs = &Bs[st][t * SPB + g];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = bs[4 * u * SPB + 8 * j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dmma(acc[0][j][0], acc[0][j][1], a[u][0], b[j]);
+                dmma(acc[1][j][0], acc[1][j][1], a[u][1], b[j]);
+            }
+            if (more) { a[u][0] = load_a(kc + SKC + 4 * u + t, m0); a[u][1] = load_a(kc + SKC + 4 * u + t, m0 + 8); }
+        }
+        __syncthreads();
+    }
+    // C fragment: row g, columns 8j + 2t, 8j + 2t + 1
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int m = m0 + 8 * r;
+        if (m < n0) {
+            double* out = part + ((size_t)span * n0 + m) * AK;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(out + 8 * j + 2 * t) = make_double2(acc[r][j][0], acc[r][j][1]);
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) skinny_finish_kernel(const double* __restrict__ part, int n0, double* __restrict__ OUT) {
+    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= (size_t)n0 * AK) return;
+    const int m = (int)(e >> 5);
+    const int rbeg = (m / SROWS) * SROWS, rend = min(rbeg + SROWS, n0);
+    const int s0 = MODE == 0 ? 0 : rbeg / SPAN;
+    const int s1 = MODE == 0 ? (rend - 1) / SPAN : (n0 - 1) / SPAN;
+    double v = 0.0;
+    for (int sp = s0; sp <= s1; ++sp) v += part[(size_t)sp * n0 * AK + e];
+    OUT[e] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // (3) partial Gram matrices of B: part[blk][a*32 + b] = sum_{r in block} B[r][a] B[r][b], 256 rows per CTA.
 // ---------------------------------------------------------------------------------------------
 constexpr int GRAM_ROWS = 256;
@@ -184,48 +286,61 @@ __global__ void __launch_bounds__(256) append_gram_kernel(const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// (4) S = S0 - sum_blk part[blk] (fixed order);  L22 = chol(S), W = L22^-1 with the 128x128 shared-memory
-// leaves of the tile Cholesky (S is embedded in an identity tile).  out22: [0,1024) L22, [1024,2048) W, both
-// row-major [a*32 + b].  *flag = 0, or 1 + global index of the first non-positive pivot (sticky over the slabs
-// of one append: once set, the later kernels of the append do nothing).
+// (4) S = S0 - sum_blk part[blk] (fixed order, 256 threads);  L22 = chol(S), W = L22^-1 by ONE warp with a row per
+// lane in registers (right-looking Cholesky with shuffle broadcasts, then row r of W from w_r L22 = e_r; the pivot
+// arithmetic is the tile leaf's potrf16_pivot).  out22: [0,1024) L22, [1024,2048) W, both row-major [a*32 + b].
+// *flag = 0, or 1 + global index of the first non-positive pivot (sticky over the slabs of one append: once set,
+// the later kernels of the append do nothing).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1) append_leaf_kernel(const double* S0, const double* part, int nparts,
-                                                                  double* out22, int* flag, int n0) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ int s_fail;
-    __shared__ double s_inv[TB];
-    double* T = smem;
+__global__ void __launch_bounds__(256) append_leaf_kernel(const double* __restrict__ S0, const double* __restrict__ part,
+                                                          int nparts, double* __restrict__ out22, int* flag, int n0) {
+    __shared__ double S[AK * (AK + 1)];
     const int tid = threadIdx.x;
     if (*flag != 0) return;                  // an earlier slab of this append failed: the flag is sticky
-    if (tid == 0) s_fail = 1 << 20;
-    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-        const int r = idx & (TB - 1), c = idx >> 7;
-        double v = (r == c) ? 1.0 : 0.0;
-        if (r < AK && c < AK) {
-            double s = 0.0;
-            for (int p = 0; p < nparts; ++p) s += part[(size_t)p * AK * AK + r * AK + c];
-            v = S0[r * AK + c] - s;
-        }
-        T[c * PM + r] = v;
+    for (int e = tid; e < AK * AK; e += 256) {
+        double s = 0.0;
+        for (int p = 0; p < nparts; ++p) s += part[(size_t)p * AK * AK + e];
+        S[(e >> 5) * (AK + 1) + (e & 31)] = S0[e] - s;
     }
     __syncthreads();
-    potrf128_smem(T, s_inv, &s_fail);
-    __syncthreads();
-    if (s_fail < TB) {
-        if (tid == 0) *flag = n0 + s_fail + 1;
+    if (tid >= 32) return;
+    const int lane = tid;
+    const unsigned full = 0xffffffffu;
+    double a[AK], dinv[AK];
+#pragma unroll
+    for (int c = 0; c < AK; ++c) a[c] = S[lane * (AK + 1) + c];
+    int bad = 1 << 20;
+#pragma unroll
+    for (int j = 0; j < AK; ++j) {
+        double inv, d;
+        potrf16_pivot(__shfl_sync(full, a[j], j), j, bad, inv, d);
+        dinv[j] = inv;
+        a[j] = (lane == j) ? d : ((lane > j) ? a[j] * inv : a[j]);
+#pragma unroll
+        for (int c = j + 1; c < AK; ++c) {
+            const double lc = __shfl_sync(full, a[j], c);
+            if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
+        }
+    }
+    if (bad < AK) {
+        if (lane == 0) *flag = n0 + bad + 1;
         return;
     }
-    for (int e = tid; e < AK * AK; e += NTHREADS) {
-        const int a = e >> 5, b = e & 31;
-        out22[e] = a >= b ? T[b * PM + a] : 0.0;
+#pragma unroll
+    for (int c = 0; c < AK; ++c) out22[lane * AK + c] = (c <= lane) ? a[c] : 0.0;
+    double w[AK];
+#pragma unroll
+    for (int c = AK - 1; c >= 0; --c) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = c + 1; k < AK; ++k) {
+            const double lkc = __shfl_sync(full, a[c], k);            // L22[k][c]; w[k] is zero for k > lane
+            if (k & 1) s1 = fma(w[k], lkc, s1); else s0 = fma(w[k], lkc, s0);
+        }
+        w[c] = (c == lane) ? dinv[c] : ((c < lane) ? -(s0 + s1) * dinv[c] : 0.0);
     }
-    __syncthreads();
-    trinv128_smem(T, s_inv, smem + R0_DBL);
-    __syncthreads();
-    for (int e = tid; e < AK * AK; e += NTHREADS) {
-        const int a = e >> 5, b = e & 31;
-        out22[AK * AK + e] = a >= b ? T[b * PM + a] : 0.0;
-    }
+#pragma unroll
+    for (int c = 0; c < AK; ++c) out22[AK * AK + lane * AK + c] = w[c];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -292,18 +407,12 @@ __global__ void __launch_bounds__(256) identity_rows_kernel(double* L, double* X
 size_t append_workspace_doubles(size_t cap) {
     // Pn, B, G (cap x 32 each) + gram partials + S0 (1024) + L22|W (2048) + flag (as one double slot)
     const size_t parts = (cap + GRAM_ROWS - 1) / GRAM_ROWS;
-    return 3 * cap * AK + parts * AK * AK + 3 * AK * AK + 8;
+    return 3 * cap * AK + parts * AK * AK + 3 * AK * AK + 8 + ((cap + SPAN - 1) / SPAN) * cap * AK;    // + split-k partials
 }
 
 cudaError_t launch_append_slab(const double* xyz, size_t ld, const double* sigma2, int n0, int k, double* L, double* X,
                                double* Dinv, double* ws, size_t cap, const KernParams& kp, int reset_flag,
                                cudaStream_t st) {
-    static int attr_done = 0;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(append_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_done = 1;
-    }
     const size_t parts_cap = (cap + GRAM_ROWS - 1) / GRAM_ROWS;
     double* Pn = ws;
     double* B = Pn + cap * AK;
@@ -312,6 +421,7 @@ cudaError_t launch_append_slab(const double* xyz, size_t ld, const double* sigma
     double* S0 = part + parts_cap * AK * AK;
     double* out22 = S0 + AK * AK;
     int* flag = reinterpret_cast<int*>(out22 + 2 * AK * AK);
+    double* kpart = out22 + 2 * AK * AK + 8;                       // split-k partials of the two skinny products
     if (reset_flag) {
         cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
@@ -320,10 +430,14 @@ cudaError_t launch_append_slab(const double* xyz, size_t ld, const double* sigma
     const int nparts = (n0 + GRAM_ROWS - 1) / GRAM_ROWS;
     append_panel_kernel<<<(n0 * AK + 255) / 256 > 0 ? (n0 * AK + 255) / 256 : 1, 256, 0, st>>>(
         xyz, xyz + ld, xyz + 2 * ld, sigma2, n0, n0, k, Pn, S0, kp);
-    skinny_tri_kernel<0><<<nblk, 256, 0, st>>>(X, ld, n0, n0, Pn, B);
+    const dim3 sgrid((n0 + SROWS - 1) / SROWS, (n0 + SPAN - 1) / SPAN);
+    const int fblocks = (n0 * AK + 255) / 256;
+    skinny_dmma_kernel<0><<<sgrid, 256, 0, st>>>(X, ld, n0, Pn, kpart);
+    skinny_finish_kernel<0><<<fblocks, 256, 0, st>>>(kpart, n0, B);
     append_gram_kernel<<<nparts, 256, 0, st>>>(B, n0, part);
-    append_leaf_kernel<<<1, NTHREADS, TILE_SMEM_BYTES, st>>>(S0, part, nparts, out22, flag, n0);
-    skinny_tri_kernel<1><<<nblk, 256, 0, st>>>(X, ld, n0, n0, B, G);
+    append_leaf_kernel<<<1, 256, 0, st>>>(S0, part, nparts, out22, flag, n0);
+    skinny_dmma_kernel<1><<<sgrid, 256, 0, st>>>(X, ld, n0, B, kpart);
+    skinny_finish_kernel<1><<<fblocks, 256, 0, st>>>(kpart, n0, G);
     append_scatter_kernel<<<((n0 + k) * AK + 255) / 256, 256, 0, st>>>(B, G, out22, flag, n0, k, L, X, ld);
     const int t0 = n0 / TB, t1 = (n0 + k - 1) / TB;
     dinv_from_x_kernel<<<t1 - t0 + 1, 256, 0, st>>>(X, ld, t0, Dinv, flag);

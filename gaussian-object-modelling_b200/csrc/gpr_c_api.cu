@@ -952,6 +952,72 @@ int gpr_predict_device(gpr_ctx* ctx, gpr_model* m, const double* d_qx, const dou
     return GPR_OK;
 }
 
+// Lattice points [g_begin, g_end) of the sampler on device di: coordinates generated on the device, mean through K4,
+// compaction of |f| <= tol on the device; only the survivors (global index, f) come back.
+static int sample_range(gpr_model* m, size_t di, const std::vector<double>& axis, unsigned long long g_begin,
+                        unsigned long long g_end, double tol, std::vector<std::pair<unsigned long long, double>>& hits,
+                        double* ms) {
+    gpr_ctx* ctx = m->ctx;
+    int rc = ensure_on_device(m, di, false);
+    if (rc) return rc;
+    DeviceCtx* dc = ctx->devs[di];
+    CU(cudaSetDevice(dc->dev));
+    ModelDev& md = m->devs[di];
+    Workspace* ws = nullptr;
+    rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    cudaStream_t st = ws->st;
+    const size_t na = axis.size();
+    const size_t chunk = (size_t)std::min<unsigned long long>(g_end - g_begin, 1ull << 21);
+    // io: q (3) | f (1) | selected f (1) | selected index (1, as 8-byte integers) | axis | counter
+    rc = ws_reserve(&ws->io, &ws->io_cap, 14 * std::max(chunk + na + 8, (size_t)TB));
+    if (rc) return rc;
+    const size_t cap = ws->io_cap / 14;
+    double* dq = ws->io; double* df = dq + 3 * cap; double* dself = df + cap;
+    unsigned long long* dselidx = reinterpret_cast<unsigned long long*>(dself + cap);
+    double* daxis = dself + 2 * cap;
+    unsigned int* dcounter = reinterpret_cast<unsigned int*>(daxis + na);
+    CU(cudaMemcpyAsync(daxis, axis.data(), na * sizeof(double), cudaMemcpyHostToDevice, st));
+    const size_t N = m->N, ld = m->cap;
+    std::vector<unsigned long long> hidx;
+    std::vector<double> hf;
+    CU(cudaEventRecord(ws->ev[0], st));
+    for (unsigned long long g0 = g_begin; g0 < g_end; g0 += chunk) {
+        const int cnt = (int)std::min<unsigned long long>(chunk, g_end - g0);
+        CU(cudaMemsetAsync(dcounter, 0, sizeof(unsigned int), st));
+        CU(launch_grid_fill(daxis, (int)na, g0, cnt, dq, dq + cap, dq + 2 * cap, st));
+        const bool warp_mode = (size_t)cnt <= (size_t)64 * dc->num_sms;
+        int nsplit = 1;
+        if (!warp_mode) {
+            nsplit = predict_split(cnt, (int)N, dc->num_sms);
+            if (nsplit > 1) { rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, predict_part_doubles(cnt, (int)N)); if (rc) return rc; }
+        }
+        CU(launch_predict(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, (int)m->n, (int)N, dq, dq + cap, dq + 2 * cap, cnt,
+                          df, nullptr, 0, nullptr, 0, (int)m->n_spd, m->kp, warp_mode, ws->mpart, nsplit, st));
+        CU(launch_grid_select(df, g0, cnt, tol, dcounter, dselidx, dself, st));
+        unsigned int found = 0;
+        CU(cudaMemcpyAsync(&found, dcounter, sizeof(found), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (found > (unsigned)cnt) {
+            char b[160];
+            snprintf(b, sizeof b, "iso-surface sampler: selection counter %u exceeds the chunk size %d", found, cnt);
+            return fail(GPR_ERR_CUDA, b);
+        }
+        if (found) {
+            hidx.resize(found); hf.resize(found);
+            CU(cudaMemcpyAsync(hidx.data(), dselidx, found * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(hf.data(), dself, found * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (unsigned int i = 0; i < found; ++i) hits.emplace_back(hidx[i], hf[i]);
+        }
+    }
+    CU(cudaEventRecord(ws->ev[1], st));
+    CU(cudaStreamSynchronize(st));
+    *ms = ev_ms(ws->ev[0], ws->ev[1]);
+    return GPR_OK;
+}
+
 int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, double step, double tol, size_t capacity,
                           double* x, double* y, double* z, double* f, double* var, size_t* count) {
     if (!ctx) return fail(GPR_ERR_INVALID, "null context");
@@ -965,65 +1031,30 @@ int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, doub
     }
     const size_t na = axis.size();
     const unsigned long long total = (unsigned long long)na * na * na;
-    int rc = ensure_on_device(m, 0, false);
-    if (rc) return rc;
-    DeviceCtx* dc = ctx->devs[0];
-    CU(cudaSetDevice(dc->dev));
-    ModelDev& md = m->devs[0];
-    Workspace* ws = nullptr;
-    rc = ws_acquire(dc, &ws);
-    if (rc) return rc;
+    // contiguous lattice ranges over the context's devices (each query is independent: the result does not depend
+    // on the split); small lattices stay on the primary device
+    const size_t nd = ctx->devs.size();
+    const size_t use = (nd > 1 && total >= ((unsigned long long)nd << 20)) ? nd : 1;
+    std::vector<std::vector<std::pair<unsigned long long, double>>> part(use);
+    std::vector<int> rcs(use, 0);
+    std::vector<std::string> errs(use);
+    std::vector<double> tms(use, 0.0);
+    auto work = [&](size_t di) {
+        rcs[di] = sample_range(m, di, axis, total * di / use, total * (di + 1) / use, tol, part[di], &tms[di]);
+        if (rcs[di]) errs[di] = g_err;
+    };
+    if (use == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (size_t di = 0; di < use; ++di) pool.emplace_back(work, di);
+        for (auto& t : pool) t.join();
+    }
+    for (size_t di = 0; di < use; ++di) if (rcs[di]) return fail(rcs[di], errs[di]);
     std::vector<std::pair<unsigned long long, double>> hits;
+    for (size_t di = 0; di < use; ++di) hits.insert(hits.end(), part[di].begin(), part[di].end());
     {
-        struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
-        cudaStream_t st = ws->st;
-        const size_t chunk = (size_t)std::min<unsigned long long>(total, 1ull << 21);
-        // io: q (3) | f (1) | selected f (1) | selected index (1, as 8-byte integers) | axis | counter
-        rc = ws_reserve(&ws->io, &ws->io_cap, 14 * std::max(chunk + na + 8, (size_t)TB));
-        if (rc) return rc;
-        const size_t cap = ws->io_cap / 14;
-        double* dq = ws->io; double* df = dq + 3 * cap; double* dself = df + cap;
-        unsigned long long* dselidx = reinterpret_cast<unsigned long long*>(dself + cap);
-        double* daxis = dself + 2 * cap;
-        unsigned int* dcounter = reinterpret_cast<unsigned int*>(daxis + na);
-        CU(cudaMemcpyAsync(daxis, axis.data(), na * sizeof(double), cudaMemcpyHostToDevice, st));
-        const size_t N = m->N, ld = m->cap;
-        std::vector<unsigned long long> hidx;
-        std::vector<double> hf;
-        CU(cudaEventRecord(ws->ev[0], st));
-        for (unsigned long long g0 = 0; g0 < total; g0 += chunk) {
-            const int cnt = (int)std::min<unsigned long long>(chunk, total - g0);
-            CU(cudaMemsetAsync(dcounter, 0, sizeof(unsigned int), st));
-            CU(launch_grid_fill(daxis, (int)na, g0, cnt, dq, dq + cap, dq + 2 * cap, st));
-            const bool warp_mode = (size_t)cnt <= (size_t)64 * dc->num_sms;
-            int nsplit = 1;
-            if (!warp_mode) {
-                nsplit = predict_split(cnt, (int)N, dc->num_sms);
-                if (nsplit > 1) { rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, predict_part_doubles(cnt, (int)N)); if (rc) return rc; }
-            }
-            CU(launch_predict(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, (int)m->n, (int)N, dq, dq + cap, dq + 2 * cap, cnt,
-                              df, nullptr, 0, nullptr, 0, (int)m->n_spd, m->kp, warp_mode, ws->mpart, nsplit, st));
-            CU(launch_grid_select(df, g0, cnt, tol, dcounter, dselidx, dself, st));
-            unsigned int found = 0;
-            CU(cudaMemcpyAsync(&found, dcounter, sizeof(found), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            if (found > (unsigned)cnt) {
-                char b[160];
-                snprintf(b, sizeof b, "iso-surface sampler: selection counter %u exceeds the chunk size %d", found, cnt);
-                return fail(GPR_ERR_CUDA, b);
-            }
-            if (found) {
-                hidx.resize(found); hf.resize(found);
-                CU(cudaMemcpyAsync(hidx.data(), dselidx, found * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-                CU(cudaMemcpyAsync(hf.data(), dself, found * sizeof(double), cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
-                for (unsigned int i = 0; i < found; ++i) hits.emplace_back(hidx[i], hf[i]);
-            }
-        }
-        CU(cudaEventRecord(ws->ev[1], st));
-        CU(cudaStreamSynchronize(st));
         std::lock_guard<std::mutex> lk(ctx->tmu);
-        ctx->timings.predict_mean_ms = ev_ms(ws->ev[0], ws->ev[1]);
+        ctx->timings.predict_mean_ms = *std::max_element(tms.begin(), tms.end());
     }
     std::sort(hits.begin(), hits.end());                 // lattice order: deterministic output
     *count = hits.size();
@@ -1041,7 +1072,7 @@ int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, doub
         // the expensive part (n^2 flop per point) only for the survivors, through the regular predict path
         std::vector<double> f2(keep);
         const double mean_ms = ctx->timings.predict_mean_ms;
-        rc = gpr_predict(ctx, m, sx.data(), sy.data(), sz.data(), keep, f2.data(), var, nullptr, nullptr, nullptr);
+        int rc = gpr_predict(ctx, m, sx.data(), sy.data(), sz.data(), keep, f2.data(), var, nullptr, nullptr, nullptr);
         if (rc) return rc;
         std::lock_guard<std::mutex> lk(ctx->tmu);
         ctx->timings.predict_mean_ms += mean_ms;

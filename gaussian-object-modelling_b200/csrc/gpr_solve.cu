@@ -281,7 +281,8 @@ cudaError_t launch_axpy1(double* a, const double* d, int n, cudaStream_t st) {
 // flag-chained triangular solves over L (nb dependent steps each).  Used by the incremental append, where X is
 // up to date anyway; the refinement step that follows removes the extra rounding of the explicit inverse.
 //   lower: CTA = 64 rows x one k-split, thread = (row, k-phase), 16 loads in flight; splits summed in order.
-//   upper: one warp per column, lanes stride down the column (coalesced), fixed-order shuffle tree.
+//   upper: CTA = 8 columns, warp = every 8th 32-row chunk of all 8 columns (coalesced, 16 loads in flight), fixed-order
+//          shuffle tree and warp sum.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tri_gemv_lower_kernel(const double* __restrict__ X, size_t ld, int n, int kspan,
                                                              const double* __restrict__ in, double* __restrict__ part) {
@@ -328,21 +329,42 @@ __global__ void __launch_bounds__(256) tri_gemv_lower_finish_kernel(const double
 
 __global__ void __launch_bounds__(256) tri_gemv_upper_kernel(const double* __restrict__ X, size_t ld, int n,
                                                              const double* __restrict__ v, double* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);          // columns near 0 are the long ones: they come first
-    if (c >= n) return;
-    const double* col = X + (size_t)c * ld;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    int r = c + lane;
-    for (; r + 96 < n; r += 128) {                               // 4 independent loads per lane in flight
+    __shared__ double red[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 8;                               // columns near 0 are the long ones: they come first
+    const double* col = X + (size_t)c0 * ld;
+    double acc[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = fma(__ldcs(col + r + 32 * u), v[r + 32 * u], acc[u]);
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+    // warp w takes the 32-row chunks w, w + 8, ... below the diagonal block; 8 columns x 2 chunks = 16 loads in flight
+    const int rbase = (c0 & ~31) + 32 * warp + lane;
+    for (int r = rbase; r < n; r += 512) {
+        const int r2 = r + 256;
+        double x0[8], x1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool cok = c0 + j < n;
+            x0[j] = (cok && r >= c0 + j) ? __ldcs(col + (size_t)j * ld + r) : 0.0;
+            x1[j] = (cok && r2 < n && r2 >= c0 + j) ? __ldcs(col + (size_t)j * ld + r2) : 0.0;
+        }
+        const double v0 = v[r], v1 = r2 < n ? v[r2] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fma(x1[j], v1, fma(x0[j], v0, acc[j]));
     }
-    for (; r < n; r += 32) acc[0] = fma(__ldcs(col + r), v[r], acc[0]);
-    double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[c] = s;
+    for (int j = 0; j < 8; ++j) {
+        double s = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[warp][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && c0 + threadIdx.x < n) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        out[c0 + threadIdx.x] = s;
+    }
 }
 
 // out = X^T (X in) for the leading n x n block of X; scratch: (vs + 1) * n doubles with vs = tri_gemv_splits(n).

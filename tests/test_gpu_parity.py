@@ -637,6 +637,27 @@ def test_model_save_and_load_round_trip(gpr, ctx, tmp_path):
         regn.load(tmp_path / "missing.bin")
 
 
+def test_sampler_sharded_over_two_devices_is_identical(gpr):
+    """One context over two GPUs: the sampler splits the lattice into contiguous ranges, one per device; the points, their
+    order and every bit of f must equal the single-device result (each lattice point is an independent query)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(1200, seed=3)
+    outs = []
+    for devs in ([0], [0, 1]):
+        c = gpr.Context(devices=devs)
+        reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=c)
+        m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+        outs.append(reg.sample_isosurface(m, lo=-1.2, hi=1.2, step=2.4 / 139, tol=0.002))     # 140^3 = 2.7 M points
+        del m
+        c.close()
+    assert len(outs[0][0]) > 100
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
 def test_tail_block_is_replicated_across_processes(gpr):
     """Two ranks under torchrun (needs 2 GPUs): the indefinite-tail model of the node's configuration is broadcast with
     NCCL and both ranks reproduce the reference fixture on their query shards."""
