@@ -9,8 +9,19 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstddef>
+#include <atomic>
 
 namespace gpr {
+
+// cudaFuncSetAttribute applies to the CURRENT device only: a launcher that raises a kernel's dynamic shared-memory
+// limit must do so once per device, not once per process (a context may sit on any device, and the query shards of
+// one context run on several).
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    static int current() { int d = 0; cudaGetDevice(&d); return d; }
+    bool done(int dev) const { return dev >= 0 && dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+    void set(int dev) { if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
 
 constexpr int TB = 128;          // tile edge
 constexpr int NTHREADS = 256;    // threads per CTA in all tile kernels

@@ -244,9 +244,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dinv_from_l_kernel(const double* 
 // ---------------------------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------------------------
-static int g_tile_attr_done = 0;
+static PerDeviceOnce g_tile_attr_done;
 static cudaError_t ensure_attrs() {
-    if (g_tile_attr_done) return cudaSuccess;
+    const int dev = PerDeviceOnce::current();
+    if (g_tile_attr_done.done(dev)) return cudaSuccess;
     {
         cudaError_t e0 = cudaFuncSetAttribute(dinv_from_l_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES);
         if (e0 != cudaSuccess) return e0;
@@ -255,7 +256,7 @@ static cudaError_t ensure_attrs() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(linv_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    g_tile_attr_done = 1;
+    g_tile_attr_done.set(dev);
     return cudaSuccess;
 }
 

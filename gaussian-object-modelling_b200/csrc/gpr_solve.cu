@@ -165,13 +165,14 @@ __global__ void __launch_bounds__(256, 1) trsv_backward_kernel(TrsvArgs a) {
 // scratch: [0]=counter [2]=abort [4..4+nb) ready.  rhs and out may not alias.
 cudaError_t launch_trsv(int backward, const double* L, size_t ld, int nb, const double* Dinv, const double* rhs,
                         double* out, int* scratch, int num_sms, cudaStream_t st) {
-    static int attr_done = 0;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    const int dev = PerDeviceOnce::current();
+    if (!attr_done.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(trsv_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(trsv_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM);
         if (e != cudaSuccess) return e;
-        attr_done = 1;
+        attr_done.set(dev);
     }
     cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(int) * (4 + (size_t)nb), st);
     if (e != cudaSuccess) return e;

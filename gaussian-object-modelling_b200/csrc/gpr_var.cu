@@ -88,12 +88,13 @@ __global__ void var_finalize_kernel(const double* partial, size_t panel_ld, int 
 
 cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* panel, size_t panel_ld, int q,
                             double* partial, double k0, double* var, cudaStream_t st) {
-    static int attr_done = 0;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    const int cur = PerDeviceOnce::current();
+    if (!attr_done.done(cur)) {
         cudaError_t e = cudaFuncSetAttribute(var_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)TILE_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = 1;
+        attr_done.set(cur);
     }
     if (q <= 0) return cudaSuccess;
     VarArgs a;

@@ -656,6 +656,21 @@ def test_sampler_sharded_over_two_devices_is_identical(gpr):
     assert len(outs[0][0]) > 100
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
+    # a context whose primary device is GPU 1, after GPU 0 has run everything: per-device kernel attributes
+    # (dynamic shared memory limits are set per device, not per process)
+    c1 = gpr.Context(devices=[1])
+    c0 = gpr.Context(devices=[0])
+    Q = W.grid_slab(16, 0, 16)
+    res = []
+    for c in (c0, c1):
+        reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=c)
+        m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+        f, v = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+        reg.update(m, P[:8, 0] * 1.01, P[:8, 1] * 1.01, P[:8, 2] * 1.01, y[:8], s2[:8])
+        res.append((m.alpha.copy(), f, v))
+        del m
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
 
 
 def test_tail_block_is_replicated_across_processes(gpr):
