@@ -117,7 +117,8 @@ int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m);
 /* Appends k points; R and the normals are not refreshed, as in the reference (:454-455, :462-477).
  * The reference re-factorises from scratch (:457-459).  Here small batches (k <= 256 and 8k <= n) take the
  * incremental path: the new rows of the Cholesky factor and of its inverse are appended (slabs of 32
- * points, two bandwidth-bound products against L^-1 each) and alpha is re-solved; larger batches refit.
+ * points, two bandwidth-bound products against L^-1 each) and alpha is re-solved through L^-1 with one step of
+ * iterative refinement (GPR_APPEND_TRSV=1: by the triangular solves over L); larger batches refit.
  * On GPR_ERR_NOT_SPD the model is left as it was before the call.  GPR_APPEND_REFIT=1 forces the refit. */
 int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
                const double* sigma2_or_null, size_t k);
