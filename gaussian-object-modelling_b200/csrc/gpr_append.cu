@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restric
 // (2') The same two products on the FP64 tensor pipe, split over k (used by the append slab; the FMA kernel
 // above stays for the few calls of the indefinite-tail build).  A 32-wide operand fits the m8n8k4 DMMA shape
 // exactly (4 n-tiles), so no flops are wasted.
-//   CTA  = 128 rows x one k-span of SPAN columns, 8 warps, warp = 16 rows (two 8-row groups sharing the panel
+//   CTA  = 128 rows x one k-span of SPAN (512) columns, 8 warps, warp = 16 rows (two 8-row groups sharing the panel
 //          fragments) over the whole span;
 //   X    fragments straight from global memory into registers (8 rows x 4 k = sector-exact pieces), each register
 //          reloaded for the next 32-k chunk right after its last use: 16 loads per lane always in flight;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) skinny_tri_kernel(const double* __restric
 //          fragment loads from global memory would touch 4 lines each and saturate the L1 pipe (measured: 94 %);
 //   part[span][m][a] partial sums, then skinny_finish_kernel adds the spans of each row in ascending order.
 // ---------------------------------------------------------------------------------------------
-constexpr int SPAN = 1024;
+constexpr int SPAN = 512;       // small uniform work items: ~650 CTAs at n = 8 250 for 296 resident slots
 constexpr int SROWS = 128;      // rows per CTA
 constexpr int SKC = 32;         // k per shared-memory chunk of the panel
 constexpr int SPB = 40;         // panel pitch in shared memory
