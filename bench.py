@@ -26,6 +26,18 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+
+# stdout carries exactly ONE line, the JSON result: everything else that writes to file descriptor 1 (NCCL prints
+# "NCCL version ..." there at communicator creation) is sent to stderr, and the result goes to the saved descriptor.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 sys.path.insert(0, ROOT)
 
 N_TRAIN = 16384
@@ -158,7 +170,7 @@ def main():
                 "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
                 "fit_ms": 1e3 * res["fit_s"], "port_blas_dtrsm_points_per_s": res["port_blas_dtrsm_points_per_s"],
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -357,7 +369,7 @@ def main():
                                         "mean_rel_inf": rel(fg, res["last_f"]), "var_rel_inf": rel(vg, res["last_v"]),
                                         "sign_mismatches": int((np.sign(fg) != np.sign(res["last_f"]))[big].sum()),
                                         "tolerance": {"alpha": "max(1e-9, 50*cond*eps)", "mean": 1e-9, "var": 1e-7}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
