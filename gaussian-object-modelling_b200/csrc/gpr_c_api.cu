@@ -1378,8 +1378,47 @@ static int append_incremental(gpr_model* m, const double* x, const double* y, co
         const int kk = (int)std::min<size_t>(32, k - o);
         CU(launch_append_slab(md.xyz, ld, m->s2, (int)(n0 + o), kk, m->L, md.linv, m->Dinv, m->aws, ld, m->kp, o == 0, st));
     }
+    // No host round trip between the slabs and the solve: alpha is solved into a scratch vector from whatever the slabs
+    // left behind and committed on the device only if the sticky flag is clear, so that a failed append leaves alpha
+    // (like L, L^-1 and Dinv) untouched; the flag is read once, at the end.
+    const int nb1 = (int)(N1 / TB);
+    // alpha = X^T (X y) through the inverse factor that the append has just brought up to date (two bandwidth-bound
+    // passes, no dependency chain), then the same refinement as after a fit with the correction also through X.
+    // GPR_APPEND_TRSV=1 uses the triangular solves over L instead.
+    static const bool use_trsv = getenv("GPR_APPEND_TRSV") && atoi(getenv("GPR_APPEND_TRSV")) != 0;
+    const size_t sol_dbl = (size_t)(32 + 1) * m->cap;                  // sized by the capacity: no reallocation per call
+    rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, residual_scratch_doubles((int)m->cap) + 3 * m->cap + sol_dbl);
+    if (rc) return rc;
+    double* rr = ws->mpart + residual_scratch_doubles((int)N1);
+    double* dd = rr + N1;
+    double* anew = dd + N1;
+    double* sol = anew + N1;
+    const int* dflag = append_flag_ptr(m->aws, ld);
+    CU(cudaMemsetAsync(anew, 0, N1 * sizeof(double), st));
+    if (use_trsv) {
+        CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
+        CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, anew, m->scratch, dc->num_sms, st));
+    } else {
+        CU(launch_solve_with_inverse(md.linv, ld, (int)n1, m->label, anew, sol, st));
+    }
+    for (int it = 0; it < std::max(1, ctx->refine_steps); ++it) {      // at least one step: it also absorbs the explicit-inverse rounding
+        CU(launch_residual(md.xyz, ld, m->s2, m->label, anew, (int)n1, (int)N1, ws->mpart, rr, m->kp, st));
+        if (use_trsv) {
+            CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, rr, m->zfwd, m->scratch, dc->num_sms, st));
+            CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, dd, m->scratch, dc->num_sms, st));
+        } else {
+            CU(launch_solve_with_inverse(md.linv, ld, (int)n1, rr, dd, sol, st));
+        }
+        CU(launch_axpy1(anew, dd, (int)n1, st));
+    }
+    CU(launch_commit_if_clear(dflag, anew, md.alpha, (int)n1, st));
+    CU(cudaEventRecord(ws->ev[2], st));
+    std::vector<double> new_alpha(n1);
+    CU(cudaMemcpyAsync(new_alpha.data(), md.alpha, n1 * sizeof(double), cudaMemcpyDeviceToHost, st));
     int flag = 0;
-    CU(cudaMemcpyAsync(&flag, append_flag_ptr(m->aws, ld), sizeof(int), cudaMemcpyDeviceToHost, st));
+    int flags[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (use_trsv) CU(cudaMemcpyAsync(flags, m->scratch, sizeof(flags), cudaMemcpyDeviceToHost, st));   // the control words belong to the last flag-chained kernel
     CU(cudaStreamSynchronize(st));
     if (flag != 0) {
         // roll back: the rows of the slabs that were committed before the failing one become padding again
@@ -1394,40 +1433,8 @@ static int append_incremental(gpr_model* m, const double* x, const double* y, co
         snprintf(b, sizeof b, "covariance matrix is not positive definite after the append: pivot %d of %zu is <= 0", flag, n1);
         return fail(GPR_ERR_NOT_SPD, b);
     }
-    const int nb1 = (int)(N1 / TB);
-    // alpha = X^T (X y) through the inverse factor that the append has just brought up to date (two bandwidth-bound
-    // passes, no dependency chain), then the same refinement as after a fit with the correction also through X.
-    // GPR_APPEND_TRSV=1 uses the triangular solves over L instead.
-    static const bool use_trsv = getenv("GPR_APPEND_TRSV") && atoi(getenv("GPR_APPEND_TRSV")) != 0;
-    const size_t sol_dbl = (size_t)(32 + 1) * m->cap;                  // sized by the capacity: no reallocation per call
-    rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, residual_scratch_doubles((int)m->cap) + 2 * m->cap + sol_dbl);
-    if (rc) return rc;
-    double* rr = ws->mpart + residual_scratch_doubles((int)N1);
-    double* dd = rr + N1;
-    double* sol = dd + N1;
-    if (use_trsv) {
-        CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, m->label, m->zfwd, m->scratch, dc->num_sms, st));
-        CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
-    } else {
-        CU(launch_solve_with_inverse(md.linv, ld, (int)n1, m->label, md.alpha, sol, st));
-    }
-    for (int it = 0; it < std::max(1, ctx->refine_steps); ++it) {      // at least one step: it also absorbs the explicit-inverse rounding
-        CU(launch_residual(md.xyz, ld, m->s2, m->label, md.alpha, (int)n1, (int)N1, ws->mpart, rr, m->kp, st));
-        if (use_trsv) {
-            CU(launch_trsv(0, m->L, ld, nb1, m->Dinv, rr, m->zfwd, m->scratch, dc->num_sms, st));
-            CU(launch_trsv(1, m->L, ld, nb1, m->Dinv, m->zfwd, dd, m->scratch, dc->num_sms, st));
-        } else {
-            CU(launch_solve_with_inverse(md.linv, ld, (int)n1, rr, dd, sol, st));
-        }
-        CU(launch_axpy1(md.alpha, dd, (int)n1, st));
-    }
-    CU(cudaEventRecord(ws->ev[2], st));
-    m->h_alpha.resize(n1);
-    CU(cudaMemcpyAsync(m->h_alpha.data(), md.alpha, n1 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    int flags[4] = {0, 0, 0, 0};
-    if (use_trsv) CU(cudaMemcpyAsync(flags, m->scratch, sizeof(flags), cudaMemcpyDeviceToHost, st));   // the control words belong to the last flag-chained kernel
-    CU(cudaStreamSynchronize(st));
     if (flags[2] != 0) return fail(GPR_ERR_CUDA, "triangular solve kernel aborted (dependency wait timed out)");
+    m->h_alpha.swap(new_alpha);
     host_append(m, x, y, z, label, sigma2, k);
     m->n = n1; m->n_spd = n1; m->N = N1; m->nb = nb1;
     for (size_t di = 1; di < m->devs.size(); ++di) { m->devs[di].have = false; m->devs[di].have_linv = false; }

@@ -24,6 +24,7 @@ size_t residual_scratch_doubles(int N);
 cudaError_t launch_residual(const double* xyz, size_t ld, const double* sigma2, const double* label, const double* alpha,
                             int n, int N, double* part, double* r, const KernParams& kp, cudaStream_t st);
 cudaError_t launch_axpy1(double* a, const double* d, int n, cudaStream_t st);
+cudaError_t launch_commit_if_clear(const int* flag, const double* src, double* dst, int n, cudaStream_t st);
 // out = X^T (X in): K^-1 applied through the resident inverse factor (two bandwidth-bound triangular matrix-vector
 // products, no dependency chain); scratch: (tri_gemv_splits(n) + 1) * n doubles.
 int tri_gemv_splits(int n);

@@ -272,6 +272,20 @@ cudaError_t launch_residual(const double* xyz, size_t ld, const double* sigma2, 
     return cudaGetLastError();
 }
 
+// dst = src unless the device flag is set (the append's sticky failure flag): lets the host queue the whole append
+// without reading the flag in between.
+__global__ void __launch_bounds__(256) commit_if_clear_kernel(const int* __restrict__ flag, const double* __restrict__ src,
+                                                              double* __restrict__ dst, int n) {
+    if (*flag != 0) return;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+cudaError_t launch_commit_if_clear(const int* flag, const double* src, double* dst, int n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    commit_if_clear_kernel<<<(n + 255) / 256, 256, 0, st>>>(flag, src, dst, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_axpy1(double* a, const double* d, int n, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     axpy1_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, d, n);
