@@ -71,6 +71,29 @@ def test_fails_loudly_without_a_gpu(gpr):
     assert e.value.code == gpr.GPR_ERR_CUDA and "no CPU fallback" in str(e.value)
 
 
+def test_header_is_plain_c99_and_links_from_c(gpr, tmp_path):
+    """the boundary is usable from plain C.  The header must compile as strict C99 and a C program
+    linked against the library must get the loud no-GPU failure (or a context, on a GPU box) — no C++ runtime types."""
+    src = tmp_path / "abi_c99.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "gpr_c_api.h"\n'
+        'int main(void) {\n'
+        '    gpr_ctx* ctx = NULL;\n'
+        '    gpr_kernel_t k; k.kind = 0; k.p0 = 4.2; k.p1 = 0.0;\n'
+        '    int rc = gpr_ctx_create(NULL, 0, &ctx);\n'
+        '    if (rc == GPR_OK) { printf("ctx devices=%d\\n", gpr_ctx_num_devices(ctx)); gpr_ctx_destroy(ctx); return 0; }\n'
+        '    printf("rc=%d msg=%s kind=%d\\n", rc, gpr_last_error(), k.kind);\n'
+        '    return rc == GPR_ERR_CUDA && strlen(gpr_last_error()) > 0 ? 0 : 1;\n'
+        '}\n')
+    pkg = os.path.join(ROOT, "gaussian-object-modelling_b200")
+    exe = tmp_path / "abi_c99"
+    cc = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                         "-o", str(exe), "-L", pkg, "-lgpr_b200", "-Wl,-rpath," + pkg], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+
+
 def test_python_mirror_argument_checks(gpr):
     """Same messages as the reference for the same conditions (gp_regressor.hpp:198,225,231,374,566,570);
     all raised before any GPU work."""
