@@ -1,5 +1,6 @@
 // gpr_solve.cu — K3: alpha = K^-1 y by two triangular solves with the Cholesky factor, each ONE
-// persistent kernel (CTA per 128-row block, dependency flags between blocks).
+// persistent kernel (CTA per 128-row block; a block's result vector carries its own readiness: consumers poll
+// the elements they need against a not-ready bit pattern, so no flag round trip and no fence sits in the chain).
 //
 // Replaces gp->alpha = gp->cholesker.solve(gp->Y) in the reference
 // (/root/reference/include/gp_regression/gp_regressor.hpp:163, :459).
@@ -10,7 +11,7 @@
 // practice: nb dependent steps.  The step is kept short by taking everything that does not depend on
 // the incoming vector off the critical path: Dinv_i = L_ii^-1 (from the factorisation) is staged in
 // shared memory with cp.async when the CTA starts, and the next L tile is loaded into registers
-// (64 doubles per thread) right after the current one has been consumed, i.e. before the flag of the
+// (64 doubles per thread) right after the current one has been consumed, i.e. before the result of the
 // next block is awaited.  Blocks are claimed from an atomic counter in dependency order, so a waiting
 // CTA only ever waits on a CTA that is already running (same argument as gpr_factor.cu).
 #include "gpr_mma.cuh"
@@ -35,6 +36,37 @@ __device__ __forceinline__ void stage_dinv(double* sD, const double* D) {
     cp_async_commit();
 }
 
+
+// Readiness travels with the data: the launcher fills `out` with an all-ones NaN pattern that no result can have
+// (a result with that pattern is stored as the canonical quiet NaN), and a consumer polls the very element it needs.
+// This takes one L2 round trip (flag, then data) and both fences out of every step of the dependency chain.
+constexpr unsigned long long TRSV_SENTINEL = 0xFFFFFFFFFFFFFFFFull;
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const double* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void publish(double* p, double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    if (b == TRSV_SENTINEL) b = 0x7FF8000000000000ull;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(b) : "memory");
+}
+// Returns the element once it is there; on abort / timeout (~2 s) raises *s_abort and returns 0.
+__device__ __forceinline__ double poll_element(const double* p, int* abort, int* s_abort) {
+    unsigned long long b = ld_volatile_u64(p);
+    if (b == TRSV_SENTINEL) {
+        const long long t0 = clock64();
+        for (;;) {
+            b = ld_volatile_u64(p);
+            if (b != TRSV_SENTINEL) break;
+            if (ld_volatile(abort) != 0) { *s_abort = 1; return 0.0; }
+            if (clock64() - t0 > 4000000000LL) { atomicExch(abort, 2); *s_abort = 1; return 0.0; }
+            __nanosleep(32);
+        }
+    }
+    return __longlong_as_double((long long)b);
+}
+
 __global__ void __launch_bounds__(256, 1) trsv_forward_kernel(TrsvArgs a) {
     extern __shared__ __align__(16) double sD[];   // Dinv_i, column-major ld 128
     __shared__ double zs[TB];
@@ -54,38 +86,35 @@ __global__ void __launch_bounds__(256, 1) trsv_forward_kernel(TrsvArgs a) {
 #pragma unroll
             for (int c = 0; c < 64; ++c) cur[c] = __ldcs(Lrow + (size_t)c * a.ld);
         }
-        double s = 0.0;
+        double s4[4] = {0.0, 0.0, 0.0, 0.0};                   // independent chains: the last step is on the critical path
         for (int k = 0; k < i; ++k) {
-            if (tid == 0 && !spin_wait(a.ready + k, a.abort)) s_abort = 1;
+            if (tid < TB) zs[tid] = poll_element(a.out + (size_t)k * TB + tid, a.abort, &s_abort);
             __syncthreads();
             if (s_abort) return;
-            if (tid < TB) zs[tid] = __ldcg(a.out + (size_t)k * TB + tid);
-            __syncthreads();
 #pragma unroll
-            for (int c = 0; c < 64; ++c) s = fma(cur[c], zs[64 * h + c], s);
+            for (int c = 0; c < 64; ++c) s4[c & 3] = fma(cur[c], zs[64 * h + c], s4[c & 3]);
             if (k + 1 < i) {
                 const double* nxt = Lrow + (size_t)(k + 1) * TB * a.ld;
 #pragma unroll
                 for (int c = 0; c < 64; ++c) cur[c] = __ldcs(nxt + (size_t)c * a.ld);
             }
+            __syncthreads();                                   // zs is overwritten by the next step's poll
         }
-        part[h][r] = s;
+        part[h][r] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         cp_async_wait<0>();
         __syncthreads();
         if (tid < TB) zs[tid] = a.rhs[(size_t)i * TB + tid] - (part[0][tid] + part[1][tid]);
         __syncthreads();
         // z_i = Dinv_i * t
-        double z = 0.0;
+        double z4[4] = {0.0, 0.0, 0.0, 0.0};                   // four independent chains of 16 instead of one of 64
         const double* D = sD + (size_t)(64 * h) * TB + r;
-#pragma unroll 16
-        for (int c = 0; c < 64; ++c) z = fma(D[c * TB], zs[64 * h + c], z);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) z4[c & 3] = fma(D[c * TB], zs[64 * h + c], z4[c & 3]);
         __syncthreads();
-        part[h][r] = z;
+        part[h][r] = (z4[0] + z4[1]) + (z4[2] + z4[3]);
         __syncthreads();
-        if (tid < TB) a.out[(size_t)i * TB + tid] = part[0][tid] + part[1][tid];
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) { __threadfence(); st_release(a.ready + i, 1); }
+        if (tid < TB) publish(a.out + (size_t)i * TB + tid, part[0][tid] + part[1][tid]);
+        __syncthreads();                                       // part / zs are reused by the next block of this CTA
     }
 }
 
@@ -115,11 +144,9 @@ __global__ void __launch_bounds__(256, 1) trsv_backward_kernel(TrsvArgs a) {
                 for (int m = 0; m < 4; ++m) cur[c][m] = __ldcs(p + (size_t)c * a.ld + 32 * m);
         }
         for (int k = a.nb - 1; k > i; --k) {
-            if (tid == 0 && !spin_wait(a.ready + k, a.abort)) s_abort = 1;
+            if (tid < TB) as[tid] = poll_element(a.out + (size_t)k * TB + tid, a.abort, &s_abort);
             __syncthreads();
             if (s_abort) return;
-            if (tid < TB) as[tid] = __ldcg(a.out + (size_t)k * TB + tid);
-            __syncthreads();
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 double v = acc[c];
@@ -134,6 +161,7 @@ __global__ void __launch_bounds__(256, 1) trsv_backward_kernel(TrsvArgs a) {
 #pragma unroll
                     for (int m = 0; m < 4; ++m) cur[c][m] = __ldcs(p + (size_t)c * a.ld + 32 * m);
             }
+            __syncthreads();                                   // as is overwritten by the next step's poll
         }
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -154,15 +182,13 @@ __global__ void __launch_bounds__(256, 1) trsv_backward_kernel(TrsvArgs a) {
             for (int m = 0; m < 4; ++m) v = fma(col[32 * m], ts[lane + 32 * m], v);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) a.out[(size_t)i * TB + 16 * warp + c] = v;
+            if (lane == 0) publish(a.out + (size_t)i * TB + 16 * warp + c, v);
         }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) { __threadfence(); st_release(a.ready + i, 1); }
+        __syncthreads();                                       // as / ts are reused by the next block of this CTA
     }
 }
 
-// scratch: [0]=counter [2]=abort [4..4+nb) ready.  rhs and out may not alias.
+// scratch: [0]=counter [2]=abort.  rhs and out may not alias; out is filled with the not-ready pattern first.
 cudaError_t launch_trsv(int backward, const double* L, size_t ld, int nb, const double* Dinv, const double* rhs,
                         double* out, int* scratch, int num_sms, cudaStream_t st) {
     static PerDeviceOnce attr_done;
@@ -175,6 +201,8 @@ cudaError_t launch_trsv(int backward, const double* L, size_t ld, int nb, const 
         attr_done.set(dev);
     }
     cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(int) * (4 + (size_t)nb), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(out, 0xFF, sizeof(double) * (size_t)nb * TB, st);       // every element "not there yet"
     if (e != cudaSuccess) return e;
     TrsvArgs a;
     a.L = L; a.ld = ld; a.nb = nb; a.Dinv = Dinv; a.rhs = rhs; a.out = out;
