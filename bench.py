@@ -322,7 +322,17 @@ def main():
         launches_var = BATCHES_PER_STEP * args.steps
         flops_per_launch = float(N_TRAIN) ** 2 * batch                # n^2 * q per variance batch
         achieved = flops_per_launch / (var_ms / launches_var * 1e-3) / 1e12
-        dmma_peak = g.selftest_peak(0, 4)
+        # The denominator: the raw DMMA issue rate of this device.  The probe draws more power than any real kernel, so
+        # a single reading taken right after the timed steps can come out LOW (clocks pulled down for a moment: one run
+        # read 29.7 TF/s where every other run read 37.0).  Take the best of several readings spread over ~2 s, and never
+        # report a "peak" below what was actually achieved or below cuBLAS DGEMM on the same device.
+        readings = []
+        for attempt in range(6):
+            readings.append(g.selftest_peak(0, 4))
+            if attempt >= 2 and max(readings) >= 1.02 * achieved:
+                break
+            time.sleep(0.4)
+        dmma_peak = max(readings)
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "var_tiles_traffic.json")
         if os.path.exists(tpath):          # dram__bytes_read+write of one launch, from the committed ncu --set full capture
@@ -336,6 +346,7 @@ def main():
         c0.record(); a64 @ a64; a64 @ a64; c1.record(); torch.cuda.synchronize(dev)
         dgemm = 2 * 2 * 8192 ** 3 / (c0.elapsed_time(c1) * 1e-3) / 1e12
         del a64
+        peak = max(dmma_peak, dgemm, achieved)          # all three are measured FP64 tensor rates of this device
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config({"queries_per_step_per_gpu": step_q,
@@ -346,12 +357,13 @@ def main():
                 "gpu_launches": 4 * BATCHES_PER_STEP * args.steps,
                 "clocks": clocks,
                 "roofline": {"kernel": "var_tiles_kernel (variance product X*K*^T + column norms)", "bound": "tensor",
-                             "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
+                             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_source": traffic_src,
                              "algorithmic_operand_bytes": 8.0 * N_TRAIN * (N_TRAIN + 128) / 2 + 8.0 * N_TRAIN * batch,
-                             "peak_source": "FP64: measured in this run, raw DMMA.8x8x4 issue rate (gpr_selftest_peak); "
-                                            "MEASURED_PEAKS.json has no FP64 entry. cuBLAS DGEMM 8192^3 in this run: %.1f TF/s" % dgemm,
-                             "cublas_dgemm_tflops": dgemm, "share_of_step": var_ms / elapsed_ms,
+                             "peak_source": "FP64: measured in this run = max(raw DMMA.8x8x4 issue rate (gpr_selftest_peak), cuBLAS DGEMM, achieved); "
+                                            "best of %d readings %s; MEASURED_PEAKS.json has no FP64 entry. cuBLAS DGEMM 8192^3 "
+                                            "in this run: %.1f TF/s" % (len(readings), ["%.1f" % r for r in readings], dgemm),
+                             "cublas_dgemm_tflops": dgemm, "dmma_probe_tflops": dmma_peak, "share_of_step": var_ms / elapsed_ms,
                              "mean_panel_kernel_ms_per_step": mean_ms / args.steps}}
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline:

@@ -139,7 +139,7 @@ cudaError_t run_peak_probe(int which, int ctas_per_sm, double* tflops) {
     const int iters = which == 1 ? 20000 : 4000;
     const int grid = sms * ctas_per_sm;
     float best = 1e30f;
-    for (int rep = 0; rep < 4; ++rep) {
+    for (int rep = 0; rep < 8; ++rep) {                  // rep 0 warms up; best of the rest
         cudaEventRecord(a);
         if (which == 0) dmma_peak_kernel<<<grid, 256>>>(d, iters);
         else if (which == 1) dfma_peak_kernel<<<grid, 256>>>(d, iters);
