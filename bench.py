@@ -6,7 +6,8 @@ sphere, label 0; 4,096 on the r = 2 sphere, label +1), sigma2 = 0.1, ThinPlate(R
 256^3 lattice on [-1.2, 1.2]^3, sharded over the ranks as contiguous index blocks (z-slabs).
 
 A "step" is one pass of the hot path over one batch of queries per GPU: fused mean + cross-covariance
-panel, then the variance product against L^-1 on the FP64 tensor pipe.  `value` is whole-job
+panel, then the variance by blocked forward substitution over the Cholesky factor (V = L^-1 K*^T in place in the
+panel, FP64 tensor pipe) — the default path of a freshly fitted model: no L^-1 is ever built for it.  `value` is whole-job
 query points / s (mean + variance) with the queries already resident in HBM; `e2e` is the same through
 the host-pointer C-ABI call gpr_predict (pinned host buffers, H2D and D2H inside the timed region).
 The fit (covariance build + Cholesky + alpha) is timed separately and reported as fit_ms on the same line.
@@ -51,7 +52,7 @@ def workload_config(extra=None):
     cfg = {"workload": "config3: synthetic sphere cloud n=16384, ThinPlate(R=4.2), sigma2=0.1, mean+variance over the "
                        "256^3 grid on [-1.2,1.2]^3 (z-slab shards)",
            "n_train": N_TRAIN, "grid": GRID_RES, "kernel": "thin_plate", "R": 4.2,
-           "cache": "inputs larger than L2: each step streams L^-1 (1.07 GB) and a 2.5 GB cross-covariance panel"}
+           "cache": "inputs larger than L2: each step streams the factor (1.07 GB) and a 2.5 GB cross-covariance panel"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -152,6 +153,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fit-reps", type=int, default=3)
+    ap.add_argument("--no-full-grid", action="store_true", help="skip the strong-scaling pass over the whole 256^3 lattice")
+    ap.add_argument("--no-fanout", action="store_true", help="skip the unchanged-caller thread fan-out measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -166,7 +169,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config({"sample_queries_per_step": res["sample_q"]}),
+                "config": workload_config(), "sample_queries_per_step": res["sample_q"],
                 "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
                 "fit_ms": 1e3 * res["fit_s"], "port_blas_dtrsm_points_per_s": res["port_blas_dtrsm_points_per_s"],
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -207,21 +210,41 @@ def main():
             model = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
             wall = 1e3 * (time.perf_counter() - t0)
             t = ctx.timings()
-            if rep > 0:
+            if rep == 0:
+                # the very first fit of the process: 2.1 GB cudaMalloc, lazy module load, no buffer cache
+                extras["fit_wall_ms_first_call"] = wall
+            else:
                 fits.append((t["fit_total_ms"], t["cov_ms"], t["chol_ms"], t["solve_ms"], wall))
         best = min(fits)
         extras.update(fit_ms=best[0], fit_cov_ms=best[1], fit_chol_ms=best[2], fit_solve_ms=best[3],
                       fit_wall_ms_e2e=min(f[4] for f in fits),      # host wall of gpr_fit (H2D of the cloud, allocation, D2H of alpha)
                       fit_chol_tflops=N_TRAIN ** 3 / 3 / (best[2] * 1e-3) / 1e12)
-        reg.prepare_variance(model)
-        extras["linv_ms_once"] = ctx.timings()["linv_ms"]
+        # time to first variance: a fresh fit followed at once by one variance batch (148*128 queries), host wall.
+        # The default path needs no L^-1 (forward substitution over L), so this is fit + one batch.
+        sms0 = torch.cuda.get_device_properties(dev).multi_processor_count
+        q1 = 128 * sms0
+        Q1 = torch.from_numpy(np.ascontiguousarray(W.grid_slab(GRID_RES, 128, 129)[:q1].T)).to(dev)
+        o1 = torch.empty(2 * q1, dtype=torch.float64, device=dev)
+        model.close()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        model = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+        t_fit = 1e3 * (time.perf_counter() - t0)
+        reg.evaluate_device(model, Q1[0].data_ptr(), Q1[1].data_ptr(), Q1[2].data_ptr(), q1, o1.data_ptr(), o1[q1:].data_ptr(), None)
+        torch.cuda.synchronize(dev)
+        extras["time_to_first_variance_ms"] = 1e3 * (time.perf_counter() - t0)
+        extras["time_to_first_variance_split"] = {"fit_wall_ms": t_fit, "first_batch_queries": q1,
+                                                  "first_batch_ms": extras["time_to_first_variance_ms"] - t_fit}
+        assert model.state().linv is None                    # nothing built L^-1
+        del Q1, o1
     bcast_bytes = 0
     if world > 1:
         warm = torch.zeros(1 << 20, dtype=torch.float64, device=dev)
         dist.broadcast(warm, src=0)                        # communicator set-up is not part of the exchange step
         barrier()
         t0 = time.perf_counter()
-        model, bcast_bytes = D.broadcast_model(reg, model, N_TRAIN, W.SYNTH_R, True, rank, dev, src=0)
+        # the exchange step: {x|y|z, alpha, L, Dinv} — what the fit leaves behind; no L^-1 is built before it
+        model, bcast_bytes = D.broadcast_model(reg, model, N_TRAIN, W.SYNTH_R, 2, rank, dev, src=0)
         barrier()
         bms = 1e3 * (time.perf_counter() - t0)
         extras.update(broadcast_ms=bms, broadcast_bytes=bcast_bytes, broadcast_GBps=bcast_bytes / bms / 1e6)
@@ -302,6 +325,52 @@ def main():
     e2e_value = world * step_q * args.steps / e2e_s
     assert np.array_equal(fo.numpy(), f_d.cpu().numpy()) and np.array_equal(vo.numpy(), v_d.cpu().numpy())
 
+    # ---- strong scaling: the WHOLE 256^3 lattice, fit -> last variance, sharded over the ranks (z-slabs) ----------
+    # fit (rank 0) + broadcast + every rank's shard of the 16.8 M queries; wall clock of the slowest rank.
+    full_grid = None
+    if not args.no_full_grid:
+        a_q, b_q = D.shard_range(total_q, rank, world)
+        za, zb = a_q // (GRID_RES * GRID_RES), -(-b_q // (GRID_RES * GRID_RES))
+        Qfull = torch.from_numpy(np.ascontiguousarray(W.grid_slab(GRID_RES, za, zb).T)).to(dev)
+        off = a_q - za * GRID_RES * GRID_RES
+        cnt = b_q - a_q
+        fo_g = torch.empty(cnt, dtype=torch.float64, device=dev)
+        vo_g = torch.empty(cnt, dtype=torch.float64, device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        fg_fit_ms = fg_bc_ms = 0.0
+        if rank == 0:
+            model.close()
+            model = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+            fg_fit_ms = 1e3 * (time.perf_counter() - t0)
+        elif model is not None:
+            model.close()
+            model = None
+        if world > 1:
+            t1 = time.perf_counter()
+            model, _ = D.broadcast_model(reg, model, N_TRAIN, W.SYNTH_R, 2, rank, dev, src=0)
+            fg_bc_ms = 1e3 * (time.perf_counter() - t1)
+        reg.evaluate_device(model, Qfull[0, off:].data_ptr(), Qfull[1, off:].data_ptr(), Qfull[2, off:].data_ptr(), cnt,
+                            fo_g.data_ptr(), vo_g.data_ptr(), None)
+        torch.cuda.synchronize(dev)
+        fg_s = time.perf_counter() - t0
+        shell = int((fo_g.abs() <= 0.01).sum().item())
+        vmin = float(vo_g.min().item())
+        if world > 1:
+            tt = torch.tensor([fg_s, fg_fit_ms, fg_bc_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            fg_s, fg_fit_ms, fg_bc_ms = (float(x) for x in tt.tolist())
+            cc = torch.tensor([float(shell), -vmin], dtype=torch.float64, device=dev)
+            dist.all_reduce(cc[:1], op=dist.ReduceOp.SUM)
+            dist.all_reduce(cc[1:], op=dist.ReduceOp.MAX)
+            shell, vmin = int(cc[0].item()), -float(cc[1].item())
+        assert vmin > 0.0
+        full_grid = {"full_grid_s": fg_s, "queries": total_q, "points_per_s": total_q / fg_s, "fit_wall_ms": fg_fit_ms,
+                     "broadcast_ms": fg_bc_ms, "points_in_shell_abs_f_le_0.01": shell, "scaling": "strong",
+                     "what": "fit on rank 0 -> broadcast of {x|y|z, alpha, L, Dinv} -> mean+variance of ALL 256^3 lattice "
+                             "points (z-slab shards), host wall of the slowest rank"}
+        del Qfull, fo_g, vo_g
+
     if rank == 0:
         # the other evaluate overloads on this GPU (device-resident, CUDA-event timed by the library), for context
         qn = min(need, 1 << 20)
@@ -322,19 +391,30 @@ def main():
         launches_var = BATCHES_PER_STEP * args.steps
         flops_per_launch = float(N_TRAIN) ** 2 * batch                # n^2 * q per variance batch
         achieved = flops_per_launch / (var_ms / launches_var * 1e-3) / 1e12
-        # The denominator: the raw DMMA issue rate of this device.  The probe draws more power than any real kernel, so
-        # a single reading taken right after the timed steps can come out LOW (clocks pulled down for a moment: one run
-        # read 29.7 TF/s where every other run read 37.0).  Take the best of several readings spread over ~2 s, and never
-        # report a "peak" below what was actually achieved or below cuBLAS DGEMM on the same device.
+        # the product form (X = L^-1 resident) on the same batches, for comparison: one-time n^3/3 inverse, then the same
+        # n^2 q flop without a dependency chain
+        assert model.state().linv is None
+        reg.prepare_variance(model)
+        linv_ms = ctx.timings()["linv_ms"]
+        pv = []
+        for s_ in range(3):
+            pv.append(step_device(s_)[0])
+        prod_ms = min(pv)
+        extras["variance_product_form"] = {"linv_ms_once": linv_ms, "var_ms_per_step": prod_ms,
+                                           "tflops": flops_per_launch * BATCHES_PER_STEP / (prod_ms * 1e-3) / 1e12,
+                                           "note": "same batches through var_tiles_kernel (product with the explicit inverse factor); "
+                                                   "the default path above needs neither the inverse nor its 8n^2 bytes"}
+        # The denominators, reported separately and never clamped: (1) the raw DMMA issue rate of this device
+        # (gpr_selftest_peak: DMMA.8x8x4 from registers, no memory traffic) — the probe draws more power than any real
+        # kernel, so a reading taken right after the timed steps can come out low; the best of several readings spread
+        # over ~2 s is used; (2) cuBLAS DGEMM 8192^3 on the same device.
         readings = []
         for attempt in range(6):
             readings.append(g.selftest_peak(0, 4))
-            if attempt >= 2 and max(readings) >= 1.02 * achieved:
-                break
             time.sleep(0.4)
         dmma_peak = max(readings)
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "var_tiles_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "var_trsm_traffic.json")
         if os.path.exists(tpath):          # dram__bytes_read+write of one launch, from the committed ncu --set full capture
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
@@ -346,32 +426,58 @@ def main():
         c0.record(); a64 @ a64; a64 @ a64; c1.record(); torch.cuda.synchronize(dev)
         dgemm = 2 * 2 * 8192 ** 3 / (c0.elapsed_time(c1) * 1e-3) / 1e12
         del a64
-        peak = max(dmma_peak, dgemm, achieved)          # all three are measured FP64 tensor rates of this device
+        peak_src = ("FP64 tensor pipe: raw DMMA.8x8x4 issue rate measured in this run (gpr_selftest_peak), best of %d readings %s; "
+                    "MEASURED_PEAKS.json has no FP64 entry.  cuBLAS DGEMM 8192^3 in this run: %.1f TF/s (frac_vs_cublas)"
+                    % (len(readings), ["%.1f" % r for r in readings], dgemm))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": workload_config({"queries_per_step_per_gpu": step_q,
-                                                                               "parallelism": "query-sharded x%d" % world}),
+                "dtype": "f64", "data": "synthetic", "config": workload_config(),
+                "queries_per_step_per_gpu": step_q, "parallelism": "query-sharded x%d" % world,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * step_q, "d2h_bytes_per_step": 16 * step_q},
-                # per variance batch: predict_thread_kernel (mean + K* panel), predict_reduce_kernel, var_tiles_kernel,
+                # per variance batch: predict_thread_kernel (mean + K* panel), predict_reduce_kernel, var_trsm_kernel,
                 # var_finalize_kernel (profiles/ncu_launches_bench_*.csv lists them)
                 "gpu_launches": 4 * BATCHES_PER_STEP * args.steps,
                 "clocks": clocks,
-                "roofline": {"kernel": "var_tiles_kernel (variance product X*K*^T + column norms)", "bound": "tensor",
-                             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "roofline": {"kernel": "var_trsm_kernel (variance: blocked forward substitution V = L^-1 K*^T in the panel + column norms)",
+                             "bound": "tensor",
+                             "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
+                             "frac_vs_cublas": achieved / dgemm,
                              "traffic": traffic, "traffic_source": traffic_src,
+                             "algorithmic_flop_per_launch": flops_per_launch,
                              "algorithmic_operand_bytes": 8.0 * N_TRAIN * (N_TRAIN + 128) / 2 + 8.0 * N_TRAIN * batch,
-                             "peak_source": "FP64: measured in this run = max(raw DMMA.8x8x4 issue rate (gpr_selftest_peak), cuBLAS DGEMM, achieved); "
-                                            "best of %d readings %s; MEASURED_PEAKS.json has no FP64 entry. cuBLAS DGEMM 8192^3 "
-                                            "in this run: %.1f TF/s" % (len(readings), ["%.1f" % r for r in readings], dgemm),
+                             "peak_source": peak_src,
                              "cublas_dgemm_tflops": dgemm, "dmma_probe_tflops": dmma_peak, "share_of_step": var_ms / elapsed_ms,
-                             "mean_panel_kernel_ms_per_step": mean_ms / args.steps}}
+                             "mean_panel_kernel_ms_per_step": mean_ms / args.steps},
+                "roofline_fit": {"kernel": "chol_tiles_kernel (tile-task Cholesky, n^3/3 flop)", "bound": "tensor",
+                                 "achieved": extras["fit_chol_tflops"], "peak": dmma_peak, "unit": "TFLOP/s",
+                                 "frac": extras["fit_chol_tflops"] / dmma_peak, "frac_vs_cublas": extras["fit_chol_tflops"] / dgemm,
+                                 "ms": extras["fit_chol_ms"], "share_of_fit": extras["fit_chol_ms"] / extras["fit_ms"],
+                                 "traffic": None}}
         line.update(extras)
+        if full_grid:
+            line["full_grid"] = full_grid
+            line["full_grid_s"] = full_grid["full_grid_s"]
+        if world == 1 and not args.no_fanout:
+            # the unchanged caller: 29 slabs x 841 std::threads x one evaluate(q = 1) (src/gp_node.cpp:1025-1038) through the
+            # drop-in headers, and the same source against the reference's own header on this box's host cores
+            try:
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fanout_bench.py"), "--cases", "mugD:node"],
+                                     capture_output=True, text=True, timeout=900)
+                fj = json.loads(out.stdout.strip().splitlines()[-1])["cases"][0]
+                line["fanout_calls_per_s"] = fj["ours"]["calls_per_s"]
+                line["fanout"] = {"workload": "mugD (n = 277), ThinPlate(2.0) — the node's own setting; 24389 single-query "
+                                              "evaluate(f, v) calls from 841 concurrent std::threads per slab",
+                                  "ours": fj["ours"], "reference_cpu": fj.get("reference"), "parity": fj.get("parity"),
+                                  "speedup_vs_reference": fj.get("speedup_vs_reference")}
+            except Exception as e:                      # the headline line must not depend on g++ being present
+                line["fanout"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             res = cpu_reference_run(2, 1)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "fit_s",
                                                         "port_blas_dtrsm_points_per_s")}
             # parity at the full bench size, on the CPU arm's last sample: our alpha against the OpenBLAS
             # Cholesky solve, our mean / variance against what the reference's evaluate() returned
+            # (tests/test_gpu_parity.py::test_headline_parity_config3 / _config5 hold the asserted versions)
             Qs = res["last_queries"]
             fg, vg = reg.evaluate(model, Qs[:, 0], Qs[:, 1], Qs[:, 2], var=True)
             rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())

@@ -49,7 +49,8 @@ class Timings(C.Structure):
 class ModelState(C.Structure):
     _fields_ = [("n", C.c_size_t), ("padded_n", C.c_size_t), ("ld", C.c_size_t), ("kernel", KernelT), ("R", C.c_double),
                 ("xyz", C.c_void_p), ("alpha", C.c_void_p), ("linv", C.c_void_p),
-                ("n_tail", C.c_size_t), ("tail_pad", C.c_size_t), ("tail_z", C.c_void_p), ("tail_sinv", C.c_void_p)]
+                ("n_tail", C.c_size_t), ("tail_pad", C.c_size_t), ("tail_z", C.c_void_p), ("tail_sinv", C.c_void_p),
+                ("lfac", C.c_void_p), ("dinv", C.c_void_p)]
 
 
 def build(force=False):
@@ -92,6 +93,7 @@ def lib():
         L.gpr_model_save.argtypes = [vp, vp, C.c_char_p, ci]
         L.gpr_model_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
         L.gpr_model_prepare_variance.argtypes = [vp, vp]
+        L.gpr_model_solve.argtypes = [vp, vp, _dp, sz, _dp]
         L.gpr_append.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, sz]
         L.gpr_model_reserve.argtypes = [vp, vp, sz]
         L.gpr_model_state_get.argtypes = [vp, vp, ci, C.POINTER(ModelState)]
@@ -112,9 +114,11 @@ C_ABI_SYMBOLS = [
     "gpr_last_timings", "gpr_fit", "gpr_model_destroy", "gpr_model_size", "gpr_model_tail_size", "gpr_model_get",
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
     "gpr_model_reserve", "gpr_sample_isosurface", "gpr_project", "gpr_model_save", "gpr_model_load",
-    "gpr_model_state_get", "gpr_model_create_replica", "gpr_model_create_replica_tail", "gpr_selftest_gemm", "gpr_selftest_leaf",
-    "gpr_selftest_factor", "gpr_selftest_peak", "gpr_selftest_factor_trace",
+    "gpr_model_state_get", "gpr_model_create_replica", "gpr_model_create_replica_tail", "gpr_model_solve",
 ]
+# Engine self-tests / pipe probes (csrc/gpr_selftest.h): exported for tests/ and bench.py, not part of the boundary.
+SELFTEST_SYMBOLS = ["gpr_selftest_gemm", "gpr_selftest_leaf", "gpr_selftest_factor", "gpr_selftest_peak",
+                    "gpr_selftest_factor_trace"]
 
 
 def _check(rc):
@@ -129,6 +133,13 @@ def _arr(a):
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _same_length(*arrays):
+    """The C side reads n entries of every array: refuse ragged input here, with the message of the C++ shim."""
+    sizes = {a.size for a in arrays if a is not None}
+    if len(sizes) > 1 or any(a is not None and a.ndim != 1 for a in arrays):
+        raise GPRegressionException("Inconsistent input data sizes")
 
 
 class Context:
@@ -233,6 +244,7 @@ class GPRegressor:
         x, y, z, label, sigma2 = map(_arr, (x, y, z, label, sigma2))
         if len(x) == 0 and len(y) == 0 and len(z) == 0 and len(label) == 0:
             raise GPRegressionException("All input data is empty!")
+        _same_length(x, y, z, label, sigma2)
         h = C.c_void_p()
         _check(lib().gpr_fit(self.ctx._h, _p(x), _p(y), _p(z), _p(label), _p(sigma2), len(x), self.kernel,
                              int(with_normals), C.byref(h)))
@@ -250,6 +262,7 @@ class GPRegressor:
         q = len(qx)
         if q == 0:
             raise GPRegressionException("All input data is empty!")
+        _same_length(qx, qy, qz)
         grad = grad or tangent
         f = np.zeros(q)
         v = np.zeros(q) if var else None
@@ -268,6 +281,7 @@ class GPRegressor:
         if model is None or not model._h:
             raise GPRegressionException("Empty model pointer")
         x, y, z, label, sigma2 = map(_arr, (x, y, z, label, sigma2))
+        _same_length(x, y, z, label, sigma2)
         _check(lib().gpr_append(self.ctx._h, model._h, _p(x), _p(y), _p(z), _p(label), _p(sigma2), len(x)))
 
     def reserve(self, model, capacity):
@@ -316,6 +330,14 @@ class GPRegressor:
 
     def prepare_variance(self, model):
         _check(lib().gpr_model_prepare_variance(self.ctx._h, model._h))
+
+    def solve(self, model, B):
+        """K^-1 B through the resident factor (the reference's public Model::cholesker.solve, gp_regressor.hpp:81)."""
+        B = np.asarray(B, dtype=np.float64)
+        Bf = np.asfortranarray(B.reshape(model.n, -1))
+        X = np.zeros_like(Bf, order="F")
+        _check(lib().gpr_model_solve(self.ctx._h, model._h, _p(Bf), Bf.shape[1], _p(X)))
+        return np.ascontiguousarray(X).reshape(B.shape)
 
     def evaluate_device(self, model, d_qx, d_qy, d_qz, q, d_f, d_var=None, d_grad=None):
         """Device-pointer variant (ints from tensor.data_ptr()); no host copies."""

@@ -2,6 +2,7 @@
 // orchestration over the kernels in this directory.  No CPU fallback anywhere: every compute entry
 // point needs a CUDA device and reports GPR_ERR_CUDA otherwise.
 #include "../../include/gpr_c_api.h"
+#include "gpr_selftest.h"
 #include "gpr_kernels.h"
 #include "gpr_mma.cuh"
 
@@ -11,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -175,7 +177,11 @@ struct ModelDev {            // what predict needs, per device
     double* linv = nullptr;  // N x N, lower tiles
     double* tZ = nullptr;    // indefinite tail (gpr_tail.cu): Z = A^-1 P in 32-column slabs, S^-1
     double* tSinv = nullptr;
-    bool have = false, have_linv = false, have_tail = false;
+    // Cholesky factor + inverses of its diagonal blocks, for the variance by forward substitution (gpr_var.cu:
+    // var_trsm_kernel).  On the primary device these alias gpr_model::L / Dinv (own_fac false); copies on the other
+    // devices of the context and in cross-process replicas are owned.
+    double* lfac = nullptr; double* dinv = nullptr;
+    bool have = false, have_linv = false, have_tail = false, have_fac = false, own_fac = false;
 };
 
 struct gpr_model {
@@ -201,6 +207,17 @@ struct gpr_model {
     std::vector<double> hx, hy, hz, hlabel, hs2, h_alpha, h_normals;   // h_normals: n_normals x 3 column-major
     size_t n_normals = 0;
     std::mutex mu;
+    // Micro-batcher of the callers' q = 1 pattern (hundreds of concurrent threads with one query each on one shared
+    // model, src/gp_node.cpp:1027-1038): concurrent small requests are combined into one batched launch.
+    struct SmallReq {
+        const double *qx, *qy, *qz; size_t q;
+        double *f, *var, *grad, *tx, *ty; size_t out_ld;
+        int rc = 0; std::string err; bool done = false;
+    };
+    std::mutex bmu;
+    std::condition_variable bcv;
+    std::vector<SmallReq*> pending;
+    bool leader = false;
 };
 
 static KernParams make_kp(gpr_kernel_t k) {
@@ -226,7 +243,9 @@ static void free_factor(gpr_model* m) {
         cudaSetDevice(d.dev);
         cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.tZ); cudaFree(d.tSinv);
         big_free(m->ctx, d.dev, d.linv, m->cap * m->cap * sizeof(double));
-        d.xyz = d.alpha = d.linv = d.tZ = d.tSinv = nullptr; d.have = d.have_linv = d.have_tail = false;
+        if (d.own_fac) { big_free(m->ctx, d.dev, d.lfac, m->cap * m->cap * sizeof(double)); cudaFree(d.dinv); }
+        d.xyz = d.alpha = d.linv = d.tZ = d.tSinv = d.lfac = d.dinv = nullptr;
+        d.have = d.have_linv = d.have_tail = d.have_fac = d.own_fac = false;
     }
 }
 
@@ -541,6 +560,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     CU(cudaMemcpy(abortflag, m->scratch, sizeof(abortflag), cudaMemcpyDeviceToHost));
     if (abortflag[2] != 0) return fail(GPR_ERR_CUDA, "triangular solve kernel aborted (dependency wait timed out)");
     md.have = true;
+    md.lfac = m->L; md.dinv = m->Dinv; md.own_fac = false; md.have_fac = m->n_tail == 0;
     {
         std::lock_guard<std::mutex> lk(ctx->tmu);
         gpr_timings& t = ctx->timings;
@@ -581,9 +601,10 @@ static int ensure_linv_primary(gpr_model* m) {
 }
 
 // Make sure device slot di holds the predict state (copied from the primary over NVLink).
-static int ensure_on_device(gpr_model* m, size_t di, bool need_linv) {
+static int ensure_on_device(gpr_model* m, size_t di, bool need_linv, bool need_fac = false) {
     std::lock_guard<std::mutex> lk(m->mu);
     if (need_linv) { int rc = ensure_linv_primary(m); if (rc) return rc; }
+    if (need_fac && !m->devs[0].have_fac) return fail(GPR_ERR_INVALID, "model holds no Cholesky factor on its primary device");
     if (di == 0) return GPR_OK;
     ModelDev& src = m->devs[0];
     ModelDev& dst = m->devs[di];
@@ -599,6 +620,15 @@ static int ensure_on_device(gpr_model* m, size_t di, bool need_linv) {
         if (!dst.linv) CU(big_alloc(m->ctx, dst.dev, (void**)&dst.linv, m->cap * m->cap * sizeof(double)));
         CU(cudaMemcpyPeer(dst.linv, dst.dev, src.linv, src.dev, m->cap * m->cap * sizeof(double)));
         dst.have_linv = true;
+    }
+    if (need_fac && !dst.have_fac) {
+        const size_t db = (size_t)m->nb * TB * TB * sizeof(double);
+        if (!dst.lfac) CU(big_alloc(m->ctx, dst.dev, (void**)&dst.lfac, m->cap * m->cap * sizeof(double)));
+        if (!dst.dinv) CU(cudaMalloc((void**)&dst.dinv, (size_t)(m->cap / TB) * TB * TB * sizeof(double)));
+        dst.own_fac = true;
+        CU(cudaMemcpyPeer(dst.lfac, dst.dev, src.lfac, src.dev, m->cap * m->cap * sizeof(double)));
+        CU(cudaMemcpyPeer(dst.dinv, dst.dev, src.dinv, src.dev, db));
+        dst.have_fac = true;
     }
     if (need_linv && m->n_tail > 0 && !dst.have_tail) {
         const size_t zb = (size_t)(m->mp / 32) * m->cap * 32 * sizeof(double), sb = (size_t)m->mp * m->mp * sizeof(double);
@@ -627,7 +657,25 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
     gpr_ctx* ctx = m->ctx;
     DeviceCtx* dc = ctx->devs[di];
     const bool want_var = io.var != nullptr, want_grad = io.grad != nullptr, want_t = io.tx != nullptr;
-    int rc = ensure_on_device(m, di, want_var);
+    // Which form of the variance (same n^2 flop per query on the FP64 tensor pipe either way):
+    //   * forward substitution over L in the K* panel (var_trsm_kernel): needs no L^-1 — the default for large
+    //     batches on a model whose inverse factor has not been built (time to first variance = the fit);
+    //   * product with X = L^-1 (var_tiles_kernel / the fused q <= 8 kernel): no dependency chain, spreads a small
+    //     batch over all SMs; used whenever X is resident anyway, for small batches and for indefinite-tail models.
+    // GPR_VAR_MODE=trsm|product forces one (tests, bench).
+    bool use_trsm = false;
+    if (want_var && io.q > 8 && m->n_tail == 0 && m->devs[0].have_fac) {
+        const char* mode_env = getenv("GPR_VAR_MODE");
+        static const long min_q = getenv("GPR_TRSM_MIN_Q") ? atol(getenv("GPR_TRSM_MIN_Q")) : 4096;
+        if (mode_env && !strcmp(mode_env, "trsm")) use_trsm = true;
+        else if (mode_env && !strcmp(mode_env, "product")) use_trsm = false;
+        else {
+            bool have_x;
+            { std::lock_guard<std::mutex> lk(m->mu); have_x = m->devs[0].have_linv; }
+            use_trsm = !have_x && (long)io.q >= min_q;
+        }
+    }
+    int rc = ensure_on_device(m, di, want_var && !use_trsm, use_trsm);
     if (rc) return rc;
     CU(cudaSetDevice(dc->dev));
     ModelDev& md = m->devs[di];
@@ -726,6 +774,7 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         CU(cudaEventRecord(ws->ev[2], st));
         if (want_var) {
             if (small_var) CU(launch_variance_small(md.linv, ld, m->nb * TB, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+            else if (use_trsm) CU(launch_variance_trsm(md.lfac, ld, m->nb, md.dinv, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
             else CU(launch_variance(md.linv, ld, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
             if (m->n_tail > 0) {
                 // indefinite tail: var -= w^T S^-1 w,  w = k_2 - Z^T k_1  (gpr_tail.cu)
@@ -898,12 +947,108 @@ int gpr_model_get_factor(const gpr_model* m, double* L) {
     return GPR_OK;
 }
 
+}  // extern "C"
+
+static int predict_host(gpr_ctx* ctx, gpr_model* m, const double* qx, const double* qy, const double* qz, size_t q,
+                        double* f, double* var, double* grad, double* tx, double* ty);
+
+// One combined launch for the small requests collected by the micro-batcher: their queries are gathered into one SoA
+// batch, evaluated through the regular batched path (so every request gets exactly the bits a batched call of the
+// same queries returns) and scattered back.  A batch of one request is passed through unchanged (fused q <= 8 kernel).
+static void run_small_batch(gpr_ctx* ctx, gpr_model* m, std::vector<gpr_model::SmallReq*>& reqs) {
+    if (reqs.size() == 1) {
+        gpr_model::SmallReq* r = reqs[0];
+        r->rc = predict_host(ctx, m, r->qx, r->qy, r->qz, r->q, r->f, r->var, r->grad, r->tx, r->ty);
+        if (r->rc) r->err = g_err;
+        return;
+    }
+    size_t total = 0;
+    bool want_var = false, want_grad = false, want_t = false;
+    for (auto* r : reqs) { total += r->q; want_var |= r->var != nullptr; want_grad |= r->grad != nullptr; want_t |= r->tx != nullptr; }
+    std::vector<double> in(3 * total), out((1 + (want_var ? 1 : 0) + (want_grad ? 3 : 0) + (want_t ? 6 : 0)) * total);
+    size_t o = 0;
+    for (auto* r : reqs) {
+        for (size_t i = 0; i < r->q; ++i) { in[o + i] = r->qx[i]; in[total + o + i] = r->qy[i]; in[2 * total + o + i] = r->qz[i]; }
+        o += r->q;
+    }
+    double* bf = out.data();
+    double* bv = want_var ? bf + total : nullptr;
+    double* bg = want_grad ? bf + (1 + (want_var ? 1 : 0)) * total : nullptr;
+    double* btx = want_t ? bg + 3 * total : nullptr;
+    double* bty = want_t ? btx + 3 * total : nullptr;
+    const int rc = predict_host(ctx, m, in.data(), in.data() + total, in.data() + 2 * total, total, bf, bv, bg, btx, bty);
+    const std::string err = rc ? g_err : std::string();
+    o = 0;
+    for (auto* r : reqs) {
+        r->rc = rc; r->err = err;
+        if (!rc)
+            for (size_t i = 0; i < r->q; ++i) {
+                r->f[i] = bf[o + i];
+                if (r->var) r->var[i] = bv[o + i];
+                for (int c = 0; c < 3; ++c) {
+                    if (r->grad) r->grad[c * r->out_ld + i] = bg[c * total + o + i];
+                    if (r->tx) { r->tx[c * r->out_ld + i] = btx[c * total + o + i]; r->ty[c * r->out_ld + i] = bty[c * total + o + i]; }
+                }
+            }
+        o += r->q;
+    }
+}
+
+// Flat combining: the first thread to arrive becomes the leader and runs its own request at once (a lone caller sees
+// the latency of the fused single-query kernel); requests that arrive while a launch is in flight queue up and are
+// served together by the next launch (at most MICRO_CAP queries).  After MICRO_ROUNDS launches the leader hands over
+// to a waiting thread, so that it cannot be kept working for others forever.
+constexpr size_t MICRO_CAP = 1024;
+constexpr int MICRO_ROUNDS = 4;
+static bool microbatch_on() { static const bool on = !(getenv("GPR_MICROBATCH") && atoi(getenv("GPR_MICROBATCH")) == 0); return on; }
+
+static int predict_small_combined(gpr_ctx* ctx, gpr_model* m, const double* qx, const double* qy, const double* qz, size_t q,
+                                  double* f, double* var, double* grad, double* tx, double* ty) {
+    gpr_model::SmallReq me;
+    me.qx = qx; me.qy = qy; me.qz = qz; me.q = q; me.f = f; me.var = var; me.grad = grad; me.tx = tx; me.ty = ty; me.out_ld = q;
+    std::unique_lock<std::mutex> lk(m->bmu);
+    m->pending.push_back(&me);
+    for (;;) {
+        if (me.done) break;
+        if (m->leader) { m->bcv.wait(lk, [&] { return me.done || !m->leader; }); continue; }
+        m->leader = true;
+        for (int round = 0; round < MICRO_ROUNDS && !m->pending.empty(); ++round) {
+            std::vector<gpr_model::SmallReq*> take;
+            size_t total = 0, cnt = 0;
+            while (cnt < m->pending.size() && total + m->pending[cnt]->q <= MICRO_CAP) total += m->pending[cnt++]->q;
+            take.assign(m->pending.begin(), m->pending.begin() + (std::ptrdiff_t)cnt);
+            m->pending.erase(m->pending.begin(), m->pending.begin() + (std::ptrdiff_t)cnt);
+            lk.unlock();
+            run_small_batch(ctx, m, take);
+            lk.lock();
+            for (auto* r : take) r->done = true;
+            m->bcv.notify_all();
+            if (me.done && round + 1 < MICRO_ROUNDS && m->pending.empty()) break;
+        }
+        m->leader = false;
+        m->bcv.notify_all();
+    }
+    lk.unlock();
+    if (me.rc) g_err = me.err;
+    return me.rc;
+}
+
+extern "C" {
+
 int gpr_predict(gpr_ctx* ctx, gpr_model* m, const double* qx, const double* qy, const double* qz, size_t q,
                 double* f, double* var, double* grad, double* tx, double* ty) {
     if (!ctx) return fail(GPR_ERR_INVALID, "null context");
     if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
     if (!qx || !qy || !qz || !f || q == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
     if ((tx == nullptr) != (ty == nullptr) || (tx && !grad)) return fail(GPR_ERR_INVALID, "tx/ty need each other and grad");
+    if (q <= 8 && microbatch_on()) return predict_small_combined(ctx, m, qx, qy, qz, q, f, var, grad, tx, ty);
+    return predict_host(ctx, m, qx, qy, qz, q, f, var, grad, tx, ty);
+}
+
+}  // extern "C"
+
+static int predict_host(gpr_ctx* ctx, gpr_model* m, const double* qx, const double* qy, const double* qz, size_t q,
+                        double* f, double* var, double* grad, double* tx, double* ty) {
     const size_t nd = ctx->devs.size();
     // Shard contiguous query ranges over the devices; tiny batches stay on the primary device.
     const size_t use = (nd > 1 && q >= 4096 * nd) ? nd : 1;
@@ -934,6 +1079,8 @@ int gpr_predict(gpr_ctx* ctx, gpr_model* m, const double* qx, const double* qy, 
     t.predict_total_ms = t.predict_mean_ms + t.predict_var_ms + t.h2d_ms + t.d2h_ms;
     return GPR_OK;
 }
+
+extern "C" {
 
 int gpr_predict_device(gpr_ctx* ctx, gpr_model* m, const double* d_qx, const double* d_qy, const double* d_qz,
                        size_t q, double* d_f, double* d_var, double* d_grad) {
@@ -1154,7 +1301,9 @@ int gpr_model_save(gpr_ctx* ctx, gpr_model* m, const char* path, int with_factor
     h.version = 1; h.kind = (unsigned)m->kernel.kind; h.p0 = m->kernel.p0; h.p1 = m->kernel.p1; h.R = m->R;
     h.n = m->n; h.n_normals = m->n_normals; h.n_tail = m->n_tail;
     h.has_s2 = m->has_s2; h.with_normals = m->with_normals;
-    h.has_factor = (with_factor && m->n_tail == 0) ? 1 : 0;          // a tail model is refitted on load
+    // a tail model is refitted on load; so is one whose internal point order differs from the caller's (L is in
+    // internal order, the stored training set in the caller's)
+    h.has_factor = (with_factor && m->n_tail == 0 && m->perm.empty()) ? 1 : 0;
     bool ok = fwrite(&h, sizeof h, 1, fh) == 1;
     auto put = [&](const std::vector<double>& v) { if (!v.empty()) ok = ok && fwrite(v.data(), sizeof(double), v.size(), fh) == v.size(); };
     put(m->hx); put(m->hy); put(m->hz); put(m->hlabel);
@@ -1186,7 +1335,23 @@ int gpr_model_load(gpr_ctx* ctx, const char* path, gpr_model** out) {
     SaveHeader h;
     if (fread(&h, sizeof h, 1, fh) != 1 || memcmp(h.magic, "GPRB200", 8) != 0 || h.version != 1 || h.kind > 2 || h.n == 0)
         return fail(GPR_ERR_INVALID, std::string(path) + " is not a GPRB200 model file");
-    gpr_model* m = new gpr_model();
+    // The header is untrusted input: every count must be consistent with the others and with the file size before
+    // anything is allocated from it.
+    {
+        const unsigned long long n64 = h.n;
+        if (n64 > (1ull << 24) || (h.n_normals != 0 && h.n_normals != n64) || h.n_tail >= n64 || h.has_s2 > 1 ||
+            h.with_normals > 1 || h.has_factor > 1 || (h.has_factor && h.n_tail != 0))
+            return fail(GPR_ERR_INVALID, std::string(path) + " has an inconsistent header");
+        unsigned long long doubles = (5ull + h.has_s2) * n64 + 3ull * h.n_normals;
+        if (h.has_factor) doubles += n64 * (n64 + 1) / 2;
+        long long fsize = -1;
+        if (fseek(fh, 0, SEEK_END) == 0) fsize = ftell(fh);
+        if (fsize < 0 || fseek(fh, (long)sizeof h, SEEK_SET) != 0 || (unsigned long long)fsize != sizeof h + 8ull * doubles)
+            return fail(GPR_ERR_INVALID, std::string(path) + " is truncated or has trailing data (size does not match its header)");
+    }
+    gpr_model* m = nullptr;
+    try {
+    m = new gpr_model();
     auto bail = [&](int rc) { free_factor(m); delete m; return rc; };
     m->ctx = ctx; m->kernel = gpr_kernel_t{(int)h.kind, h.p0, h.p1}; m->kp = make_kp(m->kernel); m->k0 = kernel_at_zero(m->kp);
     m->has_s2 = h.has_s2 != 0; m->with_normals = h.with_normals != 0;
@@ -1258,8 +1423,16 @@ int gpr_model_load(gpr_ctx* ctx, const char* path, gpr_model** out) {
 #undef LOAD_TRY
     m->h_alpha = alpha; m->h_normals = normals; m->n_normals = (size_t)h.n_normals;
     md.have = true;
+    md.lfac = m->L; md.dinv = m->Dinv; md.own_fac = false; md.have_fac = true;
     *out = m;
     return GPR_OK;
+    } catch (const std::bad_alloc&) {
+        if (m) { free_factor(m); delete m; }
+        return fail(GPR_ERR_OOM, "gpr_model_load: out of host memory");
+    } catch (const std::exception& e) {
+        if (m) { free_factor(m); delete m; }
+        return fail(GPR_ERR_INVALID, std::string("gpr_model_load: ") + e.what());
+    }
 }
 
 int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m) {
@@ -1268,6 +1441,37 @@ int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m) {
         int rc = ensure_on_device(m, di, true);
         if (rc) return rc;
     }
+    return GPR_OK;
+}
+
+int gpr_model_solve(gpr_ctx* ctx, gpr_model* m, const double* B, size_t nrhs, double* X) {
+    if (!ctx || !m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
+    if (!B || !X || nrhs == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
+    if (m->replica || !m->L) return fail(GPR_ERR_INVALID, "model holds no factor (replica)");
+    if (m->n_tail > 0 || !m->perm.empty()) return fail(GPR_ERR_INVALID, "gpr_model_solve needs a positive definite model in the caller's point order");
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceCtx* dc = ctx->devs[0];
+    CU(cudaSetDevice(dc->dev));
+    Workspace* ws = nullptr;
+    int rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    cudaStream_t st = ws->st;
+    const size_t N = m->N, ld = m->cap, n = m->n;
+    rc = ws_reserve(&ws->mpart, &ws->mpart_dbl, 2 * N);
+    if (rc) return rc;
+    double* rhs = ws->mpart; double* sol = rhs + N;
+    for (size_t c = 0; c < nrhs; ++c) {
+        CU(cudaMemsetAsync(rhs, 0, N * sizeof(double), st));
+        CU(cudaMemcpyAsync(rhs, B + c * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(launch_trsv(0, m->L, ld, m->nb, m->Dinv, rhs, m->zfwd, m->scratch, dc->num_sms, st));
+        CU(launch_trsv(1, m->L, ld, m->nb, m->Dinv, m->zfwd, sol, m->scratch, dc->num_sms, st));
+        CU(cudaMemcpyAsync(X + c * n, sol, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    int flags[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(flags, m->scratch, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flags[2] != 0) return fail(GPR_ERR_CUDA, "triangular solve kernel aborted (dependency wait timed out)");
     return GPR_OK;
 }
 
@@ -1313,6 +1517,13 @@ static int grow_capacity(gpr_model* m, size_t newcap, cudaStream_t st) {
     cudaFree(m->Dinv); cudaFree(m->scratch); cudaFree(md.linv); cudaFree(m->aws);
     md.xyz = xyz; md.alpha = alpha; m->label = label; m->s2 = s2; m->zfwd = zfwd; m->L = L; m->Dinv = Dinv;
     m->scratch = scratch; md.linv = X; m->aws = nullptr; m->aws_dbl = 0;
+    md.lfac = m->L; md.dinv = m->Dinv;
+    for (size_t di = 1; di < m->devs.size(); ++di) {       // copies in the old layout
+        ModelDev& d = m->devs[di];
+        if (d.own_fac) { cudaSetDevice(d.dev); cudaFree(d.lfac); cudaFree(d.dinv); }
+        d.lfac = d.dinv = nullptr; d.have_fac = d.own_fac = false;
+    }
+    cudaSetDevice(md.dev);
     m->cap = newcap;
     // replicas on the other devices have the old layout: drop them, they are re-copied on demand
     for (size_t di = 1; di < m->devs.size(); ++di) {
@@ -1437,7 +1648,7 @@ static int append_incremental(gpr_model* m, const double* x, const double* y, co
     m->h_alpha.swap(new_alpha);
     host_append(m, x, y, z, label, sigma2, k);
     m->n = n1; m->n_spd = n1; m->N = N1; m->nb = nb1;
-    for (size_t di = 1; di < m->devs.size(); ++di) { m->devs[di].have = false; m->devs[di].have_linv = false; }
+    for (size_t di = 1; di < m->devs.size(); ++di) { m->devs[di].have = false; m->devs[di].have_linv = false; m->devs[di].have_fac = false; }
     std::lock_guard<std::mutex> lk(ctx->tmu);
     ctx->timings.h2d_ms = ev_ms(ws->ev[0], ws->ev[1]);
     ctx->timings.append_ms = ev_ms(ws->ev[1], ws->ev[2]);
@@ -1452,7 +1663,9 @@ int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, con
     if (m->replica) return fail(GPR_ERR_INVALID, "cannot append to a replica model");
     std::lock_guard<std::mutex> lk(m->mu);
     const char* force = getenv("GPR_APPEND_REFIT");
-    const bool refit = (force && atoi(force) != 0) || k > 256 || 8 * k > m->n || m->n_tail > 0;
+    // a permuted internal order (points were evicted during the fit, with or without a tail block left) refits: the
+    // incremental path works in the caller's order
+    const bool refit = (force && atoi(force) != 0) || k > 256 || 8 * k > m->n || m->n_tail > 0 || !m->perm.empty();
     if (!refit) return append_incremental(m, x, y, z, label, sigma2, k);
     // Large batches: append on the host and refit, like the reference (gp_regressor.hpp:442-459).
     const size_t p = m->hx.size();
@@ -1499,13 +1712,15 @@ int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity) {
 
 int gpr_model_state_get(gpr_ctx* ctx, gpr_model* m, int with_linv, gpr_model_state* out) {
     if (!ctx || !m || !out) return fail(GPR_ERR_INVALID, "null pointer");
-    if (with_linv) { int rc = ensure_on_device(m, 0, true); if (rc) return rc; }
+    if (with_linv & 1) { int rc = ensure_on_device(m, 0, true); if (rc) return rc; }
     out->n = m->n; out->padded_n = m->N; out->ld = m->cap; out->kernel = m->kernel; out->R = m->R;
     out->xyz = m->devs[0].xyz; out->alpha = m->devs[0].alpha;
     out->linv = m->devs[0].have_linv ? m->devs[0].linv : nullptr;
     out->n_tail = m->n_tail; out->tail_pad = (size_t)m->mp;
     out->tail_z = m->n_tail ? m->devs[0].tZ : nullptr;
     out->tail_sinv = m->n_tail ? m->devs[0].tSinv : nullptr;
+    out->lfac = m->devs[0].have_fac ? m->devs[0].lfac : nullptr;
+    out->dinv = out->lfac ? m->devs[0].dinv : nullptr;
     return GPR_OK;
 }
 
@@ -1532,10 +1747,17 @@ int gpr_model_create_replica_tail(gpr_ctx* ctx, size_t n, size_t n_tail, gpr_ker
         cudaMalloc((void**)&md.alpha, m->N * sizeof(double)) != cudaSuccess)
         return bail(fail(GPR_ERR_OOM, "out of device memory"));
     md.have = true;
-    if (with_linv) {
+    if (with_linv & 1) {
         if (cudaMalloc((void**)&md.linv, m->N * m->N * sizeof(double)) != cudaSuccess)
             return bail(fail(GPR_ERR_OOM, "out of device memory"));
         md.have_linv = true;
+    }
+    if (with_linv & 2) {
+        if (n_tail > 0) return bail(fail(GPR_ERR_INVALID, "a replica of an indefinite-tail model takes L^-1, not the factor"));
+        if (cudaMalloc((void**)&md.lfac, m->N * m->N * sizeof(double)) != cudaSuccess ||
+            cudaMalloc((void**)&md.dinv, (size_t)m->nb * TB * TB * sizeof(double)) != cudaSuccess)
+            return bail(fail(GPR_ERR_OOM, "out of device memory"));
+        md.own_fac = true; md.have_fac = true;
     }
     if (n_tail > 0) {
         // the trailing pivot block of an indefinite matrix (gpr_tail.cu): L / L^-1 describe the leading n - n_tail points

@@ -60,6 +60,9 @@ cudaError_t launch_normalize_rows(double* g, size_t ld, int q, cudaStream_t st);
 // K3' (gpr_var.cu)
 cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* panel, size_t panel_ld, int q,
                             double* partial, double k0, double* var, cudaStream_t st);
+// Same result without L^-1: blocked forward substitution V = L^-1 K*^T in place in the panel (panel is overwritten).
+cudaError_t launch_variance_trsm(const double* L, size_t ld, int nb, const double* Dinv, double* panel, size_t panel_ld,
+                                 int q, double* partial, double k0, double* var, cudaStream_t st);
 cudaError_t launch_variance_small(const double* X, size_t ld, int N, const double* panel, size_t panel_ld, int q,
                                   double* part, double k0, double* var, cudaStream_t st);
 // K5 (gpr_append.cu): one slab of k <= 32 appended points at rows [n0, n0+k); ws: append_workspace_doubles(cap).

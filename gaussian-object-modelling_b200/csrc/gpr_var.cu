@@ -118,6 +118,135 @@ cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* pa
 }
 
 // ---------------------------------------------------------------------------------------------
+// Variance WITHOUT the explicit inverse: V = L^-1 K*^T by blocked forward substitution, in place in the
+// K* panel, one CTA per 128-query tile (the north star's "TRSM for the variance solve v = L^-1 k*";
+// reference: cholesker.solve(Kpq), gp_regressor.hpp:263, :316).
+//   for row tile i = 0 .. nb-1:   T   = K*_i - sum_{k<i} L_ik V_k      (DMMA mainloop, both operands streamed)
+//                                 V_i = Dinv_i T                       (one more DMMA tile product, T resident)
+//                                 partial[i][query] = column sums of squares of V_i;  V_i overwrites K*_i
+// Same n^2 flop per query as the product with X = L^-1 (nb(nb+1)/2 tile steps per query tile), but no
+// one-time n^3/3 inverse and no second n x n matrix per model.  The query tiles are independent, so there
+// are no flags and no cross-CTA waits; every CTA walks the same L tiles at (nearly) the same time, so L
+// is streamed from HBM once per batch and then served from L2, while the V_k tiles are private to their CTA.
+// The panel element (query c, point r) is at panel[r*panel_ld + c]: V_k is read back as the M-major j operand
+// exactly like K* in var_tiles_kernel, and written with 16-byte pieces (two adjacent queries per thread).
+// ---------------------------------------------------------------------------------------------
+struct VarTrsmArgs {
+    const double* L; size_t ld; int nb;       // Cholesky factor, lower tiles
+    const double* Dinv;                       // nb tiles of 128x128 (ld 128): inverses of the diagonal blocks of L
+    double* panel; size_t panel_ld;           // in: K*; out: V = L^-1 K*^T
+    int nqt;                                  // query tiles in this batch
+    double* partial;                          // nb x panel_ld
+};
+
+// smem tile T[s*PM + c] (M-major resident j operand: point s, query c)  =  G - acc,  G = panel tile (coalesced rows)
+__device__ __forceinline__ void trsm_residual_to_smem(const Acc& acc, const double* G, size_t ldg, double* T,
+                                                      const TileCoord& tc) {
+#pragma unroll
+    for (int mt = 0; mt < 4; mt += 2) {
+        const int c = tc.col<false>(mt);                 // columns c, c+1 belong to m-tiles mt, mt+1
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                double2 v;
+                v.x = -GPR_ACC(acc, mt, p, e); v.y = -GPR_ACC(acc, mt + 1, p, e);
+                *reinterpret_cast<double2*>(T + (size_t)tc.row(p, e) * PM + c) = v;
+            }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TB * TB / 2; idx += NTHREADS) {
+        const int c2 = idx & 63, r = idx >> 6;
+        const double2 g = __ldcg(reinterpret_cast<const double2*>(G + (size_t)r * ldg) + c2);
+        double2* d = reinterpret_cast<double2*>(T + r * PM) + c2;
+        double2 v = *d;
+        v.x += g.x; v.y += g.y;
+        *d = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) var_trsm_kernel(VarTrsmArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_abort;
+    __shared__ double sred[8][32];
+    if (threadIdx.x == 0) s_abort = 0;
+    const TileCoord tc;
+    for (int qt = blockIdx.x; qt < a.nqt; qt += gridDim.x) {
+        double* Pq = a.panel + (size_t)qt * TB;
+        for (int it = 0; it < a.nb; ++it) {
+            Acc acc;
+            acc_zero(acc);
+            // sum_{k < it} L_{it,k} V_k : i operand = rows of L (M-major), j operand = V (M-major in the panel)
+            tile_mainloop<STREAM_M, STREAM_M>(acc, a.L + (size_t)it * TB, a.ld, Pq, a.panel_ld, 8 * it, smem, &s_abort, NoWait());
+            double* G = Pq + (size_t)it * TB * a.panel_ld;
+            trsm_residual_to_smem(acc, G, a.panel_ld, smem, tc);
+            acc_zero(acc);
+            // V_it[r][c] = sum_s Dinv_it[r][s] T[s][c]
+            tile_mainloop<STREAM_M, RES_M>(acc, a.Dinv + (size_t)it * TB * TB, TB, smem, 0, 8, smem, &s_abort, NoWait());
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                double s = 0.0;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    s = fma(acc[mt][nt][0], acc[mt][nt][0], s);
+                    s = fma(acc[mt][nt][1], acc[mt][nt][1], s);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (tc.t == 0) sred[tc.warp][tc.col<false>(mt) - tc.j0] = s;
+            }
+            if (it + 1 < a.nb) {
+                // V_it replaces K*_it in the panel (read back as the j operand of the later row tiles)
+#pragma unroll
+                for (int mt = 0; mt < 4; mt += 2) {
+                    const int c = tc.col<false>(mt);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            double2 v;
+                            v.x = GPR_ACC(acc, mt, p, e); v.y = GPR_ACC(acc, mt + 1, p, e);
+                            *reinterpret_cast<double2*>(G + (size_t)tc.row(p, e) * a.panel_ld + c) = v;
+                        }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            if (threadIdx.x < TB) {
+                const int c = threadIdx.x, wj = c >> 5, lc = c & 31;
+                a.partial[(size_t)it * a.panel_ld + (size_t)qt * TB + c] = sred[2 * wj][lc] + sred[2 * wj + 1][lc];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+cudaError_t launch_variance_trsm(const double* L, size_t ld, int nb, const double* Dinv, double* panel, size_t panel_ld,
+                                 int q, double* partial, double k0, double* var, cudaStream_t st) {
+    static PerDeviceOnce attr_done;
+    const int cur = PerDeviceOnce::current();
+    if (!attr_done.done(cur)) {
+        cudaError_t e = cudaFuncSetAttribute(var_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)TILE_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done.set(cur);
+    }
+    if (q <= 0) return cudaSuccess;
+    VarTrsmArgs a;
+    a.L = L; a.ld = ld; a.nb = nb; a.Dinv = Dinv; a.panel = panel; a.panel_ld = panel_ld;
+    a.nqt = (int)(panel_ld / TB); a.partial = partial;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    var_trsm_kernel<<<(unsigned)(a.nqt < sms ? a.nqt : sms), NTHREADS, TILE_SMEM_BYTES, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    var_finalize_kernel<<<(q + 255) / 256, 256, 0, st>>>(partial, panel_ld, nb, q, k0, var);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Small-batch variance (q <= 8): the reference's callers ask for ONE query per call
 // (src/gp_node.cpp:1074, include/atlas/atlas_variance.hpp:78,:201).  v = X k* as a matrix-vector
 // product, bandwidth-bound: the lower triangle of X is read once for up to 8 queries.

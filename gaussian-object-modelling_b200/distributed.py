@@ -30,7 +30,9 @@ def as_tensor(ptr, n_doubles, device):
 
 def broadcast_model(reg, model, n, R, with_linv, rank, device, src=0):
     """Rank `src` passes its fitted `model`; the other ranks pass model=None and receive a replica.
-    Returns (model, bytes_broadcast)."""
+    with_linv: False/0 mean only; True/1 the inverse factor L^-1 (built on `src` if it was not yet); 2 the Cholesky
+    factor L + the inverses of its diagonal blocks (what a fit leaves behind: nothing to build before the exchange;
+    the replicas then compute large-batch variances by forward substitution).  Returns (model, bytes_broadcast)."""
     import torch
     import torch.distributed as dist
     n_tail = model.n_tail if rank == src else 0
@@ -44,7 +46,12 @@ def broadcast_model(reg, model, n, R, with_linv, rank, device, src=0):
     if st.ld != N:
         raise ValueError("model has spare capacity (ld %d != padded n %d): broadcast a freshly fitted model" % (st.ld, N))
     nbytes = 0
-    parts = ((st.xyz, 3 * N), (st.alpha, N)) + (((st.linv, N * N),) if with_linv else ())
+    with_linv = int(with_linv)
+    parts = ((st.xyz, 3 * N), (st.alpha, N)) + (((st.linv, N * N),) if with_linv & 1 else ())
+    if with_linv & 2:
+        if not st.lfac:
+            raise ValueError("model holds no Cholesky factor to broadcast (indefinite tail block?)")
+        parts += ((st.lfac, N * N), (st.dinv, (N // 128) * 128 * 128))
     if n_tail:                                  # indefinite tail block: Z = A^-1 P (slabs) and S^-1
         parts += ((st.tail_z, (st.tail_pad // 32) * N * 32), (st.tail_sinv, st.tail_pad * st.tail_pad))
     for ptr, cnt in parts:

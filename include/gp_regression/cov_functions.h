@@ -18,7 +18,7 @@ namespace gp_regression {
 class ThinPlate {
 public:
     ThinPlate() : ThinPlate(1.0) {}
-    explicit ThinPlate(double R) : radius_(R), cube_(R * R * R) {}
+    ThinPlate(double R) : radius_(R), cube_(R * R * R) {}
     double compute(double d) const { return 2 * d * d * d - 3 * radius_ * d * d + cube_; }
     double computediff(double d) const { return -6 * (radius_ - d); }
     double computediffdiff(double) const { return 0; }

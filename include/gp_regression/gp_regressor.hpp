@@ -8,8 +8,10 @@
 // Differences a caller can observe (documented in INTEGRATION.md):
 //   * Model::Kpp, Kppdiff, Kppdiffdiff stay empty and there is no Model::cholesker — no caller reads
 //     them; the factor lives on the device behind Model::device.
-//   * create() throws GPRegressionException("covariance matrix is not positive definite …") where
-//     Eigen's pivoted LDLT would carry on with an indefinite matrix.
+//   * an indefinite covariance (the node's ThinPlate(2.0) + external sphere setting) is factorised
+//     as a block L D L^T with one dense trailing pivot block of up to 256 offending points, so create() succeeds
+//     and agrees with Eigen's pivoted LDLT to cond*eps; only beyond that limit (or for a singular matrix) does
+//     create() throw GPRegressionException("covariance matrix is not positive definite …").
 //   * outputs N are zero-initialised before accumulation (the reference adds into uninitialised
 //     storage, gp_regressor.hpp:241/:247).
 //   * computeTangentBasis is inline (the reference defines it non-inline in a header, :29).
@@ -184,17 +186,24 @@ public:
                           std::vector<double>& f, std::vector<double>& v) {
         if (!gp) throw GPRegressionException("Empty Model pointer");
         if (!gp->device) throw GPRegressionException("Model was not created by this regressor");
-        size_t count = 0;
-        int rc = gpr_sample_isosurface(detail::context(), detail::handle(*gp), -scale, scale, pass, tol, 0, nullptr, nullptr,
-                                       nullptr, nullptr, nullptr, &count);
-        if (rc != GPR_OK) detail::raise(rc);
+        // One pass over the lattice with a capacity guess (a thin shell: ~1/16 of the lattice); the lattice is only
+        // evaluated again when the guess was too small.
+        size_t na = 0;
+        for (double a = -scale; a <= scale; a += pass) ++na;
+        size_t cap = na * na * na / 16 + 1024, count = 0;
         points.clear();
-        points.coord_x.assign(count, 0.0); points.coord_y.assign(count, 0.0); points.coord_z.assign(count, 0.0);
-        f.assign(count, 0.0); v.assign(count, 0.0);
-        if (count == 0) return;
-        rc = gpr_sample_isosurface(detail::context(), detail::handle(*gp), -scale, scale, pass, tol, count,
-                                   points.coord_x.data(), points.coord_y.data(), points.coord_z.data(), f.data(), v.data(), &count);
-        if (rc != GPR_OK) detail::raise(rc);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            points.coord_x.assign(cap, 0.0); points.coord_y.assign(cap, 0.0); points.coord_z.assign(cap, 0.0);
+            f.assign(cap, 0.0); v.assign(cap, 0.0);
+            const int rc = gpr_sample_isosurface(detail::context(), detail::handle(*gp), -scale, scale, pass, tol, cap,
+                                                 points.coord_x.data(), points.coord_y.data(), points.coord_z.data(), f.data(),
+                                                 v.data(), &count);
+            if (rc != GPR_OK) detail::raise(rc);
+            if (count <= cap) break;
+            cap = count;
+        }
+        points.coord_x.resize(count); points.coord_y.resize(count); points.coord_z.resize(count);
+        f.resize(count); v.resize(count);
     }
 
     // Extension: AtlasBase::project (include/atlas/atlas.hpp:201-276, same defaults) for any number of points in one

@@ -110,8 +110,15 @@ int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, doub
 int gpr_project(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* nx,
                 const double* ny, const double* nz, size_t count, double f_tol, double improve_tol, unsigned max_iter,
                 double step_mul, double* ox, double* oy, double* oz, int* status_or_null);
-/* Builds L^-1 now (otherwise built by the first call that asks for a variance). */
+/* Builds L^-1 now.  It is otherwise built by the first call that needs it: a variance for a batch of fewer than
+ * 4096 queries (GPR_TRSM_MIN_Q) — the fused single-query kernel and the product form read it — or gpr_append.
+ * Large batches on a model without L^-1 take the forward substitution over L instead (no n^3/3 inverse, one n x n
+ * matrix per model); once L^-1 is resident every batch uses the product form.  GPR_VAR_MODE=trsm|product forces one. */
 int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m);
+/* X = K^-1 B for nrhs right-hand sides (B, X: n x nrhs column-major, host) through the resident factor — the
+ * counterpart of the reference's public Model::cholesker.solve(b) (gp_regressor.hpp:81, :163).  Positive definite
+ * models only (GPR_ERR_INVALID for a model with an indefinite tail block). */
+int gpr_model_solve(gpr_ctx* ctx, gpr_model* m, const double* B, size_t nrhs, double* X);
 
 /* ---- update: GPRegressor::update<withNormals>  (gp_regressor.hpp:367-479) --------------------- */
 /* Appends k points; R and the normals are not refreshed, as in the reference (:454-455, :462-477).
@@ -151,25 +158,22 @@ typedef struct {
      * doubles, tail_sinv tail_pad x tail_pad; linv / the factor then describe the leading n - n_tail points */
     size_t n_tail, tail_pad;
     double* tail_z; double* tail_sinv;
+    /* the Cholesky factor itself (ld x ld, lower 128x128 tiles) and the inverses of its nb = padded_n/128 diagonal
+     * blocks (nb tiles of 128x128, leading dimension 128): what the variance by forward substitution reads.
+     * NULL for a model with an indefinite tail block. */
+    double* lfac; double* dinv;
 } gpr_model_state;
+/* with_linv is a bit set here and in the two calls below: 1 = L^-1 (built now if it was not yet), 2 = the factor
+ * L + Dinv (nothing to build: what a fit leaves behind). */
 int gpr_model_state_get(gpr_ctx* ctx, gpr_model* m, int with_linv, gpr_model_state* out);
 /* Allocates an un-fitted model of the given size on ctx's primary device; the caller fills the buffers
- * returned by gpr_model_state_get(replica, ...) (e.g. as the destination of a broadcast). */
+ * returned by gpr_model_state_get(replica, ...) (e.g. as the destination of a broadcast).  A replica that holds
+ * only the factor (with_linv = 2) computes large-batch variances by forward substitution; batches of <= 8 queries
+ * need L^-1 (with_linv & 1). */
 int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double R, int with_linv, gpr_model** out);
 /* Same for a model whose last n_tail points (internal order) form the indefinite tail block (gpr_model_tail_size). */
 int gpr_model_create_replica_tail(gpr_ctx* ctx, size_t n, size_t n_tail, gpr_kernel_t kernel, double R, int with_linv,
                                   gpr_model** out);
-
-/* ---- self-tests of the tile engine (used by tests/, device pointers, one 128-tile granularity) -- */
-int gpr_selftest_gemm(const double* hA, const double* hB, int b_kmajor, double* hC, int m_tiles, int n_tiles, int k);
-int gpr_selftest_leaf(double* h_tile_inout, double* h_inv_out, int* info);
-int gpr_selftest_factor(double* hA_inout, int n_tiles, double* h_linv_or_null, int serial, long long* pivot);
-/* Timeline of the tile-task Cholesky: 4 ns stamps per task (n_tiles(n_tiles+1)/2 tasks, column-major
- * task order); leaf_cycles[2] = SM cycles of the in-CTA 128x128 Cholesky and triangular inverse. */
-int gpr_selftest_factor_trace(int n_tiles, long long* h_trace, long long* leaf_cycles_or_null);
-/* Raw pipe probes (CUDA-event timed): which = 0 FP64 tensor (DMMA.8x8x4), 1 FP64 FMA, 2 / 3 both pipes
- * mixed (16 DMMA with 32 / 128 DFMA per thread); total TFLOP/s. */
-int gpr_selftest_peak(int which, int ctas_per_sm, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,9 @@ Three checkers live here:
                     only if oracle/_ref was built where /root/reference exists.
 * ``blas_*``      — the same mathematics with numpy/scipy (OpenBLAS LAPACK on all host cores): the
                     "best-effort CPU" flavour of BASELINE.md §5, used as the timed CPU baseline.
+* ``certify``     — extended-precision a-posteriori certificate of mean / variance from ANY approximate
+                    solves (residuals in long double, K never stored): the independent check at the
+                    headline sizes n = 16 384 / 65 536 where no CPU factorisation fits a test's budget.
 """
 from .oracle import (Oracle, Reference, build, have_reference, blas_fit, blas_predict,
-                     kernel_value, tangent_basis)
+                     kernel_value, tangent_basis, residual, certify)

@@ -22,6 +22,7 @@
 //
 // Build: g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -pthread
 
+#include <immintrin.h>
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
@@ -403,6 +404,38 @@ static void tangent_basis(const T g[3], T N[3], T Tx[3], T Ty[3]) {
 
 }  // namespace orc
 
+// hi/lo (rows x m4, double-double accumulators) += kt (rows x jn, pitch ktp) * Wt (jn x m4), every product exact
+// (p = k*w, e = fma(k, w, -p)) and every sum a Knuth two-sum; 4 columns per AVX2 lane group, 16 columns of
+// accumulators held in registers across the jn loop.
+namespace orc {
+__attribute__((target("avx2,fma")))
+static void dd_accumulate_avx2(const double* kt, int ktp, int rows, int jn, const double* Wt, int m4, double* hi, double* lo) {
+    for (int r = 0; r < rows; ++r) {
+        const double* kr = kt + (size_t)r * ktp;
+        for (int c0 = 0; c0 < m4; c0 += 16) {
+            const int nv = std::min(4, (m4 - c0) / 4);
+            __m256d h[4], l[4];
+            for (int v = 0; v < nv; ++v) { h[v] = _mm256_loadu_pd(hi + (size_t)r * m4 + c0 + 4 * v); l[v] = _mm256_loadu_pd(lo + (size_t)r * m4 + c0 + 4 * v); }
+            for (int jj = 0; jj < jn; ++jj) {
+                const __m256d k = _mm256_set1_pd(kr[jj]);
+                const double* w = Wt + (size_t)jj * m4 + c0;
+                for (int v = 0; v < nv; ++v) {
+                    const __m256d wv = _mm256_loadu_pd(w + 4 * v);
+                    const __m256d p = _mm256_mul_pd(k, wv);
+                    const __m256d e = _mm256_fmsub_pd(k, wv, p);            // exact error of the product
+                    const __m256d s = _mm256_add_pd(h[v], p);               // two-sum(h, p)
+                    const __m256d bb = _mm256_sub_pd(s, h[v]);
+                    const __m256d err = _mm256_add_pd(_mm256_sub_pd(h[v], _mm256_sub_pd(s, bb)), _mm256_sub_pd(p, bb));
+                    h[v] = s;
+                    l[v] = _mm256_add_pd(l[v], _mm256_add_pd(err, e));
+                }
+            }
+            for (int v = 0; v < nv; ++v) { _mm256_storeu_pd(hi + (size_t)r * m4 + c0 + 4 * v, h[v]); _mm256_storeu_pd(lo + (size_t)r * m4 + c0 + 4 * v, l[v]); }
+        }
+    }
+}
+}  // namespace orc
+
 // ---------------------------------------------------------------------------------
 // C interface for ctypes.  precision: 0 = double, 1 = long double (x87 80-bit; used
 // to attribute error between two double implementations).
@@ -474,6 +507,73 @@ void orc_tangent_basis(const double* grad, int q, double* N, double* Tx, double*
             N[(size_t)c * q + i] = n[c]; Tx[(size_t)c * q + i] = tx[c]; Ty[(size_t)c * q + i] = ty[c];
         }
     }
+}
+
+// Extended-precision residuals R = B - K W for m right-hand sides (B, W, R: n x m column-major), K assembled entry by
+// entry as create() does (gp_regressor.hpp:144-159: k(D_ij) + [i == j] sigma2_i; difference-form distance, the
+// documented deviation (i)) and never stored.  Every product K_ij * W_jc is formed exactly (FMA error term) and
+// accumulated in double-double (Knuth two-sum), i.e. with ~106-bit sums; without AVX2+FMA hardware the fallback
+// accumulates in long double (x87, 64-bit mantissa) in blocks of 256.
+// Used by the headline-size parity tests (n = 16 384 / 65 536), where no CPU factorisation fits a test's time budget:
+// for ANY approximate solution w of K w = k*, v = k(0) - k*^T w - w^T r - O(|r|^2 / lambda_min(K)) with r = k* - K w,
+// so a small certified residual pins the variance independently of how w was obtained.
+void orc_residual(const double* x, const double* y, const double* z, const double* sigma2_or_null, int n, int kind,
+                  double p0, double p1, const double* B, const double* W, int m, double* R, int threads) {
+    orc::Kern<double> kern(kind, p0, p1);
+    const int m4 = (m + 3) / 4 * 4;
+    std::vector<double> Wt((size_t)n * m4, 0.0);            // row-major copy, rows padded to 4: Wt[j*m4 + c]
+    for (int c = 0; c < m; ++c)
+        for (int j = 0; j < n; ++j) Wt[(size_t)j * m4 + c] = W[(size_t)c * n + j];
+    if (threads < 1) threads = 1;
+    const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+    constexpr int RT = 16, JB = 256;                        // row tile, column block
+    const int ntiles = (n + RT - 1) / RT;
+    auto work = [&](int t) {
+        std::vector<double> hi((size_t)RT * m4), lo((size_t)RT * m4), kt((size_t)RT * JB);
+        std::vector<long double> tot((size_t)RT * m4);
+        for (int tile = t; tile < ntiles; tile += threads) {
+            const int i0 = tile * RT, rows = std::min(RT, n - i0);
+            std::fill(hi.begin(), hi.end(), 0.0); std::fill(lo.begin(), lo.end(), 0.0);
+            std::fill(tot.begin(), tot.end(), 0.0L);
+            for (int j0 = 0; j0 < n; j0 += JB) {
+                const int jn = std::min(JB, n - j0);
+                for (int r = 0; r < rows; ++r) {
+                    const int i = i0 + r;
+                    const double pi[3] = {x[i], y[i], z[i]};
+                    for (int jj = 0; jj < jn; ++jj) {
+                        const int j = j0 + jj;
+                        const double pj[3] = {x[j], y[j], z[j]};
+                        double kij = kern.compute(orc::dist(pi, pj, 0));
+                        if (i == j && sigma2_or_null) kij += sigma2_or_null[i];
+                        kt[(size_t)r * JB + jj] = kij;
+                    }
+                }
+                if (fast) orc::dd_accumulate_avx2(kt.data(), JB, rows, jn, &Wt[(size_t)j0 * m4], m4, hi.data(), lo.data());
+                else {
+                    std::vector<long double> blk(m4);
+                    for (int r = 0; r < rows; ++r) {
+                        std::fill(blk.begin(), blk.end(), 0.0L);
+                        for (int jj = 0; jj < jn; ++jj) {
+                            const long double kl = kt[(size_t)r * JB + jj];
+                            const double* wr = &Wt[(size_t)(j0 + jj) * m4];
+                            for (int c = 0; c < m; ++c) blk[c] += kl * (long double)wr[c];
+                        }
+                        for (int c = 0; c < m; ++c) tot[(size_t)r * m4 + c] += blk[c];
+                    }
+                }
+            }
+            for (int r = 0; r < rows; ++r)
+                for (int c = 0; c < m; ++c) {
+                    const long double kw = fast ? (long double)hi[(size_t)r * m4 + c] + (long double)lo[(size_t)r * m4 + c]
+                                                : tot[(size_t)r * m4 + c];
+                    R[(size_t)c * n + i0 + r] = (double)((long double)B[(size_t)c * n + i0 + r] - kw);
+                }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
 }
 
 double orc_kernel(int kind, double p0, double p1, double d, int diff) {

@@ -57,6 +57,22 @@ def node_cases():
         run_case("ref_%s_thinplate_R2_node" % name, P, y, s2, "thin_plate", 2.0, 0.0, grid[::step], normals=True)
 
 
+def lattice_cases():
+    """The node's fakeDeterministicSampling lattice (src/gp_node.cpp:998-1100: 29^3 points, one evaluate(q = 1) per point,
+    keep |f| <= 0.01, the variance is the intensity) run through the reference's own evaluate() on mugD, for the SPD
+    setting (R = max pairwise distance) and for the node's own ThinPlate(2.0).  Stored: the lattice indices with
+    |f| <= 0.02 (the kept shell plus a margin), their f and v, and the number of kept points."""
+    grid = W.node_grid()
+    P, y, s2 = W.node_training_set(W.read_pcd_xyz(os.path.join(REF, "mugD.pcd")))
+    for tag, R in (("spd", W.max_pairwise_distance(P)), ("R2_node", 2.0)):
+        ref = oracle.Reference("thin_plate", R, 0.0).fit(P[:, 0], P[:, 1], P[:, 2], y, s2)
+        f, v = ref.evaluate_mt(grid[:, 0], grid[:, 1], grid[:, 2], var=True, threads=os.cpu_count() or 1, per_call=1)
+        band = np.flatnonzero(np.abs(f) <= 0.02)
+        np.savez_compressed(os.path.join(GOLD, "ref_mugD_lattice_%s.npz" % tag), P=P, y=y, s2=s2, p0=R, idx=band.astype(np.int32),
+                            f=f[band], v=v[band], kept=int((np.abs(f) <= 0.01).sum()), lattice=len(grid))
+        print("lattice", tag, "kept", int((np.abs(f) <= 0.01).sum()), "band", len(band))
+
+
 def main():
     oracle.build()
     grid = W.node_grid()
@@ -67,11 +83,12 @@ def main():
              upd=(np.array([[0.3, 0.1, -0.2], [0.0, 0.5, 0.4], [-0.6, 0.2, 0.1]]), np.zeros(3), np.full(3, 0.05)))
     # config 2: kettle / jug, Gaussian(1,1) defaults, outputs at the training points
     P, y, s2 = W.node_training_set(cloud("kettle"))
-    run_case("ref_kettle_gaussian", P, y, s2, "gaussian", 1.0, 1.0, P[::7], normals=True)
+    run_case("ref_kettle_gaussian", P, y, s2, "gaussian", 1.0, 1.0, P, normals=True)      # ALL training points (config 2)
     P, y, s2 = W.node_training_set(cloud("jug"))
-    run_case("ref_jug_gaussian", P, y, s2, "gaussian", 1.0, 1.0, P[::5], normals=True)
+    run_case("ref_jug_gaussian", P, y, s2, "gaussian", 1.0, 1.0, P, normals=True)
     run_case("ref_jug_laplace", P, y, s2, "laplace", 1.0, 1.0, grid[::211], normals=False)
     node_cases()
+    lattice_cases()
     # the reference's argument checks
     msgs = [oracle.Reference().error_message(i) for i in range(4)]
     np.savez(os.path.join(GOLD, "ref_error_messages.npz"), messages=np.array(msgs))
@@ -82,5 +99,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "node":
         oracle.build()
         node_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "lattice":
+        oracle.build()
+        lattice_cases()
     else:
         main()

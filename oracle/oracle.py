@@ -56,12 +56,51 @@ def _load():
         L.orc_tangent_basis.argtypes = [_dp, C.c_int, _dp, _dp, _dp]
         L.orc_kernel.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.orc_kernel.restype = C.c_double
+        L.orc_residual.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp, C.c_int, _dp, C.c_int]
         _lib = L
     return _lib
 
 
 def kernel_value(kind, p0, p1, d, diff=False):
     return _load().orc_kernel(KINDS[kind], float(p0), float(p1), float(d), int(diff))
+
+
+def residual(P, sigma2, kind, p0, p1, B, W, threads=None):
+    """R = B - K W in extended precision (K never stored; oracle/gpr_oracle.cpp: orc_residual).  B, W: (n, m)."""
+    P = np.asarray(P, dtype=np.float64)
+    n = P.shape[0]
+    Bf = np.asfortranarray(np.asarray(B, dtype=np.float64).reshape(n, -1))
+    Wf = np.asfortranarray(np.asarray(W, dtype=np.float64).reshape(n, -1))
+    R = np.zeros_like(Bf, order="F")
+    x, y, z, s2 = (_f64(P[:, 0]), _f64(P[:, 1]), _f64(P[:, 2]), _f64(sigma2))
+    _load().orc_residual(_p(x), _p(y), _p(z), _p(s2), n, KINDS[kind], float(p0), float(p1), _p(Bf), _p(Wf), Bf.shape[1],
+                         _p(R), int(threads or os.cpu_count() or 1))
+    return np.ascontiguousarray(R)
+
+
+def certify(P, y, sigma2, kind, p0, p1, Q, alpha, W, threads=None):
+    """A-posteriori certificate of mean and variance at queries Q (q,3) from ANY approximate solves
+    alpha ~ K^-1 y and W[:, j] ~ K^-1 k*_j (n, q):  with r = k* - K w and r_a = y - K alpha (extended precision),
+        v = k(0) - k*^T w - w^T r - r^T K^-1 r,      f = k*^T alpha + w^T r_a + (second order),
+    identities that hold exactly for symmetric K (gp_regressor.hpp:318-319, :305 restated).  Returns a dict with
+    f, v, the neglected second-order bounds (|r|^2 / min sigma2: K = PSD kernel + diag(sigma2)) and the residual norms."""
+    P = np.asarray(P, dtype=np.float64)
+    Q = np.asarray(Q, dtype=np.float64)
+    Ks = _kern(kind, p0, p1, _pdist(P, Q))                         # (n, q): columns k*_j
+    B = np.concatenate([Ks, np.asarray(y, dtype=np.float64)[:, None]], axis=1)
+    Wa = np.concatenate([np.asarray(W, dtype=np.float64), np.asarray(alpha, dtype=np.float64)[:, None]], axis=1)
+    R = residual(P, sigma2, kind, p0, p1, B, Wa, threads)
+    ld = np.longdouble
+    k0 = float(_kern(kind, p0, p1, np.zeros(1))[0])
+    Wl, Rl, Kl = Wa[:, :-1].astype(ld), R[:, :-1].astype(ld), Ks.astype(ld)
+    v = ld(k0) - (Kl * Wl).sum(axis=0) - (Wl * Rl).sum(axis=0)
+    f = (Kl * Wa[:, -1:].astype(ld)).sum(axis=0) + (Wl * R[:, -1:].astype(ld)).sum(axis=0)
+    lam = float(np.min(sigma2)) if sigma2 is not None else None
+    r2 = (Rl * Rl).sum(axis=0)
+    return {"f": f.astype(np.float64), "v": v.astype(np.float64), "Ks": Ks, "R": R,
+            "v_second_order": None if lam is None else float(r2.max()) / lam,
+            "f_second_order": None if lam is None else float(np.sqrt(r2.max() * (R[:, -1].astype(ld) ** 2).sum())) / lam,
+            "resid_inf": float(np.abs(R[:, :-1]).max()), "resid_alpha_inf": float(np.abs(R[:, -1]).max())}
 
 
 def tangent_basis(grad):

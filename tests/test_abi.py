@@ -9,8 +9,8 @@ import pytest
 from conftest import ROOT
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "gpr_c_api.h")).read()
+def _declared_symbols(path=None):
+    text = open(path or os.path.join(ROOT, "include", "gpr_c_api.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(gpr_[a-z_0-9]+)\s*\(", text)))
 
@@ -18,12 +18,15 @@ def _declared_symbols():
 def test_header_and_library_agree(gpr):
     declared = _declared_symbols()
     assert sorted(gpr.C_ABI_SYMBOLS) == declared
+    assert not [s for s in declared if "selftest" in s]       # probes live in the test-only header
+    selftests = _declared_symbols(os.path.join(ROOT, "gaussian-object-modelling_b200", "csrc", "gpr_selftest.h"))
+    assert sorted(gpr.SELFTEST_SYMBOLS) == selftests
     lib = gpr.lib()
-    for s in declared:
+    for s in declared + selftests:
         assert hasattr(lib, s), s
     out = subprocess.run(["nm", "-D", "--defined-only", gpr.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r" T (gpr_[a-z_0-9]+)", out))
-    assert exported == set(declared)
+    assert exported == set(declared) | set(selftests)
 
 
 def test_no_torch_types_in_the_abi():
