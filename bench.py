@@ -248,6 +248,17 @@ def main():
         barrier()
         bms = 1e3 * (time.perf_counter() - t0)
         extras.update(broadcast_ms=bms, broadcast_bytes=bcast_bytes, broadcast_GBps=bcast_bytes / bms / 1e6)
+        # the same exchange fused into the producer: the replicas receive every tile of L and Dinv from inside the Cholesky
+        # kernel (peer stores over NVLink); what remains exposed after the fit is the 32n-byte {x|y|z, alpha} broadcast
+        model.close()
+        model = None
+        model, pinfo = D.fit_and_publish(reg, (lambda: reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)) if rank == 0 else None,
+                                         N_TRAIN, W.SYNTH_R, rank, dev, src=0)
+        if rank == 0:
+            t = ctx.timings()
+            pinfo.update(fit_ms=t["fit_total_ms"], chol_ms=t["chol_ms"], chol_ms_without_peers=extras["fit_chol_ms"])
+            extras["fit_publish"] = pinfo
+            extras["broadcast_exposed_ms"] = pinfo["exposed_ms"]
 
     # ---- this rank's block of the 256^3 query grid --------------------------------------------------
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -339,17 +350,17 @@ def main():
         barrier()
         t0 = time.perf_counter()
         fg_fit_ms = fg_bc_ms = 0.0
-        if rank == 0:
-            model.close()
-            model = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
-            fg_fit_ms = 1e3 * (time.perf_counter() - t0)
-        elif model is not None:
+        if model is not None:
             model.close()
             model = None
-        if world > 1:
-            t1 = time.perf_counter()
-            model, _ = D.broadcast_model(reg, model, N_TRAIN, W.SYNTH_R, 2, rank, dev, src=0)
-            fg_bc_ms = 1e3 * (time.perf_counter() - t1)
+        if world == 1:
+            model = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+            fg_fit_ms = 1e3 * (time.perf_counter() - t0)
+        else:
+            model, pi2 = D.fit_and_publish(reg, (lambda: reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)) if rank == 0 else None,
+                                           N_TRAIN, W.SYNTH_R, rank, dev, src=0)
+            if rank == 0:
+                fg_fit_ms, fg_bc_ms = pi2["fit_wall_ms"], pi2["exposed_ms"]
         reg.evaluate_device(model, Qfull[0, off:].data_ptr(), Qfull[1, off:].data_ptr(), Qfull[2, off:].data_ptr(), cnt,
                             fo_g.data_ptr(), vo_g.data_ptr(), None)
         torch.cuda.synchronize(dev)
@@ -367,8 +378,9 @@ def main():
         assert vmin > 0.0
         full_grid = {"full_grid_s": fg_s, "queries": total_q, "points_per_s": total_q / fg_s, "fit_wall_ms": fg_fit_ms,
                      "broadcast_ms": fg_bc_ms, "points_in_shell_abs_f_le_0.01": shell, "scaling": "strong",
-                     "what": "fit on rank 0 -> broadcast of {x|y|z, alpha, L, Dinv} -> mean+variance of ALL 256^3 lattice "
-                             "points (z-slab shards), host wall of the slowest rank"}
+                     "what": "replica set-up (IPC handles) -> fit on rank 0 publishing L and Dinv into the replicas from inside the "
+                             "Cholesky kernel -> {x|y|z, alpha} broadcast -> mean+variance of ALL 256^3 lattice points "
+                             "(z-slab shards); host wall of the slowest rank"}
         del Qfull, fo_g, vo_g
 
     if rank == 0:

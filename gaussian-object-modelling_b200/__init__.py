@@ -90,10 +90,18 @@ def lib():
         L.gpr_predict_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
         L.gpr_sample_isosurface.argtypes = [vp, vp, cd, cd, cd, cd, sz, _dp, _dp, _dp, _dp, _dp, C.POINTER(sz)]
         L.gpr_project.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, _dp, sz, cd, cd, C.c_uint, cd, _dp, _dp, _dp, C.POINTER(ci)]
+        L.gpr_sample_chart.argtypes = [vp, vp, _dp, C.POINTER(sz), sz, _dp, _dp, C.c_ulonglong, _dp, _dp, _dp, _dp, _dp, C.POINTER(sz)]
         L.gpr_model_save.argtypes = [vp, vp, C.c_char_p, ci]
         L.gpr_model_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
         L.gpr_model_prepare_variance.argtypes = [vp, vp]
         L.gpr_model_solve.argtypes = [vp, vp, _dp, sz, _dp]
+        L.gpr_model_ipc_export.argtypes = [vp, vp, vp]
+        L.gpr_ctx_set_fit_peers.argtypes = [vp, vp, ci, sz]
+        L.gpr_ctx_clear_fit_peers.argtypes = [vp]
+        L.gpr_ctx_last_fit_published.argtypes = [vp]
+        L.gpr_pcd_read_xyz.argtypes = [C.c_char_p, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.POINTER(sz)]
+        L.gpr_free.argtypes = [vp]
+        L.gpr_free.restype = None
         L.gpr_append.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, sz]
         L.gpr_model_reserve.argtypes = [vp, vp, sz]
         L.gpr_model_state_get.argtypes = [vp, vp, ci, C.POINTER(ModelState)]
@@ -115,6 +123,8 @@ C_ABI_SYMBOLS = [
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
     "gpr_model_reserve", "gpr_sample_isosurface", "gpr_project", "gpr_model_save", "gpr_model_load",
     "gpr_model_state_get", "gpr_model_create_replica", "gpr_model_create_replica_tail", "gpr_model_solve",
+    "gpr_pcd_read_xyz", "gpr_free", "gpr_sample_chart",
+    "gpr_model_ipc_export", "gpr_ctx_set_fit_peers", "gpr_ctx_clear_fit_peers", "gpr_ctx_last_fit_published",
 ]
 # Engine self-tests / pipe probes (csrc/gpr_selftest.h): exported for tests/ and bench.py, not part of the boundary.
 SELFTEST_SYMBOLS = ["gpr_selftest_gemm", "gpr_selftest_leaf", "gpr_selftest_factor", "gpr_selftest_peak",
@@ -142,6 +152,19 @@ def _same_length(*arrays):
         raise GPRegressionException("Inconsistent input data sizes")
 
 
+def pcd_read_xyz(path):
+    """The C-ABI PCD reader (gpr_pcd_read_xyz): (n, 3) float64.  Host only, needs no GPU."""
+    L = lib()
+    px, py, pz, n = _dp(), _dp(), _dp(), C.c_size_t()
+    _check(L.gpr_pcd_read_xyz(str(path).encode(), C.byref(px), C.byref(py), C.byref(pz), C.byref(n)))
+    try:
+        out = np.stack([np.ctypeslib.as_array(p, shape=(n.value,)).copy() for p in (px, py, pz)], axis=1)
+    finally:
+        for p in (px, py, pz):
+            L.gpr_free(p)
+    return out
+
+
 class Context:
     def __init__(self, devices=None):
         self._h = C.c_void_p()
@@ -165,6 +188,19 @@ class Context:
     @property
     def num_devices(self):
         return lib().gpr_ctx_num_devices(self._h)
+
+    def set_fit_peers(self, handles, n):
+        """handles: list of 128-byte CUDA IPC handle blobs (Model.ipc_export of the other ranks' replicas)."""
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob)) if blob else None
+        _check(lib().gpr_ctx_set_fit_peers(self._h, C.cast(buf, C.c_void_p) if buf else None, len(handles), int(n)))
+
+    def clear_fit_peers(self):
+        _check(lib().gpr_ctx_clear_fit_peers(self._h))
+
+    @property
+    def last_fit_published(self):
+        return bool(lib().gpr_ctx_last_fit_published(self._h))
 
     def timings(self):
         t = Timings()
@@ -218,6 +254,12 @@ class Model:
         Lm = np.zeros((n, n), order="F")
         _check(lib().gpr_model_get_factor(self._h, _p(Lm)))
         return Lm
+
+    def ipc_export(self):
+        """128-byte CUDA IPC handle blob of this replica's factor buffers (L, Dinv) for Context.set_fit_peers."""
+        buf = C.create_string_buffer(128)
+        _check(lib().gpr_model_ipc_export(self.ctx._h, self._h, C.cast(buf, C.c_void_p)))
+        return buf.raw
 
     def state(self, with_linv=False):
         s = ModelState()
@@ -319,6 +361,22 @@ class GPRegressor:
                                  f_tol, improve_tol, int(max_iter), step_mul, _p(out[0]), _p(out[1]), _p(out[2]),
                                  st.ctypes.data_as(C.POINTER(C.c_int))))
         return np.ascontiguousarray(out.T), st
+
+    def sample_charts(self, model, frames, counts, r=None, th=None, seed=0):
+        """Batched AtlasVariance::sampleOnChart (include/atlas/atlas_variance.hpp:147-219).  frames: (c, 13) rows
+        [C, N, Tx, Ty, R]; counts: (c,) samples per chart; r, th: optional uniform variates (sum(counts),) each.
+        Returns (samples (total, 3), f, v, order) with order[o_c + k] = in-chart index of the k-th largest variance."""
+        fr = np.ascontiguousarray(np.asarray(frames, dtype=np.float64).reshape(-1, 13))
+        cn = np.ascontiguousarray(np.asarray(counts, dtype=np.uint64))
+        total = int(cn.sum())
+        r, th = _arr(r), _arr(th)
+        if (r is not None and r.size != total) or (th is not None and th.size != total) or cn.size != fr.shape[0]:
+            raise GPRegressionException("Inconsistent input data sizes")
+        sx, sy, sz_, f, v = (np.zeros(total) for _ in range(5))
+        order = np.zeros(total, dtype=np.uint64)
+        _check(lib().gpr_sample_chart(self.ctx._h, model._h, _p(fr), cn.ctypes.data_as(C.POINTER(C.c_size_t)), fr.shape[0], _p(r), _p(th),
+                                      int(seed), _p(sx), _p(sy), _p(sz_), _p(f), _p(v), order.ctypes.data_as(C.POINTER(C.c_size_t))))
+        return np.stack([sx, sy, sz_], axis=1), f, v, order.astype(np.int64)
 
     def save(self, model, path, with_factor=True):
         _check(lib().gpr_model_save(self.ctx._h, model._h, str(path).encode(), int(with_factor)))

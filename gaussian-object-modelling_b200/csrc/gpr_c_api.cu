@@ -13,7 +13,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <limits>
 #include <mutex>
+#include <random>
 #include <string>
 #include <thread>
 #include <vector>
@@ -27,6 +29,7 @@ static thread_local std::string g_err;
 static thread_local long long g_pivot = 0;
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+void gpr_set_last_error_internal(const char* msg) { g_err = msg ? msg : ""; }      // for gpr_io.cu
 
 #define CU(call)                                                                                   \
     do {                                                                                           \
@@ -87,6 +90,12 @@ struct gpr_ctx {
     struct Big { void* p; size_t bytes; int dev; };
     std::vector<Big> big_cache;
     std::mutex cmu;
+    // Replicas on other GPUs (other processes: CUDA IPC mappings) that the next fits publish their factor into while the
+    // Cholesky kernel runs (gpr_ctx_set_fit_peers).  peer_N: padded size the mappings were made for.
+    CholPeers peers{};
+    std::vector<void*> peer_maps;          // what cudaIpcOpenMemHandle returned (closed by gpr_ctx_clear_fit_peers)
+    size_t peer_N = 0;
+    bool last_fit_published = false;
 };
 
 static std::mutex g_live_mu;
@@ -361,9 +370,12 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
             CU(cudaMemcpyAsync(&Rbits_host, rbits, sizeof(double), cudaMemcpyDeviceToHost, st));
             CU(cudaEventRecord(ws->ev[2], st));
         }
-        CU(launch_cholesky(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st));
+        // first attempt: every finished tile also goes to the registered peer replicas (gpr_ctx_set_fit_peers)
+        const bool publish = moved == 0 && ctx->peers.n > 0 && ctx->peer_N == N && !ctx->chol_serial;
+        CU(launch_cholesky(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st, nullptr, publish ? &ctx->peers : nullptr));
         CU(cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        ctx->last_fit_published = publish && info[1] == 0;
         if (info[1] == 0) break;                                   // positive definite
         const size_t p = (size_t)info[1] - 1;                      // internal index of the failing pivot
         // Offending points are moved ("evicted") to the end of the internal order; once the failing pivot lies
@@ -866,6 +878,7 @@ int gpr_ctx_destroy(gpr_ctx* ctx) {
         std::lock_guard<std::mutex> lk(g_live_mu);
         g_live_ctx.erase(std::remove(g_live_ctx.begin(), g_live_ctx.end(), ctx), g_live_ctx.end());
     }
+    gpr_ctx_clear_fit_peers(ctx);
     for (auto& b : ctx->big_cache) { cudaSetDevice(b.dev); cudaFree(b.p); }
     ctx->big_cache.clear();
     for (DeviceCtx* dc : ctx->devs) {
@@ -884,6 +897,60 @@ int gpr_ctx_destroy(gpr_ctx* ctx) {
 }
 
 int gpr_ctx_num_devices(const gpr_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int gpr_ctx_clear_fit_peers(gpr_ctx* ctx) {
+    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
+    if (!ctx->peer_maps.empty()) {
+        CU(cudaSetDevice(ctx->devs[0]->dev));
+        for (void* p : ctx->peer_maps) cudaIpcCloseMemHandle(p);
+    }
+    ctx->peer_maps.clear();
+    ctx->peers = CholPeers{};
+    ctx->peer_N = 0;
+    return GPR_OK;
+}
+
+int gpr_model_ipc_export(gpr_ctx* ctx, gpr_model* m, void* handles128) {
+    if (!ctx || !m || !handles128) return fail(GPR_ERR_INVALID, "null pointer");
+    if (!m->replica || !m->devs[0].lfac || !m->devs[0].dinv || !m->devs[0].own_fac)
+        return fail(GPR_ERR_INVALID, "gpr_model_ipc_export needs a replica created with the factor buffers (with_linv & 2)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CU(cudaSetDevice(m->devs[0].dev));
+    cudaIpcMemHandle_t h[2];
+    CU(cudaIpcGetMemHandle(&h[0], m->devs[0].lfac));
+    CU(cudaIpcGetMemHandle(&h[1], m->devs[0].dinv));
+    memcpy(handles128, h, sizeof h);
+    return GPR_OK;
+}
+
+int gpr_ctx_set_fit_peers(gpr_ctx* ctx, const void* handles128, int n_peers, size_t n) {
+    if (!ctx || (n_peers > 0 && !handles128)) return fail(GPR_ERR_INVALID, "null pointer");
+    if (n_peers < 0 || n_peers > MAX_CHOL_PEERS) return fail(GPR_ERR_INVALID, "at most 7 peers");
+    int rc = gpr_ctx_clear_fit_peers(ctx);
+    if (rc) return rc;
+    if (n_peers == 0) return GPR_OK;
+    CU(cudaSetDevice(ctx->devs[0]->dev));
+    const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handles128);
+    for (int i = 0; i < n_peers; ++i) {
+        void *pl = nullptr, *pd = nullptr;
+        cudaIpcMemHandle_t hl, hd;
+        memcpy(&hl, &h[2 * i], sizeof hl); memcpy(&hd, &h[2 * i + 1], sizeof hd);
+        cudaError_t e = cudaIpcOpenMemHandle(&pl, hl, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) { ctx->peer_maps.push_back(pl); e = cudaIpcOpenMemHandle(&pd, hd, cudaIpcMemLazyEnablePeerAccess); }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            gpr_ctx_clear_fit_peers(ctx);
+            return fail(GPR_ERR_CUDA, std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
+        }
+        ctx->peer_maps.push_back(pd);
+        ctx->peers.L[i] = static_cast<double*>(pl); ctx->peers.Dinv[i] = static_cast<double*>(pd);
+    }
+    ctx->peers.n = n_peers;
+    ctx->peer_N = (n + TB - 1) / TB * TB;
+    return GPR_OK;
+}
+
+int gpr_ctx_last_fit_published(const gpr_ctx* ctx) { return ctx && ctx->last_fit_published ? 1 : 0; }
 
 int gpr_last_timings(const gpr_ctx* ctx, gpr_timings* out) {
     if (!ctx || !out) return fail(GPR_ERR_INVALID, "null pointer");
@@ -1232,6 +1299,45 @@ int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, doub
     return GPR_OK;
 }
 
+}  // extern "C"
+
+// Points [a, b) of a batched projection on device slot di.
+static int project_range(gpr_model* m, size_t di, const double* const src[6], size_t a, size_t b, double f_tol, double improve_tol,
+                         unsigned max_iter, double step_mul, double* ox, double* oy, double* oz, int* hstat, double* ms) {
+    gpr_ctx* ctx = m->ctx;
+    int rc = ensure_on_device(m, di, false);
+    if (rc) return rc;
+    DeviceCtx* dc = ctx->devs[di];
+    CU(cudaSetDevice(dc->dev));
+    ModelDev& md = m->devs[di];
+    Workspace* ws = nullptr;
+    rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    cudaStream_t st = ws->st;
+    const size_t count = b - a;
+    rc = ws_reserve(&ws->io, &ws->io_cap, 14 * std::max(count, (size_t)TB));
+    if (rc) return rc;
+    const size_t cap = ws->io_cap / 14, ld = m->cap;
+    double* din = ws->io;                  // x|y|z|nx|ny|nz
+    double* dout = din + 6 * cap;          // x|y|z
+    int* dstat = reinterpret_cast<int*>(dout + 3 * cap);
+    for (int c = 0; c < 6; ++c) CU(cudaMemcpyAsync(din + c * cap, src[c] + a, count * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(ws->ev[0], st));
+    CU(launch_project(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, (int)m->n, din, cap, (int)count, f_tol, improve_tol,
+                      (int)max_iter, step_mul, dout, dstat, m->kp, st));
+    CU(cudaEventRecord(ws->ev[1], st));
+    CU(cudaMemcpyAsync(ox + a, dout, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(oy + a, dout + cap, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(oz + a, dout + 2 * cap, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hstat + a, dstat, count * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *ms = ev_ms(ws->ev[0], ws->ev[1]);
+    return GPR_OK;
+}
+
+extern "C" {
+
 int gpr_project(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* nx,
                 const double* ny, const double* nz, size_t count, double f_tol, double improve_tol, unsigned max_iter,
                 double step_mul, double* ox, double* oy, double* oz, int* status) {
@@ -1239,42 +1345,112 @@ int gpr_project(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, co
     if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
     if (!x || !y || !z || !nx || !ny || !nz || !ox || !oy || !oz || count == 0) return fail(GPR_ERR_INVALID, "All input data is empty!");
     if (count > (size_t)1 << 24 || max_iter > (unsigned)1 << 24) return fail(GPR_ERR_INVALID, "too many points or iterations");
-    int rc = ensure_on_device(m, 0, false);
-    if (rc) return rc;
-    DeviceCtx* dc = ctx->devs[0];
-    CU(cudaSetDevice(dc->dev));
-    ModelDev& md = m->devs[0];
-    Workspace* ws = nullptr;
-    rc = ws_acquire(dc, &ws);
-    if (rc) return rc;
-    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
-    cudaStream_t st = ws->st;
-    rc = ws_reserve(&ws->io, &ws->io_cap, 14 * std::max(count, (size_t)TB));
-    if (rc) return rc;
-    const size_t cap = ws->io_cap / 14, ld = m->cap;
-    double* din = ws->io;                  // x|y|z|nx|ny|nz
-    double* dout = din + 6 * cap;          // x|y|z
-    int* dstat = reinterpret_cast<int*>(dout + 3 * cap);
     const double* src[6] = {x, y, z, nx, ny, nz};
-    for (int c = 0; c < 6; ++c) CU(cudaMemcpyAsync(din + c * cap, src[c], count * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(ws->ev[0], st));
-    CU(launch_project(md.xyz, md.xyz + ld, md.xyz + 2 * ld, md.alpha, (int)m->n, din, cap, (int)count, f_tol, improve_tol,
-                      (int)max_iter, step_mul, dout, dstat, m->kp, st));
-    CU(cudaEventRecord(ws->ev[1], st));
     std::vector<int> hstat(count);
-    CU(cudaMemcpyAsync(ox, dout, count * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(oy, dout + cap, count * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(oz, dout + 2 * cap, count * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(hstat.data(), dstat, count * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    // every point is an independent iteration (one CTA each): contiguous ranges over the context's devices once there
+    // are enough points to fill them; the result does not depend on the split
+    const size_t nd = ctx->devs.size();
+    const size_t use = (nd > 1 && count >= 64 * nd) ? nd : 1;
+    std::vector<int> rcs(use, 0);
+    std::vector<std::string> errs(use);
+    std::vector<double> tms(use, 0.0);
+    auto work = [&](size_t di) {
+        rcs[di] = project_range(m, di, src, count * di / use, count * (di + 1) / use, f_tol, improve_tol, max_iter, step_mul,
+                                ox, oy, oz, hstat.data(), &tms[di]);
+        if (rcs[di]) errs[di] = g_err;
+    };
+    if (use == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (size_t di = 0; di < use; ++di) pool.emplace_back(work, di);
+        for (auto& t : pool) t.join();
+    }
+    for (size_t di = 0; di < use; ++di) if (rcs[di]) return fail(rcs[di], errs[di]);
     {
         std::lock_guard<std::mutex> lk(ctx->tmu);
-        ctx->timings.predict_mean_ms = ev_ms(ws->ev[0], ws->ev[1]);
+        ctx->timings.predict_mean_ms = *std::max_element(tms.begin(), tms.end());
         ctx->timings.predict_total_ms = ctx->timings.predict_mean_ms;
     }
     bool bad = false;
     for (size_t i = 0; i < count; ++i) { if (status) status[i] = hstat[i]; bad = bad || hstat[i] == INT_MIN; }
     if (bad) return fail(GPR_ERR_INVALID, "f is nan or inf");       // include/atlas/atlas.hpp:230
+    return GPR_OK;
+}
+
+int gpr_sample_chart(gpr_ctx* ctx, gpr_model* m, const double* frames, const size_t* counts, size_t n_charts,
+                     const double* r_in, const double* th_in, unsigned long long seed, double* sx, double* sy, double* sz,
+                     double* f, double* v, size_t* order) {
+    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
+    if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
+    if (!frames || !counts || n_charts == 0 || (r_in == nullptr) != (th_in == nullptr)) return fail(GPR_ERR_INVALID, "All input data is empty!");
+    if (n_charts > (size_t)1 << 20) return fail(GPR_ERR_INVALID, "too many charts");
+    std::vector<unsigned long long> offs(n_charts + 1, 0);
+    for (size_t c = 0; c < n_charts; ++c) {
+        if (counts[c] > (size_t)1 << 20) return fail(GPR_ERR_INVALID, "too many samples on one chart");
+        offs[c + 1] = offs[c] + counts[c];
+    }
+    const size_t total = (size_t)offs[n_charts];
+    if (total == 0) return GPR_OK;
+    if (total > (size_t)1 << 26) return fail(GPR_ERR_INVALID, "too many samples");
+    std::vector<double> rr, tt;
+    if (!r_in) {
+        // the reference's generator and call order (include/random_generation.hpp:9-27; atlas_variance.hpp:176-177: r then th
+        // per sample), seeded by the caller instead of std::random_device
+        std::mt19937_64 eng(seed);
+        rr.resize(total); tt.resize(total);
+        std::uniform_real_distribution<double> dr(0.8, std::nextafter(1.0, std::numeric_limits<double>::max())), dt(0.0, 2 * M_PI);
+        for (size_t i = 0; i < total; ++i) { rr[i] = dr(eng); tt[i] = dt(eng); }
+        r_in = rr.data(); th_in = tt.data();
+    }
+    int rc = ensure_on_device(m, 0, false);
+    if (rc) return rc;
+    DeviceCtx* dc = ctx->devs[0];
+    CU(cudaSetDevice(dc->dev));
+    Workspace* ws = nullptr;
+    rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    cudaStream_t st = ws->st;
+    // io: q (3 x total) | f | v | r | th | order (8-byte ints) | frames (13 n) | offsets (n + 1) | bad flag
+    const size_t need = 8 * total + 13 * n_charts + (n_charts + 1) + 2;
+    rc = ws_reserve(&ws->io, &ws->io_cap, std::max(need, (size_t)14 * TB));
+    if (rc) return rc;
+    double* dq = ws->io; double* df = dq + 3 * total; double* dv = df + total; double* dr_ = dv + total; double* dth = dr_ + total;
+    unsigned long long* dord = reinterpret_cast<unsigned long long*>(dth + total);
+    double* dfr = dth + 2 * total;
+    unsigned long long* doff = reinterpret_cast<unsigned long long*>(dfr + 13 * n_charts);
+    int* dbad = reinterpret_cast<int*>(doff + n_charts + 1);
+    CU(cudaMemcpyAsync(dfr, frames, 13 * n_charts * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(doff, offs.data(), (n_charts + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dr_, r_in, total * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dth, th_in, total * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(dbad, 0, sizeof(int), st));
+    CU(launch_chart_fill(dfr, doff, (int)n_charts, dr_, dth, (int)total, dq, dq + total, dq + 2 * total, st));
+    CU(cudaStreamSynchronize(st));
+    PredictIO io;
+    io.qx = dq; io.qy = dq + total; io.qz = dq + 2 * total; io.q = total; io.offset = 0;
+    io.f = df; io.var = dv; io.grad = nullptr; io.tx = nullptr; io.ty = nullptr; io.out_ld = total; io.device_ptrs = true;
+    double tm = 0, tv = 0, th2 = 0, td = 0;
+    rc = predict_on_device(m, 0, io, &tm, &tv, &th2, &td);
+    if (rc) return rc;
+    CU(cudaSetDevice(dc->dev));
+    CU(launch_chart_rank(df, dv, doff, (int)n_charts, dord, dbad, st));
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (sx) CU(cudaMemcpyAsync(sx, dq, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sy) CU(cudaMemcpyAsync(sy, dq + total, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sz) CU(cudaMemcpyAsync(sz, dq + 2 * total, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (f) CU(cudaMemcpyAsync(f, df, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (v) CU(cudaMemcpyAsync(v, dv, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    std::vector<unsigned long long> hord(order ? total : 0);
+    if (order) CU(cudaMemcpyAsync(hord.data(), dord, total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (order) for (size_t i = 0; i < total; ++i) order[i] = (size_t)hord[i];
+    {
+        std::lock_guard<std::mutex> lk(ctx->tmu);
+        ctx->timings.predict_mean_ms = tm; ctx->timings.predict_var_ms = tv; ctx->timings.predict_total_ms = tm + tv;
+    }
+    if (bad) return fail(GPR_ERR_INVALID, "v is nan or inf");          // include/atlas/atlas_variance.hpp:210
     return GPR_OK;
 }
 

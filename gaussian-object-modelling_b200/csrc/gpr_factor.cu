@@ -38,6 +38,14 @@ struct CholArgs {
     int* info;        // 0, or 1 + global index of the first non-positive pivot
     int* abort;       // raised on failure so that waiting CTAs leave
     long long* trace; // optional: 4 globaltimer stamps per task (claim, accumulated, solved, published)
+    // Replication fused into the producer (multi-GPU predict): every finished tile of L and of Dinv is also
+    // stored into the same position of up to MAX_CHOL_PEERS peer buffers (other GPUs' replicas, mapped through CUDA IPC /
+    // peer access, same leading dimension), so the replicas are complete when the factorisation ends — the n x n
+    // broadcast that used to follow the fit disappears from the critical path.  Posted NVLink writes, no handshake:
+    // the consumers synchronise with the end of the kernel (stream sync + the launcher's barrier).
+    int n_peers;
+    double* peerA[MAX_CHOL_PEERS];
+    double* peerDinv[MAX_CHOL_PEERS];
 };
 
 // Task order.  Column j contributes, in this order, (j+1,j), (j+1,j+1), (j+2,j), ..., (nb-1,j); task 0 is
@@ -125,9 +133,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
                 return;
             }
             store_lower_tile(T, Gij, a.ld);
+            for (int pr = 0; pr < a.n_peers; ++pr) store_lower_tile(T, a.peerA[pr] + (Gij - a.A), a.ld);
             __syncthreads();
             trinv128_smem(T, s_inv, smem + R0_DBL);
             store_lower_tile(T, a.Dinv + (size_t)j * TB * TB, TB);
+            for (int pr = 0; pr < a.n_peers; ++pr) store_lower_tile(T, a.peerDinv[pr] + (size_t)j * TB * TB, TB);
         } else {
             if (tid == 0 && !spin_wait(a.ready + (size_t)j * a.nb + j, a.abort)) s_abort = 1;
             __syncthreads();
@@ -136,6 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
             // L_ij[r][c] = sum_k T[r][k] Dinv_j[c][k]
             tile_mainloop<RES_M, STREAM_M>(acc, T, 0, a.Dinv + (size_t)j * TB * TB, TB, 8, smem, &s_abort, NoWait());
             store_tile<false, 1>(acc, Gij, a.ld, tc);
+            for (int pr = 0; pr < a.n_peers; ++pr) store_tile<false, 1>(acc, a.peerA[pr] + (Gij - a.A), a.ld, tc);
         }
         if (a.trace && tid == 0) a.trace[4 * (size_t)task_id + 2] = globaltimer_ns();
         __threadfence();
@@ -262,13 +273,19 @@ static cudaError_t ensure_attrs() {
 
 // sync: the scratch ints are [0]=counter [1]=info [2]=abort followed by nb*nb ready flags.
 cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, int serial,
-                            cudaStream_t st, long long* trace) {
+                            cudaStream_t st, long long* trace, const CholPeers* peers) {
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(scratch, 0, sizeof(int) * (4 + (size_t)nb * nb), st);
     if (e != cudaSuccess) return e;
     CholArgs a;
     a.A = A; a.ld = ld; a.nb = nb; a.Dinv = Dinv; a.trace = trace;
+    a.n_peers = 0;
+    for (int pr = 0; pr < MAX_CHOL_PEERS; ++pr) { a.peerA[pr] = nullptr; a.peerDinv[pr] = nullptr; }
+    if (peers && !serial) {
+        a.n_peers = peers->n < MAX_CHOL_PEERS ? peers->n : MAX_CHOL_PEERS;
+        for (int pr = 0; pr < a.n_peers; ++pr) { a.peerA[pr] = peers->L[pr]; a.peerDinv[pr] = peers->Dinv[pr]; }
+    }
     a.counter = scratch; a.info = scratch + 1; a.abort = scratch + 2; a.ready = scratch + 4;
     const int ntasks = nb * (nb + 1) / 2;
     a.task_begin = 0;

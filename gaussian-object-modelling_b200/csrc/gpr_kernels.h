@@ -10,9 +10,12 @@ namespace gpr {
 cudaError_t launch_cov_build(const double* x, const double* y, const double* z, const double* sigma2, int n, int nb,
                              int tile_row0, double* K, size_t ld, unsigned long long* rmax_bits, const KernParams& kp,
                              cudaStream_t st);
-// K2 (gpr_factor.cu).  scratch: at least 4 + nb*nb ints.
+// K2 (gpr_factor.cu).  scratch: at least 4 + nb*nb ints.  peers: replicas (same ld) that receive every finished tile of
+// L and Dinv through peer stores while the factorisation runs.
+constexpr int MAX_CHOL_PEERS = 7;
+struct CholPeers { int n; double* L[MAX_CHOL_PEERS]; double* Dinv[MAX_CHOL_PEERS]; };
 cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, int serial,
-                            cudaStream_t st, long long* trace = nullptr);
+                            cudaStream_t st, long long* trace = nullptr, const CholPeers* peers = nullptr);
 cudaError_t launch_dinv_from_l(const double* L, size_t ld, int nb, double* Dinv, cudaStream_t st);
 cudaError_t launch_linv(const double* L, double* X, size_t ld, int nb, const double* Dinv, int* scratch, int num_sms,
                         cudaStream_t st);
@@ -51,6 +54,11 @@ cudaError_t launch_grid_fill(const double* axis, int na, unsigned long long g0, 
                              double* qz, cudaStream_t st);
 cudaError_t launch_grid_select(const double* f, unsigned long long g0, int count, double tol, unsigned int* counter,
                                unsigned long long* sel_idx, double* sel_f, cudaStream_t st);
+// Batched AtlasVariance::sampleOnChart: annulus samples on the charts' tangent discs; per-chart order by variance.
+cudaError_t launch_chart_fill(const double* frames, const unsigned long long* offsets, int n_charts, const double* r,
+                              const double* th, int total, double* qx, double* qy, double* qz, cudaStream_t st);
+cudaError_t launch_chart_rank(const double* f, const double* v, const unsigned long long* offsets, int n_charts,
+                              unsigned long long* order, int* bad, cudaStream_t st);
 // Batched gradient-descent projection onto f = 0 (AtlasBase::project), one CTA per point.
 cudaError_t launch_project(const double* px, const double* py, const double* pz, const double* alpha, int n,
                            const double* xyz_in, size_t ld, int count, double f_tol, double improve_tol, int max_iter,

@@ -632,6 +632,63 @@ cudaError_t launch_grid_select(const double* f, unsigned long long g0, int count
 }
 
 // ---------------------------------------------------------------------------------------------
+// Batched AtlasVariance::sampleOnChart (include/atlas/atlas_variance.hpp:147-219): uniform annulus samples on the
+// tangent disc of each chart, pK = Tkl * (R sqrt(r) cos th, R sqrt(r) sin th, 0, 1) with Tkl = [Tx Ty N C] (:166-195),
+// then — after the batched mean + variance of all samples — the per-chart order by decreasing variance (:214-218).
+// frames: 13 doubles per chart (C, N, Tx, Ty, R); offsets: n_charts + 1 prefix sums of the sample counts.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chart_fill_kernel(const double* __restrict__ frames, const unsigned long long* __restrict__ offsets,
+                                                         int n_charts, const double* __restrict__ r, const double* __restrict__ th,
+                                                         int total, double* qx, double* qy, double* qz) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    int lo = 0, hi = n_charts;                         // chart c with offsets[c] <= i < offsets[c+1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offsets[mid] <= (unsigned long long)i) lo = mid; else hi = mid; }
+    const double* F = frames + 13 * (size_t)lo;
+    const double R = F[12];
+    const double sr = sqrt(r[i]);
+    const double a = __dmul_rn(__dmul_rn(R, sr), cos(th[i]));
+    const double b = __dmul_rn(__dmul_rn(R, sr), sin(th[i]));
+    double out[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)                        // row c of Tkl times (a, b, 0, 1), accumulated left to right
+        out[c] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(F[6 + c], a), __dmul_rn(F[9 + c], b)), __dmul_rn(F[3 + c], 0.0)), F[c]);
+    qx[i] = out[0]; qy[i] = out[1]; qz[i] = out[2];
+}
+
+// One CTA per chart: rank of every sample by (variance descending, index ascending); flags non-finite f / v.
+__global__ void __launch_bounds__(256) chart_rank_kernel(const double* __restrict__ f, const double* __restrict__ v,
+                                                         const unsigned long long* __restrict__ offsets,
+                                                         unsigned long long* order, int* bad) {
+    const unsigned long long o0 = offsets[blockIdx.x], o1 = offsets[blockIdx.x + 1];
+    const int cnt = (int)(o1 - o0);
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+        const double vi = v[o0 + i];
+        if (!isfinite(vi) || !isfinite(f[o0 + i])) atomicExch(bad, 1);
+        int rank = 0;
+        for (int j = 0; j < cnt; ++j) {
+            const double vj = v[o0 + j];
+            rank += (vj > vi) || (vj == vi && j < i);
+        }
+        order[o0 + rank] = (unsigned long long)i;
+    }
+}
+
+cudaError_t launch_chart_fill(const double* frames, const unsigned long long* offsets, int n_charts, const double* r,
+                              const double* th, int total, double* qx, double* qy, double* qz, cudaStream_t st) {
+    if (total <= 0) return cudaSuccess;
+    chart_fill_kernel<<<(total + 255) / 256, 256, 0, st>>>(frames, offsets, n_charts, r, th, total, qx, qy, qz);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_chart_rank(const double* f, const double* v, const unsigned long long* offsets, int n_charts,
+                              unsigned long long* order, int* bad, cudaStream_t st) {
+    if (n_charts <= 0) return cudaSuccess;
+    chart_rank_kernel<<<n_charts, 256, 0, st>>>(f, v, offsets, order, bad);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batched projection onto the iso-surface f = 0: AtlasBase::project
 // (include/atlas/atlas.hpp:201-276) is a fixed-step gradient descent that calls evaluate(q = 1) twice per
 // iteration, up to 500 iterations, for ONE point.  Here one CTA owns one point and runs the whole iteration

@@ -65,6 +65,59 @@ def broadcast_model(reg, model, n, R, with_linv, rank, device, src=0):
     return model, nbytes
 
 
+def fit_and_publish(reg, fit, n, R, rank, device, src=0):
+    """The exchange step fused into the fit.  Every rank but `src` creates its replica FIRST and exports CUDA IPC handles
+    of its factor buffers; `src` registers them (gpr_ctx_set_fit_peers) and then runs `fit()` (a callable returning the
+    fitted Model): its Cholesky kernel stores every finished tile of L and Dinv into all replicas over NVLink while it
+    factorises, so when the fit returns only {x|y|z, alpha} (32 n bytes) are left to broadcast.  If the matrix turns out
+    indefinite (trailing-block path) nothing was published and the state is broadcast the old way.
+    Returns (model, info) with info = {published, fit_wall_ms (src), exposed_ms: src's fit end -> every rank ready}."""
+    import time
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    replica, blob = None, None
+    if rank != src:
+        replica = reg.create_replica(n, R, 2)
+        blob = replica.ipc_export()
+    blobs = [None] * world
+    dist.all_gather_object(blobs, blob)
+    if rank == src:
+        reg.ctx.set_fit_peers([b for r, b in enumerate(blobs) if r != src], n)
+    dist.barrier(device_ids=[device.index])
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    model, published, n_tail = replica, 0.0, 0.0
+    if rank == src:
+        model = fit()
+        published, n_tail = float(reg.ctx.last_fit_published), float(model.n_tail)
+    t_fit = time.perf_counter()
+    meta = torch.tensor([published, n_tail], dtype=torch.float64, device=device)
+    dist.broadcast(meta, src=src)
+    published = bool(meta[0].item())
+    nbytes = 0
+    if published:
+        st = model.state(with_linv=0)
+        N = st.padded_n
+        for ptr, cnt in ((st.xyz, 3 * N), (st.alpha, N)):
+            dist.broadcast(as_tensor(ptr, cnt, device), src=src)
+            nbytes += 8 * cnt
+    else:
+        if rank != src:
+            model.close()
+            model = None
+        model, nbytes = broadcast_model(reg, model, n, R, 1, rank, device, src=src)
+    dist.barrier(device_ids=[device.index])
+    torch.cuda.synchronize(device)
+    t_end = time.perf_counter()
+    if rank == src:
+        reg.ctx.clear_fit_peers()
+    info = {"published": published, "fit_wall_ms": 1e3 * (t_fit - t0) if rank == src else None,
+            "exposed_ms": 1e3 * (t_end - t_fit) if rank == src else None, "small_state_bytes": nbytes,
+            "factor_bytes_per_peer": 8 * (((n + 127) // 128 * 128) ** 2 + ((n + 127) // 128) * 128 * 128)}
+    return model, info
+
+
 def broadcast_arrays(arrays, src=0):
     """gloo/CPU counterpart used by the tests: broadcast a list of numpy float64 arrays in place."""
     import torch

@@ -22,6 +22,7 @@
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <utility>
 #include <vector>
 
 #if defined(__has_include)
@@ -204,6 +205,49 @@ public:
         }
         points.coord_x.resize(count); points.coord_y.resize(count); points.coord_z.resize(count);
         f.resize(count); v.resize(count);
+    }
+
+    // Extension: AtlasVariance::sampleOnChart (include/atlas/atlas_variance.hpp:147-219) for any number of charts in one
+    // call.  centers / normals / tx / ty: c x 3 (Chart::getCenter / getNormal / getTanBasisOne / getTanBasisTwo), radii: c,
+    // counts: samples per chart (the reference: ceil(|disc_samples_factor| * R)).  On return samples[k] (counts[k] x 3) and
+    // vars_ids[k] are what the reference leaves in Chart::samples and Chart::vars_ids (sorted by decreasing variance).
+    // The uniform variates come from mt19937_64(seed) with the reference's distributions (random_generation.hpp:16-27).
+    void sampleOnCharts(Model::ConstPtr gp, const Eigen::MatrixXd& centers, const Eigen::MatrixXd& normals,
+                        const Eigen::MatrixXd& tx, const Eigen::MatrixXd& ty, const std::vector<double>& radii,
+                        const std::vector<size_t>& counts, unsigned long long seed, std::vector<Eigen::MatrixXd>& samples,
+                        std::vector<std::vector<std::pair<double, std::size_t> > >& vars_ids) {
+        if (!gp) throw GPRegressionException("Empty Model pointer");
+        if (!gp->device) throw GPRegressionException("Model was not created by this regressor");
+        const size_t c = (size_t)centers.rows();
+        if (c == 0 || centers.cols() != 3 || (size_t)normals.rows() != c || (size_t)tx.rows() != c || (size_t)ty.rows() != c ||
+            radii.size() != c || counts.size() != c)
+            throw GPRegressionException("Inconsistent input data sizes");
+        std::vector<double> frames(13 * c);
+        size_t total = 0;
+        for (size_t k = 0; k < c; ++k) {
+            for (int a = 0; a < 3; ++a) {
+                frames[13 * k + a] = centers((Eigen::Index)k, a); frames[13 * k + 3 + a] = normals((Eigen::Index)k, a);
+                frames[13 * k + 6 + a] = tx((Eigen::Index)k, a); frames[13 * k + 9 + a] = ty((Eigen::Index)k, a);
+            }
+            frames[13 * k + 12] = radii[k];
+            total += counts[k];
+        }
+        std::vector<double> sx(total), sy(total), sz(total), f(total), v(total);
+        std::vector<size_t> order(total);
+        const int rc = gpr_sample_chart(detail::context(), detail::handle(*gp), frames.data(), counts.data(), c, nullptr, nullptr,
+                                        seed, sx.data(), sy.data(), sz.data(), f.data(), v.data(), order.data());
+        if (rc != GPR_OK) detail::raise(rc);
+        samples.assign(c, Eigen::MatrixXd());
+        vars_ids.assign(c, std::vector<std::pair<double, std::size_t> >());
+        size_t o = 0;
+        for (size_t k = 0; k < c; ++k) {
+            samples[k].resize((Eigen::Index)counts[k], 3);
+            for (size_t i = 0; i < counts[k]; ++i) {
+                samples[k]((Eigen::Index)i, 0) = sx[o + i]; samples[k]((Eigen::Index)i, 1) = sy[o + i]; samples[k]((Eigen::Index)i, 2) = sz[o + i];
+                vars_ids[k].push_back(std::make_pair(v[o + order[o + i]], order[o + i]));
+            }
+            o += counts[k];
+        }
     }
 
     // Extension: AtlasBase::project (include/atlas/atlas.hpp:201-276, same defaults) for any number of points in one

@@ -110,6 +110,23 @@ int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, doub
 int gpr_project(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* nx,
                 const double* ny, const double* nz, size_t count, double f_tol, double improve_tol, unsigned max_iter,
                 double step_mul, double* ox, double* oy, double* oz, int* status_or_null);
+/* Batched AtlasVariance::sampleOnChart (include/atlas/atlas_variance.hpp:147-219: per chart, ceil(|disc_samples_factor| R)
+ * uniform annulus samples on the tangent disc, one evaluate(f, v) each, then sorted by decreasing variance) for any number
+ * of charts in one call: the samples are generated on the device, evaluated as ONE batch, and ranked per chart on the device.
+ *   frames : n_charts x 13 doubles, per chart: centre C (3), normal N (3), tangent basis Tx (3), Ty (3), radius R
+ *            (Chart::getCenter / getNormal / getTanBasisOne / getTanBasisTwo / getRadius, include/atlas/atlas.hpp:17-106)
+ *   counts : samples per chart;  total = their sum
+ *   r, th  : `total` uniform variates each, r in [0.8, 1], th in [0, 2 pi), in chart order — the reference draws them from a
+ *            process-global mt19937_64 seeded by std::random_device (include/random_generation.hpp:9-27), i.e. NOT reproducibly;
+ *            pass both for a deterministic result, or both NULL to have them drawn from mt19937_64(seed) with the reference's
+ *            distributions and call order (r, then th, per sample)
+ *   sx, sy, sz, f, v (host, `total` each, any may be NULL): sample points (Chart::samples rows), their mean and variance
+ *   order  (host, `total`, may be NULL): for chart c with offset o_c, order[o_c + k] = index within the chart of the sample
+ *            with the k-th largest variance (Chart::vars_ids after the sort, :214-218; equal variances by index)
+ * Returns GPR_ERR_INVALID "v is nan or inf" if any f or v is not finite (the reference throws, :202-211). */
+int gpr_sample_chart(gpr_ctx* ctx, gpr_model* m, const double* frames, const size_t* counts, size_t n_charts,
+                     const double* r_or_null, const double* th_or_null, unsigned long long seed, double* sx, double* sy,
+                     double* sz, double* f, double* v, size_t* order);
 /* Builds L^-1 now.  It is otherwise built by the first call that needs it: a variance for a batch of fewer than
  * 4096 queries (GPR_TRSM_MIN_Q) — the fused single-query kernel and the product form read it — or gpr_append.
  * Large batches on a model without L^-1 take the forward substitution over L instead (no n^3/3 inverse, one n x n
@@ -141,6 +158,13 @@ int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity);
  * rebuilt; L^-1 is rebuilt on the first variance request), otherwise by refitting the stored training set. */
 int gpr_model_save(gpr_ctx* ctx, gpr_model* m, const char* path, int with_factor);
 int gpr_model_load(gpr_ctx* ctx, const char* path, gpr_model** out);
+
+/* ---- point-cloud input ----------------------------------------------------------------- */
+/* Minimal PCD v0.7 reader — what the reference obtains from PCL (pcl::io::loadPCDFile, src/gp_node.cpp:557): the x, y, z
+ * fields (4-byte floats, widened to double) of an ascii / binary / binary_compressed (LZF) file, as three malloc'ed arrays
+ * of *n doubles that the caller releases with gpr_free.  Other fields (rgba, normals) are skipped.  Host only. */
+int gpr_pcd_read_xyz(const char* path, double** x, double** y, double** z, size_t* n);
+void gpr_free(void* p);
 
 /* ---- replication across processes (one process per GPU, launched by bench.py) ----------------- */
 /* The fitted state that predict needs, as raw device pointers on the primary device, so that the
@@ -174,6 +198,19 @@ int gpr_model_create_replica(gpr_ctx* ctx, size_t n, gpr_kernel_t kernel, double
 /* Same for a model whose last n_tail points (internal order) form the indefinite tail block (gpr_model_tail_size). */
 int gpr_model_create_replica_tail(gpr_ctx* ctx, size_t n, size_t n_tail, gpr_kernel_t kernel, double R, int with_linv,
                                   gpr_model** out);
+/* Replication fused into the factorisation (one process per GPU on one NVLink box).  Instead of broadcasting the n x n
+ * factor after the fit, every rank but the fitting one creates its replica first (gpr_model_create_replica with
+ * with_linv = 2) and exports CUDA IPC handles of its factor buffers (128 bytes: L, then Dinv); the launcher gathers them
+ * on the fitting rank, which registers them; from then on every gpr_fit on that context whose padded size matches stores
+ * each finished 128 x 128 tile of L and Dinv into all registered replicas from inside the Cholesky kernel (posted NVLink
+ * peer writes), so the replicas are complete when gpr_fit returns; only {x|y|z, alpha} (32 n bytes) remain to be
+ * broadcast.  gpr_ctx_last_fit_published tells whether the last fit published (it does not when the matrix turned out
+ * indefinite and the trailing-block path was taken: broadcast L^-1 and the tail block then).  The replicas may be used
+ * after the launcher's barrier that follows gpr_fit.  At most 7 peers. */
+int gpr_model_ipc_export(gpr_ctx* ctx, gpr_model* replica, void* handles128);
+int gpr_ctx_set_fit_peers(gpr_ctx* ctx, const void* handles128_each, int n_peers, size_t n);
+int gpr_ctx_clear_fit_peers(gpr_ctx* ctx);
+int gpr_ctx_last_fit_published(const gpr_ctx* ctx);
 
 #ifdef __cplusplus
 }

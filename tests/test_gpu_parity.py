@@ -785,6 +785,59 @@ def test_unchanged_caller_fanout_bench_against_the_reference_arm(gpr, tmp_path):
         assert res["ours"]["total_s"] <= 1.25 * res["reference"]["total_s"], res
 
 
+def test_batched_sample_on_chart_matches_the_atlas_loop(gpr, orc, ctx):
+    """SURVEY §8(f).3: AtlasVariance::sampleOnChart (include/atlas/atlas_variance.hpp:147-219) for many charts in one call,
+    against the reference's loop transcribed over single-query evaluations of the CPU ORACLE: same annulus points
+    (pK = Tkl * pL, :166-195) from the same uniform variates, same mean / variance, same order by decreasing variance
+    (vars_ids after the sort, :214-218).  Charts are built like createNode does (:68-105): gradient and variance at the
+    centre, computeTangentBasis, radius = -0.3 v + 0.2 (:65, src/gp_node.cpp:959), ceil(200 R) samples."""
+    g = load_golden("ref_mugD_thinplate_R2_node")                 # the node's own setting (indefinite K)
+    P = g["P"]
+    reg = _reg(gpr, ctx, g)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"])
+    o = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], g["y"], g["s2"], "thin_plate", g["p0"], 0.0, factor="ldlt")
+    centres = P[:262:23]                                            # 12 surface points of the cloud
+    fc, vc, gc = o.predict(centres[:, 0], centres[:, 1], centres[:, 2], var=True, grad=True)
+    N, Tx, Ty = orc.tangent_basis(gc)
+    R = -0.3 * vc + 0.2
+    counts = np.ceil(200 * R).astype(np.int64)
+    frames = np.hstack([centres, N, Tx, Ty, R[:, None]])
+    rng = np.random.default_rng(3)
+    total = int(counts.sum())
+    r, th = rng.uniform(0.8, 1.0, total), rng.uniform(0.0, 2 * np.pi, total)
+    pts, f, v, order = reg.sample_charts(m, frames, counts, r, th)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    for c in range(len(centres)):
+        sl = slice(off[c], off[c + 1])
+        a = R[c] * np.sqrt(r[sl]) * np.cos(th[sl])
+        b = R[c] * np.sqrt(r[sl]) * np.sin(th[sl])
+        pk = Tx[c][None, :] * a[:, None] + Ty[c][None, :] * b[:, None] + N[c][None, :] * 0.0 + centres[c][None, :]
+        assert np.abs(pts[sl] - pk).max() <= 1e-14
+        fo = np.zeros(counts[c]); vo = np.zeros(counts[c])
+        for i in range(counts[c]):                                  # one evaluate(f, v) per sample, like :201
+            fi, vi, _ = o.predict(pk[i:i + 1, 0], pk[i:i + 1, 1], pk[i:i + 1, 2], var=True)
+            fo[i], vo[i] = fi[0], vi[0]
+        assert np.abs(f[sl] - fo).max() <= TOL_MEAN * max(np.abs(fo).max(), 1.0)
+        assert np.abs(v[sl] - vo).max() <= TOL_VAR * np.abs(vo).max()
+        ids = order[sl]
+        assert sorted(ids.tolist()) == list(range(counts[c]))       # a permutation of the chart's samples
+        assert (np.diff(v[sl][ids]) <= 0).all()                     # decreasing in our own variances, exactly
+        ref_ids = sorted(range(counts[c]), key=lambda i: (-vo[i], i))
+        tol = 2 * TOL_VAR * np.abs(vo).max()
+        assert (np.abs(vo[ids] - vo[ref_ids]) <= tol).all()         # same order as the reference loop up to ties within tolerance
+        assert ids[0] == ref_ids[0] or abs(vo[ids[0]] - vo[ref_ids[0]]) <= tol       # the sample getNextState picks (:121-122)
+    # library-drawn variates: deterministic per seed, inside the annulus, in the tangent plane
+    p1, f1, v1, o1 = reg.sample_charts(m, frames, counts, seed=7)
+    p2, f2, v2, o2 = reg.sample_charts(m, frames, counts, seed=7)
+    p3 = reg.sample_charts(m, frames, counts, seed=8)[0]
+    assert np.array_equal(p1, p2) and np.array_equal(v1, v2) and np.array_equal(o1, o2) and not np.array_equal(p1, p3)
+    for c in range(len(centres)):
+        d = p1[off[c]:off[c + 1]] - centres[c]
+        rad = np.linalg.norm(d, axis=1)
+        assert (rad >= np.sqrt(0.8) * R[c] * (1 - 1e-12)).all() and (rad <= R[c] * (1 + 1e-12)).all()
+        assert np.abs(d @ N[c]).max() <= 1e-12
+
+
 def test_model_save_and_load_round_trip(gpr, ctx, tmp_path):
     """Export / import: with the stored factor the loaded model answers without refactorising
     (same alpha and factor bits); without it (and for an indefinite-tail model) it is refitted from the stored
@@ -840,6 +893,13 @@ def test_sampler_sharded_over_two_devices_is_identical(gpr):
         reg = gpr.GPRegressor("thin_plate", W.SYNTH_R, ctx=c)
         m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
         outs.append(reg.sample_isosurface(m, lo=-1.2, hi=1.2, step=2.4 / 139, tol=0.002))     # 140^3 = 2.7 M points
+        # the batched projection is sharded the same way (one CTA per point, contiguous ranges per device)
+        rng = np.random.default_rng(4)
+        d = rng.standard_normal((300, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        start = d * rng.uniform(0.9, 1.2, size=(300, 1))
+        _, g0 = reg.evaluate(m, start[:, 0], start[:, 1], start[:, 2], grad=True)
+        po, ps = reg.project(m, start, g0, f_tol=1e-3, improve_tol=1e-9, max_iter=60, step_mul=0.2)
+        outs[-1] = outs[-1] + (po, ps)
         del m
         c.close()
     assert len(outs[0][0]) > 100
@@ -871,3 +931,15 @@ def test_tail_block_is_replicated_across_processes(gpr):
     out = subprocess.run([os.sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29541", os.path.join(ROOT, "tools", "tail_replica_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "TAIL_REPLICA_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_factor_is_published_to_replicas_during_the_fit(gpr):
+    """Two ranks under torchrun (needs 2 GPUs): the replication fused into the Cholesky kernel (peer stores through CUDA IPC
+    mappings, distributed.fit_and_publish) — sharded results bit-identical to rank 0's own, identical to the legacy
+    broadcast path, and the indefinite configuration falls back to the broadcast."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([os.sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29543", os.path.join(ROOT, "tools", "publish_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "PUBLISH_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -156,3 +156,82 @@ def test_standalone_cmake_build(tmp_path):
     assert out.returncode == 0 and "All input data is empty!" in out.stdout
     syms = subprocess.run(["nm", "-D", "--defined-only", os.path.join(b, "libgpr_b200.so")], capture_output=True, text=True).stdout
     assert " gpr_fit" in syms and " gpr_predict" in syms and " gpr_append" in syms
+
+
+def _lzf_compress(data):
+    """Greedy LZF compressor (test helper): emits literal runs and back references, like PCL's writer does."""
+    out, lit, i, n = bytearray(), bytearray(), 0, len(data)
+    table = {}
+
+    def flush():
+        j = 0
+        while j < len(lit):
+            run = lit[j:j + 32]
+            out.append(len(run) - 1)
+            out.extend(run)
+            j += 32
+        lit.clear()
+
+    while i < n:
+        key = bytes(data[i:i + 3])
+        ref = table.get(key) if len(key) == 3 else None
+        if len(key) == 3:
+            table[key] = i
+        if ref is not None and 0 < i - ref <= 8192:
+            length = 3
+            while i + length < n and length < 264 and data[ref + length] == data[i + length]:
+                length += 1
+            flush()
+            dist, l2 = i - ref - 1, length - 2
+            if l2 < 7:
+                out.append((l2 << 5) | (dist >> 8))
+            else:
+                out.append((7 << 5) | (dist >> 8))
+                out.append(l2 - 7)
+            out.append(dist & 0xFF)
+            i += length
+        else:
+            lit.append(data[i])
+            i += 1
+    flush()
+    return bytes(out)
+
+
+def test_c_abi_pcd_reader(gpr, tmp_path):
+    """gpr_pcd_read_xyz (csrc/gpr_io.cu; the reference uses PCL, src/gp_node.cpp:557): ascii / binary / binary_compressed,
+    x y z among other fields, float32 widened to double; malformed input is refused with a message.  No GPU needed."""
+    import struct
+    rng = np.random.default_rng(5)
+    n = 300
+    xyz = rng.standard_normal((n, 3)).astype(np.float32)
+    xyz[40:90] = xyz[40]                                       # repeated records: the LZF stream gets back references
+    rgba = rng.integers(0, 1 << 32, size=n, dtype=np.uint32)
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS rgba x y z\nSIZE 4 4 4 4\nTYPE U F F F\n"
+           "COUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA %s\n")
+    rec = np.zeros(n, dtype=[("rgba", "<u4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4")])
+    rec["rgba"], rec["x"], rec["y"], rec["z"] = rgba, xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    (tmp_path / "b.pcd").write_bytes((hdr % (n, n, "binary")).encode() + rec.tobytes())
+    soa = rgba.tobytes() + xyz[:, 0].tobytes() + xyz[:, 1].tobytes() + xyz[:, 2].tobytes()
+    comp = _lzf_compress(soa)
+    assert len(comp) < len(soa)                                # back references were emitted
+    (tmp_path / "c.pcd").write_bytes((hdr % (n, n, "binary_compressed")).encode() + struct.pack("<II", len(comp), len(soa)) + comp)
+    with open(tmp_path / "a.pcd", "w") as fh:
+        fh.write(hdr % (n, n, "ascii"))
+        for i in range(n):
+            fh.write("%d %.9g %.9g %.9g\n" % (rgba[i], xyz[i, 0], xyz[i, 1], xyz[i, 2]))
+    for name in ("a.pcd", "b.pcd", "c.pcd"):
+        got = gpr.pcd_read_xyz(tmp_path / name)
+        assert got.dtype == np.float64 and np.array_equal(got, xyz.astype(np.float64)), name
+        assert np.array_equal(got, gpr.workloads.read_pcd_xyz(str(tmp_path / name)))       # the Python reader of the benches
+    (tmp_path / "bad.pcd").write_bytes((hdr % (n, n, "binary_compressed")).encode() + struct.pack("<II", len(comp), len(soa)) + comp[:-7])
+    (tmp_path / "short.pcd").write_bytes((hdr % (n, n, "binary")).encode() + rec.tobytes()[:-5])
+    (tmp_path / "nofields.pcd").write_bytes(b"VERSION 0.7\nDATA ascii\n1 2 3\n")
+    for name in ("bad.pcd", "short.pcd", "nofields.pcd", "missing.pcd"):
+        with pytest.raises(gpr.GPRegressionException):
+            gpr.pcd_read_xyz(tmp_path / name)
+    # the reference's own clouds, where they exist (not on the GPU box), against the committed decoded fixtures
+    res = "/root/reference/resources"
+    if os.path.isdir(res):
+        for name in ("mugD", "kettle", "jug"):
+            gold = np.load(os.path.join(ROOT, "tests", "golden", name + "_xyz.npy")).astype(np.float64)
+            assert np.array_equal(gpr.pcd_read_xyz(os.path.join(res, name + ".pcd")), gold)
