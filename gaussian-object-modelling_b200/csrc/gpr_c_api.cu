@@ -222,9 +222,9 @@ struct gpr_model {
         const double *qx, *qy, *qz; size_t q;
         double *f, *var, *grad, *tx, *ty; size_t out_ld;
         int rc = 0; std::string err; bool done = false;
+        std::condition_variable cv;        // one per request: a finished launch wakes exactly the threads it served
     };
     std::mutex bmu;
-    std::condition_variable bcv;
     std::vector<SmallReq*> pending;
     bool leader = false;
 };
@@ -1077,7 +1077,7 @@ static int predict_small_combined(gpr_ctx* ctx, gpr_model* m, const double* qx, 
     m->pending.push_back(&me);
     for (;;) {
         if (me.done) break;
-        if (m->leader) { m->bcv.wait(lk, [&] { return me.done || !m->leader; }); continue; }
+        if (m->leader) { me.cv.wait(lk, [&] { return me.done || !m->leader; }); continue; }
         m->leader = true;
         for (int round = 0; round < MICRO_ROUNDS && !m->pending.empty(); ++round) {
             std::vector<gpr_model::SmallReq*> take;
@@ -1088,12 +1088,10 @@ static int predict_small_combined(gpr_ctx* ctx, gpr_model* m, const double* qx, 
             lk.unlock();
             run_small_batch(ctx, m, take);
             lk.lock();
-            for (auto* r : take) r->done = true;
-            m->bcv.notify_all();
-            if (me.done && round + 1 < MICRO_ROUNDS && m->pending.empty()) break;
+            for (auto* r : take) { r->done = true; if (r != &me) r->cv.notify_one(); }
         }
         m->leader = false;
-        m->bcv.notify_all();
+        if (!m->pending.empty()) m->pending.front()->cv.notify_one();      // hand over: the oldest waiter becomes the leader
     }
     lk.unlock();
     if (me.rc) g_err = me.err;
