@@ -90,6 +90,7 @@ def lib():
         L.gpr_predict_device.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
         L.gpr_sample_isosurface.argtypes = [vp, vp, cd, cd, cd, cd, sz, _dp, _dp, _dp, _dp, _dp, C.POINTER(sz)]
         L.gpr_project.argtypes = [vp, vp, _dp, _dp, _dp, _dp, _dp, _dp, sz, cd, cd, C.c_uint, cd, _dp, _dp, _dp, C.POINTER(ci)]
+        L.gpr_sample_marching.argtypes = [vp, vp, cd, cd, cd, C.c_float, C.c_float, cd, sz, _dp, _dp, _dp, _dp, _dp, C.POINTER(sz), C.POINTER(sz)]
         L.gpr_sample_chart.argtypes = [vp, vp, _dp, C.POINTER(sz), sz, _dp, _dp, C.c_ulonglong, _dp, _dp, _dp, _dp, _dp, C.POINTER(sz)]
         L.gpr_model_save.argtypes = [vp, vp, C.c_char_p, ci]
         L.gpr_model_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
@@ -123,7 +124,7 @@ C_ABI_SYMBOLS = [
     "gpr_model_get_factor", "gpr_predict", "gpr_predict_device", "gpr_model_prepare_variance", "gpr_append",
     "gpr_model_reserve", "gpr_sample_isosurface", "gpr_project", "gpr_model_save", "gpr_model_load",
     "gpr_model_state_get", "gpr_model_create_replica", "gpr_model_create_replica_tail", "gpr_model_solve",
-    "gpr_pcd_read_xyz", "gpr_free", "gpr_sample_chart",
+    "gpr_pcd_read_xyz", "gpr_free", "gpr_sample_chart", "gpr_sample_marching",
     "gpr_model_ipc_export", "gpr_ctx_set_fit_peers", "gpr_ctx_clear_fit_peers", "gpr_ctx_last_fit_published",
 ]
 # Engine self-tests / pipe probes (csrc/gpr_selftest.h): exported for tests/ and bench.py, not part of the boundary.
@@ -361,6 +362,17 @@ class GPRegressor:
                                  f_tol, improve_tol, int(max_iter), step_mul, _p(out[0]), _p(out[1]), _p(out[2]),
                                  st.ctypes.data_as(C.POINTER(C.c_int))))
         return np.ascontiguousarray(out.T), st
+
+    def sample_marching(self, model, lo=-1.1, hi=1.1, step=0.1, leaf=0.06, leaf_pass=0.02, tol=0.01, var=True, capacity=1 << 20):
+        """Batched counterpart of the node's marchingSampling (src/gp_node.cpp:1103-1292; defaults of its call at :258):
+        returns (points (k,3), f, var, cubes_visited)."""
+        cnt, cubes = C.c_size_t(), C.c_size_t()
+        xs, ys, zs, f = (np.zeros(capacity) for _ in range(4))
+        v = np.zeros(capacity) if var else None
+        _check(lib().gpr_sample_marching(self.ctx._h, model._h, lo, hi, step, leaf, leaf_pass, tol, capacity, _p(xs), _p(ys), _p(zs),
+                                         _p(f), _p(v), C.byref(cnt), C.byref(cubes)))
+        k = min(cnt.value, capacity)
+        return np.stack([xs[:k], ys[:k], zs[:k]], axis=1), f[:k], (None if v is None else v[:k]), cubes.value
 
     def sample_charts(self, model, frames, counts, r=None, th=None, seed=0):
         """Batched AtlasVariance::sampleOnChart (include/atlas/atlas_variance.hpp:147-219).  frames: (c, 13) rows

@@ -7,6 +7,8 @@
 #include "gpr_mma.cuh"
 
 #include <algorithm>
+#include <array>
+#include <set>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -286,6 +288,64 @@ static bool invert_small(std::vector<double>& S, int mp, std::vector<double>& in
 
 constexpr size_t MAX_TAIL = 256;
 
+// Elimination of the trailing pivot block of an indefinite matrix (gpr_tail.cu), given the Cholesky factor of the leading
+// n_spd points in m->L: (re)builds B, Z, S^-1 and alpha.  build_linv: also form X = L^-1 of the leading block (the fit);
+// an incremental append has already brought X up to date.  Frees and reallocates the tail buffers (their leading
+// dimension is the model capacity).
+static int tail_eliminate(gpr_model* m, DeviceCtx* dc, Workspace* ws, bool build_linv) {
+    gpr_ctx* ctx = m->ctx;
+    ModelDev& md = m->devs[0];
+    cudaStream_t st = ws->st;
+    const size_t N = m->cap;
+    cudaFree(m->tB); cudaFree(md.tZ); cudaFree(md.tSinv); cudaFree(m->tmisc);
+    m->tB = md.tZ = md.tSinv = m->tmisc = nullptr;
+    const size_t p = m->n_spd, mt = m->n_tail;
+    const int nslab = (int)((mt + 31) / 32), mp = 32 * nslab;
+    m->mp = mp;
+    const size_t part_dbl = tail_gram_part_doubles((int)p, mp);
+    // tmisc: C | S | t | a2 | gram partials | panel tmp (N x 32) | rhs (N) | S0 dummy (1024)
+    const size_t misc = 2 * (size_t)mp * mp + 2 * mp + part_dbl + 32 * N + N + 1024;
+    CU(cudaMalloc((void**)&m->tB, (size_t)nslab * N * 32 * sizeof(double)));
+    CU(cudaMalloc((void**)&md.tZ, (size_t)nslab * N * 32 * sizeof(double)));
+    CU(cudaMalloc((void**)&md.tSinv, (size_t)mp * mp * sizeof(double)));
+    CU(cudaMalloc((void**)&m->tmisc, misc * sizeof(double)));
+    if (!md.linv) CU(big_alloc(ctx, dc->dev, (void**)&md.linv, N * N * sizeof(double)));
+    double* tC = m->tmisc; double* tS = tC + (size_t)mp * mp; double* tt = tS + (size_t)mp * mp; double* ta2 = tt + mp;
+    double* tpart = ta2 + mp; double* tPn = tpart + part_dbl; double* trhs = tPn + 32 * N; double* tS0 = trhs + N;
+    // alpha_1 part 1: z_f = X y_1, z_1 = A^-1 y_1 (the tail labels must not enter the leading solve)
+    CU(cudaMemsetAsync(trhs, 0, N * sizeof(double), st));
+    CU(cudaMemcpyAsync(trhs, m->label, p * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(launch_trsv(0, m->L, N, m->nb, m->Dinv, trhs, m->zfwd, m->scratch, dc->num_sms, st));
+    CU(launch_trsv(1, m->L, N, m->nb, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
+    // X = L^-1 of the leading block, then B = X P and Z = X^T B slab by slab
+    if (build_linv) CU(launch_linv(m->L, md.linv, N, m->nb, m->Dinv, m->scratch, dc->num_sms, st));
+    for (int s = 0; s < nslab; ++s) {
+        const int kk = (int)std::min<size_t>(32, mt - 32 * (size_t)s);
+        double* Bs = m->tB + (size_t)s * N * 32;
+        double* Zs = md.tZ + (size_t)s * N * 32;
+        CU(launch_append_panel(md.xyz, N, m->s2, (int)p, (int)(p + 32 * (size_t)s), kk, tPn, tS0, m->kp, st));
+        CU(launch_skinny(0, md.linv, N, (int)p, (int)p, tPn, Bs, st));
+        CU(launch_skinny(1, md.linv, N, (int)p, (int)p, Bs, Zs, st));
+    }
+    CU(launch_tail_cc(md.xyz, N, m->s2, (int)p, (int)mt, mp, tC, m->kp, st));
+    CU(launch_tail_schur(m->tB, N, (int)p, mp, tC, tpart, tS, st));
+    std::vector<double> hS((size_t)mp * mp), hSinv;
+    CU(cudaMemcpyAsync(hS.data(), tS, hS.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    int lflags[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(lflags, m->scratch, sizeof(lflags), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (lflags[2] != 0) return fail(GPR_ERR_CUDA, "L^-1 kernel aborted (dependency wait timed out)");
+    if (!invert_small(hS, mp, hSinv)) {
+        g_pivot = (long long)p + 1;
+        return fail(GPR_ERR_NOT_SPD, "covariance matrix is singular: the Schur complement of the trailing pivot block cannot be inverted");
+    }
+    CU(cudaMemcpyAsync(md.tSinv, hSinv.data(), hSinv.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(launch_tail_alpha(m->tB, md.tZ, N, (int)p, (int)mt, mp, m->zfwd, m->label, md.tSinv, tt, ta2, md.alpha, st));
+    CU(cudaStreamSynchronize(st));      // hSinv must outlive the copy
+    md.have_linv = true; md.have_tail = true;
+    return GPR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // fit
 // ------------------------------------------------------------------------------------------------
@@ -492,50 +552,8 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
             CU(launch_axpy1(md.alpha, dd, (int)n, st));
         }
     } else {
-        const size_t p = m->n_spd, mt = m->n_tail;
-        const int nslab = (int)((mt + 31) / 32), mp = 32 * nslab;
-        m->mp = mp;
-        const size_t part_dbl = tail_gram_part_doubles((int)p, mp);
-        // tmisc: C | S | t | a2 | gram partials | panel tmp (N x 32) | rhs (N) | S0 dummy (1024)
-        const size_t misc = 2 * (size_t)mp * mp + 2 * mp + part_dbl + 32 * N + N + 1024;
-        CU(cudaMalloc((void**)&m->tB, (size_t)nslab * N * 32 * sizeof(double)));
-        CU(cudaMalloc((void**)&md.tZ, (size_t)nslab * N * 32 * sizeof(double)));
-        CU(cudaMalloc((void**)&md.tSinv, (size_t)mp * mp * sizeof(double)));
-        CU(cudaMalloc((void**)&m->tmisc, misc * sizeof(double)));
-        if (!md.linv) CU(big_alloc(ctx, dc->dev, (void**)&md.linv, N * N * sizeof(double)));
-        double* tC = m->tmisc; double* tS = tC + (size_t)mp * mp; double* tt = tS + (size_t)mp * mp; double* ta2 = tt + mp;
-        double* tpart = ta2 + mp; double* tPn = tpart + part_dbl; double* trhs = tPn + 32 * N; double* tS0 = trhs + N;
-        // alpha_1 part 1: z_f = X y_1, z_1 = A^-1 y_1 (the tail labels must not enter the leading solve)
-        CU(cudaMemsetAsync(trhs, 0, N * sizeof(double), st));
-        CU(cudaMemcpyAsync(trhs, m->label, p * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        CU(launch_trsv(0, m->L, N, m->nb, m->Dinv, trhs, m->zfwd, m->scratch, dc->num_sms, st));
-        CU(launch_trsv(1, m->L, N, m->nb, m->Dinv, m->zfwd, md.alpha, m->scratch, dc->num_sms, st));
-        // X = L^-1 of the leading block, then B = X P and Z = X^T B slab by slab
-        CU(launch_linv(m->L, md.linv, N, m->nb, m->Dinv, m->scratch, dc->num_sms, st));
-        for (int s = 0; s < nslab; ++s) {
-            const int kk = (int)std::min<size_t>(32, mt - 32 * (size_t)s);
-            double* Bs = m->tB + (size_t)s * N * 32;
-            double* Zs = md.tZ + (size_t)s * N * 32;
-            CU(launch_append_panel(md.xyz, N, m->s2, (int)p, (int)(p + 32 * (size_t)s), kk, tPn, tS0, m->kp, st));
-            CU(launch_skinny(0, md.linv, N, (int)p, (int)p, tPn, Bs, st));
-            CU(launch_skinny(1, md.linv, N, (int)p, (int)p, Bs, Zs, st));
-        }
-        CU(launch_tail_cc(md.xyz, N, m->s2, (int)p, (int)mt, mp, tC, m->kp, st));
-        CU(launch_tail_schur(m->tB, N, (int)p, mp, tC, tpart, tS, st));
-        std::vector<double> hS((size_t)mp * mp), hSinv;
-        CU(cudaMemcpyAsync(hS.data(), tS, hS.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-        int lflags[4] = {0, 0, 0, 0};
-        CU(cudaMemcpyAsync(lflags, m->scratch, sizeof(lflags), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (lflags[2] != 0) return fail(GPR_ERR_CUDA, "L^-1 kernel aborted (dependency wait timed out)");
-        if (!invert_small(hS, mp, hSinv)) {
-            g_pivot = (long long)p + 1;
-            return fail(GPR_ERR_NOT_SPD, "covariance matrix is singular: the Schur complement of the trailing pivot block cannot be inverted");
-        }
-        CU(cudaMemcpyAsync(md.tSinv, hSinv.data(), hSinv.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(launch_tail_alpha(m->tB, md.tZ, N, (int)p, (int)mt, mp, m->zfwd, m->label, md.tSinv, tt, ta2, md.alpha, st));
-        CU(cudaStreamSynchronize(st));      // hSinv must outlive the copy
-        md.have_linv = true; md.have_tail = true;
+        rc = tail_eliminate(m, dc, ws, true);
+        if (rc) return rc;
     }
     CU(cudaEventRecord(ws->ev[4], st));
     m->h_alpha.resize(n);
@@ -1375,6 +1393,123 @@ int gpr_project(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, co
     return GPR_OK;
 }
 
+// Batched counterpart of the node's marchingSampling / marchingCubes (src/gp_node.cpp:1103-1190, :1195-1292): a flood fill
+// over cubes of edge `leaf` that follows the iso-surface.  The reference runs one std::thread per cube, recursively, and
+// one evaluate(q = 1) per cube sample; here every WAVE of the flood fill (all frontier cubes) is one batched mean
+// evaluation, followed by one batched variance evaluation of the wave's kept samples.  Coordinates follow the
+// reference's arithmetic exactly: the start point and the cube centres are pcl::PointXYZ (float), a sample coordinate
+// is the float expression start.x - leaf/2 + i*pass widened to double (:1209-1211).
+int gpr_sample_marching(gpr_ctx* ctx, gpr_model* m, double grid_lo, double grid_hi, double grid_step, float leaf, float pass,
+                        double tol, size_t capacity, double* x, double* y, double* z, double* f, double* var, size_t* count,
+                        size_t* cubes) {
+    if (!ctx) return fail(GPR_ERR_INVALID, "null context");
+    if (!m) return fail(GPR_ERR_INVALID, "Empty Model pointer");
+    if (!count || !(grid_step > 0.0) || !(grid_hi >= grid_lo) || !(leaf > 0.0f) || !(pass > 0.0f) || !(tol >= 0.0))
+        return fail(GPR_ERR_INVALID, "bad lattice, cube size or null count");
+    *count = 0;
+    if (cubes) *cubes = 0;
+    // 1. the starting point: first lattice point, in the reference's scan order (x outermost), with |f| <= tol (:1124-1150)
+    std::vector<double> axis;
+    for (double a = grid_lo; a <= grid_hi; a += grid_step) {
+        axis.push_back(a);
+        if (axis.size() > 1024) return fail(GPR_ERR_INVALID, "start lattice has more than 1024 points per axis");
+    }
+    const size_t na = axis.size(), nl = na * na * na;
+    std::vector<double> lx(nl), ly(nl), lz(nl), lf(nl);
+    for (size_t i = 0, g = 0; i < na; ++i)
+        for (size_t j = 0; j < na; ++j)
+            for (size_t k = 0; k < na; ++k, ++g) { lx[g] = axis[i]; ly[g] = axis[j]; lz[g] = axis[k]; }
+    int rc = predict_host(ctx, m, lx.data(), ly.data(), lz.data(), nl, lf.data(), nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    size_t s0 = nl;
+    for (size_t g = 0; g < nl; ++g) if (std::fabs(lf[g]) <= tol) { s0 = g; break; }
+    if (s0 == nl) return fail(GPR_ERR_INVALID, "No starting point found. Relax grid pass.");          // :1153
+    const float sx = (float)lx[s0], sy = (float)ly[s0], sz = (float)lz[s0];
+    const long steps = std::lround(leaf / pass);                                                          // :1201
+    if (steps < 1 || steps > 64) return fail(GPR_ERR_INVALID, "leaf / pass must round to 1 .. 64");
+    const size_t per_cube = (size_t)(steps + 1) * (steps + 1) * (steps + 1);
+    // 2. flood fill by waves.  A cube is identified by its integer offset from the start cube; its centre is obtained
+    // like the reference's recursion does, by repeated float additions of +-leaf along the path — which is the same
+    // value for every path only up to float rounding, so the centre is computed canonically: x first, then y, then z.
+    typedef std::array<long, 3> Idx;
+    auto centre = [&](const Idx& c, float out[3]) {
+        const float s[3] = {sx, sy, sz};
+        for (int a = 0; a < 3; ++a) {
+            float v = s[a];
+            for (long t = 0; t < std::labs(c[a]); ++t) v = c[a] > 0 ? v + leaf : v - leaf;
+            out[a] = v;
+        }
+    };
+    std::set<Idx> visited;
+    std::set<Idx> emitted;                       // lattice index of a kept sample in units of `pass`: shared faces are emitted once
+    std::vector<Idx> frontier(1, Idx{{0, 0, 0}});
+    visited.insert(frontier[0]);
+    std::vector<double> ox, oy, oz, of;
+    size_t ncubes = 0;
+    const size_t MAX_CUBES = (size_t)1 << 20;
+    while (!frontier.empty()) {
+        std::sort(frontier.begin(), frontier.end());
+        const size_t nc = frontier.size();
+        ncubes += nc;
+        if (ncubes > MAX_CUBES) return fail(GPR_ERR_INVALID, "marching sampler: more than 2^20 cubes");
+        std::vector<double> qx(nc * per_cube), qy(nc * per_cube), qz(nc * per_cube), qf(nc * per_cube);
+        for (size_t c = 0; c < nc; ++c) {
+            float ctr[3];
+            centre(frontier[c], ctr);
+            size_t p = c * per_cube;
+            for (long i = 0; i <= steps; ++i)
+                for (long j = 0; j <= steps; ++j)
+                    for (long k = 0; k <= steps; ++k, ++p) {
+                        qx[p] = (double)(ctr[0] - leaf / 2 + (float)i * pass);                             // :1209-1211
+                        qy[p] = (double)(ctr[1] - leaf / 2 + (float)j * pass);
+                        qz[p] = (double)(ctr[2] - leaf / 2 + (float)k * pass);
+                    }
+        }
+        rc = predict_host(ctx, m, qx.data(), qy.data(), qz.data(), qx.size(), qf.data(), nullptr, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        std::vector<Idx> next;
+        for (size_t c = 0; c < nc; ++c) {
+            bool where[6] = {false, false, false, false, false, false};
+            size_t p = c * per_cube;
+            const Idx& ci = frontier[c];
+            for (long i = 0; i <= steps; ++i)
+                for (long j = 0; j <= steps; ++j)
+                    for (long k = 0; k <= steps; ++k, ++p) {
+                        if (!(std::fabs(qf[p]) <= tol)) continue;                                        // :1218
+                        if (i == 0) where[0] = true;
+                        if (i == steps) where[1] = true;
+                        if (j == 0) where[2] = true;
+                        if (j == steps) where[3] = true;
+                        if (k == 0) where[4] = true;
+                        if (k == steps) where[5] = true;
+                        const Idx li{{ci[0] * steps + i, ci[1] * steps + j, ci[2] * steps + k}};
+                        if (emitted.insert(li).second) { ox.push_back(qx[p]); oy.push_back(qy[p]); oz.push_back(qz[p]); of.push_back(qf[p]); }
+                    }
+            for (int d = 0; d < 6; ++d) {                                                                 // :1262-1288
+                if (!where[d]) continue;
+                Idx nb = ci;
+                nb[d / 2] += (d % 2) ? 1 : -1;
+                if (visited.insert(nb).second) next.push_back(nb);
+            }
+        }
+        frontier.swap(next);
+    }
+    *count = ox.size();
+    if (cubes) *cubes = ncubes;
+    const size_t keep = std::min(ox.size(), capacity);
+    if (keep == 0) return GPR_OK;
+    if (var) {
+        std::vector<double> f2(keep);
+        rc = predict_host(ctx, m, ox.data(), oy.data(), oz.data(), keep, f2.data(), var, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    if (x) memcpy(x, ox.data(), keep * sizeof(double));
+    if (y) memcpy(y, oy.data(), keep * sizeof(double));
+    if (z) memcpy(z, oz.data(), keep * sizeof(double));
+    if (f) memcpy(f, of.data(), keep * sizeof(double));
+    return GPR_OK;
+}
+
 int gpr_sample_chart(gpr_ctx* ctx, gpr_model* m, const double* frames, const size_t* counts, size_t n_charts,
                      const double* r_in, const double* th_in, unsigned long long seed, double* sx, double* sy, double* sz,
                      double* f, double* v, size_t* order) {
@@ -1829,6 +1964,106 @@ static int append_incremental(gpr_model* m, const double* x, const double* y, co
     return GPR_OK;
 }
 
+}  // extern "C"
+
+// Incremental update of a model with an indefinite tail block (the node's real setting: cb_update adds touch points to a
+// ThinPlate(2.0) model, src/gp_node.cpp:652-763, and refits from scratch).  The new points join the positive definite
+// leading block — rows of L and of X = L^-1 are appended by the same slab kernels as for an SPD model, with the tail
+// points moved behind them in the internal order — and the trailing block is eliminated again against the extended X
+// (B, Z, S^-1, alpha: bandwidth-bound passes over X, gpr_tail.cu), instead of two n^3/3 factorisations.
+// Returns 1000 (no error set) when the new points do not fit the leading block (non-positive pivot): the caller refits,
+// which re-runs the eviction logic.  Caller holds m->mu.
+constexpr int TAIL_APPEND_FALLBACK = 1000;
+static int append_tail_incremental(gpr_model* m, const double* x, const double* y, const double* z, const double* label,
+                                   const double* sigma2, size_t k) {
+    gpr_ctx* ctx = m->ctx;
+    DeviceCtx* dc = ctx->devs[0];
+    CU(cudaSetDevice(dc->dev));
+    ModelDev& md0 = m->devs[0];
+    if (!md0.have_linv || !md0.have_tail) return TAIL_APPEND_FALLBACK;
+    Workspace* ws = nullptr;
+    int rc = ws_acquire(dc, &ws);
+    if (rc) return rc;
+    struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
+    cudaStream_t st = ws->st;
+    const size_t p = m->n_spd, mt = m->n_tail, n0 = m->n, n1 = n0 + k;
+    const size_t N1 = (n1 + TB - 1) / TB * TB;
+    if (N1 > m->cap) {
+        rc = grow_capacity(m, std::max(N1, (m->cap * 5 / 4 + TB - 1) / TB * TB), st);
+        if (rc) return rc;
+    }
+    ModelDev& md = m->devs[0];
+    const size_t ld = m->cap;
+    const size_t need = append_workspace_doubles(ld);
+    if (m->aws_dbl < need) {
+        cudaFree(m->aws); m->aws = nullptr; m->aws_dbl = 0;
+        CU(cudaMalloc((void**)&m->aws, need * sizeof(double)));
+        m->aws_dbl = need;
+    }
+    CU(cudaEventRecord(ws->ev[0], st));
+    // everything behind the leading block becomes padding in L / X (tile rows beyond the leading block may hold what a
+    // failed first factorisation attempt left there), with matching diagonal-block inverses
+    CU(launch_identity_rows(m->L, md.linv, ld, (int)p, (int)ld, (int)ld, st));
+    CU(launch_dinv_from_x(md.linv, ld, (int)(p / TB), (int)(ld / TB - p / TB), m->Dinv, st));
+    // internal order: [leading block | new points | tail]: move the tail's coordinates, labels and noise k places up
+    rc = ws_reserve(&ws->io, &ws->io_cap, std::max((size_t)14 * TB, 5 * mt));
+    if (rc) return rc;
+    double* tmp = ws->io;
+    const double* srcs[5] = {md.xyz + p, md.xyz + ld + p, md.xyz + 2 * ld + p, m->label + p, m->s2 + p};
+    double* dsts[5] = {md.xyz + p + k, md.xyz + ld + p + k, md.xyz + 2 * ld + p + k, m->label + p + k, m->s2 + p + k};
+    for (int c = 0; c < 5; ++c) CU(cudaMemcpyAsync(tmp + c * mt, srcs[c], mt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    for (int c = 0; c < 5; ++c) CU(cudaMemcpyAsync(dsts[c], tmp + c * mt, mt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(md.xyz + p, x, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(md.xyz + ld + p, y, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(md.xyz + 2 * ld + p, z, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->label + p, label, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (sigma2) CU(cudaMemcpyAsync(m->s2 + p, sigma2, k * sizeof(double), cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(m->s2 + p, 0, k * sizeof(double), st));
+    CU(cudaEventRecord(ws->ev[1], st));
+    for (size_t o = 0; o < k; o += 32) {
+        const int kk = (int)std::min<size_t>(32, k - o);
+        CU(launch_append_slab(md.xyz, ld, m->s2, (int)(p + o), kk, m->L, md.linv, m->Dinv, m->aws, ld, m->kp, o == 0, st));
+    }
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, append_flag_ptr(m->aws, ld), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flag != 0) return TAIL_APPEND_FALLBACK;            // the device state is rebuilt from the host copies by the refit
+    // bookkeeping of the new shape, then the trailing block against the extended factor
+    std::vector<size_t> np;
+    np.reserve(n1);
+    for (size_t i = 0; i < p; ++i) np.push_back(m->perm.empty() ? i : m->perm[i]);
+    for (size_t i = 0; i < k; ++i) np.push_back(n0 + i);
+    for (size_t i = p; i < n0; ++i) np.push_back(m->perm.empty() ? i : m->perm[i]);
+    m->n_spd = p + k; m->nb = (int)((p + k + TB - 1) / TB); m->n = n1; m->N = N1;
+    rc = tail_eliminate(m, dc, ws, false);
+    if (rc) {                                              // e.g. a singular Schur complement: refit decides
+        m->n_spd = p; m->nb = (int)((p + TB - 1) / TB); m->n = n0; m->N = (n0 + TB - 1) / TB * TB;
+        return rc == GPR_ERR_NOT_SPD ? TAIL_APPEND_FALLBACK : rc;
+    }
+    CU(cudaEventRecord(ws->ev[2], st));
+    m->perm.swap(np);
+    host_append(m, x, y, z, label, sigma2, k);
+    std::vector<double> a_int(n1);
+    CU(cudaMemcpyAsync(a_int.data(), md.alpha, n1 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    m->h_alpha.assign(n1, 0.0);
+    for (size_t i = 0; i < n1; ++i) m->h_alpha[m->perm[i]] = a_int[i];
+    for (size_t di = 1; di < m->devs.size(); ++di) {       // copies on the other devices: re-made on demand (the tail slabs' leading dimension may have changed)
+        ModelDev& d = m->devs[di];
+        cudaSetDevice(d.dev);
+        cudaFree(d.tZ); cudaFree(d.tSinv);
+        d.tZ = d.tSinv = nullptr;
+        d.have = d.have_linv = d.have_tail = d.have_fac = false;
+    }
+    cudaSetDevice(dc->dev);
+    std::lock_guard<std::mutex> lk(ctx->tmu);
+    ctx->timings.h2d_ms = ev_ms(ws->ev[0], ws->ev[1]);
+    ctx->timings.append_ms = ev_ms(ws->ev[1], ws->ev[2]);
+    return GPR_OK;
+}
+
+extern "C" {
+
 int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
                const double* sigma2, size_t k) {
     if (!ctx) return fail(GPR_ERR_INVALID, "null context");
@@ -1839,7 +2074,14 @@ int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, con
     const char* force = getenv("GPR_APPEND_REFIT");
     // a permuted internal order (points were evicted during the fit, with or without a tail block left) refits: the
     // incremental path works in the caller's order
-    const bool refit = (force && atoi(force) != 0) || k > 256 || 8 * k > m->n || m->n_tail > 0 || !m->perm.empty();
+    const bool forced = force && atoi(force) != 0;
+    const bool small = k <= 256 && 8 * k <= m->n;
+    if (!forced && small && m->n_tail > 0 && m->n_spd >= 8 * k) {
+        // indefinite-tail model: rows appended to the leading block, trailing block eliminated again
+        const int rc = append_tail_incremental(m, x, y, z, label, sigma2, k);
+        if (rc != TAIL_APPEND_FALLBACK) return rc;
+    }
+    const bool refit = forced || !small || m->n_tail > 0 || !m->perm.empty();
     if (!refit) return append_incremental(m, x, y, z, label, sigma2, k);
     // Large batches: append on the host and refit, like the reference (gp_regressor.hpp:442-459).
     const size_t p = m->hx.size();

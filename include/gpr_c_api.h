@@ -100,6 +100,19 @@ int gpr_predict_device(gpr_ctx* ctx, gpr_model* m, const double* d_qx, const dou
  * `capacity` are written). */
 int gpr_sample_isosurface(gpr_ctx* ctx, gpr_model* m, double lo, double hi, double step, double tol, size_t capacity,
                           double* x, double* y, double* z, double* f, double* var_or_null, size_t* count);
+/* Batched counterpart of the node's marchingSampling / marchingCubes (src/gp_node.cpp:1103-1292; called with leaf 0.06,
+ * pass 0.02 at :258): a flood fill over cubes of edge `leaf` that follows the iso-surface — start at the first point of the
+ * lattice lo, lo+step, ... <= hi (x outermost; the reference: -1.1 .. 1.1 step 0.1) with |f| <= tol, sample every cube on
+ * its (round(leaf/pass) + 1)^3 lattice, keep the samples with |f| <= tol (the variance is their intensity) and expand across
+ * every face that a kept sample touches.  The reference runs one std::thread per cube and one evaluate(q = 1) per sample;
+ * here every wave of the flood fill is one batched evaluation.  Same float (pcl::PointXYZ) coordinate arithmetic.  Samples
+ * on a face shared by two cubes are returned once (the reference removes them afterwards with a PCL voxel filter, which
+ * also averages near-duplicates: that PCL post-processing is not reproduced).  Outputs (host, `capacity` each or NULL) in
+ * discovery order (waves; cubes of a wave by index); *count = kept samples (may exceed capacity), *cubes = cubes visited.
+ * GPR_ERR_INVALID "No starting point found. Relax grid pass." as the reference prints (:1153). */
+int gpr_sample_marching(gpr_ctx* ctx, gpr_model* m, double lo, double hi, double step, float leaf, float pass, double tol,
+                        size_t capacity, double* x, double* y, double* z, double* f, double* var_or_null, size_t* count,
+                        size_t* cubes_or_null);
 /* Batched projection onto the iso-surface f = 0 — AtlasBase::project (include/atlas/atlas.hpp:201-276: fixed-step
  * gradient descent, two evaluate(q = 1) calls per iteration, up to max_iter = 500 iterations per point).
  * Same update rule (x -= step_mul * f(x) * g, g = last accepted un-normalised gradient, first one given by the
@@ -143,12 +156,16 @@ int gpr_model_solve(gpr_ctx* ctx, gpr_model* m, const double* B, size_t nrhs, do
  * incremental path: the new rows of the Cholesky factor and of its inverse are appended (slabs of 32
  * points, two bandwidth-bound products against L^-1 each) and alpha is re-solved through L^-1 with one step of
  * iterative refinement (GPR_APPEND_TRSV=1: by the triangular solves over L); larger batches refit.
+ * A model with an indefinite tail block (the node's real setting, whose cb_update refits per touch, src/gp_node.cpp:652-763)
+ * is updated incrementally too: the new points join the positive definite leading block (rows of L and L^-1 appended,
+ * the tail points moved behind them in the internal order) and the trailing block is eliminated again against the
+ * extended L^-1; if a new point does not fit the leading block (non-positive pivot) the call falls back to the refit.
  * On GPR_ERR_NOT_SPD the model is left as it was before the call.  GPR_APPEND_REFIT=1 forces the refit. */
 int gpr_append(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, const double* z, const double* label,
                const double* sigma2_or_null, size_t k);
 /* Pre-allocates room for `capacity` points so that later appends do not reallocate (growth is otherwise
  * geometric, x1.25).  Invalidates pointers returned earlier by gpr_model_state_get.  No effect on a model with an
- * indefinite tail block (its updates refit). */
+ * indefinite tail block (it grows on demand when it is appended to). */
 int gpr_model_reserve(gpr_ctx* ctx, gpr_model* m, size_t capacity);
 
 /* ---- export / import (the reference has no persistence for the GP) ----------------- */

@@ -838,6 +838,138 @@ def test_batched_sample_on_chart_matches_the_atlas_loop(gpr, orc, ctx):
         assert np.abs(d @ N[c]).max() <= 1e-12
 
 
+def _oracle_marching(o, lo, hi, step, leaf, pas, tol):
+    """src/gp_node.cpp:1103-1292 transcribed (start search :1124-1150, marchingCubes :1195-1292) with the CPU oracle answering
+    the evaluate calls; float32 coordinate arithmetic like pcl::PointXYZ; cubes identified by integer offsets (the reference's
+    octree voxel test), cube centres by repeated float additions of the leaf size."""
+    f32 = np.float32
+    leaf, pas = f32(leaf), f32(pas)
+    axis, a = [], lo
+    while a <= hi:
+        axis.append(a)
+        a += step
+    G = np.array([(x, y, z) for x in axis for y in axis for z in axis])
+    fl = o.predict(G[:, 0], G[:, 1], G[:, 2], threads=os.cpu_count() or 1)[0]
+    hit = np.flatnonzero(np.abs(fl) <= tol)
+    assert len(hit)
+    start = G[hit[0]].astype(f32)
+    steps = int(np.round(leaf / pas))
+
+    def centre(c):
+        out = []
+        for ax in range(3):
+            v = start[ax]
+            for _ in range(abs(c[ax])):
+                v = f32(v + leaf) if c[ax] > 0 else f32(v - leaf)
+            out.append(v)
+        return out
+
+    visited, frontier, kept, cubes = {(0, 0, 0)}, [(0, 0, 0)], {}, 0
+    while frontier:
+        nxt = []
+        for c in sorted(frontier):
+            cubes += 1
+            ctr = centre(c)
+            pts, ijk = [], []
+            for i in range(steps + 1):
+                for j in range(steps + 1):
+                    for k in range(steps + 1):
+                        pts.append([float(f32(f32(ctr[0] - leaf / f32(2)) + f32(f32(i) * pas))),
+                                    float(f32(f32(ctr[1] - leaf / f32(2)) + f32(f32(j) * pas))),
+                                    float(f32(f32(ctr[2] - leaf / f32(2)) + f32(f32(k) * pas)))])
+                        ijk.append((i, j, k))
+            pts = np.array(pts)
+            ff, vv, _ = o.predict(pts[:, 0], pts[:, 1], pts[:, 2], var=True, threads=os.cpu_count() or 1)
+            where = [False] * 6
+            for p, (i, j, k), fi, vi in zip(pts, ijk, ff, vv):
+                if abs(fi) <= tol:
+                    for d, cond in enumerate((i == 0, i == steps, j == 0, j == steps, k == 0, k == steps)):
+                        where[d] = where[d] or cond
+                    kept.setdefault((c[0] * steps + i, c[1] * steps + j, c[2] * steps + k), (p, fi, vi))
+            for d in range(6):
+                if where[d]:
+                    nb = list(c)
+                    nb[d // 2] += 1 if d % 2 else -1
+                    nb = tuple(nb)
+                    if nb not in visited:
+                        visited.add(nb)
+                        nxt.append(nb)
+        frontier = nxt
+    return kept, cubes
+
+
+def test_batched_marching_sampler_matches_the_node_loop(gpr, orc, ctx):
+    """SURVEY §8(f).2, second half: the node's marchingSampling / marchingCubes (src/gp_node.cpp:1103-1292) as a wave-by-wave
+    batched flood fill, against the reference loop transcribed over the CPU oracle: same starting point, same set of
+    visited cubes, same kept samples (coordinates bit for bit, f and v within tolerance)."""
+    g = load_golden("ref_mugD_lattice_spd")
+    P, y, s2, R = g["P"], g["y"], g["s2"], float(g["p0"])
+    reg = gpr.GPRegressor("thin_plate", R, ctx=ctx)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+    o = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, "thin_plate", R, 0.0, factor="llt")
+    kw = dict(lo=-1.1, hi=1.1, step=0.1, leaf=0.12, tol=0.01)          # a coarser leaf than the node's 0.06 keeps the CPU loop short
+    pts, f, v, cubes = reg.sample_marching(m, leaf_pass=0.04, **kw)
+    kept, ref_cubes = _oracle_marching(o, kw["lo"], kw["hi"], kw["step"], kw["leaf"], 0.04, kw["tol"])
+    fo = np.array([k[1] for k in kept.values()])
+    edge = np.abs(np.abs(fo) - 0.01) < 1e-9
+    assert len(pts) > 200 and v.min() > 0
+    if not edge.any():
+        assert cubes == ref_cubes and len(pts) == len(kept)
+        ref_pts = np.array([k[0] for k in kept.values()])
+        order_g = np.lexsort((pts[:, 2], pts[:, 1], pts[:, 0]))
+        order_r = np.lexsort((ref_pts[:, 2], ref_pts[:, 1], ref_pts[:, 0]))
+        assert np.array_equal(pts[order_g], ref_pts[order_r])
+        vo = np.array([k[2] for k in kept.values()])
+        assert np.abs(f[order_g] - fo[order_r]).max() <= 1e-9
+        assert np.abs(v[order_g] - vo[order_r]).max() <= TOL_VAR * np.abs(vo).max()
+    # the node's own parameters (leaf 0.06, pass 0.02, :258): runs, stays on the surface, bounded output
+    pts2, f2, v2, cubes2 = reg.sample_marching(m)
+    assert len(pts2) > len(pts) and np.abs(f2).max() <= 0.01 and cubes2 > cubes
+    with pytest.raises(gpr.GPRegressionException, match="No starting point"):
+        reg.sample_marching(m, tol=1e-12)
+
+
+@pytest.mark.parametrize("case,batches", [("ref_mugD_thinplate_R2_node", (3, 5, 30)), ("ref_jug_thinplate_R2_node", (33, 30, 20))])
+def test_incremental_update_of_an_indefinite_tail_model(gpr, orc, ctx, case, batches):
+    """update<>() on the node's own configuration (ThinPlate(2.0), 15 external points: indefinite K).  The reference's
+    update refits with the pivoted LDLT (gp_regressor.hpp:442-459); here the touch points are appended to the positive
+    definite leading block and the trailing block is eliminated again (no refit: append_ms > 0).  Checked against the
+    pivoted-LDLT oracle (which refits, like the reference) after every batch, and against a fresh fit; crosses a tile
+    boundary and a capacity growth."""
+    g = load_golden(case)
+    P, y, s2, Q = g["P"], g["y"], g["s2"], g["Q"]
+    reg = _reg(gpr, ctx, g)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+    assert m.n_tail == 15
+    o = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, "thin_plate", g["p0"], 0.0, factor="ldlt")
+    rng = np.random.default_rng(len(P))
+    allP, ally, alls = [P], [y], [s2]
+    for k in batches:
+        idx = rng.choice(len(P) - 15, size=k, replace=False)
+        Pn = P[idx] * (1.0 + 0.02 * rng.standard_normal((k, 1))) + 0.01 * rng.standard_normal((k, 3))   # touches near the surface
+        yn, sn = np.zeros(k), np.full(k, 0.05)
+        reg.update(m, Pn[:, 0], Pn[:, 1], Pn[:, 2], yn, sn)
+        assert ctx.timings()["append_ms"] > 0.0 and m.n_tail == 15
+        o.update(Pn[:, 0], Pn[:, 1], Pn[:, 2], yn, sn)
+        allP.append(Pn); ally.append(yn); alls.append(sn)
+        assert relerr(m.alpha, o.alpha) <= TOL_ALPHA
+        f, v, gr = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True)
+        fo, vo, go = o.predict(Q[:, 0], Q[:, 1], Q[:, 2], var=True, grad=True, threads=4)
+        assert relerr(f, fo) <= TOL_MEAN and relerr(gr, go) <= TOL_MEAN and _signs_agree(f, fo)
+        assert np.abs(v - vo).max() <= TOL_VAR * np.abs(vo).max()
+        f1, v1 = reg.evaluate(m, Q[:1, 0], Q[:1, 1], Q[:1, 2], var=True)                        # fused single-query kernel
+        assert abs(f1[0] - fo[0]) <= TOL_MEAN * np.abs(fo).max() and abs(v1[0] - vo[0]) <= TOL_VAR * np.abs(vo).max()
+    A, ya, sa = np.vstack(allP), np.concatenate(ally), np.concatenate(alls)
+    fresh = reg.create(A[:, 0], A[:, 1], A[:, 2], ya, sa)
+    assert fresh.n == m.n and fresh.n_tail == 15 and relerr(m.alpha, fresh.alpha) <= TOL_ALPHA
+    # a point that cannot join the leading block (far outside, farther than R from the cloud): falls back to the refit,
+    # which moves it into the trailing block
+    far = np.array([[0.0, 0.0, 2.6]])
+    reg.update(m, far[:, 0], far[:, 1], far[:, 2], np.ones(1), np.full(1, 0.1))
+    o.update(far[:, 0], far[:, 1], far[:, 2], np.ones(1), np.full(1, 0.1))
+    assert m.n_tail >= 16 and relerr(m.alpha, o.alpha) <= TOL_ALPHA
+
+
 def test_model_save_and_load_round_trip(gpr, ctx, tmp_path):
     """Export / import: with the stored factor the loaded model answers without refactorising
     (same alpha and factor bits); without it (and for an indefinite-tail model) it is refitted from the stored
