@@ -31,10 +31,11 @@ alg = {  # algorithmic work per launch
     "trsv_forward_kernel": ("bytes", 4.0 * n * n),
     "trsv_backward_kernel": ("bytes", 4.0 * n * n),
     "var_tiles_kernel": ("flop", float(n) * n * q),
+    "var_trsm_kernel": ("flop", float(n) * n * q),
     "predict_thread_kernel": ("pairs", float(n) * q),
 }
 lines = ["# ncu summary: %s" % rep.split("/")[-1], "",
-         "One fit at n = %d + L^-1 + one mean+variance batch of %d queries (tools/prof_target.py), `ncu --set full "
+         "One fit at n = %d + one mean+variance batch of %d queries (tools/prof_target.py), `ncu --set full "
          "--clock-control none`. Durations are cold-cache, serialised ncu replays: compare shares, not absolutes." % (n, q), "",
          "| kernel | " + " | ".join(w[1] for w in want) + " | algorithmic work | achieved |", "|---|" + "---|" * (len(want) + 2)]
 for r in rows[2:]:
