@@ -112,6 +112,7 @@ def lib():
         L.gpr_selftest_leaf.argtypes = [_dp, _dp, C.POINTER(ci)]
         L.gpr_selftest_factor.argtypes = [_dp, ci, _dp, ci, C.POINTER(C.c_longlong)]
         L.gpr_selftest_peak.argtypes = [ci, ci, _dp]
+        L.gpr_selftest_i8gemm.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
         L.gpr_selftest_factor_trace.argtypes = [ci, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         _lib = L
     return _lib
@@ -129,7 +130,7 @@ C_ABI_SYMBOLS = [
 ]
 # Engine self-tests / pipe probes (csrc/gpr_selftest.h): exported for tests/ and bench.py, not part of the boundary.
 SELFTEST_SYMBOLS = ["gpr_selftest_gemm", "gpr_selftest_leaf", "gpr_selftest_factor", "gpr_selftest_peak",
-                    "gpr_selftest_factor_trace"]
+                    "gpr_selftest_factor_trace", "gpr_selftest_i8gemm"]
 
 
 def _check(rc):
@@ -448,6 +449,19 @@ def selftest_factor(A, want_inverse=False, serial=False):
     if rc not in (GPR_OK, GPR_ERR_NOT_SPD):
         _check(rc)
     return np.tril(A), (None if X is None else np.ascontiguousarray(X)), piv.value
+
+
+def selftest_i8gemm(A, B, levels=None, tri=False):
+    """Raw level accumulators of the INT8 tensor-core engine: A (S, M, K), B (S, N, K) int8 -> C (levels, M, N) int32 with
+    C[l] = sum_{t+u=l} A[t] @ B[u].T (row tile r of a lower-triangular A only visits k < 128 (r + 1))."""
+    A = np.ascontiguousarray(A, dtype=np.int8)
+    B = np.ascontiguousarray(B, dtype=np.int8)
+    S, M, K = A.shape
+    N = B.shape[1]
+    levels = S if levels is None else levels
+    Cm = np.zeros((levels, M, N), dtype=np.int32)
+    _check(lib().gpr_selftest_i8gemm(A.ctypes.data, B.ctypes.data, S, levels, M, N, K, int(tri), Cm.ctypes.data))
+    return Cm
 
 
 def selftest_peak(which, ctas_per_sm=4):

@@ -71,6 +71,8 @@ struct Workspace {
     double* tailw = nullptr; size_t tailw_dbl = 0;     // W = Z^T k_1 of the indefinite-tail correction
     double* hio = nullptr; double* hio_dev = nullptr;  // pinned host buffer mapped into the device (q <= 8 path)
     double* small = nullptr; size_t small_dbl = 0; size_t small_N = 0;   // scratch + tickets of the fused small-batch kernel
+    signed char* oz_ks = nullptr; size_t oz_ks_bytes = 0;                // int8 slices of the K* panel (gpr_ozaki.cu)
+    int* oz_ctrl = nullptr;
 };
 
 struct DeviceCtx {
@@ -193,6 +195,8 @@ struct ModelDev {            // what predict needs, per device
     // devices of the context and in cross-process replicas are owned.
     double* lfac = nullptr; double* dinv = nullptr;
     bool have = false, have_linv = false, have_tail = false, have_fac = false, own_fac = false;
+    // int8 slices of X = L^-1 and its per-row power-of-two scales, for the variance on the INT8 tensor cores (gpr_ozaki.cu)
+    signed char* oz_xs = nullptr; double* oz_scale = nullptr; int oz_S = 0; size_t oz_ld = 0;
 };
 
 struct gpr_model {
@@ -255,6 +259,8 @@ static void free_factor(gpr_model* m) {
         cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.tZ); cudaFree(d.tSinv);
         big_free(m->ctx, d.dev, d.linv, m->cap * m->cap * sizeof(double));
         if (d.own_fac) { big_free(m->ctx, d.dev, d.lfac, m->cap * m->cap * sizeof(double)); cudaFree(d.dinv); }
+        cudaFree(d.oz_xs); cudaFree(d.oz_scale);
+        d.oz_xs = nullptr; d.oz_scale = nullptr; d.oz_S = 0; d.oz_ld = 0;
         d.xyz = d.alpha = d.linv = d.tZ = d.tSinv = d.lfac = d.dinv = nullptr;
         d.have = d.have_linv = d.have_tail = d.have_fac = d.own_fac = false;
     }
@@ -671,6 +677,24 @@ static int ensure_on_device(gpr_model* m, size_t di, bool need_linv, bool need_f
     return GPR_OK;
 }
 
+// Slices of X = L^-1 for the INT8 tensor-core variance (gpr_ozaki.cu), built once per model, device and slice count.
+static int ensure_ozaki_slices(gpr_model* m, size_t di, int S, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    ModelDev& md = m->devs[di];
+    if (md.oz_xs && md.oz_S == S && md.oz_ld == m->cap) return GPR_OK;
+    CU(cudaSetDevice(md.dev));
+    cudaFree(md.oz_xs); cudaFree(md.oz_scale);
+    md.oz_xs = nullptr; md.oz_scale = nullptr; md.oz_S = 0;
+    const size_t ld = m->cap;
+    CU(cudaMalloc((void**)&md.oz_xs, (size_t)S * ld * ld));
+    CU(cudaMalloc((void**)&md.oz_scale, 2 * ld * sizeof(double)));          // scales | row-max scratch
+    CU(launch_ozaki_slice_x(md.linv, ld, m->nb * TB, S, md.oz_xs, md.oz_scale,
+                            reinterpret_cast<unsigned long long*>(md.oz_scale + ld), st));
+    CU(cudaStreamSynchronize(st));
+    md.oz_S = S; md.oz_ld = ld;
+    return GPR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // predict on one device.  in_dev/out_dev: pointers are device memory of that device.
 // ------------------------------------------------------------------------------------------------
@@ -693,8 +717,20 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
     //   * product with X = L^-1 (var_tiles_kernel / the fused q <= 8 kernel): no dependency chain, spreads a small
     //     batch over all SMs; used whenever X is resident anyway, for small batches and for indefinite-tail models.
     // GPR_VAR_MODE=trsm|product forces one (tests, bench).
-    bool use_trsm = false;
-    if (want_var && io.q > 8 && m->n_tail == 0 && m->devs[0].have_fac) {
+    bool use_trsm = false, use_oz = false;
+    int oz_S = 7, oz_levels = 7;
+    if (want_var && io.q > 8 && m->n_tail == 0) {
+        // GPR_VAR_MODE=ozaki: the product with X on the INT8 tensor cores (tcgen05 kind::i8), FP64-equivalent by slicing;
+        // GPR_OZAKI_SLICES (default 7) slices of 7 bits per operand, GPR_OZAKI_LEVELS (default = slices) levels kept.
+        const char* mode_env = getenv("GPR_VAR_MODE");
+        if (mode_env && !strcmp(mode_env, "ozaki")) {
+            use_oz = true;
+            if (const char* e = getenv("GPR_OZAKI_SLICES")) oz_S = std::max(2, std::min(8, atoi(e)));
+            oz_levels = oz_S;
+            if (const char* e = getenv("GPR_OZAKI_LEVELS")) oz_levels = std::max(1, std::min(8, atoi(e)));
+        }
+    }
+    if (!use_oz && want_var && io.q > 8 && m->n_tail == 0 && m->devs[0].have_fac) {
         const char* mode_env = getenv("GPR_VAR_MODE");
         static const long min_q = getenv("GPR_TRSM_MIN_Q") ? atol(getenv("GPR_TRSM_MIN_Q")) : 4096;
         if (mode_env && !strcmp(mode_env, "trsm")) use_trsm = true;
@@ -705,7 +741,7 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
             use_trsm = !have_x && (long)io.q >= min_q;
         }
     }
-    int rc = ensure_on_device(m, di, want_var && !use_trsm, use_trsm);
+    int rc = ensure_on_device(m, di, want_var && !use_trsm, use_trsm);          // the INT8 path needs X = L^-1 too
     if (rc) return rc;
     CU(cudaSetDevice(dc->dev));
     ModelDev& md = m->devs[di];
@@ -772,6 +808,19 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         if (rc) return rc;
         rc = ws_reserve(&ws->partial, &ws->partial_dbl, std::max((size_t)m->nb * panel_ld_max, (size_t)8 * 8 * N));
         if (rc) return rc;
+        if (use_oz) {
+            const size_t need = (size_t)oz_S * panel_ld_max * ld;
+            if (ws->oz_ks_bytes < need) {
+                if (ws->oz_ks) CU(cudaFree(ws->oz_ks));
+                ws->oz_ks = nullptr; ws->oz_ks_bytes = 0;
+                CU(cudaMalloc((void**)&ws->oz_ks, need));
+                CU(cudaMemsetAsync(ws->oz_ks, 0, need, st));
+                ws->oz_ks_bytes = need;
+            }
+            if (!ws->oz_ctrl) CU(cudaMalloc((void**)&ws->oz_ctrl, 4 * sizeof(int)));
+            rc = ensure_ozaki_slices(m, di, oz_S, st);
+            if (rc) return rc;
+        }
     }
     float t_mean = 0, t_var = 0, t_h2d = 0, t_d2h = 0;
     for (size_t b0 = 0; b0 < io.q; b0 += batch) {
@@ -804,6 +853,17 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         CU(cudaEventRecord(ws->ev[2], st));
         if (want_var) {
             if (small_var) CU(launch_variance_small(md.linv, ld, m->nb * TB, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+            else if (use_oz) {
+                // slice the K* panel (one power-of-two scale: |k*| <= k(0) for these kernels), multiply on the INT8 tensor
+                // cores, recombine + column norms in the kernel's FP64 epilogue, then the usual fixed-order finalize
+                int ge = 0;
+                frexp(m->k0, &ge);
+                const double cs = ldexp(1.0, ge);
+                CU(launch_ozaki_slice_panel(ws->panel, pld, (int)bq, m->nb * TB, 1.0 / cs, oz_S, ws->oz_ks, ld, pld, st));
+                CU(launch_ozaki_product(md.oz_xs, ld, ld * ld, m->nb, ws->oz_ks, ld, pld * ld, (int)bq, pld, (size_t)m->nb * TB, 1, oz_S,
+                                        oz_levels, md.oz_scale, cs, ws->partial, ws->oz_ctrl, nullptr, st));
+                CU(launch_var_finalize(ws->partial, pld, m->nb, (int)bq, m->k0, v, st));
+            }
             else if (use_trsm) CU(launch_variance_trsm(md.lfac, ld, m->nb, md.dinv, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
             else CU(launch_variance(md.linv, ld, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
             if (m->n_tail > 0) {
@@ -835,6 +895,11 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         CU(cudaStreamSynchronize(st));
         t_h2d += ev_ms(ws->ev[0], ws->ev[1]); t_mean += ev_ms(ws->ev[1], ws->ev[2]);
         t_var += ev_ms(ws->ev[2], ws->ev[3]); t_d2h += ev_ms(ws->ev[3], ws->ev[4]);
+    }
+    if (use_oz) {
+        int ctrl[2] = {0, 0};
+        CU(cudaMemcpy(ctrl, ws->oz_ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
+        if (ctrl[1] != 0) return fail(GPR_ERR_CUDA, "INT8 tensor-core variance kernel aborted (a pipeline wait timed out)");
     }
     if (mean_ms) *mean_ms = t_mean;
     if (var_ms) *var_ms = t_var;
@@ -903,6 +968,7 @@ int gpr_ctx_destroy(gpr_ctx* ctx) {
         cudaSetDevice(dc->dev);
         for (Workspace* ws : dc->free_ws) {
             cudaFree(ws->io); cudaFree(ws->panel); cudaFree(ws->partial); cudaFree(ws->mpart); cudaFree(ws->small); cudaFree(ws->tailw);
+            cudaFree(ws->oz_ks); cudaFree(ws->oz_ctrl);
             if (ws->hio) cudaFreeHost(ws->hio);
             for (auto& e : ws->ev) cudaEventDestroy(e);
             cudaStreamDestroy(ws->st);
@@ -2291,6 +2357,35 @@ int gpr_selftest_factor_trace(int nb, long long* h_trace, long long* leaf_cycles
     }
     cudaFree(A); cudaFree(D); cudaFree(scratch); cudaFree(tr);
     return info[1] || info[2] ? GPR_ERR_CUDA : GPR_OK;
+}
+
+// INT8 tensor-core engine self-test (gpr_ozaki.cu): raw level accumulators C[l] = sum_{t+u=l} A_t B_u^T for int8 slice
+// tensors A [S][M][K], B [S][N][K] (host, K contiguous); M multiple of 128, N of 64, K of 64; tri: A lower triangular by
+// 128-row tiles (row tile r only visits k < 128 (r + 1)).  hC: [levels][M][N] int32.
+int gpr_selftest_i8gemm(const signed char* hA, const signed char* hB, int S, int levels, int M, int Nq, int K, int tri, int* hC) {
+    if (!hA || !hB || !hC || M % 128 || Nq % 64 || K % 64 || S < 1 || S > 8) return fail(GPR_ERR_INVALID, "bad shape");
+    signed char *A, *B; int *C, *ctrl; double *scale, *partial;
+    const size_t qpad = (size_t)(Nq + 127) / 128 * 128;
+    CU(cudaMalloc((void**)&A, (size_t)S * M * K));
+    CU(cudaMalloc((void**)&B, (size_t)S * Nq * K));
+    CU(cudaMalloc((void**)&C, (size_t)levels * M * Nq * sizeof(int)));
+    CU(cudaMalloc((void**)&ctrl, 4 * sizeof(int)));
+    CU(cudaMalloc((void**)&scale, (size_t)M * sizeof(double)));
+    CU(cudaMalloc((void**)&partial, (size_t)(M / 128) * qpad * sizeof(double)));
+    CU(cudaMemcpy(A, hA, (size_t)S * M * K, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(B, hB, (size_t)S * Nq * K, cudaMemcpyHostToDevice));
+    CU(cudaMemset(C, 0, (size_t)levels * M * Nq * sizeof(int)));
+    std::vector<double> ones(M, 1.0);
+    CU(cudaMemcpy(scale, ones.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice));
+    CU(launch_ozaki_product(A, (size_t)K, (size_t)M * K, M / 128, B, (size_t)K, (size_t)Nq * K, Nq, qpad, (size_t)K, tri, S, levels, scale, 1.0,
+                            partial, ctrl, C, 0));
+    CU(cudaDeviceSynchronize());
+    int hctrl[2];
+    CU(cudaMemcpy(hctrl, ctrl, sizeof hctrl, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hC, C, (size_t)levels * M * Nq * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(ctrl); cudaFree(scale); cudaFree(partial);
+    if (hctrl[1] != 0) return fail(GPR_ERR_CUDA, "INT8 tensor-core kernel aborted (a pipeline wait timed out)");
+    return GPR_OK;
 }
 
 int gpr_selftest_peak(int which, int ctas_per_sm, double* tflops) {

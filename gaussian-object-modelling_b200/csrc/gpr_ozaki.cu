@@ -1,0 +1,406 @@
+// gpr_ozaki.cu — K3'': the variance product V = X K*^T (X = L^-1) on the INT8 tensor cores of sm_100a
+// (tcgen05.mma kind::i8, TMEM int32 accumulators, TMA operand feeds), FP64-equivalent by Ozaki-style slicing.
+//
+// Why: the FP64 tensor pipe (DMMA) is the roof of var_tiles_kernel / var_trsm_kernel (37 TF/s); tcgen05 has no f64
+// kind, but it multiplies 8-bit integers EXACTLY into 32-bit accumulators at ~60x that rate.  So
+//   X   ~ 2^(e_i) * sum_t 2^(-6-7t) A_t      (row i scaled by a power of two, A_t int8 slices, |A_t| <= 64)
+//   K*  ~ 2^(g)   * sum_u 2^(-6-7u) B_u      (one power-of-two scale per batch, B_u int8 slices)
+//   V_iq = 2^(e_i+g) * sum_l 2^(-12-7l) * [ sum_{t+u=l} sum_k A_t[i,k] B_u[q,k] ]          l = 0 .. levels-1
+// where every bracket is an exact integer (|.| < 2^31 for k <= 65536 and up to 8 pairs per level) computed by int8
+// MMAs, and the few levels are recombined in FP64 in the epilogue, which also reduces the squared column norms per
+// 128-row tile exactly like the DMMA kernels (partial[row tile][query] -> var_finalize_kernel).  Slices beyond
+// `levels` are dropped: truncation error ~ 2^(-7 levels) relative to (row max of X) x (max of K*) x sqrt(k) — the
+// slice count is chosen against the variance tolerance (profiles/ozaki_slicing_study_r2.json, tools/ozaki_study.py).
+//
+// Kernel structure (one CTA per SM, 128 threads, persistent over (row tile, query tile) tasks):
+//   * operands: int8 slice tensors [slice][row][k] (k contiguous = K-major), fetched by TMA (3-D boxes
+//     {64 k, 128 or 64 rows, S slices}, SWIZZLE_64B) into a ring of shared-memory stages, completion on mbarriers;
+//   * one thread issues the TMA loads and the tcgen05.mma instructions (M = 128, N = 64, K = 32 per instruction; all
+//     slice pairs of a k-block reuse the stage), tcgen05.commit releases a stage / signals the epilogue;
+//   * accumulators: `levels` x 64 TMEM columns (<= 512), one 128 x 64 int32 tile per level;
+//   * epilogue: all four warps read their 32 TMEM lanes with tcgen05.ld, recombine in FP64, square, reduce.
+// X is lower triangular: row tile rt only visits k < 128 (rt + 1).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "gpr_common.cuh"
+#include "gpr_kernels.h"
+
+namespace gpr {
+
+constexpr int OZ_BM = 128;        // rows of X per task (UMMA M)
+constexpr int OZ_BN = 64;         // queries per task (UMMA N)
+constexpr int OZ_BK = 64;         // k per pipeline stage (bytes per row = SWIZZLE_64B span); 2 MMAs of K = 32
+constexpr int OZ_THREADS = 128;
+constexpr int OZ_TMEM_COLS = 512;
+constexpr int OZ_A_SLICE_BYTES = OZ_BM * OZ_BK;     // 8 KB
+constexpr int OZ_B_SLICE_BYTES = OZ_BN * OZ_BK;     // 4 KB
+constexpr long long OZ_TIMEOUT = 4000000000LL;      // cycles (~2 s): a bug must not hang the GPU
+
+struct OzArgs {
+    int S, levels;                // slices per operand; levels = pairs (t, u) with t + u < levels are used
+    int stages;                   // pipeline depth
+    int nrt, nqt;                 // row tiles (128), query tiles (64)
+    int tri;                      // 1: row tile rt needs k < 128 (rt + 1) only
+    int kblocks;                  // K / 64 (tri == 0)
+    const double* row_scale;      // per row of X: 2^(e_i)
+    double col_scale;             // 2^(g)
+    double* partial;              // [nrt][q_pad]
+    size_t q_pad;
+    int* ctrl;                    // [0] task counter, [1] abort flag
+    int* dbg;                     // optional raw accumulators [levels][nrt*128][nqt*64]
+    int gr, gq;                   // co-scheduled group: gr row tiles x gq query tiles
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Returns false after ~2 s (a lost arrival must end the kernel, not hang the device).
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > OZ_TIMEOUT) return false;
+    return true;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor of one K-major slice tile written by TMA with SWIZZLE_64B: rows of 64 bytes, 8-row
+// groups 512 bytes apart (SBO), leading-dimension field 1 (ignored for swizzled K-major), descriptor version 1
+// (sm_100), layout type 4 = SWIZZLE_64B.  byte_off: K offset inside the 64-byte row (0 or 32).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr, uint32_t byte_off) {
+    uint64_t d = (uint64_t)(((smem_addr + byte_off) >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+// Instruction descriptor, kind::i8: D = S32 (c_format 2), A and B signed 8-bit (format 1), both K-major, N >> 3, M >> 4.
+__device__ __forceinline__ uint32_t umma_idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a) {
+    extern __shared__ __align__(1024) uint8_t oz_smem[];
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accum_bar;
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_task, s_abort;
+    __shared__ double sred[4][OZ_BN];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t stage_bytes = (uint32_t)a.S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)oz_smem + 1023) & ~(uintptr_t)1023);
+
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        s_abort = 0;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(OZ_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = umma_idesc_i8(OZ_BM, OZ_BN);
+
+    uint32_t jglob = 0;                 // k-blocks issued so far by this CTA (ring position; thread 0 only)
+    uint32_t task_parity = 0;
+    const int per_group = a.gr * a.gq;
+    const int qgroups = (a.nqt + a.gq - 1) / a.gq;
+    const int rgroups = (a.nrt + a.gr - 1) / a.gr;
+    const int ntasks = rgroups * qgroups * per_group;
+
+    for (;;) {
+        if (tid == 0) { s_task = atomicAdd(a.ctrl, 1); if (ld_volatile(a.ctrl + 1) != 0) s_abort = 1; }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        const int task = s_task;
+        if (task >= ntasks || s_abort) break;
+        const int g = task / per_group, w = task % per_group;
+        const int rg = g / qgroups, qg = g % qgroups;
+        const int rt = a.nrt - 1 - (rg * a.gr + w % a.gr);          // longest rows first
+        const int qt = qg * a.gq + w / a.gr;
+        if (rt < 0 || qt >= a.nqt) continue;                        // padding of the group grid (block-uniform)
+        const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
+
+        if (tid == 0) {
+            bool ok = true;
+            auto load = [&](uint32_t j, int kb) {
+                const uint32_t s = j % (uint32_t)a.stages, u = j / (uint32_t)a.stages;
+                if (u > 0 && !mbar_wait(&empty_bar[s], (u - 1) & 1)) { ok = false; return; }
+                uint8_t* sa = base + (size_t)s * stage_bytes;
+                uint8_t* sb = sa + (size_t)a.S * OZ_A_SLICE_BYTES;
+                mbar_expect_tx(&full_bar[s], stage_bytes);
+                tma_load_3d(sa, &tmA, &full_bar[s], kb * OZ_BK, rt * OZ_BM, 0);
+                tma_load_3d(sb, &tmB, &full_bar[s], kb * OZ_BK, qt * OZ_BN, 0);
+            };
+            const int pre = nkb < a.stages ? nkb : a.stages;
+            for (int i = 0; i < pre && ok; ++i) load(jglob + i, i);
+            for (int i = 0; i < nkb && ok; ++i) {
+                const uint32_t j = jglob + i, s = j % (uint32_t)a.stages, u = j / (uint32_t)a.stages;
+                if (!mbar_wait(&full_bar[s], u & 1)) { ok = false; break; }
+                tc_fence_after();
+                const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+                const uint32_t sb = sa + (uint32_t)a.S * OZ_A_SLICE_BYTES;
+                for (int l = 0; l < a.levels; ++l) {
+                    const uint32_t d = tmem + (uint32_t)(l * OZ_BN);
+                    bool first = (i == 0);
+                    for (int t = 0; t <= l; ++t) {
+                        const int uu = l - t;
+                        if (t >= a.S || uu >= a.S) continue;
+#pragma unroll
+                        for (int ks = 0; ks < OZ_BK / 32; ++ks) {
+                            umma_i8(d, umma_desc_sw64(sa + t * OZ_A_SLICE_BYTES, ks * 32),
+                                    umma_desc_sw64(sb + uu * OZ_B_SLICE_BYTES, ks * 32), idesc, first ? 0u : 1u);
+                            first = false;
+                        }
+                    }
+                }
+                umma_commit(&empty_bar[s]);                            // stage free once these MMAs have read it
+                if (i >= 1 && i - 1 + a.stages < nkb) load(jglob + i - 1 + a.stages, i - 1 + a.stages);
+            }
+            if (ok) umma_commit(&accum_bar);                           // all MMAs of the task done -> epilogue
+            else { atomicExch(a.ctrl + 1, 1); s_abort = 1; }
+            jglob += (uint32_t)nkb;
+        }
+        __syncwarp();
+        // ---- epilogue: every thread owns TMEM lane = its row of the tile -------------------------------------
+        bool got = mbar_wait(&accum_bar, task_parity);
+        if (!got) { atomicExch(a.ctrl + 1, 1); }
+        task_parity ^= 1;
+        tc_fence_after();
+        const int row = rt * OZ_BM + tid;
+        const double rs = a.row_scale[row] * a.col_scale;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+        for (int c = 0; c < OZ_BN / 16; ++c) {
+            double acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+            for (int l = a.levels - 1; l >= 0; --l) {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + (uint32_t)(l * OZ_BN + 16 * c), v);
+                const double wl = __longlong_as_double((long long)(1023 - 12 - 7 * l) << 52);      // 2^(-12-7l)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = fma((double)(int)v[j], wl, acc[j]);
+                if (a.dbg) {
+                    const size_t ldq = (size_t)a.nqt * OZ_BN;
+                    int* o = a.dbg + ((size_t)l * a.nrt * OZ_BM + row) * ldq + (size_t)qt * OZ_BN + 16 * c;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = (int)v[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const double vv = acc[j] * rs;
+                double s = vv * vv;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) sred[warp][16 * c + j] = s;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (tid < OZ_BN)
+            a.partial[(size_t)rt * a.q_pad + (size_t)qt * OZ_BN + tid] = (sred[0][tid] + sred[1][tid]) + (sred[2][tid] + sred[3][tid]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(OZ_TMEM_COLS) : "memory");
+}
+
+// ---- slicing kernels ---------------------------------------------------------------------------------------
+// Row maxima of |X| over the lower triangle (X column-major, ld): bits of the (non-negative) doubles order like
+// integers, so atomicMax on the bit pattern is exact.
+__global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict__ X, size_t ld, int n, unsigned long long* rowmax) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int k0 = blockIdx.y * 256;
+    if (i >= n) return;
+    double m = 0.0;
+    const int k1 = min(k0 + 256, i + 1);
+    for (int k = k0; k < k1; ++k) m = fmax(m, fabs(X[(size_t)k * ld + i]));
+    if (m > 0.0) atomicMax(rowmax + i, (unsigned long long)__double_as_longlong(m));
+}
+// row_scale[i] = 2^ceil(log2(max)) (>= max, a power of two; 1 for an empty row)
+__global__ void oz_rowscale_kernel(const unsigned long long* rowmax, int n, double* row_scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = __longlong_as_double((long long)rowmax[i]);
+    int e = 0;
+    if (m > 0.0) { frexp(m, &e); }                       // m = f * 2^e, f in [0.5, 1)  ->  2^e >= m
+    row_scale[i] = ldexp(1.0, e);
+}
+// One value -> S signed slices: v in [-1, 1];  I_0 = rint(64 v), r = 64 v - I_0;  I_t = rint(128 r), r = 128 r - I_t ...
+__device__ __forceinline__ void oz_slice(double v, int S, signed char* out, size_t stride) {
+    double r = v * 64.0;
+    for (int t = 0; t < S; ++t) {
+        const double it = rint(r);
+        out[(size_t)t * stride] = (signed char)(int)it;
+        r = (r - it) * 128.0;
+    }
+}
+// Slices of a column-major FP64 matrix M (element (row r, col c) at M[c*ld + r]) into K-major int8 tensors
+// out[t][r][c] (c contiguous, row pitch out_ld, slice pitch out_slice): 64 x 64 tiles through shared memory so that both the
+// FP64 reads (along r) and the byte writes (along c) are coalesced.  scale_rows: per-row power-of-two scale (X), or
+// nullptr with one common scale inv_scale (the K* panel).  tri: entries with c > r are structural zeros.
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ M, size_t ld, int rows, int cols,
+                                                        const double* __restrict__ scale_rows, double inv_scale, int tri,
+                                                        int S, signed char* __restrict__ out, size_t out_ld, size_t out_slice) {
+    __shared__ double tile[64][65];
+    const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    if (tri && c0 > r0 + 63) return;                     // block entirely above the diagonal: left zero by the memset
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        const int rr = e & 63, cc = e >> 6;
+        const int r = r0 + rr, c = c0 + cc;
+        tile[rr][cc] = (r < rows && c < cols && !(tri && c > r)) ? M[(size_t)c * ld + r] : 0.0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        const int cc = e & 63, rr = e >> 6;
+        const int r = r0 + rr, c = c0 + cc;
+        if (r >= rows || c >= cols) continue;
+        const double sc = scale_rows ? 1.0 / scale_rows[r] : inv_scale;
+        oz_slice(tile[rr][cc] * sc, S, out + (size_t)r * out_ld + c, out_slice);
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// [slice][row][k] int8, k contiguous with row pitch `pitch` bytes and slice pitch `slice_pitch`; box {64, box_rows, S}.
+static cudaError_t make_map(CUtensorMap* tm, const signed char* ptr, size_t k_extent, size_t rows, int S, size_t pitch,
+                            size_t slice_pitch, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return cudaErrorNotSupported;
+    cuuint64_t dims[3] = {(cuuint64_t)k_extent, (cuuint64_t)rows, (cuuint64_t)S};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)slice_pitch};
+    cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, (cuuint32_t)S};
+    cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<signed char*>(ptr), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+int ozaki_stages(int S) {
+    const int stage = S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
+    int st = (int)((220 * 1024) / stage);
+    return st > 6 ? 6 : (st < 1 ? 1 : st);
+}
+
+// Launch over slice tensors that are already built.  As: [S][rows_pad][k_pad] (rows_pad = 128 nrt, k pitch = a_pitch);
+// Bs: [S][q_pad][k_pad'] (k pitch = b_pitch).  ctrl: 2 ints.  dbg: optional raw accumulators.
+cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a_slice, int nrt, const signed char* Bs, size_t b_pitch,
+                                 size_t b_slice, int q, size_t q_pad, size_t k_extent, int tri, int S, int levels,
+                                 const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, cudaStream_t st) {
+    static PerDeviceOnce attr_done;
+    const int cur = PerDeviceOnce::current();
+    const size_t smem = (size_t)220 * 1024 + 1024;
+    if (!attr_done.done(cur)) {
+        cudaError_t e = cudaFuncSetAttribute(ozaki_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done.set(cur);
+    }
+    if (S < 1 || S > 8 || levels < 1 || levels > 8 || levels * OZ_BN > OZ_TMEM_COLS) return cudaErrorInvalidValue;
+    CUtensorMap tmA, tmB;
+    cudaError_t e = make_map(&tmA, As, k_extent, (size_t)nrt * OZ_BM, S, a_pitch, a_slice, OZ_BM);
+    if (e != cudaSuccess) return e;
+    e = make_map(&tmB, Bs, k_extent, q_pad, S, b_pitch, b_slice, OZ_BN);
+    if (e != cudaSuccess) return e;
+    OzArgs a;
+    a.S = S; a.levels = levels; a.stages = ozaki_stages(S);
+    a.nrt = nrt; a.nqt = (int)((q + OZ_BN - 1) / OZ_BN); a.tri = tri; a.kblocks = (int)(k_extent / OZ_BK);
+    a.row_scale = row_scale; a.col_scale = col_scale; a.partial = partial; a.q_pad = q_pad; a.ctrl = ctrl; a.dbg = dbg;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    a.gr = 4;
+    a.gq = sms / a.gr > 0 ? sms / a.gr : 1;
+    if (a.gq > a.nqt) a.gq = a.nqt;
+    if (a.gr > a.nrt) a.gr = a.nrt;
+    e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const int tasks = ((a.nrt + a.gr - 1) / a.gr) * ((a.nqt + a.gq - 1) / a.gq) * a.gr * a.gq;
+    ozaki_var_kernel<<<tasks < sms ? tasks : sms, OZ_THREADS, smem, st>>>(tmA, tmB, a);
+    return cudaGetLastError();
+}
+
+// Slices of X = L^-1 (lower triangular, column-major n x n with leading dimension ld; rows padded to 128 nrt):
+// Xs[t][i][k], row pitch = slice row count = ld.  rowmax: ld 8-byte words of scratch.
+cudaError_t launch_ozaki_slice_x(const double* X, size_t ld, int n_rows, int S, signed char* Xs, double* row_scale,
+                                 unsigned long long* rowmax, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(rowmax, 0, ld * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(Xs, 0, (size_t)S * ld * ld, st);
+    if (e != cudaSuccess) return e;
+    oz_rowmax_kernel<<<dim3((n_rows + 255) / 256, (n_rows + 255) / 256), 256, 0, st>>>(X, ld, n_rows, rowmax);
+    oz_rowscale_kernel<<<(int)((ld + 255) / 256), 256, 0, st>>>(rowmax, (int)ld, row_scale);
+    oz_slice_kernel<<<dim3((n_rows + 63) / 64, (n_rows + 63) / 64), 256, 0, st>>>(X, ld, n_rows, n_rows, row_scale, 0.0, 1, S, Xs, ld,
+                                                                                ld * ld);
+    return cudaGetLastError();
+}
+
+// Slices of the K* panel (element (query c, point k) at panel[k*panel_ld + c]) -> Ks[u][query][k] with k pitch k_pitch.
+cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q, int n_k, double inv_scale, int S,
+                                     signed char* Ks, size_t k_pitch, size_t q_pad, cudaStream_t st) {
+    // here the "rows" of the slice tensor are the queries and its "columns" the points: M(row = query, col = k) = panel[k*ld + query]
+    oz_slice_kernel<<<dim3((q + 63) / 64, (n_k + 63) / 64), 256, 0, st>>>(panel, panel_ld, q, n_k, nullptr, inv_scale, 0, S, Ks, k_pitch,
+                                                                        q_pad * k_pitch);
+    return cudaGetLastError();
+}
+
+}  // namespace gpr

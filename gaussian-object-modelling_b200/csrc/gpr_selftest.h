@@ -17,6 +17,10 @@ int gpr_selftest_factor_trace(int n_tiles, long long* h_trace, long long* leaf_c
  * mixed (16 DMMA with 32 / 128 DFMA per thread); total TFLOP/s. */
 int gpr_selftest_peak(int which, int ctas_per_sm, double* tflops);
 
+/* INT8 tensor-core engine (gpr_ozaki.cu: tcgen05.mma kind::i8 + TMEM + TMA): raw level accumulators
+ * C[l] = sum_{t+u=l} A_t B_u^T for int8 slice tensors A [S][M][K], B [S][N][K] (K contiguous); hC: [levels][M][N]. */
+int gpr_selftest_i8gemm(const signed char* hA, const signed char* hB, int S, int levels, int M, int N, int K, int tri, int* hC);
+
 #ifdef __cplusplus
 }
 #endif

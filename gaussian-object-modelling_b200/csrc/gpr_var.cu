@@ -86,6 +86,12 @@ __global__ void var_finalize_kernel(const double* partial, size_t panel_ld, int 
     var[i] = k0 - s;
 }
 
+cudaError_t launch_var_finalize(const double* partial, size_t panel_ld, int nb, int q, double k0, double* var, cudaStream_t st) {
+    if (q <= 0) return cudaSuccess;
+    var_finalize_kernel<<<(q + 255) / 256, 256, 0, st>>>(partial, panel_ld, nb, q, k0, var);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* panel, size_t panel_ld, int q,
                             double* partial, double k0, double* var, cudaStream_t st) {
     static PerDeviceOnce attr_done;
