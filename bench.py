@@ -6,8 +6,10 @@ sphere, label 0; 4,096 on the r = 2 sphere, label +1), sigma2 = 0.1, ThinPlate(R
 256^3 lattice on [-1.2, 1.2]^3, sharded over the ranks as contiguous index blocks (z-slabs).
 
 A "step" is one pass of the hot path over one batch of queries per GPU: fused mean + cross-covariance
-panel, then the variance by blocked forward substitution over the Cholesky factor (V = L^-1 K*^T in place in the
-panel, FP64 tensor pipe) — the default path of a freshly fitted model: no L^-1 is ever built for it.  `value` is whole-job
+panel, then the variance product V = L^-1 K*^T (n^2 flop per query) in the library's default form for large batches: on
+the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators, TMA feeds), FP64-equivalent by Ozaki slicing (7 x 7-bit
+slices per operand, FP64 recombination; every call spot-checked against the FP64 tensor pipe).  The two FP64 forms
+(forward substitution over L, product with L^-1 on the DMMA pipe) are timed on the same batches and reported beside it.  `value` is whole-job
 query points / s (mean + variance) with the queries already resident in HBM; `e2e` is the same through
 the host-pointer C-ABI call gpr_predict (pinned host buffers, H2D and D2H inside the timed region).
 The fit (covariance build + Cholesky + alpha) is timed separately and reported as fit_ms on the same line.
@@ -52,7 +54,8 @@ def workload_config(extra=None):
     cfg = {"workload": "config3: synthetic sphere cloud n=16384, ThinPlate(R=4.2), sigma2=0.1, mean+variance over the "
                        "256^3 grid on [-1.2,1.2]^3 (z-slab shards)",
            "n_train": N_TRAIN, "grid": GRID_RES, "kernel": "thin_plate", "R": 4.2,
-           "cache": "inputs larger than L2: each step streams the factor (1.07 GB) and a 2.5 GB cross-covariance panel"}
+           "cache": "inputs larger than L2: each step streams the int8 slices of L^-1 (0.94 GB of 1.9 GB, lower triangle) and of a "
+                    "2.5 GB cross-covariance panel (2.2 GB)"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -219,23 +222,36 @@ def main():
         extras.update(fit_ms=best[0], fit_cov_ms=best[1], fit_chol_ms=best[2], fit_solve_ms=best[3],
                       fit_wall_ms_e2e=min(f[4] for f in fits),      # host wall of gpr_fit (H2D of the cloud, allocation, D2H of alpha)
                       fit_chol_tflops=N_TRAIN ** 3 / 3 / (best[2] * 1e-3) / 1e12)
-        # time to first variance: a fresh fit followed at once by one variance batch (148*128 queries), host wall.
-        # The default path needs no L^-1 (forward substitution over L), so this is fit + one batch.
+        # time to first variance: a fresh fit followed at once by one variance batch (148*128 queries), host wall — for the
+        # default form (INT8 tensor cores: + one-time L^-1 and slicing) and for the forward substitution (needs nothing but L)
         sms0 = torch.cuda.get_device_properties(dev).multi_processor_count
         q1 = 128 * sms0
         Q1 = torch.from_numpy(np.ascontiguousarray(W.grid_slab(GRID_RES, 128, 129)[:q1].T)).to(dev)
         o1 = torch.empty(2 * q1, dtype=torch.float64, device=dev)
-        model.close()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        model = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
-        t_fit = 1e3 * (time.perf_counter() - t0)
-        reg.evaluate_device(model, Q1[0].data_ptr(), Q1[1].data_ptr(), Q1[2].data_ptr(), q1, o1.data_ptr(), o1[q1:].data_ptr(), None)
-        torch.cuda.synchronize(dev)
-        extras["time_to_first_variance_ms"] = 1e3 * (time.perf_counter() - t0)
-        extras["time_to_first_variance_split"] = {"fit_wall_ms": t_fit, "first_batch_queries": q1,
-                                                  "first_batch_ms": extras["time_to_first_variance_ms"] - t_fit}
-        assert model.state().linv is None                    # nothing built L^-1
+        ttfv = {}
+        for mode in ("trsm", "default"):
+            if mode == "trsm":
+                os.environ["GPR_VAR_MODE"] = "trsm"
+            else:
+                os.environ.pop("GPR_VAR_MODE", None)
+            model.close()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            model = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+            t_fit = 1e3 * (time.perf_counter() - t0)
+            reg.evaluate_device(model, Q1[0].data_ptr(), Q1[1].data_ptr(), Q1[2].data_ptr(), q1, o1.data_ptr(), o1[q1:].data_ptr(), None)
+            torch.cuda.synchronize(dev)
+            tot = 1e3 * (time.perf_counter() - t0)
+            tt = ctx.timings()
+            ttfv[mode] = {"total_ms": tot, "fit_wall_ms": t_fit, "first_batch_queries": q1, "first_batch_wall_ms": tot - t_fit,
+                          "of_which_linv_ms": tt["linv_ms"] if mode == "default" else 0.0, "variance_ms": tt["predict_var_ms"]}
+            if mode == "trsm":
+                assert model.state().linv is None                # nothing built L^-1
+        os.environ.pop("GPR_VAR_MODE", None)
+        extras["time_to_first_variance_ms"] = ttfv["default"]["total_ms"]
+        extras["time_until_variance_path_ready_ms"] = {"forward_substitution": ttfv["trsm"]["fit_wall_ms"],
+                                                       "round1_flow_fit_plus_inverse": ttfv["default"]["fit_wall_ms"] + ttfv["default"]["of_which_linv_ms"]}
+        extras["time_to_first_variance_split"] = ttfv
         del Q1, o1
     bcast_bytes = 0
     if world > 1:
@@ -282,8 +298,10 @@ def main():
         reg.evaluate_device(model, Qd[0, o:].data_ptr(), Qd[1, o:].data_ptr(), Qd[2, o:].data_ptr(), step_q,
                             f_d.data_ptr(), v_d.data_ptr(), None)
         t = ctx.timings()
+        oz_ms[0] += t["ozaki_ms"]
         return t["predict_var_ms"], t["predict_mean_ms"]
 
+    oz_ms = [0.0]
     sampler = ClockSampler(local_rank)
     for s in range(args.warmup):
         step_device(s)
@@ -292,6 +310,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     var_ms = mean_ms = 0.0
+    oz_ms[0] = 0.0
     for s in range(args.warmup, args.warmup + args.steps):
         vm, mm = step_device(s)
         var_ms += vm
@@ -300,10 +319,11 @@ def main():
     barrier()
     clocks = sampler.stop()
     elapsed_ms = e0.elapsed_time(e1)
+    oz_kernel_ms = oz_ms[0]
     if world > 1:
-        tmax = torch.tensor([elapsed_ms, var_ms, mean_ms], dtype=torch.float64, device=dev)
+        tmax = torch.tensor([elapsed_ms, var_ms, mean_ms, oz_kernel_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed_ms, var_ms, mean_ms = (float(x) for x in tmax.tolist())
+        elapsed_ms, var_ms, mean_ms, oz_kernel_ms = (float(x) for x in tmax.tolist())
     value = world * step_q * args.steps / (elapsed_ms * 1e-3)
     assert bool(torch.isfinite(f_d).all()) and float(v_d.min()) > 0.0
 
@@ -401,32 +421,49 @@ def main():
         others["mean_only_pair_evals_per_s"] = others["mean_only_pts_per_s_1gpu"] * N_TRAIN
         extras["other_overloads"] = others
         launches_var = BATCHES_PER_STEP * args.steps
-        flops_per_launch = float(N_TRAIN) ** 2 * batch                # n^2 * q per variance batch
-        achieved = flops_per_launch / (var_ms / launches_var * 1e-3) / 1e12
-        # the product form (X = L^-1 resident) on the same batches, for comparison: one-time n^3/3 inverse, then the same
-        # n^2 q flop without a dependency chain
-        assert model.state().linv is None
-        reg.prepare_variance(model)
-        linv_ms = ctx.timings()["linv_ms"]
-        pv = []
-        for s_ in range(3):
-            pv.append(step_device(s_)[0])
-        prod_ms = min(pv)
-        extras["variance_product_form"] = {"linv_ms_once": linv_ms, "var_ms_per_step": prod_ms,
-                                           "tflops": flops_per_launch * BATCHES_PER_STEP / (prod_ms * 1e-3) / 1e12,
-                                           "note": "same batches through var_tiles_kernel (product with the explicit inverse factor); "
-                                                   "the default path above needs neither the inverse nor its 8n^2 bytes"}
-        # The denominators, reported separately and never clamped: (1) the raw DMMA issue rate of this device
-        # (gpr_selftest_peak: DMMA.8x8x4 from registers, no memory traffic) — the probe draws more power than any real
-        # kernel, so a reading taken right after the timed steps can come out low; the best of several readings spread
-        # over ~2 s is used; (2) cuBLAS DGEMM 8192^3 on the same device.
+        flops_per_launch = float(N_TRAIN) ** 2 * batch                # n^2 * q per variance batch, FP64 count
+        fp64_equiv = flops_per_launch / (var_ms / launches_var * 1e-3) / 1e12
+        # the INT8 kernel's own work: 2 ops x (slice pairs t + u < S) x (lower triangle by 128-row tiles) x queries
+        oz_slices = int(os.environ.get("GPR_OZAKI_SLICES", "7"))
+        oz_pairs = oz_slices * (oz_slices + 1) // 2
+        int8_ops_per_launch = 2.0 * oz_pairs * (N_TRAIN * (N_TRAIN + 128) / 2.0) * batch
+        default_is_int8 = oz_kernel_ms > 0.0
+        achieved = int8_ops_per_launch / (oz_kernel_ms / launches_var * 1e-3) / 1e12 if default_is_int8 else fp64_equiv
+        # the two FP64 forms on the same batches (forced through the environment, read per call)
+        forms = {}
+        for mode in ("product", "trsm"):
+            os.environ["GPR_VAR_MODE"] = mode
+            if mode == "product":
+                reg.prepare_variance(model)
+            pv = [step_device(s_)[0] for s_ in range(3)]
+            forms[mode] = {"var_ms_per_step": min(pv), "fp64_tflops": flops_per_launch * BATCHES_PER_STEP / (min(pv) * 1e-3) / 1e12,
+                           "pts_per_s": step_q / ((min(pv) + mean_ms / args.steps) * 1e-3)}
+        os.environ.pop("GPR_VAR_MODE", None)
+        forms["product"]["kernel"] = "var_tiles_kernel (product with the explicit inverse factor, DMMA)"
+        forms["trsm"]["kernel"] = "var_trsm_kernel (blocked forward substitution over L in the K* panel, DMMA; needs no inverse)"
+        forms["int8_default" if default_is_int8 else "default"] = {
+            "var_ms_per_step": var_ms / args.steps, "fp64_equivalent_tflops": fp64_equiv, "pts_per_s": value / world,
+            "kernel": "ozaki_var_kernel<%d> (tcgen05.mma kind::i8 + TMEM + TMA)" % oz_slices, "kernel_ms_per_step": oz_kernel_ms / args.steps,
+            "other_ms_per_step": "panel slicing (oz_slice_kernel), finalize and the per-call FP64 spot check: %.2f" % ((var_ms - oz_kernel_ms) / args.steps)}
+        extras["variance_forms"] = forms
+        # The denominators, reported separately and never clamped.  INT8: MEASURED_PEAKS.json holds no int8 entry; the int8
+        # tensor rate is twice the bf16 rate on this part (4.5 vs 2.25 PFLOP/s nominal), so the peak used is 2 x the measured
+        # sustained bf16 figure (the kernel is timed inside a long step), with the nominal 4500 beside it.  FP64: (1) the raw
+        # DMMA issue rate of this device (gpr_selftest_peak), best of several readings; (2) cuBLAS DGEMM 8192^3.
         readings = []
         for attempt in range(6):
             readings.append(g.selftest_peak(0, 4))
             time.sleep(0.4)
         dmma_peak = max(readings)
+        mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp_path):
+            mp = json.load(open(mp_path))
+            bf16_sus, bf16_burst, peak_kind = mp.get("bf16_tflops_sustained", 1350.8), mp.get("bf16_tflops", 1595.1), "of measured"
+        else:
+            bf16_sus, bf16_burst, peak_kind = 1400.0, 1590.0, "of fallback"
+        int8_peak = 2.0 * bf16_sus
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "var_trsm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "ozaki_traffic.json" if default_is_int8 else "var_trsm_traffic.json")
         if os.path.exists(tpath):          # dram__bytes_read+write of one launch, from the committed ncu --set full capture
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
@@ -438,28 +475,41 @@ def main():
         c0.record(); a64 @ a64; a64 @ a64; c1.record(); torch.cuda.synchronize(dev)
         dgemm = 2 * 2 * 8192 ** 3 / (c0.elapsed_time(c1) * 1e-3) / 1e12
         del a64
-        peak_src = ("FP64 tensor pipe: raw DMMA.8x8x4 issue rate measured in this run (gpr_selftest_peak), best of %d readings %s; "
-                    "MEASURED_PEAKS.json has no FP64 entry.  cuBLAS DGEMM 8192^3 in this run: %.1f TF/s (frac_vs_cublas)"
-                    % (len(readings), ["%.1f" % r for r in readings], dgemm))
+        peak_src = ("INT8 tensor cores: 2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s; %.1f TF/s bf16 sustained, %.1f burst; no int8 "
+                    "entry there; nominal int8 dense 4500 TOP/s).  FP64 tensor pipe for the fp64-equivalent figures: raw DMMA.8x8x4 issue "
+                    "rate measured in this run (gpr_selftest_peak), best of %d readings %s; cuBLAS DGEMM 8192^3 in this run: %.1f TF/s"
+                    % (peak_kind, bf16_sus, bf16_burst, len(readings), ["%.1f" % r for r in readings], dgemm))
+        if default_is_int8:
+            roof = {"kernel": "ozaki_var_kernel<%d> (variance product X K*^T on the INT8 tensor cores: tcgen05.mma kind::i8, TMEM int32 "
+                              "accumulators, TMA feeds; FP64 recombination + column norms in the epilogue)" % oz_slices,
+                    "bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8 multiply-adds x 2)",
+                    "frac": achieved / int8_peak, "peak_nominal": 4500.0, "frac_of_nominal": achieved / 4500.0,
+                    "algorithmic_int8_ops_per_launch": int8_ops_per_launch, "slices": oz_slices, "slice_pairs": oz_pairs,
+                    "fp64_equivalent_tflops": fp64_equiv, "fp64_equivalent_vs_dmma_peak": fp64_equiv / dmma_peak,
+                    "fp64_equivalent_vs_cublas_dgemm": fp64_equiv / dgemm}
+        else:
+            roof = {"kernel": "var_trsm_kernel", "bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
+                    "frac": achieved / dmma_peak, "frac_vs_cublas": achieved / dgemm}
+        roof.update({"traffic": traffic, "traffic_source": traffic_src, "algorithmic_flop_per_launch_fp64": flops_per_launch,
+                     "algorithmic_operand_bytes": (oz_slices if default_is_int8 else 8.0) * (N_TRAIN * (N_TRAIN + 128) / 2 + N_TRAIN * batch),
+                     "peak_source": peak_src, "cublas_dgemm_tflops": dgemm, "dmma_probe_tflops": dmma_peak,
+                     "share_of_step": (oz_kernel_ms if default_is_int8 else var_ms) / elapsed_ms,
+                     "mean_panel_kernel_ms_per_step": mean_ms / args.steps,
+                     "fp64_forms": {"var_trsm_kernel": {"achieved": forms["trsm"]["fp64_tflops"], "peak": dmma_peak, "unit": "TFLOP/s",
+                                                        "frac": forms["trsm"]["fp64_tflops"] / dmma_peak},
+                                    "var_tiles_kernel": {"achieved": forms["product"]["fp64_tflops"], "peak": dmma_peak, "unit": "TFLOP/s",
+                                                         "frac": forms["product"]["fp64_tflops"] / dmma_peak}}})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": workload_config(),
+                "dtype": "f64 (int8-sliced: exact int8 x int8 -> int32 tensor-core products, FP64 recombination)" if default_is_int8 else "f64",
+                "data": "synthetic", "config": workload_config(),
                 "queries_per_step_per_gpu": step_q, "parallelism": "query-sharded x%d" % world,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * step_q, "d2h_bytes_per_step": 16 * step_q},
-                # per variance batch: predict_thread_kernel (mean + K* panel), predict_reduce_kernel, var_trsm_kernel,
-                # var_finalize_kernel (profiles/ncu_launches_bench_*.csv lists them)
-                "gpu_launches": 4 * BATCHES_PER_STEP * args.steps,
+                # per variance batch: predict_thread_kernel (mean + K* panel), predict_reduce_kernel, oz_slice_kernel, ozaki_var_kernel,
+                # var_finalize_kernel; per call: the spot check (var_tiles_kernel + var_finalize_kernel)
+                "gpu_launches": (5 * BATCHES_PER_STEP + 2) * args.steps if default_is_int8 else 4 * BATCHES_PER_STEP * args.steps,
                 "clocks": clocks,
-                "roofline": {"kernel": "var_trsm_kernel (variance: blocked forward substitution V = L^-1 K*^T in the panel + column norms)",
-                             "bound": "tensor",
-                             "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
-                             "frac_vs_cublas": achieved / dgemm,
-                             "traffic": traffic, "traffic_source": traffic_src,
-                             "algorithmic_flop_per_launch": flops_per_launch,
-                             "algorithmic_operand_bytes": 8.0 * N_TRAIN * (N_TRAIN + 128) / 2 + 8.0 * N_TRAIN * batch,
-                             "peak_source": peak_src,
-                             "cublas_dgemm_tflops": dgemm, "dmma_probe_tflops": dmma_peak, "share_of_step": var_ms / elapsed_ms,
-                             "mean_panel_kernel_ms_per_step": mean_ms / args.steps},
+                "roofline": roof,
                 "roofline_fit": {"kernel": "chol_tiles_kernel (tile-task Cholesky, n^3/3 flop)", "bound": "tensor",
                                  "achieved": extras["fit_chol_tflops"], "peak": dmma_peak, "unit": "TFLOP/s",
                                  "frac": extras["fit_chol_tflops"] / dmma_peak, "frac_vs_cublas": extras["fit_chol_tflops"] / dgemm,

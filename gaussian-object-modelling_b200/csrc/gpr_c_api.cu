@@ -221,6 +221,7 @@ struct gpr_model {
     std::vector<ModelDev> devs;
     std::vector<double> hx, hy, hz, hlabel, hs2, h_alpha, h_normals;   // h_normals: n_normals x 3 column-major
     size_t n_normals = 0;
+    bool oz_disabled = false;        // the INT8 tensor-core variance failed its FP64 spot check on this model: FP64 paths only
     std::mutex mu;
     // Micro-batcher of the callers' q = 1 pattern (hundreds of concurrent threads with one query each on one shared
     // model, src/gp_node.cpp:1027-1038): concurrent small requests are combined into one batched launch.
@@ -614,16 +615,20 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
 static int ensure_linv_primary(gpr_model* m) {
     ModelDev& md = m->devs[0];
     if (md.have_linv) return GPR_OK;
-    if (m->replica) return fail(GPR_ERR_INVALID, "replica model was created without L^-1");
+    if (m->replica && !(md.have_fac && md.lfac && md.dinv)) return fail(GPR_ERR_INVALID, "replica model was created without L^-1 and without the factor");
     DeviceCtx* dc = m->ctx->devs[0];
     CU(cudaSetDevice(dc->dev));
     if (!md.linv) CU(big_alloc(m->ctx, dc->dev, (void**)&md.linv, m->cap * m->cap * sizeof(double)));
+    // a replica that received the factor builds its own inverse from it (every GPU in parallel, nothing to exchange)
+    const double* Lsrc = m->L ? m->L : md.lfac;
+    const double* Dsrc = m->Dinv ? m->Dinv : md.dinv;
+    if (!m->scratch) CU(cudaMalloc((void**)&m->scratch, (8 + (size_t)(m->cap / TB) * (m->cap / TB)) * sizeof(int)));
     Workspace* ws = nullptr;
     int rc = ws_acquire(dc, &ws);
     if (rc) return rc;
     struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
     CU(cudaEventRecord(ws->ev[0], ws->st));
-    CU(launch_linv(m->L, md.linv, m->cap, m->nb, m->Dinv, m->scratch, dc->num_sms, ws->st));
+    CU(launch_linv(Lsrc, md.linv, m->cap, m->nb, Dsrc, m->scratch, dc->num_sms, ws->st));
     if (m->cap > m->N) CU(launch_identity_rows(md.linv, nullptr, m->cap, (int)m->N, (int)m->cap, (int)m->cap, ws->st));
     CU(cudaEventRecord(ws->ev[1], ws->st));
     int flags[4] = {0, 0, 0, 0};
@@ -720,25 +725,28 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
     bool use_trsm = false, use_oz = false;
     int oz_S = 7, oz_levels = 7;
     if (want_var && io.q > 8 && m->n_tail == 0) {
-        // GPR_VAR_MODE=ozaki: the product with X on the INT8 tensor cores (tcgen05 kind::i8), FP64-equivalent by slicing;
-        // GPR_OZAKI_SLICES (default 7) slices of 7 bits per operand, GPR_OZAKI_LEVELS (default = slices) levels kept.
+        // Three forms of the same n^2 flop per query:
+        //   ozaki   : product with X = L^-1 on the INT8 tensor cores (tcgen05 kind::i8, gpr_ozaki.cu), FP64-equivalent by
+        //             slicing (GPR_OZAKI_SLICES, default 7 slices of 7 bits: ~1e-9 of the variance; spot-checked against the
+        //             FP64 product on every call) — ~2x the DMMA rate; needs X and its int8 slices (one-time per model);
+        //   product : product with X on the FP64 tensor pipe (var_tiles_kernel);
+        //   trsm    : forward substitution over L (var_trsm_kernel) — no X at all.
+        // Default: ozaki for calls of >= GPR_OZAKI_MIN_Q (16384) queries (the one-time L^-1 + slicing pays off after about
+        // one batch); otherwise product if X is resident, else trsm for >= GPR_TRSM_MIN_Q (4096) queries, else product.
         const char* mode_env = getenv("GPR_VAR_MODE");
-        if (mode_env && !strcmp(mode_env, "ozaki")) {
-            use_oz = true;
-            if (const char* e = getenv("GPR_OZAKI_SLICES")) oz_S = std::max(2, std::min(8, atoi(e)));
-            oz_levels = oz_S;
-            if (const char* e = getenv("GPR_OZAKI_LEVELS")) oz_levels = std::max(1, std::min(8, atoi(e)));
-        }
-    }
-    if (!use_oz && want_var && io.q > 8 && m->n_tail == 0 && m->devs[0].have_fac) {
-        const char* mode_env = getenv("GPR_VAR_MODE");
+        static const long oz_min_q = getenv("GPR_OZAKI_MIN_Q") ? atol(getenv("GPR_OZAKI_MIN_Q")) : 16384;
         static const long min_q = getenv("GPR_TRSM_MIN_Q") ? atol(getenv("GPR_TRSM_MIN_Q")) : 4096;
-        if (mode_env && !strcmp(mode_env, "trsm")) use_trsm = true;
-        else if (mode_env && !strcmp(mode_env, "product")) use_trsm = false;
+        if (const char* e = getenv("GPR_OZAKI_SLICES")) oz_S = std::max(2, std::min(8, atoi(e)));
+        oz_levels = oz_S;
+        const bool can_trsm = m->devs[0].have_fac;
+        if (mode_env && !strcmp(mode_env, "ozaki")) use_oz = true;
+        else if (mode_env && !strcmp(mode_env, "trsm")) use_trsm = can_trsm;
+        else if (mode_env && !strcmp(mode_env, "product")) { }
         else {
-            bool have_x;
-            { std::lock_guard<std::mutex> lk(m->mu); have_x = m->devs[0].have_linv; }
-            use_trsm = !have_x && (long)io.q >= min_q;
+            bool have_x, dis;
+            { std::lock_guard<std::mutex> lk(m->mu); have_x = m->devs[0].have_linv; dis = m->oz_disabled; }
+            if (!dis && (long)io.q >= oz_min_q) use_oz = true;
+            else use_trsm = can_trsm && !have_x && (long)io.q >= min_q;
         }
     }
     int rc = ensure_on_device(m, di, want_var && !use_trsm, use_trsm);          // the INT8 path needs X = L^-1 too
@@ -822,8 +830,9 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
             if (rc) return rc;
         }
     }
-    float t_mean = 0, t_var = 0, t_h2d = 0, t_d2h = 0;
+    float t_mean = 0, t_var = 0, t_h2d = 0, t_d2h = 0, t_oz = 0;
     for (size_t b0 = 0; b0 < io.q; b0 += batch) {
+        bool oz_timed = false;
         const size_t bq = std::min(batch, io.q - b0);
         const size_t g0 = io.offset + b0;
         const double *qx, *qy, *qz;
@@ -860,9 +869,33 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
                 frexp(m->k0, &ge);
                 const double cs = ldexp(1.0, ge);
                 CU(launch_ozaki_slice_panel(ws->panel, pld, (int)bq, m->nb * TB, 1.0 / cs, oz_S, ws->oz_ks, ld, pld, st));
+                CU(cudaEventRecord(ws->ev[5], st));
                 CU(launch_ozaki_product(md.oz_xs, ld, ld * ld, m->nb, ws->oz_ks, ld, pld * ld, (int)bq, pld, (size_t)m->nb * TB, 1, oz_S,
                                         oz_levels, md.oz_scale, cs, ws->partial, ws->oz_ctrl, nullptr, st));
+                CU(cudaEventRecord(ws->ev[6], st));
+                oz_timed = true;
                 CU(launch_var_finalize(ws->partial, pld, m->nb, (int)bq, m->k0, v, st));
+                if (b0 == 0) {
+                    // spot check of this call: the first query tile again on the FP64 tensor pipe (one tile: ~2 % of a batch)
+                    const int cq = (int)std::min<size_t>(bq, TB);
+                    rc = ws_reserve(&ws->tailw, &ws->tailw_dbl, (size_t)m->nb * TB + 2 * TB);
+                    if (rc) return rc;
+                    double* chk_part = ws->tailw; double* chk_v = chk_part + (size_t)m->nb * TB;
+                    CU(launch_variance(md.linv, ld, m->nb, ws->panel, TB, cq, chk_part, m->k0, chk_v, st, pld));
+                    double hv[2 * TB];
+                    CU(cudaMemcpyAsync(hv, v, cq * sizeof(double), cudaMemcpyDeviceToHost, st));
+                    CU(cudaMemcpyAsync(hv + TB, chk_v, cq * sizeof(double), cudaMemcpyDeviceToHost, st));
+                    CU(cudaStreamSynchronize(st));
+                    double dmax = 0.0, vmax = 0.0;
+                    for (int i = 0; i < cq; ++i) { dmax = std::max(dmax, std::fabs(hv[i] - hv[TB + i])); vmax = std::max(vmax, std::fabs(hv[TB + i])); }
+                    if (!(dmax <= 1e-8 * std::max(vmax, 1e-300))) {
+                        // not accurate enough for this model (conditioning beyond what the slice count covers): this batch and
+                        // everything after it on this model go through the FP64 product form
+                        { std::lock_guard<std::mutex> lk(m->mu); m->oz_disabled = true; }
+                        use_oz = false;
+                        CU(launch_variance(md.linv, ld, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+                    }
+                }
             }
             else if (use_trsm) CU(launch_variance_trsm(md.lfac, ld, m->nb, md.dinv, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
             else CU(launch_variance(md.linv, ld, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
@@ -895,7 +928,9 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         CU(cudaStreamSynchronize(st));
         t_h2d += ev_ms(ws->ev[0], ws->ev[1]); t_mean += ev_ms(ws->ev[1], ws->ev[2]);
         t_var += ev_ms(ws->ev[2], ws->ev[3]); t_d2h += ev_ms(ws->ev[3], ws->ev[4]);
+        if (oz_timed) t_oz += ev_ms(ws->ev[5], ws->ev[6]);
     }
+    { std::lock_guard<std::mutex> lk(ctx->tmu); ctx->timings.ozaki_ms = t_oz; }
     if (use_oz) {
         int ctrl[2] = {0, 0};
         CU(cudaMemcpy(ctrl, ws->oz_ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));

@@ -67,7 +67,7 @@ cudaError_t launch_tangent_basis(const double* grad, size_t ld, int q, double* T
 cudaError_t launch_normalize_rows(double* g, size_t ld, int q, cudaStream_t st);
 // K3' (gpr_var.cu)
 cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* panel, size_t panel_ld, int q,
-                            double* partial, double k0, double* var, cudaStream_t st);
+                            double* partial, double k0, double* var, cudaStream_t st, size_t panel_pitch = 0);
 // Same result without L^-1: blocked forward substitution V = L^-1 K*^T in place in the panel (panel is overwritten).
 cudaError_t launch_variance_trsm(const double* L, size_t ld, int nb, const double* Dinv, double* panel, size_t panel_ld,
                                  int q, double* partial, double k0, double* var, cudaStream_t st);

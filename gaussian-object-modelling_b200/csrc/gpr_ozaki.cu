@@ -33,7 +33,6 @@ namespace gpr {
 constexpr int OZ_BM = 128;        // rows of X per task (UMMA M)
 constexpr int OZ_BN = 64;         // queries per task (UMMA N)
 constexpr int OZ_BK = 64;         // k per pipeline stage (bytes per row = SWIZZLE_64B span); 2 MMAs of K = 32
-constexpr int OZ_THREADS = 128;
 constexpr int OZ_TMEM_COLS = 512;
 constexpr int OZ_A_SLICE_BYTES = OZ_BM * OZ_BK;     // 8 KB
 constexpr int OZ_B_SLICE_BYTES = OZ_BN * OZ_BK;     // 4 KB
@@ -115,24 +114,33 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int M, int N) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(OZ_THREADS, 1)
+// Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warps 2..5 = epilogue (TMEM lane
+// quarter = warp % 4).  Tasks are dealt round-robin (task = blockIdx.x + i * gridDim.x, longest rows first), so every
+// role derives the same task sequence without communication.  With N = 64 a tcgen05.mma lasts only ~32-48 cycles: the
+// issuing thread's instruction count per MMA is what limits the rate, hence the fully unrolled, descriptor-incrementing
+// issue loop (template on the slice count) and the separate producer warp.
+constexpr int OZ_NTHREADS = 192;
+
+template <int S>
+__global__ void __launch_bounds__(OZ_NTHREADS, 1)
 ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a) {
     extern __shared__ __align__(1024) uint8_t oz_smem[];
-    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accum_bar;
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accum_full, accum_empty;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_task, s_abort;
     __shared__ double sred[4][OZ_BN];
 
+    constexpr int LEVELS = S;
+    constexpr uint32_t STAGE_BYTES = (uint32_t)S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t stage_bytes = (uint32_t)a.S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)oz_smem + 1023) & ~(uintptr_t)1023);
+    const int stages = a.stages;
 
     if (tid == 0) {
-        for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&accum_bar, 1);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&accum_full, 1);
+        mbar_init(&accum_empty, 4);                       // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        s_abort = 0;
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(OZ_TMEM_COLS) : "memory");
@@ -142,109 +150,133 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t idesc = umma_idesc_i8(OZ_BM, OZ_BN);
 
-    uint32_t jglob = 0;                 // k-blocks issued so far by this CTA (ring position; thread 0 only)
-    uint32_t task_parity = 0;
     const int per_group = a.gr * a.gq;
     const int qgroups = (a.nqt + a.gq - 1) / a.gq;
     const int rgroups = (a.nrt + a.gr - 1) / a.gr;
     const int ntasks = rgroups * qgroups * per_group;
-
-    for (;;) {
-        if (tid == 0) { s_task = atomicAdd(a.ctrl, 1); if (ld_volatile(a.ctrl + 1) != 0) s_abort = 1; }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        const int task = s_task;
-        if (task >= ntasks || s_abort) break;
+    auto decode = [&](int task, int& rt, int& qt) {
         const int g = task / per_group, w = task % per_group;
         const int rg = g / qgroups, qg = g % qgroups;
-        const int rt = a.nrt - 1 - (rg * a.gr + w % a.gr);          // longest rows first
-        const int qt = qg * a.gq + w / a.gr;
-        if (rt < 0 || qt >= a.nqt) continue;                        // padding of the group grid (block-uniform)
-        const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
+        rt = a.nrt - 1 - (rg * a.gr + w % a.gr);                    // longest rows first
+        qt = qg * a.gq + w / a.gr;
+        return rt >= 0 && qt < a.nqt;
+    };
 
-        if (tid == 0) {
-            bool ok = true;
-            auto load = [&](uint32_t j, int kb) {
-                const uint32_t s = j % (uint32_t)a.stages, u = j / (uint32_t)a.stages;
-                if (u > 0 && !mbar_wait(&empty_bar[s], (u - 1) & 1)) { ok = false; return; }
-                uint8_t* sa = base + (size_t)s * stage_bytes;
-                uint8_t* sb = sa + (size_t)a.S * OZ_A_SLICE_BYTES;
-                mbar_expect_tx(&full_bar[s], stage_bytes);
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        uint32_t j = 0;
+        bool ok = true;
+        for (int task = blockIdx.x; task < ntasks && ok; task += gridDim.x) {
+            int rt, qt;
+            if (!decode(task, rt, qt)) continue;
+            const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
+            for (int kb = 0; kb < nkb; ++kb, ++j) {
+                const uint32_t s = j % (uint32_t)stages, u = j / (uint32_t)stages;
+                if (u > 0 && !mbar_wait(&empty_bar[s], (u - 1) & 1)) { ok = false; break; }
+                uint8_t* sa = base + (size_t)s * STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 tma_load_3d(sa, &tmA, &full_bar[s], kb * OZ_BK, rt * OZ_BM, 0);
-                tma_load_3d(sb, &tmB, &full_bar[s], kb * OZ_BK, qt * OZ_BN, 0);
-            };
-            const int pre = nkb < a.stages ? nkb : a.stages;
-            for (int i = 0; i < pre && ok; ++i) load(jglob + i, i);
-            for (int i = 0; i < nkb && ok; ++i) {
-                const uint32_t j = jglob + i, s = j % (uint32_t)a.stages, u = j / (uint32_t)a.stages;
+                tma_load_3d(sa + S * OZ_A_SLICE_BYTES, &tmB, &full_bar[s], kb * OZ_BK, qt * OZ_BN, 0);
+            }
+        }
+        if (!ok) atomicExch(a.ctrl + 1, 1);
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma_idesc_i8(OZ_BM, OZ_BN);
+        constexpr uint32_t DESC_HI = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);      // SBO | version 1 | SWIZZLE_64B
+        uint32_t j = 0, tcount = 0;
+        bool ok = true;
+        for (int task = blockIdx.x; task < ntasks && ok; task += gridDim.x) {
+            int rt, qt;
+            if (!decode(task, rt, qt)) continue;
+            const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
+            if (tcount > 0 && !mbar_wait(&accum_empty, (tcount - 1) & 1)) { ok = false; break; }   // epilogue has drained TMEM
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; ++kb, ++j) {
+                const uint32_t s = j % (uint32_t)stages, u = j / (uint32_t)stages;
                 if (!mbar_wait(&full_bar[s], u & 1)) { ok = false; break; }
                 tc_fence_after();
-                const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
-                const uint32_t sb = sa + (uint32_t)a.S * OZ_A_SLICE_BYTES;
-                for (int l = 0; l < a.levels; ++l) {
-                    const uint32_t d = tmem + (uint32_t)(l * OZ_BN);
-                    bool first = (i == 0);
+                const uint32_t sa = smem_u32(base + (size_t)s * STAGE_BYTES);
+                const uint32_t a_lo = (((sa >> 4) & 0x3FFFu) | (1u << 16));
+                const uint32_t b_lo = a_lo + (uint32_t)(S * OZ_A_SLICE_BYTES >> 4);
+                const uint32_t keep = kb > 0 ? 1u : 0u;
+#pragma unroll
+                for (int l = 0; l < LEVELS; ++l) {
+#pragma unroll
                     for (int t = 0; t <= l; ++t) {
-                        const int uu = l - t;
-                        if (t >= a.S || uu >= a.S) continue;
 #pragma unroll
                         for (int ks = 0; ks < OZ_BK / 32; ++ks) {
-                            umma_i8(d, umma_desc_sw64(sa + t * OZ_A_SLICE_BYTES, ks * 32),
-                                    umma_desc_sw64(sb + uu * OZ_B_SLICE_BYTES, ks * 32), idesc, first ? 0u : 1u);
-                            first = false;
+                            const uint64_t da = ((uint64_t)DESC_HI << 32) | (a_lo + (uint32_t)(t * (OZ_A_SLICE_BYTES >> 4) + 2 * ks));
+                            const uint64_t db = ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)((l - t) * (OZ_B_SLICE_BYTES >> 4) + 2 * ks));
+                            umma_i8(tmem + (uint32_t)(l * OZ_BN), da, db, idesc, (t == 0 && ks == 0) ? keep : 1u);
                         }
                     }
                 }
                 umma_commit(&empty_bar[s]);                            // stage free once these MMAs have read it
-                if (i >= 1 && i - 1 + a.stages < nkb) load(jglob + i - 1 + a.stages, i - 1 + a.stages);
             }
-            if (ok) umma_commit(&accum_bar);                           // all MMAs of the task done -> epilogue
-            else { atomicExch(a.ctrl + 1, 1); s_abort = 1; }
-            jglob += (uint32_t)nkb;
+            if (!ok) break;
+            umma_commit(&accum_full);                                  // all MMAs of the task done -> epilogue
+            ++tcount;
         }
-        __syncwarp();
-        // ---- epilogue: every thread owns TMEM lane = its row of the tile -------------------------------------
-        bool got = mbar_wait(&accum_bar, task_parity);
-        if (!got) { atomicExch(a.ctrl + 1, 1); }
-        task_parity ^= 1;
-        tc_fence_after();
-        const int row = rt * OZ_BM + tid;
-        const double rs = a.row_scale[row] * a.col_scale;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-#pragma unroll 1
-        for (int c = 0; c < OZ_BN / 16; ++c) {
-            double acc[16];
+        if (!ok) atomicExch(a.ctrl + 1, 1);
+    } else if (warp >= 2) {
+        // ===== epilogue: thread owns TMEM lane = its row of the tile =====
+        const int q4 = warp & 3;                                       // TMEM lane quarter this warp may read
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        uint32_t tcount = 0;
+        bool ok = true;
+        for (int task = blockIdx.x; task < ntasks && ok; task += gridDim.x) {
+            int rt, qt;
+            if (!decode(task, rt, qt)) continue;
+            if (!mbar_wait(&accum_full, tcount & 1)) { ok = false; break; }
+            ++tcount;
+            tc_fence_after();
+            const int row = rt * OZ_BM + q4 * 32 + lane;
+            const double rs = a.row_scale[row] * a.col_scale;
+            double ss[OZ_BN / 16][16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = 0.0;
-            for (int l = a.levels - 1; l >= 0; --l) {
-                uint32_t v[16];
-                tmem_ld16(tmem + lane_base + (uint32_t)(l * OZ_BN + 16 * c), v);
-                const double wl = __longlong_as_double((long long)(1023 - 12 - 7 * l) << 52);      // 2^(-12-7l)
+            for (int c = 0; c < OZ_BN / 16; ++c) {
+                double acc[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = fma((double)(int)v[j], wl, acc[j]);
-                if (a.dbg) {
-                    const size_t ldq = (size_t)a.nqt * OZ_BN;
-                    int* o = a.dbg + ((size_t)l * a.nrt * OZ_BM + row) * ldq + (size_t)qt * OZ_BN + 16 * c;
+                for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = (int)v[j];
+                for (int l = LEVELS - 1; l >= 0; --l) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + lane_base + (uint32_t)(l * OZ_BN + 16 * c), v);
+                    const double wl = __longlong_as_double((long long)(1023 - 12 - 7 * l) << 52);      // 2^(-12-7l)
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) acc[jj] = fma((double)(int)v[jj], wl, acc[jj]);
+                    if (a.dbg) {
+                        const size_t ldq = (size_t)a.nqt * OZ_BN;
+                        int* o = a.dbg + ((size_t)l * a.nrt * OZ_BM + row) * ldq + (size_t)qt * OZ_BN + 16 * c;
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) o[jj] = (int)v[jj];
+                    }
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const double vv = acc[j] * rs;
-                double s = vv * vv;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) sred[warp][16 * c + j] = s;
+                for (int jj = 0; jj < 16; ++jj) { const double vv = acc[jj] * rs; ss[c][jj] = vv * vv; }
             }
+            // TMEM is drained: the MMA issuer may start the next task while the column norms are reduced
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
+#pragma unroll
+            for (int c = 0; c < OZ_BN / 16; ++c)
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    double sv = ss[c][jj];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                    if (lane == 0) sred[q4][16 * c + jj] = sv;
+                }
+            asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps
+            const int et = tid - 64;
+            if (et < OZ_BN)
+                a.partial[(size_t)rt * a.q_pad + (size_t)qt * OZ_BN + et] = (sred[0][et] + sred[1][et]) + (sred[2][et] + sred[3][et]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        tc_fence_before();
-        __syncthreads();
-        if (tid < OZ_BN)
-            a.partial[(size_t)rt * a.q_pad + (size_t)qt * OZ_BN + tid] = (sred[0][tid] + sred[1][tid]) + (sred[2][tid] + sred[3][tid]);
+        if (!ok) atomicExch(a.ctrl + 1, 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -347,15 +379,28 @@ int ozaki_stages(int S) {
 cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a_slice, int nrt, const signed char* Bs, size_t b_pitch,
                                  size_t b_slice, int q, size_t q_pad, size_t k_extent, int tri, int S, int levels,
                                  const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, cudaStream_t st) {
-    static PerDeviceOnce attr_done;
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, OzArgs);
+    KernelFn fn = nullptr;
+    switch (S) {
+        case 1: fn = ozaki_var_kernel<1>; break;
+        case 2: fn = ozaki_var_kernel<2>; break;
+        case 3: fn = ozaki_var_kernel<3>; break;
+        case 4: fn = ozaki_var_kernel<4>; break;
+        case 5: fn = ozaki_var_kernel<5>; break;
+        case 6: fn = ozaki_var_kernel<6>; break;
+        case 7: fn = ozaki_var_kernel<7>; break;
+        case 8: fn = ozaki_var_kernel<8>; break;
+        default: return cudaErrorInvalidValue;
+    }
+    if (levels != S) return cudaErrorInvalidValue;          // every level t + u < S is kept
+    static PerDeviceOnce attr_done[9];
     const int cur = PerDeviceOnce::current();
     const size_t smem = (size_t)220 * 1024 + 1024;
-    if (!attr_done.done(cur)) {
-        cudaError_t e = cudaFuncSetAttribute(ozaki_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!attr_done[S].done(cur)) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done.set(cur);
+        attr_done[S].set(cur);
     }
-    if (S < 1 || S > 8 || levels < 1 || levels > 8 || levels * OZ_BN > OZ_TMEM_COLS) return cudaErrorInvalidValue;
     CUtensorMap tmA, tmB;
     cudaError_t e = make_map(&tmA, As, k_extent, (size_t)nrt * OZ_BM, S, a_pitch, a_slice, OZ_BM);
     if (e != cudaSuccess) return e;
@@ -375,7 +420,7 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
     e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);
     if (e != cudaSuccess) return e;
     const int tasks = ((a.nrt + a.gr - 1) / a.gr) * ((a.nqt + a.gq - 1) / a.gq) * a.gr * a.gq;
-    ozaki_var_kernel<<<tasks < sms ? tasks : sms, OZ_THREADS, smem, st>>>(tmA, tmB, a);
+    fn<<<tasks < sms ? tasks : sms, OZ_NTHREADS, smem, st>>>(tmA, tmB, a);
     return cudaGetLastError();
 }
 

@@ -22,7 +22,8 @@ struct VarArgs {
     const double* X; size_t ld; int nb;       // L^-1, lower triangular tiles
     const double* panel; size_t panel_ld;     // K*: element (query, k) at panel[k*panel_ld + query]
     int nqt;                                  // query tiles in this batch (panel_ld / 128)
-    double* partial;                          // nb x panel_ld
+    double* partial;                          // nb x part_ld
+    size_t part_ld;
     int gi, gq, qgroups;                      // row-tile pairs / query tiles per co-scheduled group, number of query groups
 };
 
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) var_tiles_kernel(VarArgs a) {
         __syncthreads();
         if (threadIdx.x < TB) {
             const int c = threadIdx.x, wj = c >> 5, lc = c & 31;
-            a.partial[(size_t)it * a.panel_ld + (size_t)qt * TB + c] = sred[2 * wj][lc] + sred[2 * wj + 1][lc];
+            a.partial[(size_t)it * a.part_ld + (size_t)qt * TB + c] = sred[2 * wj][lc] + sred[2 * wj + 1][lc];
         }
         __syncthreads();
     }
@@ -92,8 +93,9 @@ cudaError_t launch_var_finalize(const double* partial, size_t panel_ld, int nb, 
     return cudaGetLastError();
 }
 
+// panel_pitch: 0, or the real pitch of a panel that is wider than the panel_ld (query tiles) to be processed here.
 cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* panel, size_t panel_ld, int q,
-                            double* partial, double k0, double* var, cudaStream_t st) {
+                            double* partial, double k0, double* var, cudaStream_t st, size_t panel_pitch) {
     static PerDeviceOnce attr_done;
     const int cur = PerDeviceOnce::current();
     if (!attr_done.done(cur)) {
@@ -104,8 +106,8 @@ cudaError_t launch_variance(const double* X, size_t ld, int nb, const double* pa
     }
     if (q <= 0) return cudaSuccess;
     VarArgs a;
-    a.X = X; a.ld = ld; a.nb = nb; a.panel = panel; a.panel_ld = panel_ld;
-    a.nqt = (int)(panel_ld / TB); a.partial = partial;
+    a.X = X; a.ld = ld; a.nb = nb; a.panel = panel; a.panel_ld = panel_pitch ? panel_pitch : panel_ld;
+    a.nqt = (int)(panel_ld / TB); a.partial = partial; a.part_ld = panel_ld;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -45,6 +45,7 @@ typedef struct {
     double predict_mean_ms, predict_var_ms, predict_total_ms;
     double h2d_ms, d2h_ms;
     double append_ms;               /* last gpr_append: device time of the incremental update incl. the alpha re-solve */
+    double ozaki_ms;                /* last predict on the primary device: time inside the INT8 tensor-core variance kernel (0 if another form ran) */
 } gpr_timings;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -140,10 +141,16 @@ int gpr_project(gpr_ctx* ctx, gpr_model* m, const double* x, const double* y, co
 int gpr_sample_chart(gpr_ctx* ctx, gpr_model* m, const double* frames, const size_t* counts, size_t n_charts,
                      const double* r_or_null, const double* th_or_null, unsigned long long seed, double* sx, double* sy,
                      double* sz, double* f, double* v, size_t* order);
-/* Builds L^-1 now.  It is otherwise built by the first call that needs it: a variance for a batch of fewer than
- * 4096 queries (GPR_TRSM_MIN_Q) — the fused single-query kernel and the product form read it — or gpr_append.
- * Large batches on a model without L^-1 take the forward substitution over L instead (no n^3/3 inverse, one n x n
- * matrix per model); once L^-1 is resident every batch uses the product form.  GPR_VAR_MODE=trsm|product forces one. */
+/* Builds L^-1 now.  It is otherwise built by the first call that needs it.  The variance (n^2 flop per query) has three
+ * forms, chosen per call (GPR_VAR_MODE=ozaki|product|trsm forces one):
+ *   >= 16384 queries (GPR_OZAKI_MIN_Q): product with L^-1 on the INT8 tensor cores (tcgen05 kind::i8 + TMEM + TMA),
+ *      FP64-equivalent by Ozaki slicing (GPR_OZAKI_SLICES = 7 slices of 7 bits: ~1e-9 of the variance), ~2x the FP64
+ *      tensor-pipe rate; needs L^-1 and its int8 slices (built once per model); every call re-computes its first query
+ *      tile on the FP64 tensor pipe and falls back to the FP64 product form for the model if they differ by > 1e-8;
+ *   otherwise, if L^-1 is resident (or < 4096 queries, GPR_TRSM_MIN_Q: the fused single-query kernel needs it anyway, and
+ *      so does gpr_append): product with L^-1 on the FP64 tensor pipe;
+ *   otherwise: forward substitution over L (no inverse at all, one n x n matrix per model).
+ * Models with an indefinite tail block always use the FP64 product form. */
 int gpr_model_prepare_variance(gpr_ctx* ctx, gpr_model* m);
 /* X = K^-1 B for nrhs right-hand sides (B, X: n x nrhs column-major, host) through the resident factor — the
  * counterpart of the reference's public Model::cholesker.solve(b) (gp_regressor.hpp:81, :163).  Positive definite

@@ -79,3 +79,21 @@ def test_tile_cholesky_rejects_indefinite(gpr):
 def test_fp64_pipe_probes(gpr):
     dmma, dfma = gpr.selftest_peak(0, 4), gpr.selftest_peak(1, 4)
     assert 10.0 < dmma < 80.0 and 10.0 < dfma < 80.0       # B200: ~37 / ~34 TF/s; wide bounds: a power-capped box must not fail a parity suite
+
+
+@pytest.mark.parametrize("S,M,N,K,tri", [(1, 128, 64, 64, False), (2, 256, 128, 512, False), (3, 384, 192, 384, True),
+                                         (7, 512, 320, 1024, True), (8, 256, 64, 2048, False)])
+def test_int8_tensor_core_engine_is_exact(gpr, S, M, N, K, tri):
+    """gpr_ozaki.cu: tcgen05.mma kind::i8 into TMEM int32 accumulators, operands by TMA (SWIZZLE_64B, K-major), one
+    accumulator per level l = t + u.  Integer arithmetic: the result must equal numpy's int64 product exactly."""
+    rng = np.random.default_rng(S * 1000 + K)
+    A = rng.integers(-64, 65, size=(S, M, K), dtype=np.int8)
+    B = rng.integers(-64, 65, size=(S, N, K), dtype=np.int8)
+    C = gpr.selftest_i8gemm(A, B, S, tri)
+    A64 = A.astype(np.int64)
+    if tri:
+        for r in range(M // 128):
+            A64[:, r * 128:(r + 1) * 128, 128 * (r + 1):] = 0
+    for l in range(S):
+        E = sum(A64[t] @ B[l - t].astype(np.int64).T for t in range(l + 1))
+        assert np.array_equal(C[l].astype(np.int64), E), l

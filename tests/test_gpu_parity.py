@@ -381,12 +381,16 @@ def _headline_parity(gpr, orc, ctx, monkeypatch, n, res, nq, with_blas):
     monkeypatch.setenv("GPR_VAR_MODE", "product")
     f_p, v_p = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
     assert m.state().linv is not None
+    monkeypatch.setenv("GPR_VAR_MODE", "ozaki")                       # INT8 tensor cores (tcgen05), FP64-equivalent by slicing
+    f_o, v_o = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    assert ctx.timings()["ozaki_ms"] > 0.0
     monkeypatch.delenv("GPR_VAR_MODE")
     f_1 = np.zeros(8); v_1 = np.zeros(8)
     for i in range(8):                                               # the callers' pattern: one query per call
         fi, vi = reg.evaluate(m, Q[i:i + 1, 0], Q[i:i + 1, 1], Q[i:i + 1, 2], var=True)
         f_1[i], v_1[i] = fi[0], vi[0]
-    for name, f, v, sl in (("trsm", f_t, v_t, slice(None)), ("product", f_p, v_p, slice(None)), ("single", f_1, v_1, slice(0, 8))):
+    for name, f, v, sl in (("trsm", f_t, v_t, slice(None)), ("product", f_p, v_p, slice(None)), ("ozaki_int8", f_o, v_o, slice(None)),
+                           ("single", f_1, v_1, slice(0, 8))):
         report["mean_rel_" + name] = float(np.abs(f - fc[sl]).max() / np.abs(fc).max())
         report["var_rel_" + name] = float(np.abs(v - vc[sl]).max() / np.abs(vc).max())
         assert report["mean_rel_" + name] <= TOL_MEAN, report
@@ -417,12 +421,17 @@ def test_headline_parity_config3(gpr, orc, ctx, monkeypatch):
     reg, m, P, y, s2 = _headline_parity(gpr, orc, ctx, monkeypatch, 16384, 256, 255, with_blas=True)
     W = gpr.workloads
     Q = W.grid_slab(256, 128, 129)[:148 * 128]
-    f, v = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    f, v = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)    # a full batch: by default the INT8 tensor-core form
+    t = ctx.timings()
+    assert t["predict_var_ms"] > 0 and t["ozaki_ms"] > 0
     assert np.isfinite(f).all() and v.min() > 0.0 and v.max() < W.SYNTH_R ** 3
+    monkeypatch.setenv("GPR_VAR_MODE", "product")
+    f2, v2 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    monkeypatch.delenv("GPR_VAR_MODE")
+    assert ctx.timings()["ozaki_ms"] == 0.0 and np.array_equal(f, f2)
+    assert np.abs(v - v2).max() <= 1e-8 * np.abs(v2).max()         # 10x inside the tolerance on all 18,944 queries
     fs = reg.evaluate(m, P[::64, 0], P[::64, 1], P[::64, 2])
     assert np.abs(fs - y[::64]).max() < 0.2          # sigma2 = 0.1 smoothing, not interpolation
-    t = ctx.timings()
-    assert t["predict_var_ms"] > 0
     m.close()
 
 
@@ -710,6 +719,37 @@ def test_variance_by_forward_substitution_matches_oracle_and_product_form(gpr, o
     og = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, "gaussian", 1.0, 1.0, factor="llt")
     fgo, vgo, _ = og.predict(Q[sub, 0], Q[sub, 1], Q[sub, 2], var=True, threads=os.cpu_count() or 1)
     assert relerr(fg, fgo) <= TOL_MEAN and np.abs(vg - vgo).max() <= TOL_VAR * np.abs(vgo).max()
+
+
+@pytest.mark.parametrize("n,q,kind", [(1500, 3000, "thin_plate"), (2304, 20000, "thin_plate"), (1000, 700, "gaussian")])
+def test_variance_on_int8_tensor_cores_matches_oracle(gpr, orc, ctx, monkeypatch, n, q, kind):
+    """K3'' (gpr_ozaki.cu): the variance product on the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators, TMA
+    operand feeds), FP64-equivalent by Ozaki slicing, against the oracle and the FP64 product form; ragged n and q; slice
+    counts 7 (default) and 8; bit-reproducible."""
+    W = gpr.workloads
+    P, y, s2 = W.synthetic_cloud(n, seed=31)
+    Q = np.random.default_rng(n).uniform(-1.2, 1.2, size=(q, 3))
+    p0, p1 = (W.SYNTH_R, 0.0) if kind == "thin_plate" else (1.0, 1.0)
+    reg = gpr.GPRegressor(kind, p0, p1, ctx=ctx)
+    m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2)
+    monkeypatch.setenv("GPR_VAR_MODE", "product")
+    f_p, v_p = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    monkeypatch.setenv("GPR_VAR_MODE", "ozaki")
+    o = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, kind, p0, p1, factor="llt")
+    sub = slice(0, q, max(1, q // 400))
+    fo, vo, _ = o.predict(Q[sub, 0], Q[sub, 1], Q[sub, 2], var=True, threads=os.cpu_count() or 1)
+    for slices in ("7", "8"):
+        monkeypatch.setenv("GPR_OZAKI_SLICES", slices)
+        f_o, v_o = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+        assert ctx.timings()["ozaki_ms"] > 0.0
+        f_o2, v_o2 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+        assert np.array_equal(v_o, v_o2) and np.array_equal(f_o, f_p)
+        assert np.abs(v_o - v_p).max() <= 1e-8 * np.abs(v_p).max()
+        assert relerr(f_o[sub], fo) <= TOL_MEAN and np.abs(v_o[sub] - vo).max() <= TOL_VAR * np.abs(vo).max()
+    # too few slices: the per-call FP64 spot check catches it and the call (and the model from then on) falls back
+    monkeypatch.setenv("GPR_OZAKI_SLICES", "3")
+    f_b, v_b = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+    assert np.abs(v_b - v_p).max() <= 1e-10 * np.abs(v_p).max()     # the FP64 product form answered
 
 
 def test_default_variance_path_needs_no_inverse_for_large_batches(gpr, ctx):
