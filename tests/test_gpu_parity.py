@@ -205,14 +205,14 @@ def test_node_configuration_indefinite_matrix(gpr, ctx, case):
     fb, vb = reg.evaluate(m, big[:, 0], big[:, 1], big[:, 2], var=True)
     assert relerr(fb[:len(Q)], g["f"]) <= TOL_MEAN and np.abs(vb[:len(Q)] - g["v"]).max() <= TOL_VAR * np.abs(g["v"]).max()
     assert np.array_equal(fb[:len(Q)], fb[-len(Q):]) and np.array_equal(vb[:len(Q)], vb[-len(Q):])
-    # update() on such a model refits: the two new surface points come AFTER the external points in the caller's
-    # order, yet only the 15 external points end up in the trailing block (they are moved behind the new points
+    # update() on such a model is incremental too: the two new surface points come AFTER the external points in the caller's
+    # order, yet only the 15 external points stay in the trailing block (they are moved behind the new points
     # in the internal order); alpha comes back in the caller's order and agrees with a fresh fit of all 279
     reg.update(m, [0.3, 0.0], [0.1, 0.5], [-0.2, 0.4], [0.0, 0.0], [0.05, 0.05])
     assert m.n == len(P) + 2 and m.n_tail == 15
     P2 = np.vstack([P, [[0.3, 0.1, -0.2], [0.0, 0.5, 0.4]]])
     fresh = reg.create(P2[:, 0], P2[:, 1], P2[:, 2], np.concatenate([g["y"], [0.0, 0.0]]), np.concatenate([g["s2"], [0.05, 0.05]]))
-    assert fresh.n_tail == 15 and np.array_equal(fresh.alpha, m.alpha)
+    assert fresh.n_tail == 15 and relerr(m.alpha, fresh.alpha) <= 1e-12
 
 
 def test_closed_form_posteriors(gpr, ctx):
