@@ -196,7 +196,7 @@ struct ModelDev {            // what predict needs, per device
     double* lfac = nullptr; double* dinv = nullptr;
     bool have = false, have_linv = false, have_tail = false, have_fac = false, own_fac = false;
     // int8 slices of X = L^-1 and its per-row power-of-two scales, for the variance on the INT8 tensor cores (gpr_ozaki.cu)
-    signed char* oz_xs = nullptr; double* oz_scale = nullptr; int oz_S = 0; size_t oz_ld = 0;
+    signed char* oz_xs = nullptr; double* oz_scale = nullptr; int oz_S = 0, oz_base = 0; size_t oz_ld = 0;
 };
 
 struct gpr_model {
@@ -683,20 +683,20 @@ static int ensure_on_device(gpr_model* m, size_t di, bool need_linv, bool need_f
 }
 
 // Slices of X = L^-1 for the INT8 tensor-core variance (gpr_ozaki.cu), built once per model, device and slice count.
-static int ensure_ozaki_slices(gpr_model* m, size_t di, int S, cudaStream_t st) {
+static int ensure_ozaki_slices(gpr_model* m, size_t di, int S, int base254, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(m->mu);
     ModelDev& md = m->devs[di];
-    if (md.oz_xs && md.oz_S == S && md.oz_ld == m->cap) return GPR_OK;
+    if (md.oz_xs && md.oz_S == S && md.oz_base == base254 && md.oz_ld == m->cap) return GPR_OK;
     CU(cudaSetDevice(md.dev));
     cudaFree(md.oz_xs); cudaFree(md.oz_scale);
     md.oz_xs = nullptr; md.oz_scale = nullptr; md.oz_S = 0;
     const size_t ld = m->cap;
     CU(cudaMalloc((void**)&md.oz_xs, (size_t)S * ld * ld));
     CU(cudaMalloc((void**)&md.oz_scale, 2 * ld * sizeof(double)));          // scales | row-max scratch
-    CU(launch_ozaki_slice_x(md.linv, ld, m->nb * TB, S, md.oz_xs, md.oz_scale,
+    CU(launch_ozaki_slice_x(md.linv, ld, m->nb * TB, S, base254, md.oz_xs, md.oz_scale,
                             reinterpret_cast<unsigned long long*>(md.oz_scale + ld), st));
     CU(cudaStreamSynchronize(st));
-    md.oz_S = S; md.oz_ld = ld;
+    md.oz_S = S; md.oz_base = base254; md.oz_ld = ld;
     return GPR_OK;
 }
 
@@ -709,6 +709,8 @@ struct PredictIO {
     size_t out_ld;          // leading dimension of grad/tx/ty in the caller's arrays
     size_t offset;          // first query handled here
     bool device_ptrs;
+    size_t q_call = 0;      // queries of the whole user call (the variance form is chosen on it, so that sharding a call over
+                            // the devices of a context never changes the form); 0 = q
 };
 
 static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, double* mean_ms, double* var_ms,
@@ -723,7 +725,7 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
     //     batch over all SMs; used whenever X is resident anyway, for small batches and for indefinite-tail models.
     // GPR_VAR_MODE=trsm|product forces one (tests, bench).
     bool use_trsm = false, use_oz = false;
-    int oz_S = 7, oz_levels = 7;
+    int oz_S = 7, oz_base254 = 0;
     if (want_var && io.q > 8 && m->n_tail == 0) {
         // Three forms of the same n^2 flop per query:
         //   ozaki   : product with X = L^-1 on the INT8 tensor cores (tcgen05 kind::i8, gpr_ozaki.cu), FP64-equivalent by
@@ -736,17 +738,26 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         const char* mode_env = getenv("GPR_VAR_MODE");
         static const long oz_min_q = getenv("GPR_OZAKI_MIN_Q") ? atol(getenv("GPR_OZAKI_MIN_Q")) : 16384;
         static const long min_q = getenv("GPR_TRSM_MIN_Q") ? atol(getenv("GPR_TRSM_MIN_Q")) : 4096;
+        // digit system: base 254 (|digit| <= 127, 8 bits per slice: 6 slices) while no int32 accumulator can overflow
+        // (k <= 22016), else base 128 (|digit| <= 64, 7 bits per slice: 7 slices; k <= 74752).  GPR_OZAKI_BASE / _SLICES override.
+        const long long kext = (long long)m->nb * TB;
+        oz_base254 = kext <= ozaki_max_k(6, 1) ? 1 : 0;
+        if (const char* e = getenv("GPR_OZAKI_BASE")) oz_base254 = atoi(e) == 254 ? 1 : 0;
+        oz_S = oz_base254 ? 6 : 7;
         if (const char* e = getenv("GPR_OZAKI_SLICES")) oz_S = std::max(2, std::min(8, atoi(e)));
-        oz_levels = oz_S;
+        const bool oz_fits = kext <= ozaki_max_k(oz_S, oz_base254);
         const bool can_trsm = m->devs[0].have_fac;
-        if (mode_env && !strcmp(mode_env, "ozaki")) use_oz = true;
+        if (mode_env && !strcmp(mode_env, "ozaki")) use_oz = oz_fits;
         else if (mode_env && !strcmp(mode_env, "trsm")) use_trsm = can_trsm;
         else if (mode_env && !strcmp(mode_env, "product")) { }
         else {
-            bool have_x, dis;
-            { std::lock_guard<std::mutex> lk(m->mu); have_x = m->devs[0].have_linv; dis = m->oz_disabled; }
-            if (!dis && (long)io.q >= oz_min_q) use_oz = true;
-            else use_trsm = can_trsm && !have_x && (long)io.q >= min_q;
+            // sticky: once the int8 slices of a model exist every batch of more than 8 queries uses them, so that for a given
+            // model state the result of a query does not depend on how the queries are split into calls
+            bool have_x, dis, have_slices;
+            { std::lock_guard<std::mutex> lk(m->mu); have_x = m->devs[0].have_linv; dis = m->oz_disabled; have_slices = m->devs[0].oz_xs != nullptr; }
+            const long qc = (long)(io.q_call ? io.q_call : io.q);
+            if (!dis && oz_fits && (qc >= oz_min_q || have_slices)) use_oz = true;
+            else use_trsm = can_trsm && !have_x && qc >= min_q;
         }
     }
     int rc = ensure_on_device(m, di, want_var && !use_trsm, use_trsm);          // the INT8 path needs X = L^-1 too
@@ -826,7 +837,7 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
                 ws->oz_ks_bytes = need;
             }
             if (!ws->oz_ctrl) CU(cudaMalloc((void**)&ws->oz_ctrl, 4 * sizeof(int)));
-            rc = ensure_ozaki_slices(m, di, oz_S, st);
+            rc = ensure_ozaki_slices(m, di, oz_S, oz_base254, st);
             if (rc) return rc;
         }
     }
@@ -868,10 +879,10 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
                 int ge = 0;
                 frexp(m->k0, &ge);
                 const double cs = ldexp(1.0, ge);
-                CU(launch_ozaki_slice_panel(ws->panel, pld, (int)bq, m->nb * TB, 1.0 / cs, oz_S, ws->oz_ks, ld, pld, st));
+                CU(launch_ozaki_slice_panel(ws->panel, pld, (int)bq, m->nb * TB, 1.0 / cs, oz_S, oz_base254, ws->oz_ks, ld, pld, st));
                 CU(cudaEventRecord(ws->ev[5], st));
-                CU(launch_ozaki_product(md.oz_xs, ld, ld * ld, m->nb, ws->oz_ks, ld, pld * ld, (int)bq, pld, (size_t)m->nb * TB, 1, oz_S,
-                                        oz_levels, md.oz_scale, cs, ws->partial, ws->oz_ctrl, nullptr, st));
+                CU(launch_ozaki_product(md.oz_xs, ld, ld * ld, m->nb, ws->oz_ks, ld, pld * ld, pld, (int)bq, pld, (size_t)m->nb * TB, 1, oz_S,
+                                        oz_base254, md.oz_scale, cs, ws->partial, ws->oz_ctrl, nullptr, 0, st));
                 CU(cudaEventRecord(ws->ev[6], st));
                 oz_timed = true;
                 CU(launch_var_finalize(ws->partial, pld, m->nb, (int)bq, m->k0, v, st));
@@ -1244,6 +1255,7 @@ static int predict_host(gpr_ctx* ctx, gpr_model* m, const double* qx, const doub
         const size_t a = q * di / use, b = q * (di + 1) / use;
         io.qx = qx; io.qy = qy; io.qz = qz; io.q = b - a; io.offset = a;
         io.f = f; io.var = var; io.grad = grad; io.tx = tx; io.ty = ty; io.out_ld = q; io.device_ptrs = false;
+        io.q_call = q;
         rcs[di] = predict_on_device(m, di, io, &tm[di], &tv[di], &th[di], &td[di]);
         if (rcs[di]) errs[di] = g_err;
     };
@@ -2398,26 +2410,27 @@ int gpr_selftest_factor_trace(int nb, long long* h_trace, long long* leaf_cycles
 // tensors A [S][M][K], B [S][N][K] (host, K contiguous); M multiple of 128, N of 64, K of 64; tri: A lower triangular by
 // 128-row tiles (row tile r only visits k < 128 (r + 1)).  hC: [levels][M][N] int32.
 int gpr_selftest_i8gemm(const signed char* hA, const signed char* hB, int S, int levels, int M, int Nq, int K, int tri, int* hC) {
-    if (!hA || !hB || !hC || M % 128 || Nq % 64 || K % 64 || S < 1 || S > 8) return fail(GPR_ERR_INVALID, "bad shape");
+    if (!hA || !hB || !hC || M % 128 || Nq % 16 || K % 64 || S < 1 || S > 8 || levels != S) return fail(GPR_ERR_INVALID, "bad shape");
     signed char *A, *B; int *C, *ctrl; double *scale, *partial;
     const size_t qpad = (size_t)(Nq + 127) / 128 * 128;
     CU(cudaMalloc((void**)&A, (size_t)S * M * K));
     CU(cudaMalloc((void**)&B, (size_t)S * Nq * K));
-    CU(cudaMalloc((void**)&C, (size_t)levels * M * Nq * sizeof(int)));
+    CU(cudaMalloc((void**)&C, (size_t)S * M * Nq * sizeof(int)));
     CU(cudaMalloc((void**)&ctrl, 4 * sizeof(int)));
     CU(cudaMalloc((void**)&scale, (size_t)M * sizeof(double)));
     CU(cudaMalloc((void**)&partial, (size_t)(M / 128) * qpad * sizeof(double)));
     CU(cudaMemcpy(A, hA, (size_t)S * M * K, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(B, hB, (size_t)S * Nq * K, cudaMemcpyHostToDevice));
-    CU(cudaMemset(C, 0, (size_t)levels * M * Nq * sizeof(int)));
+    CU(cudaMemset(C, 0, (size_t)S * M * Nq * sizeof(int)));
     std::vector<double> ones(M, 1.0);
     CU(cudaMemcpy(scale, ones.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice));
-    CU(launch_ozaki_product(A, (size_t)K, (size_t)M * K, M / 128, B, (size_t)K, (size_t)Nq * K, Nq, qpad, (size_t)K, tri, S, levels, scale, 1.0,
-                            partial, ctrl, C, 0));
+    // the tensor of B has exactly Nq rows: query tiles reaching beyond it are zero-filled by TMA
+    CU(launch_ozaki_product(A, (size_t)K, (size_t)M * K, M / 128, B, (size_t)K, (size_t)Nq * K, (size_t)Nq, Nq, qpad, (size_t)K, tri, S, 0, scale,
+                            1.0, partial, ctrl, C, (size_t)Nq, 0));
     CU(cudaDeviceSynchronize());
     int hctrl[2];
     CU(cudaMemcpy(hctrl, ctrl, sizeof hctrl, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(hC, C, (size_t)levels * M * Nq * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hC, C, (size_t)S * M * Nq * sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(ctrl); cudaFree(scale); cudaFree(partial);
     if (hctrl[1] != 0) return fail(GPR_ERR_CUDA, "INT8 tensor-core kernel aborted (a pipeline wait timed out)");
     return GPR_OK;

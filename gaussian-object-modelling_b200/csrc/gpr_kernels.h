@@ -75,13 +75,15 @@ cudaError_t launch_variance_small(const double* X, size_t ld, int N, const doubl
                                   double* part, double k0, double* var, cudaStream_t st);
 cudaError_t launch_var_finalize(const double* partial, size_t panel_ld, int nb, int q, double k0, double* var, cudaStream_t st);
 // K3'' (gpr_ozaki.cu): the variance product on the INT8 tensor cores (tcgen05 kind::i8 + TMEM + TMA), FP64-equivalent by slicing.
-int ozaki_stages(int S);
+int ozaki_tile_n(int S);
+long long ozaki_max_k(int S, int base254);
 cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a_slice, int nrt, const signed char* Bs, size_t b_pitch,
-                                 size_t b_slice, int q, size_t q_pad, size_t k_extent, int tri, int S, int levels,
-                                 const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, cudaStream_t st);
-cudaError_t launch_ozaki_slice_x(const double* X, size_t ld, int n_rows, int S, signed char* Xs, double* row_scale,
+                                 size_t b_slice, size_t b_rows, int q, size_t q_pad, size_t k_extent, int tri, int S, int base254,
+                                 const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, size_t dbg_ld,
+                                 cudaStream_t st);
+cudaError_t launch_ozaki_slice_x(const double* X, size_t ld, int n_rows, int S, int base254, signed char* Xs, double* row_scale,
                                  unsigned long long* rowmax, cudaStream_t st);
-cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q, int n_k, double inv_scale, int S,
+cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q, int n_k, double inv_scale, int S, int base254,
                                      signed char* Ks, size_t k_pitch, size_t q_pad, cudaStream_t st);
 // K5 (gpr_append.cu): one slab of k <= 32 appended points at rows [n0, n0+k); ws: append_workspace_doubles(cap).
 size_t append_workspace_doubles(size_t cap);

@@ -2,23 +2,26 @@
 // (tcgen05.mma kind::i8, TMEM int32 accumulators, TMA operand feeds), FP64-equivalent by Ozaki-style slicing.
 //
 // Why: the FP64 tensor pipe (DMMA) is the roof of var_tiles_kernel / var_trsm_kernel (37 TF/s); tcgen05 has no f64
-// kind, but it multiplies 8-bit integers EXACTLY into 32-bit accumulators at ~60x that rate.  So
-//   X   ~ 2^(e_i) * sum_t 2^(-6-7t) A_t      (row i scaled by a power of two, A_t int8 slices, |A_t| <= 64)
-//   K*  ~ 2^(g)   * sum_u 2^(-6-7u) B_u      (one power-of-two scale per batch, B_u int8 slices)
-//   V_iq = 2^(e_i+g) * sum_l 2^(-12-7l) * [ sum_{t+u=l} sum_k A_t[i,k] B_u[q,k] ]          l = 0 .. levels-1
-// where every bracket is an exact integer (|.| < 2^31 for k <= 65536 and up to 8 pairs per level) computed by int8
-// MMAs, and the few levels are recombined in FP64 in the epilogue, which also reduces the squared column norms per
-// 128-row tile exactly like the DMMA kernels (partial[row tile][query] -> var_finalize_kernel).  Slices beyond
-// `levels` are dropped: truncation error ~ 2^(-7 levels) relative to (row max of X) x (max of K*) x sqrt(k) — the
-// slice count is chosen against the variance tolerance (profiles/ozaki_slicing_study_r2.json, tools/ozaki_study.py).
+// kind, but it multiplies 8-bit integers EXACTLY into 32-bit accumulators at ~60x that rate.  So, with digits d in base B,
+//   X   = 2^(e_i) * sum_t A_t / (F B^t)      (row i scaled by a power of two; A_t int8 digit slices)
+//   K*  = 2^(g)   * sum_u B_u / (F B^u)      (one power-of-two scale per batch; B_u int8 digit slices)
+//   V_iq = 2^(e_i+g) * sum_l w_l * [ sum_{t+u=l} sum_k A_t[i,k] B_u[q,k] ],   w_l = 1 / (F^2 B^l),   l = 0 .. S-1
+// where every bracket is an exact integer computed by int8 MMAs and the S levels are recombined in FP64 in the epilogue,
+// which also reduces the squared column norms per 128-row tile exactly like the DMMA kernels
+// (partial[row tile][query] -> var_finalize_kernel).  Two digit systems:
+//   base 254: F = 127, |digit| <= 127 (7.99 bits per slice); exact while S * 127^2 * k < 2^31, i.e. k <= 22016 for S = 6;
+//   base 128: F = 64,  |digit| <= 64  (7 bits per slice);    exact while S * 64^2 * k < 2^31, i.e. k <= 74752 for S = 7.
+// Slices beyond level S - 1 are dropped: truncation ~ B^(-S) relative to (row max of X) x (max of K*) x sqrt(k); the slice
+// count is chosen against the variance tolerance (profiles/ozaki_slicing_study_r2.json, tools/ozaki_study.py), and every
+// call is spot-checked against the FP64 tensor pipe by the caller (gpr_c_api.cu).
 //
-// Kernel structure (one CTA per SM, 128 threads, persistent over (row tile, query tile) tasks):
+// Kernel structure (one CTA per SM, persistent over (row tile, query tile) tasks dealt round-robin):
 //   * operands: int8 slice tensors [slice][row][k] (k contiguous = K-major), fetched by TMA (3-D boxes
-//     {64 k, 128 or 64 rows, S slices}, SWIZZLE_64B) into a ring of shared-memory stages, completion on mbarriers;
-//   * one thread issues the TMA loads and the tcgen05.mma instructions (M = 128, N = 64, K = 32 per instruction; all
-//     slice pairs of a k-block reuse the stage), tcgen05.commit releases a stage / signals the epilogue;
-//   * accumulators: `levels` x 64 TMEM columns (<= 512), one 128 x 64 int32 tile per level;
-//   * epilogue: all four warps read their 32 TMEM lanes with tcgen05.ld, recombine in FP64, square, reduce.
+//     {64 k, 128 or BN rows, S slices}, SWIZZLE_64B) into a ring of shared-memory stages, completion on mbarriers;
+//   * warp 0: TMA producer; warp 1: one thread issues the tcgen05.mma instructions (M = 128, N = BN = 64 or 80, K = 32 per
+//     instruction; all slice pairs of a k-block reuse the stage); tcgen05.commit releases a stage / signals the epilogue;
+//   * accumulators: S levels x BN TMEM columns (<= 512), one 128 x BN int32 tile per level;
+//   * warps 2..5: epilogue — each thread reads its TMEM lane (row) with tcgen05.ld, recombines in FP64, squares, reduces.
 // X is lower triangular: row tile rt only visits k < 128 (rt + 1).
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -31,11 +34,10 @@
 namespace gpr {
 
 constexpr int OZ_BM = 128;        // rows of X per task (UMMA M)
-constexpr int OZ_BN = 64;         // queries per task (UMMA N)
+constexpr int OZ_BN_MAX = 80;     // queries per task (UMMA N): 64 or 80 (S * BN <= 512 TMEM columns)
 constexpr int OZ_BK = 64;         // k per pipeline stage (bytes per row = SWIZZLE_64B span); 2 MMAs of K = 32
 constexpr int OZ_TMEM_COLS = 512;
 constexpr int OZ_A_SLICE_BYTES = OZ_BM * OZ_BK;     // 8 KB
-constexpr int OZ_B_SLICE_BYTES = OZ_BN * OZ_BK;     // 4 KB
 constexpr long long OZ_TIMEOUT = 4000000000LL;      // cycles (~2 s): a bug must not hang the GPU
 
 struct OzArgs {
@@ -49,8 +51,10 @@ struct OzArgs {
     double* partial;              // [nrt][q_pad]
     size_t q_pad;
     int* ctrl;                    // [0] task counter, [1] abort flag
-    int* dbg;                     // optional raw accumulators [levels][nrt*128][nqt*64]
+    int* dbg;                     // optional raw accumulators [S][nrt*128][dbg_ld]
+    size_t dbg_ld;
     int gr, gq;                   // co-scheduled group: gr row tiles x gq query tiles
+    double wl[8];                 // level weights 1 / (F^2 B^l)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -121,13 +125,16 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int M, int N) {
 // issue loop (template on the slice count) and the separate producer warp.
 constexpr int OZ_NTHREADS = 192;
 
-template <int S>
+template <int S, int BN>
 __global__ void __launch_bounds__(OZ_NTHREADS, 1)
 ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a) {
     extern __shared__ __align__(1024) uint8_t oz_smem[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accum_full, accum_empty;
     __shared__ uint32_t s_tmem;
-    __shared__ double sred[4][OZ_BN];
+    __shared__ double sred[4][OZ_BN_MAX];
+    static_assert(S * BN <= OZ_TMEM_COLS && BN % 16 == 0 && BN <= OZ_BN_MAX, "TMEM budget");
+    constexpr int OZ_BN = BN;
+    constexpr int OZ_B_SLICE_BYTES = BN * OZ_BK;
 
     constexpr int LEVELS = S;
     constexpr uint32_t STAGE_BYTES = (uint32_t)S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
@@ -234,8 +241,7 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const int row = rt * OZ_BM + q4 * 32 + lane;
             const double rs = a.row_scale[row] * a.col_scale;
-            double ss[OZ_BN / 16][16];
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < OZ_BN / 16; ++c) {
                 double acc[16];
 #pragma unroll
@@ -244,35 +250,34 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int l = LEVELS - 1; l >= 0; --l) {
                     uint32_t v[16];
                     tmem_ld16(tmem + lane_base + (uint32_t)(l * OZ_BN + 16 * c), v);
-                    const double wl = __longlong_as_double((long long)(1023 - 12 - 7 * l) << 52);      // 2^(-12-7l)
+                    const double wl = a.wl[l];
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) acc[jj] = fma((double)(int)v[jj], wl, acc[jj]);
                     if (a.dbg) {
-                        const size_t ldq = (size_t)a.nqt * OZ_BN;
-                        int* o = a.dbg + ((size_t)l * a.nrt * OZ_BM + row) * ldq + (size_t)qt * OZ_BN + 16 * c;
+                        int* o = a.dbg + ((size_t)l * a.nrt * OZ_BM + row) * a.dbg_ld;
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) o[jj] = (int)v[jj];
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const size_t col = (size_t)qt * OZ_BN + 16 * c + jj;
+                            if (col < a.dbg_ld) o[col] = (int)v[jj];
+                        }
                     }
                 }
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) { const double vv = acc[jj] * rs; ss[c][jj] = vv * vv; }
-            }
-            // TMEM is drained: the MMA issuer may start the next task while the column norms are reduced
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
-#pragma unroll
-            for (int c = 0; c < OZ_BN / 16; ++c)
-#pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
-                    double sv = ss[c][jj];
+                    const double vv = acc[jj] * rs;
+                    double sv = vv * vv;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
                     if (lane == 0) sred[q4][16 * c + jj] = sv;
                 }
+            }
+            // TMEM is drained: the MMA issuer may start the next task
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps
             const int et = tid - 64;
-            if (et < OZ_BN)
+            if (et < OZ_BN && (size_t)qt * OZ_BN + et < a.q_pad)
                 a.partial[(size_t)rt * a.q_pad + (size_t)qt * OZ_BN + et] = (sred[0][et] + sred[1][et]) + (sred[2][et] + sred[3][et]);
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
@@ -305,13 +310,14 @@ __global__ void oz_rowscale_kernel(const unsigned long long* rowmax, int n, doub
     if (m > 0.0) { frexp(m, &e); }                       // m = f * 2^e, f in [0.5, 1)  ->  2^e >= m
     row_scale[i] = ldexp(1.0, e);
 }
-// One value -> S signed slices: v in [-1, 1];  I_0 = rint(64 v), r = 64 v - I_0;  I_t = rint(128 r), r = 128 r - I_t ...
-__device__ __forceinline__ void oz_slice(double v, int S, signed char* out, size_t stride) {
-    double r = v * 64.0;
+// One value -> S signed digits in base B with first scale F (F = B / 2): v in [-1, 1];  d_0 = rint(F v), r = F v - d_0 in
+// [-1/2, 1/2];  d_t = rint(B r) in [-F, F], r = B r - d_t ...   (B = 128, F = 64 or B = 254, F = 127: all digits fit int8)
+__device__ __forceinline__ void oz_slice(double v, int S, double first, double base, signed char* out, size_t stride) {
+    double r = v * first;
     for (int t = 0; t < S; ++t) {
         const double it = rint(r);
         out[(size_t)t * stride] = (signed char)(int)it;
-        r = (r - it) * 128.0;
+        r = (r - it) * base;
     }
 }
 // Slices of a column-major FP64 matrix M (element (row r, col c) at M[c*ld + r]) into K-major int8 tensors
@@ -320,7 +326,8 @@ __device__ __forceinline__ void oz_slice(double v, int S, signed char* out, size
 // nullptr with one common scale inv_scale (the K* panel).  tri: entries with c > r are structural zeros.
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ M, size_t ld, int rows, int cols,
                                                         const double* __restrict__ scale_rows, double inv_scale, int tri,
-                                                        int S, signed char* __restrict__ out, size_t out_ld, size_t out_slice) {
+                                                        int S, double first, double base, signed char* __restrict__ out, size_t out_ld,
+                                                        size_t out_slice) {
     __shared__ double tile[64][65];
     const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
     if (tri && c0 > r0 + 63) return;                     // block entirely above the diagonal: left zero by the memset
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
         const int r = r0 + rr, c = c0 + cc;
         if (r >= rows || c >= cols) continue;
         const double sc = scale_rows ? 1.0 / scale_rows[r] : inv_scale;
-        oz_slice(tile[rr][cc] * sc, S, out + (size_t)r * out_ld + c, out_slice);
+        oz_slice(tile[rr][cc] * sc, S, first, base, out + (size_t)r * out_ld + c, out_slice);
     }
 }
 
@@ -368,48 +375,55 @@ static cudaError_t make_map(CUtensorMap* tm, const signed char* ptr, size_t k_ex
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-int ozaki_stages(int S) {
-    const int stage = S * (OZ_A_SLICE_BYTES + OZ_B_SLICE_BYTES);
+// Pipeline stages that fit the shared-memory budget.
+int ozaki_stages(int S, int BN) {
+    const int stage = S * (OZ_A_SLICE_BYTES + BN * OZ_BK);
     int st = (int)((220 * 1024) / stage);
     return st > 6 ? 6 : (st < 1 ? 1 : st);
 }
+int ozaki_tile_n(int S) { return S * 80 <= OZ_TMEM_COLS ? 80 : 64; }
+// Largest k extent for which every level accumulator stays below 2^31 in the worst case.
+long long ozaki_max_k(int S, int base254) {
+    const long long d = base254 ? 127 : 64;
+    return ((1LL << 31) - 1) / ((long long)S * d * d);
+}
 
-// Launch over slice tensors that are already built.  As: [S][rows_pad][k_pad] (rows_pad = 128 nrt, k pitch = a_pitch);
-// Bs: [S][q_pad][k_pad'] (k pitch = b_pitch).  ctrl: 2 ints.  dbg: optional raw accumulators.
-cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a_slice, int nrt, const signed char* Bs, size_t b_pitch,
-                                 size_t b_slice, int q, size_t q_pad, size_t k_extent, int tri, int S, int levels,
-                                 const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, cudaStream_t st) {
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, OzArgs);
-    KernelFn fn = nullptr;
-    switch (S) {
-        case 1: fn = ozaki_var_kernel<1>; break;
-        case 2: fn = ozaki_var_kernel<2>; break;
-        case 3: fn = ozaki_var_kernel<3>; break;
-        case 4: fn = ozaki_var_kernel<4>; break;
-        case 5: fn = ozaki_var_kernel<5>; break;
-        case 6: fn = ozaki_var_kernel<6>; break;
-        case 7: fn = ozaki_var_kernel<7>; break;
-        case 8: fn = ozaki_var_kernel<8>; break;
-        default: return cudaErrorInvalidValue;
-    }
-    if (levels != S) return cudaErrorInvalidValue;          // every level t + u < S is kept
-    static PerDeviceOnce attr_done[9];
+template <int S, int BN>
+static cudaError_t launch_oz(const CUtensorMap& tmA, const CUtensorMap& tmB, const OzArgs& a, int grid, size_t smem, cudaStream_t st) {
+    static PerDeviceOnce attr_done;
     const int cur = PerDeviceOnce::current();
-    const size_t smem = (size_t)220 * 1024 + 1024;
-    if (!attr_done[S].done(cur)) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!attr_done.done(cur)) {
+        cudaError_t e = cudaFuncSetAttribute(ozaki_var_kernel<S, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done[S].set(cur);
+        attr_done.set(cur);
     }
+    ozaki_var_kernel<S, BN><<<grid, OZ_NTHREADS, smem, st>>>(tmA, tmB, a);
+    return cudaGetLastError();
+}
+
+// Launch over slice tensors that are already built.  As: [S][a_rows][k] (k pitch a_pitch, a_rows = 128 nrt); Bs: [S][b_rows][k]
+// (k pitch b_pitch).  base254: digit system (selects the level weights).  partial: [nrt][q_pad].  ctrl: 2 ints.
+// dbg: optional raw accumulators [S][a_rows][dbg_ld].
+cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a_slice, int nrt, const signed char* Bs, size_t b_pitch,
+                                 size_t b_slice, size_t b_rows, int q, size_t q_pad, size_t k_extent, int tri, int S, int base254,
+                                 const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, size_t dbg_ld,
+                                 cudaStream_t st) {
+    if (S < 1 || S > 8) return cudaErrorInvalidValue;
+    if ((long long)k_extent > ozaki_max_k(S, base254)) return cudaErrorInvalidValue;       // an accumulator could overflow
+    const int BN = ozaki_tile_n(S);
+    const size_t smem = (size_t)220 * 1024 + 1024;
     CUtensorMap tmA, tmB;
     cudaError_t e = make_map(&tmA, As, k_extent, (size_t)nrt * OZ_BM, S, a_pitch, a_slice, OZ_BM);
     if (e != cudaSuccess) return e;
-    e = make_map(&tmB, Bs, k_extent, q_pad, S, b_pitch, b_slice, OZ_BN);
+    e = make_map(&tmB, Bs, k_extent, b_rows, S, b_pitch, b_slice, BN);
     if (e != cudaSuccess) return e;
     OzArgs a;
-    a.S = S; a.levels = levels; a.stages = ozaki_stages(S);
-    a.nrt = nrt; a.nqt = (int)((q + OZ_BN - 1) / OZ_BN); a.tri = tri; a.kblocks = (int)(k_extent / OZ_BK);
-    a.row_scale = row_scale; a.col_scale = col_scale; a.partial = partial; a.q_pad = q_pad; a.ctrl = ctrl; a.dbg = dbg;
+    a.S = S; a.levels = S; a.stages = ozaki_stages(S, BN);
+    a.nrt = nrt; a.nqt = (int)((q + BN - 1) / BN); a.tri = tri; a.kblocks = (int)(k_extent / OZ_BK);
+    a.row_scale = row_scale; a.col_scale = col_scale; a.partial = partial; a.q_pad = q_pad; a.ctrl = ctrl; a.dbg = dbg; a.dbg_ld = dbg_ld;
+    const double F = base254 ? 127.0 : 64.0, B = base254 ? 254.0 : 128.0;
+    double w = 1.0 / (F * F);
+    for (int l = 0; l < 8; ++l) { a.wl[l] = w; w /= B; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -420,13 +434,22 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
     e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);
     if (e != cudaSuccess) return e;
     const int tasks = ((a.nrt + a.gr - 1) / a.gr) * ((a.nqt + a.gq - 1) / a.gq) * a.gr * a.gq;
-    fn<<<tasks < sms ? tasks : sms, OZ_NTHREADS, smem, st>>>(tmA, tmB, a);
-    return cudaGetLastError();
+    const int grid = tasks < sms ? tasks : sms;
+    switch (S) {
+        case 1: return launch_oz<1, 80>(tmA, tmB, a, grid, smem, st);
+        case 2: return launch_oz<2, 80>(tmA, tmB, a, grid, smem, st);
+        case 3: return launch_oz<3, 80>(tmA, tmB, a, grid, smem, st);
+        case 4: return launch_oz<4, 80>(tmA, tmB, a, grid, smem, st);
+        case 5: return launch_oz<5, 80>(tmA, tmB, a, grid, smem, st);
+        case 6: return launch_oz<6, 80>(tmA, tmB, a, grid, smem, st);
+        case 7: return launch_oz<7, 64>(tmA, tmB, a, grid, smem, st);
+        default: return launch_oz<8, 64>(tmA, tmB, a, grid, smem, st);
+    }
 }
 
 // Slices of X = L^-1 (lower triangular, column-major n x n with leading dimension ld; rows padded to 128 nrt):
 // Xs[t][i][k], row pitch = slice row count = ld.  rowmax: ld 8-byte words of scratch.
-cudaError_t launch_ozaki_slice_x(const double* X, size_t ld, int n_rows, int S, signed char* Xs, double* row_scale,
+cudaError_t launch_ozaki_slice_x(const double* X, size_t ld, int n_rows, int S, int base254, signed char* Xs, double* row_scale,
                                  unsigned long long* rowmax, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(rowmax, 0, ld * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
@@ -434,16 +457,17 @@ cudaError_t launch_ozaki_slice_x(const double* X, size_t ld, int n_rows, int S, 
     if (e != cudaSuccess) return e;
     oz_rowmax_kernel<<<dim3((n_rows + 255) / 256, (n_rows + 255) / 256), 256, 0, st>>>(X, ld, n_rows, rowmax);
     oz_rowscale_kernel<<<(int)((ld + 255) / 256), 256, 0, st>>>(rowmax, (int)ld, row_scale);
-    oz_slice_kernel<<<dim3((n_rows + 63) / 64, (n_rows + 63) / 64), 256, 0, st>>>(X, ld, n_rows, n_rows, row_scale, 0.0, 1, S, Xs, ld,
-                                                                                ld * ld);
+    oz_slice_kernel<<<dim3((n_rows + 63) / 64, (n_rows + 63) / 64), 256, 0, st>>>(X, ld, n_rows, n_rows, row_scale, 0.0, 1, S,
+                                                                                base254 ? 127.0 : 64.0, base254 ? 254.0 : 128.0, Xs, ld, ld * ld);
     return cudaGetLastError();
 }
 
 // Slices of the K* panel (element (query c, point k) at panel[k*panel_ld + c]) -> Ks[u][query][k] with k pitch k_pitch.
-cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q, int n_k, double inv_scale, int S,
+cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q, int n_k, double inv_scale, int S, int base254,
                                      signed char* Ks, size_t k_pitch, size_t q_pad, cudaStream_t st) {
     // here the "rows" of the slice tensor are the queries and its "columns" the points: M(row = query, col = k) = panel[k*ld + query]
-    oz_slice_kernel<<<dim3((q + 63) / 64, (n_k + 63) / 64), 256, 0, st>>>(panel, panel_ld, q, n_k, nullptr, inv_scale, 0, S, Ks, k_pitch,
+    oz_slice_kernel<<<dim3((q + 63) / 64, (n_k + 63) / 64), 256, 0, st>>>(panel, panel_ld, q, n_k, nullptr, inv_scale, 0, S,
+                                                                        base254 ? 127.0 : 64.0, base254 ? 254.0 : 128.0, Ks, k_pitch,
                                                                         q_pad * k_pitch);
     return cudaGetLastError();
 }

@@ -27,8 +27,8 @@ def expect(A, B, levels, tri):
 
 
 # stage 1: one slice, one tile, one k-block ... then bigger
-for (S, levels, M, N, K, tri) in ((1, 1, 128, 64, 64, False), (1, 1, 128, 64, 256, False), (2, 2, 256, 128, 512, False),
-                                  (3, 3, 384, 192, 384, True), (7, 7, 512, 320, 1024, True)):
+for (S, levels, M, N, K, tri) in ((1, 1, 128, 64, 64, False), (1, 1, 128, 80, 256, False), (2, 2, 256, 128, 512, False),
+                                  (3, 3, 384, 192, 384, True), (6, 6, 512, 336, 1024, True), (7, 7, 512, 320, 1024, True)):
     A = rng.integers(-64, 65, size=(S, M, K), dtype=np.int8)
     B = rng.integers(-64, 65, size=(S, N, K), dtype=np.int8)
     t0 = time.time()
@@ -55,12 +55,13 @@ for n, q in ((2304, 5000), (4096, 20000)):
     os.environ["GPR_VAR_MODE"] = "product"
     f0, v0 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
     os.environ["GPR_VAR_MODE"] = "ozaki"
-    for S in (5, 6, 7, 8):
+    for base, S in ((254, 5), (254, 6), (254, 7), (128, 6), (128, 7), (128, 8)):
         os.environ["GPR_OZAKI_SLICES"] = str(S)
+        os.environ["GPR_OZAKI_BASE"] = str(base)
         f1, v1 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
         t = ctx.timings()
-        print("n=%d q=%d slices=%d: var rel diff vs FP64 product %.3e  (var_ms %.2f, mean_ms %.2f)"
-              % (n, q, S, np.abs(v1 - v0).max() / np.abs(v0).max(), t["predict_var_ms"], t["predict_mean_ms"]), flush=True)
+        print("n=%d q=%d base=%d slices=%d: var rel diff vs FP64 product %.3e  (var_ms %.2f, int8 kernel %.2f, mean_ms %.2f)"
+              % (n, q, base, S, np.abs(v1 - v0).max() / np.abs(v0).max(), t["predict_var_ms"], t["ozaki_ms"], t["predict_mean_ms"]), flush=True)
     del m
 if stage_max < 3:
     sys.exit(0)
@@ -76,11 +77,21 @@ f0, v0 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
 f0, v0 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
 print("n=16384 product form: var_ms %.2f" % ctx.timings()["predict_var_ms"], flush=True)
 os.environ["GPR_VAR_MODE"] = "ozaki"
-for S in (6, 7, 8):
+rows = []
+for base, S in ((254, 5), (254, 6), (254, 7), (128, 6), (128, 7), (128, 8)):
     os.environ["GPR_OZAKI_SLICES"] = str(S)
+    os.environ["GPR_OZAKI_BASE"] = str(base)
     for rep in range(2):
         f1, v1 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
     t = ctx.timings()
     flop = float(n) ** 2 * len(Q)
-    print("n=16384 slices=%d: var rel diff %.3e, var_ms %.2f (%.1f FP64-equivalent TF/s), mean_ms %.2f"
-          % (S, np.abs(v1 - v0).max() / np.abs(v0).max(), t["predict_var_ms"], flop / (t["predict_var_ms"] * 1e-3) / 1e12, t["predict_mean_ms"]), flush=True)
+    rows.append({"n": n, "queries": len(Q), "digit_base": base, "slices": S, "slice_pairs": S * (S + 1) // 2, "tile_n": 80 if S <= 6 else 64,
+                 "var_rel_diff_vs_fp64_product": float(np.abs(v1 - v0).max() / np.abs(v0).max()), "var_ms": t["predict_var_ms"],
+                 "int8_kernel_ms": t["ozaki_ms"], "fp64_equivalent_tflops": flop / (t["predict_var_ms"] * 1e-3) / 1e12,
+                 "int8_tops": 2.0 * (S * (S + 1) // 2) * (n * (n + 128) / 2.0) * len(Q) / (t["ozaki_ms"] * 1e-3) / 1e12 if t["ozaki_ms"] > 0 else None})
+    print(rows[-1], flush=True)
+import json
+out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+if os.path.isdir(out):
+    json.dump({"what": "INT8 tensor-core variance (gpr_ozaki.cu) at the headline size: accuracy and speed per digit system / slice count; "
+                       "FP64 product form (var_tiles_kernel) on the same batch: %.2f ms" % 0.0, "rows": rows}, open(os.path.join(out, "ozaki_table.json"), "w"), indent=1)
