@@ -7,8 +7,8 @@ sphere, label 0; 4,096 on the r = 2 sphere, label +1), sigma2 = 0.1, ThinPlate(R
 
 A "step" is one pass of the hot path over one batch of queries per GPU: fused mean + cross-covariance
 panel, then the variance product V = L^-1 K*^T (n^2 flop per query) in the library's default form for large batches: on
-the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators, TMA feeds), FP64-equivalent by Ozaki slicing (7 x 7-bit
-slices per operand, FP64 recombination; every call spot-checked against the FP64 tensor pipe).  The two FP64 forms
+the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators, TMA feeds), FP64-equivalent by Ozaki slicing (6 slices of
+base-254 digits per operand at this n, FP64 recombination; every call spot-checked against the FP64 tensor pipe).  The two FP64 forms
 (forward substitution over L, product with L^-1 on the DMMA pipe) are timed on the same batches and reported beside it.  `value` is whole-job
 query points / s (mean + variance) with the queries already resident in HBM; `e2e` is the same through
 the host-pointer C-ABI call gpr_predict (pinned host buffers, H2D and D2H inside the timed region).
@@ -299,9 +299,12 @@ def main():
                             f_d.data_ptr(), v_d.data_ptr(), None)
         t = ctx.timings()
         oz_ms[0] += t["ozaki_ms"]
+        if t["ozaki_slices"] > 0:
+            oz_used[0] = int(t["ozaki_slices"])
         return t["predict_var_ms"], t["predict_mean_ms"]
 
     oz_ms = [0.0]
+    oz_used = [0]
     sampler = ClockSampler(local_rank)
     for s in range(args.warmup):
         step_device(s)
@@ -424,7 +427,7 @@ def main():
         flops_per_launch = float(N_TRAIN) ** 2 * batch                # n^2 * q per variance batch, FP64 count
         fp64_equiv = flops_per_launch / (var_ms / launches_var * 1e-3) / 1e12
         # the INT8 kernel's own work: 2 ops x (slice pairs t + u < S) x (lower triangle by 128-row tiles) x queries
-        oz_slices = int(os.environ.get("GPR_OZAKI_SLICES", "7"))
+        oz_slices = oz_used[0] if oz_used[0] else 6
         oz_pairs = oz_slices * (oz_slices + 1) // 2
         int8_ops_per_launch = 2.0 * oz_pairs * (N_TRAIN * (N_TRAIN + 128) / 2.0) * batch
         default_is_int8 = oz_kernel_ms > 0.0
@@ -485,6 +488,7 @@ def main():
                     "bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8 multiply-adds x 2)",
                     "frac": achieved / int8_peak, "peak_nominal": 4500.0, "frac_of_nominal": achieved / 4500.0,
                     "algorithmic_int8_ops_per_launch": int8_ops_per_launch, "slices": oz_slices, "slice_pairs": oz_pairs,
+                    "digit_base": 254 if oz_slices <= 6 else 128,
                     "fp64_equivalent_tflops": fp64_equiv, "fp64_equivalent_vs_dmma_peak": fp64_equiv / dmma_peak,
                     "fp64_equivalent_vs_cublas_dgemm": fp64_equiv / dgemm}
         else:

@@ -222,6 +222,7 @@ struct gpr_model {
     std::vector<double> hx, hy, hz, hlabel, hs2, h_alpha, h_normals;   // h_normals: n_normals x 3 column-major
     size_t n_normals = 0;
     bool oz_disabled = false;        // the INT8 tensor-core variance failed its FP64 spot check on this model: FP64 paths only
+    int oz_bump = 0;                 // extra slices this model needs beyond the default (raised by a failed spot check)
     std::mutex mu;
     // Micro-batcher of the callers' q = 1 pattern (hundreds of concurrent threads with one query each on one shared
     // model, src/gp_node.cpp:1027-1038): concurrent small requests are combined into one batched launch.
@@ -743,8 +744,11 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         const long long kext = (long long)m->nb * TB;
         oz_base254 = kext <= ozaki_max_k(6, 1) ? 1 : 0;
         if (const char* e = getenv("GPR_OZAKI_BASE")) oz_base254 = atoi(e) == 254 ? 1 : 0;
-        oz_S = oz_base254 ? 6 : 7;
-        if (const char* e = getenv("GPR_OZAKI_SLICES")) oz_S = std::max(2, std::min(8, atoi(e)));
+        int bump;
+        { std::lock_guard<std::mutex> lk(m->mu); bump = m->oz_bump; }
+        oz_S = std::min(8, (oz_base254 ? 6 : 7) + bump);
+        if (const char* e = getenv("GPR_OZAKI_SLICES")) oz_S = std::max(2, std::min(8, atoi(e) + bump));
+        if (oz_base254 && kext > ozaki_max_k(oz_S, 1) && !getenv("GPR_OZAKI_BASE")) { oz_base254 = 0; oz_S = std::min(8, oz_S + 1); }
         const bool oz_fits = kext <= ozaki_max_k(oz_S, oz_base254);
         const bool can_trsm = m->devs[0].have_fac;
         if (mode_env && !strcmp(mode_env, "ozaki")) use_oz = oz_fits;
@@ -812,11 +816,26 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         if (d2h_ms) *d2h_ms = 0.0;
         return GPR_OK;
     }
+    // workspace and model-side slices of the INT8 form for the current (oz_S, oz_base254)
+    size_t oz_panel_ld_max = 0;
+    auto prep_oz = [&]() -> int {
+        const size_t need = (size_t)oz_S * oz_panel_ld_max * m->cap;
+        if (ws->oz_ks_bytes < need) {
+            if (ws->oz_ks) CU(cudaFree(ws->oz_ks));
+            ws->oz_ks = nullptr; ws->oz_ks_bytes = 0;
+            CU(cudaMalloc((void**)&ws->oz_ks, need));
+            CU(cudaMemsetAsync(ws->oz_ks, 0, need, st));
+            ws->oz_ks_bytes = need;
+        }
+        if (!ws->oz_ctrl) CU(cudaMalloc((void**)&ws->oz_ctrl, 4 * sizeof(int)));
+        return ensure_ozaki_slices(m, di, oz_S, oz_base254, st);
+    };
     const bool small_var = want_var && io.q <= 8;
     size_t batch = io.q;
     if (want_var && !small_var) batch = std::min(io.q, ctx->query_tile ? ctx->query_tile : (size_t)TB * dc->num_sms);
     else batch = std::min(io.q, (size_t)1 << 22);
     const size_t panel_ld_max = (batch + TB - 1) / TB * TB;
+    oz_panel_ld_max = panel_ld_max;
     rc = ws_reserve(&ws->io, &ws->io_cap, 14 * std::max(batch, (size_t)TB));
     if (rc) return rc;
     const size_t cap = ws->io_cap / 14;
@@ -828,16 +847,7 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         rc = ws_reserve(&ws->partial, &ws->partial_dbl, std::max((size_t)m->nb * panel_ld_max, (size_t)8 * 8 * N));
         if (rc) return rc;
         if (use_oz) {
-            const size_t need = (size_t)oz_S * panel_ld_max * ld;
-            if (ws->oz_ks_bytes < need) {
-                if (ws->oz_ks) CU(cudaFree(ws->oz_ks));
-                ws->oz_ks = nullptr; ws->oz_ks_bytes = 0;
-                CU(cudaMalloc((void**)&ws->oz_ks, need));
-                CU(cudaMemsetAsync(ws->oz_ks, 0, need, st));
-                ws->oz_ks_bytes = need;
-            }
-            if (!ws->oz_ctrl) CU(cudaMalloc((void**)&ws->oz_ctrl, 4 * sizeof(int)));
-            rc = ensure_ozaki_slices(m, di, oz_S, oz_base254, st);
+            rc = prep_oz();
             if (rc) return rc;
         }
     }
@@ -879,14 +889,15 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
                 int ge = 0;
                 frexp(m->k0, &ge);
                 const double cs = ldexp(1.0, ge);
-                CU(launch_ozaki_slice_panel(ws->panel, pld, (int)bq, m->nb * TB, 1.0 / cs, oz_S, oz_base254, ws->oz_ks, ld, pld, st));
-                CU(cudaEventRecord(ws->ev[5], st));
-                CU(launch_ozaki_product(md.oz_xs, ld, ld * ld, m->nb, ws->oz_ks, ld, pld * ld, pld, (int)bq, pld, (size_t)m->nb * TB, 1, oz_S,
-                                        oz_base254, md.oz_scale, cs, ws->partial, ws->oz_ctrl, nullptr, 0, st));
-                CU(cudaEventRecord(ws->ev[6], st));
-                oz_timed = true;
-                CU(launch_var_finalize(ws->partial, pld, m->nb, (int)bq, m->k0, v, st));
-                if (b0 == 0) {
+                for (;;) {
+                    CU(launch_ozaki_slice_panel(ws->panel, pld, (int)bq, m->nb * TB, 1.0 / cs, oz_S, oz_base254, ws->oz_ks, ld, pld, st));
+                    CU(cudaEventRecord(ws->ev[5], st));
+                    CU(launch_ozaki_product(md.oz_xs, ld, ld * ld, m->nb, ws->oz_ks, ld, pld * ld, pld, (int)bq, pld, (size_t)m->nb * TB, 1,
+                                            oz_S, oz_base254, md.oz_scale, cs, ws->partial, ws->oz_ctrl, nullptr, 0, st));
+                    CU(cudaEventRecord(ws->ev[6], st));
+                    oz_timed = true;
+                    CU(launch_var_finalize(ws->partial, pld, m->nb, (int)bq, m->k0, v, st));
+                    if (b0 != 0) break;
                     // spot check of this call: the first query tile again on the FP64 tensor pipe (one tile: ~2 % of a batch)
                     const int cq = (int)std::min<size_t>(bq, TB);
                     rc = ws_reserve(&ws->tailw, &ws->tailw_dbl, (size_t)m->nb * TB + 2 * TB);
@@ -899,13 +910,24 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
                     CU(cudaStreamSynchronize(st));
                     double dmax = 0.0, vmax = 0.0;
                     for (int i = 0; i < cq; ++i) { dmax = std::max(dmax, std::fabs(hv[i] - hv[TB + i])); vmax = std::max(vmax, std::fabs(hv[TB + i])); }
-                    if (!(dmax <= 1e-8 * std::max(vmax, 1e-300))) {
-                        // not accurate enough for this model (conditioning beyond what the slice count covers): this batch and
-                        // everything after it on this model go through the FP64 product form
-                        { std::lock_guard<std::mutex> lk(m->mu); m->oz_disabled = true; }
-                        use_oz = false;
-                        CU(launch_variance(md.linv, ld, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+                    if (dmax <= 1e-8 * std::max(vmax, 1e-300)) break;
+                    // Not accurate enough for this model (conditioning beyond what the slice count covers): one more slice
+                    // (x128 / x254 finer) if the accumulators still cannot overflow — remembered on the model — else this batch
+                    // and everything after it on this model go through the FP64 product form.
+                    const bool forced_slices = getenv("GPR_OZAKI_SLICES") != nullptr;
+                    int nS = oz_S + 1, nbase = oz_base254;
+                    if (nbase && (long long)m->nb * TB > ozaki_max_k(nS, 1)) nbase = 0;
+                    if (!forced_slices && nS <= 8 && (long long)m->nb * TB <= ozaki_max_k(nS, nbase)) {
+                        { std::lock_guard<std::mutex> lk(m->mu); m->oz_bump += 1; }
+                        oz_S = nS; oz_base254 = nbase;
+                        rc = prep_oz();
+                        if (rc) return rc;
+                        continue;
                     }
+                    { std::lock_guard<std::mutex> lk(m->mu); m->oz_disabled = true; }
+                    use_oz = false;
+                    CU(launch_variance(md.linv, ld, m->nb, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
+                    break;
                 }
             }
             else if (use_trsm) CU(launch_variance_trsm(md.lfac, ld, m->nb, md.dinv, ws->panel, pld, (int)bq, ws->partial, m->k0, v, st));
@@ -941,7 +963,7 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         t_var += ev_ms(ws->ev[2], ws->ev[3]); t_d2h += ev_ms(ws->ev[3], ws->ev[4]);
         if (oz_timed) t_oz += ev_ms(ws->ev[5], ws->ev[6]);
     }
-    { std::lock_guard<std::mutex> lk(ctx->tmu); ctx->timings.ozaki_ms = t_oz; }
+    { std::lock_guard<std::mutex> lk(ctx->tmu); ctx->timings.ozaki_ms = t_oz; ctx->timings.ozaki_slices = t_oz > 0 ? (double)oz_S : 0.0; }
     if (use_oz) {
         int ctrl[2] = {0, 0};
         CU(cudaMemcpy(ctrl, ws->oz_ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));

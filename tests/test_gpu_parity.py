@@ -740,10 +740,11 @@ def test_variance_on_int8_tensor_cores_matches_oracle(gpr, orc, ctx, monkeypatch
     o = orc.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, kind, p0, p1, factor="llt")
     sub = slice(0, q, max(1, q // 400))
     fo, vo, _ = o.predict(Q[sub, 0], Q[sub, 1], Q[sub, 2], var=True, threads=os.cpu_count() or 1)
-    for slices in ("7", "8"):
-        monkeypatch.setenv("GPR_OZAKI_SLICES", slices)
+    for slices in (None, "7", "8"):
+        if slices:
+            monkeypatch.setenv("GPR_OZAKI_SLICES", slices)
         f_o, v_o = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
-        assert ctx.timings()["ozaki_ms"] > 0.0
+        assert ctx.timings()["ozaki_ms"] > 0.0 and ctx.timings()["ozaki_slices"] == float(slices or 6)
         f_o2, v_o2 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
         assert np.array_equal(v_o, v_o2) and np.array_equal(f_o, f_p)
         assert np.abs(v_o - v_p).max() <= 1e-8 * np.abs(v_p).max()

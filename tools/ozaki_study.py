@@ -2,11 +2,12 @@
 """CPU study for VERDICT r1 #7: can the variance product V = X K*^T (X = L^-1) run on the INT8 tensor cores (tcgen05
 kind::i8, TMEM int32 accumulators) by Ozaki-style slicing, at the variance tolerance of the north star (1e-7 of max v)?
 
-Emulation (exact integer arithmetic, numpy int64): rows of X and columns of K*^T are scaled by a power of two (their
-largest magnitude), cut into S signed slices of `bits` bits each (round-to-nearest, remainder carried to the next slice),
-and V ~ sum over slice pairs (t, u) with t + u <= level_max of 2^(-bits (t + u + 2)) X_t K_u^T with every slice product an
-exact integer matrix product (what an int8 MMA with int32 accumulation computes for k <= 2^31 / 127^2 terms), recombined in
-float64.  Reports, per (S, level_max): number of int8 GEMMs, max |dv| / max v against the long-double variance.
+Emulation of csrc/gpr_ozaki.cu in exact integer arithmetic (numpy int64): rows of X are scaled by a power of two, the K*
+batch by one power of two, both are cut into S signed digits of base 254 (|digit| <= 127) or base 128 (|digit| <= 64)
+(round-to-nearest, remainder carried to the next digit), and V = sum over levels l < S of [sum_{t+u=l} X_t K_u^T] / (F^2 B^l)
+with every bracket an exact integer matrix product (what the int8 MMAs accumulate in int32), recombined in float64.
+Reports, per (base, S): number of int8 GEMMs, max |dv| / max v against the long-double variance.  The measured table at
+the headline size is profiles/ozaki_table_r2.json (tools/ozaki_check.py on the GPU).
 
   python tools/ozaki_study.py [n=2048] [q=128] > profiles/ozaki_slicing_study_r2.json
 """
@@ -22,16 +23,30 @@ import gpr_b200 as g          # host-side workloads only
 import oracle
 
 
-def slices(M, axis, S, bits):
-    """M ~ 2^e * sum_t 2^(-bits (t + 1)) I_t along `axis` scaling; I_t integer with |I_t| <= 2^(bits-1)."""
-    e = np.ceil(np.log2(np.abs(M).max(axis=axis, keepdims=True) + 1e-300))
-    rem = M / np.exp2(e)                              # in [-1, 1]
+def slices(M, axis, S, base):
+    """M = 2^e * sum_t D_t / (F base^t), F = base / 2: the kernel's digit systems (oz_slice in csrc/gpr_ozaki.cu):
+    base 128 -> |digit| <= 64, base 254 -> |digit| <= 127."""
+    F = base / 2.0
+    m = np.abs(M).max(axis=axis, keepdims=True)
+    e = np.where(m > 0, np.floor(np.log2(np.maximum(m, 1e-300))) + 1, 0.0)      # 2^e > max, like frexp
+    rem = M / np.exp2(e) * F
     out = []
     for t in range(S):
-        scaled = rem * float(1 << bits)
-        it = np.rint(scaled)
+        it = np.rint(rem)
         out.append(it.astype(np.int64))
-        rem = scaled - it                             # in [-0.5, 0.5]
+        rem = (rem - it) * base
+    assert max(int(np.abs(o).max()) for o in out) <= F
+    return e, out
+
+
+def slices_fixed(M, e, S, base):
+    F = base / 2.0
+    rem = M / 2.0 ** e * F
+    out = []
+    for t in range(S):
+        it = np.rint(rem)
+        out.append(it.astype(np.int64))
+        rem = (rem - it) * base
     return e, out
 
 
@@ -54,26 +69,27 @@ def main():
     rows = []
     out = {"n": n, "queries": q, "max_v": float(np.abs(v_ref).max()), "fp64_product_rel_err": float(np.abs(v_f64 - v_ref).max() / np.abs(v_ref).max()),
            "abs_row_sum_X_times_K": float((np.abs(X) @ np.abs(Ks)).max()), "rows": rows}
-    for bits in (7, 6):
-        for S in (5, 6, 7, 8, 9):
-            ex, Xs = slices(X, 1, S, bits)
-            ek, Ksl = slices(Ks, 0, S, bits)
-            for level_max in (S - 1, S, 2 * S - 2):
-                V = np.zeros((n, q))
-                gemms = 0
-                for lvl in range(level_max + 1):
-                    acc = np.zeros((n, q), dtype=np.int64)
-                    for t in range(S):
-                        u = lvl - t
-                        if 0 <= u < S:
-                            acc += Xs[t] @ Ksl[u]
-                            gemms += 1
-                    V += acc.astype(np.float64) * 2.0 ** (-bits * (lvl + 2))
-                V *= np.exp2(ex) * np.exp2(ek)
-                v = k0 - (V * V).sum(axis=0)
-                rows.append({"bits": bits, "slices": S, "level_max": level_max, "int8_gemms": gemms,
-                             "var_rel_err": float(np.abs(v - v_ref).max() / np.abs(v_ref).max())})
-                print(rows[-1], file=sys.stderr)
+    for base in (254, 128):
+        F = base / 2.0
+        for S in (4, 5, 6, 7, 8):
+            ex, Xs = slices(X, 1, S, base)
+            ek, Ksl = slices(Ks, 0, S, base)
+            ek[:] = ek.max()                              # the kernel uses ONE scale for the whole K* batch (2^g >= k(0))
+            ek, Ksl = slices_fixed(Ks, float(ek.max()), S, base)
+            V = np.zeros((n, q))
+            gemms = 0
+            for lvl in range(S):                          # levels t + u < S are kept
+                acc = np.zeros((n, q), dtype=np.int64)
+                for t in range(lvl + 1):
+                    acc += Xs[t] @ Ksl[lvl - t]
+                    gemms += 1
+                assert np.abs(acc).max() < 2 ** 31        # what an int32 TMEM accumulator must hold
+                V += acc.astype(np.float64) / (F * F * float(base) ** lvl)
+            V *= np.exp2(ex) * np.exp2(ek)
+            v = k0 - (V * V).sum(axis=0)
+            rows.append({"digit_base": base, "slices": S, "int8_gemms": gemms,
+                         "var_rel_err": float(np.abs(v - v_ref).max() / np.abs(v_ref).max())})
+            print(rows[-1], file=sys.stderr)
     print(json.dumps(out, indent=1))
 
 
