@@ -28,6 +28,7 @@ model, info = D.fit_and_publish(reg, (lambda: reg.create(P[:, 0], P[:, 1], P[:, 
                                 n, W.SYNTH_R, rank, dev, src=0)
 assert info["published"]
 a, b = D.shard_range(len(Q), rank, world)
+os.environ["GPR_VAR_MODE"] = "trsm"                              # whatever the shard size: the form that needs only the factor
 f, v = reg.evaluate(model, Q[a:b, 0], Q[a:b, 1], Q[a:b, 2], var=True)
 assert model.state().linv is None                                # no inverse factor anywhere
 fs = [None] * world; vs = [None] * world
@@ -45,6 +46,7 @@ if rank == 0:
     print("publish: n=%d world=%d fit %.2f ms exposed %.3f ms factor %.1f MB/peer identical=%s"
           % (n, world, info["fit_wall_ms"], info["exposed_ms"], info["factor_bytes_per_peer"] / 1e6, same))
     ok = same and v0.min() > 0
+os.environ.pop("GPR_VAR_MODE", None)
 # an indefinite matrix (the node's setting): nothing is published, the state is broadcast the old way
 z = np.load(os.path.join(ROOT, "tests", "golden", "ref_mugD_thinplate_R2_node.npz"))
 Pn, Qn = z["P"], np.vstack([z["Q"]] * 8)
