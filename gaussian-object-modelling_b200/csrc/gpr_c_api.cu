@@ -196,7 +196,7 @@ struct ModelDev {            // what predict needs, per device
     double* lfac = nullptr; double* dinv = nullptr;
     bool have = false, have_linv = false, have_tail = false, have_fac = false, own_fac = false;
     // int8 slices of X = L^-1 and its per-row power-of-two scales, for the variance on the INT8 tensor cores (gpr_ozaki.cu)
-    signed char* oz_xs = nullptr; double* oz_scale = nullptr; int oz_S = 0, oz_base = 0; size_t oz_ld = 0;
+    signed char* oz_xs = nullptr; double* oz_scale = nullptr; int oz_S = 0, oz_base = 0; size_t oz_ld = 0, oz_n = 0;   // oz_n: model size the slices were cut for
 };
 
 struct gpr_model {
@@ -687,7 +687,7 @@ static int ensure_on_device(gpr_model* m, size_t di, bool need_linv, bool need_f
 static int ensure_ozaki_slices(gpr_model* m, size_t di, int S, int base254, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(m->mu);
     ModelDev& md = m->devs[di];
-    if (md.oz_xs && md.oz_S == S && md.oz_base == base254 && md.oz_ld == m->cap) return GPR_OK;
+    if (md.oz_xs && md.oz_S == S && md.oz_base == base254 && md.oz_ld == m->cap && md.oz_n == m->n) return GPR_OK;     // an append changes n: re-slice
     CU(cudaSetDevice(md.dev));
     cudaFree(md.oz_xs); cudaFree(md.oz_scale);
     md.oz_xs = nullptr; md.oz_scale = nullptr; md.oz_S = 0;
@@ -697,7 +697,7 @@ static int ensure_ozaki_slices(gpr_model* m, size_t di, int S, int base254, cuda
     CU(launch_ozaki_slice_x(md.linv, ld, m->nb * TB, S, base254, md.oz_xs, md.oz_scale,
                             reinterpret_cast<unsigned long long*>(md.oz_scale + ld), st));
     CU(cudaStreamSynchronize(st));
-    md.oz_S = S; md.oz_base = base254; md.oz_ld = ld;
+    md.oz_S = S; md.oz_base = base254; md.oz_ld = ld; md.oz_n = m->n;
     return GPR_OK;
 }
 

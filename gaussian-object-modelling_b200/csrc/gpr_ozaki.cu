@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "gpr_common.cuh"
 #include "gpr_kernels.h"
@@ -427,7 +428,10 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    a.gr = 4;
+    // co-resident tasks form a (gr row tiles) x (gq query tiles) rectangle: an A slice tile is then shared by gq CTAs and a B
+    // slice tile by gr CTAs through L2 (GPR_OZ_GR overrides gr; sweep in profiles/ozaki_group_sweep_r2.json)
+    static const int gr_env = getenv("GPR_OZ_GR") ? atoi(getenv("GPR_OZ_GR")) : 0;
+    a.gr = gr_env >= 1 && gr_env <= 64 ? gr_env : 5;          // 5 x 29: 41.5 ms per batch at n = 16384 (4 x 37: 48.2, 8 x 18: 45.3)
     a.gq = sms / a.gr > 0 ? sms / a.gr : 1;
     if (a.gq > a.nqt) a.gq = a.nqt;
     if (a.gr > a.nrt) a.gr = a.nrt;

@@ -749,6 +749,19 @@ def test_variance_on_int8_tensor_cores_matches_oracle(gpr, orc, ctx, monkeypatch
         assert np.array_equal(v_o, v_o2) and np.array_equal(f_o, f_p)
         assert np.abs(v_o - v_p).max() <= 1e-8 * np.abs(v_p).max()
         assert relerr(f_o[sub], fo) <= TOL_MEAN and np.abs(v_o[sub] - vo).max() <= TOL_VAR * np.abs(vo).max()
+    if kind == "thin_plate":
+        # an incremental update changes X: the slices are cut again for the grown model
+        monkeypatch.delenv("GPR_OZAKI_SLICES")
+        Pn, yn, sn = W.touch_batches(1, 24)[0]
+        reg.update(m, Pn[:, 0], Pn[:, 1], Pn[:, 2], yn, sn)
+        o.update(Pn[:, 0], Pn[:, 1], Pn[:, 2], yn, sn)
+        f_u, v_u = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+        assert ctx.timings()["ozaki_ms"] > 0.0
+        fo2, vo2, _ = o.predict(Q[sub, 0], Q[sub, 1], Q[sub, 2], var=True, threads=os.cpu_count() or 1)
+        assert relerr(f_u[sub], fo2) <= TOL_MEAN and np.abs(v_u[sub] - vo2).max() <= TOL_VAR * np.abs(vo2).max()
+        monkeypatch.setenv("GPR_VAR_MODE", "product")
+        f_p, v_p = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
+        monkeypatch.setenv("GPR_VAR_MODE", "ozaki")
     # too few slices: the per-call FP64 spot check catches it and the call (and the model from then on) falls back
     monkeypatch.setenv("GPR_OZAKI_SLICES", "3")
     f_b, v_b = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
