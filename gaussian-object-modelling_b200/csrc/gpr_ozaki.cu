@@ -120,8 +120,8 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int M, int N) {
 
 // ---- the kernel ---------------------------------------------------------------------------------------------
 // Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warps 2..5 = epilogue (TMEM lane
-// quarter = warp % 4).  Tasks are dealt round-robin (task = blockIdx.x + i * gridDim.x, longest rows first), so every
-// role derives the same task sequence without communication.  With N = 64 a tcgen05.mma lasts only ~32-48 cycles: the
+// quarter = warp % 4).  Tasks (pairs of row tiles x one query tile) are dealt round-robin (task = blockIdx.x + i * gridDim.x),
+// so every role derives the same task sequence without communication.  With N = 64 a tcgen05.mma lasts only ~32-48 cycles: the
 // issuing thread's instruction count per MMA is what limits the rate, hence the fully unrolled, descriptor-incrementing
 // issue loop (template on the slice count) and the separate producer warp.
 constexpr int OZ_NTHREADS = 192;
@@ -161,23 +161,30 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int per_group = a.gr * a.gq;
     const int qgroups = (a.nqt + a.gq - 1) / a.gq;
-    const int rgroups = (a.nrt + a.gr - 1) / a.gr;
+    // A task is a PAIR of row tiles (nrt-1-p, p) for one query tile, done one after the other (h = 0, 1): with a lower
+    // triangular A the two k ranges add up to nrt + 1 blocks of 128 for every pair, so all tasks have the same length and
+    // the CTAs that run together stay in step — which is what lets them share operand tiles through L2.
+    const int npairs = (a.nrt + 1) / 2;
+    const int rgroups = (npairs + a.gr - 1) / a.gr;
     const int ntasks = rgroups * qgroups * per_group;
-    auto decode = [&](int task, int& rt, int& qt) {
+    auto decode = [&](int task, int h, int& rt, int& qt) {
         const int g = task / per_group, w = task % per_group;
         const int rg = g / qgroups, qg = g % qgroups;
-        rt = a.nrt - 1 - (rg * a.gr + w % a.gr);                    // longest rows first
+        const int pr = rg * a.gr + w % a.gr;
         qt = qg * a.gq + w / a.gr;
-        return rt >= 0 && qt < a.nqt;
+        rt = h == 0 ? a.nrt - 1 - pr : pr;
+        return pr < npairs && qt < a.nqt && !(h == 1 && pr == a.nrt - 1 - pr);       // odd nrt: the middle row tile is its own pair
     };
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         uint32_t j = 0;
         bool ok = true;
-        for (int task = blockIdx.x; task < ntasks && ok; task += gridDim.x) {
+        for (int it = 0; ok; ++it) {
+            const int task = blockIdx.x + (it >> 1) * gridDim.x;
+            if (task >= ntasks) break;
             int rt, qt;
-            if (!decode(task, rt, qt)) continue;
+            if (!decode(task, it & 1, rt, qt)) continue;
             const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
             for (int kb = 0; kb < nkb; ++kb, ++j) {
                 const uint32_t s = j % (uint32_t)stages, u = j / (uint32_t)stages;
@@ -195,9 +202,11 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr uint32_t DESC_HI = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);      // SBO | version 1 | SWIZZLE_64B
         uint32_t j = 0, tcount = 0;
         bool ok = true;
-        for (int task = blockIdx.x; task < ntasks && ok; task += gridDim.x) {
+        for (int it = 0; ok; ++it) {
+            const int task = blockIdx.x + (it >> 1) * gridDim.x;
+            if (task >= ntasks) break;
             int rt, qt;
-            if (!decode(task, rt, qt)) continue;
+            if (!decode(task, it & 1, rt, qt)) continue;
             const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
             if (tcount > 0 && !mbar_wait(&accum_empty, (tcount - 1) & 1)) { ok = false; break; }   // epilogue has drained TMEM
             tc_fence_after();
@@ -234,9 +243,11 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
         uint32_t tcount = 0;
         bool ok = true;
-        for (int task = blockIdx.x; task < ntasks && ok; task += gridDim.x) {
+        for (int it = 0; ok; ++it) {
+            const int task = blockIdx.x + (it >> 1) * gridDim.x;
+            if (task >= ntasks) break;
             int rt, qt;
-            if (!decode(task, rt, qt)) continue;
+            if (!decode(task, it & 1, rt, qt)) continue;
             if (!mbar_wait(&accum_full, tcount & 1)) { ok = false; break; }
             ++tcount;
             tc_fence_after();
@@ -428,16 +439,17 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // co-resident tasks form a (gr row tiles) x (gq query tiles) rectangle: an A slice tile is then shared by gq CTAs and a B
+    // co-resident tasks form a (gr row-tile pairs) x (gq query tiles) rectangle: an A slice tile is then shared by gq CTAs and a B
     // slice tile by gr CTAs through L2 (GPR_OZ_GR overrides gr; sweep in profiles/ozaki_group_sweep_r2.json)
     static const int gr_env = getenv("GPR_OZ_GR") ? atoi(getenv("GPR_OZ_GR")) : 0;
-    a.gr = gr_env >= 1 && gr_env <= 64 ? gr_env : 5;          // 5 x 29: 41.5 ms per batch at n = 16384 (4 x 37: 48.2, 8 x 18: 45.3)
+    a.gr = gr_env >= 1 && gr_env <= 64 ? gr_env : 10;         // 10 pairs x 14 query tiles; with paired row tiles 3..12 are within 6 % (41.4 - 44.0 ms per batch at n = 16384)
     a.gq = sms / a.gr > 0 ? sms / a.gr : 1;
+    const int npairs = (a.nrt + 1) / 2;
     if (a.gq > a.nqt) a.gq = a.nqt;
-    if (a.gr > a.nrt) a.gr = a.nrt;
+    if (a.gr > npairs) a.gr = npairs;
     e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    const int tasks = ((a.nrt + a.gr - 1) / a.gr) * ((a.nqt + a.gq - 1) / a.gq) * a.gr * a.gq;
+    const int tasks = ((npairs + a.gr - 1) / a.gr) * ((a.nqt + a.gq - 1) / a.gq) * a.gr * a.gq;
     const int grid = tasks < sms ? tasks : sms;
     switch (S) {
         case 1: return launch_oz<1, 80>(tmA, tmB, a, grid, smem, st);

@@ -57,6 +57,7 @@ for case in range(cases):
         if normals:
             errs["normals"] = float(np.abs(m.get()["normals"] - o.get()["normals"]).max()) / max(1e-8, 100 * cond * 2.2e-16)
         steps = []
+        modes = []
         # optional appends
         for _ in range(int(rng.integers(0, 3))):
             k = int(rng.integers(1, 70))
@@ -78,7 +79,16 @@ for case in range(cases):
             errs["alpha_after_append_%d" % len(steps)] = rel(m.alpha, o.alpha) / (2 * tol_a)
         for q in [int(x) for x in rng.choice([1, 2, 5, 8, 9, 63, 130, 1000, 9500, 20000], size=3, replace=False)]:
             Q = rng.uniform(-1.2, 1.2, (q, 3))
+            # the form of the variance: the library's own choice, or one forced (INT8 tensor cores / FP64 product / FP64
+            # forward substitution; a forced form the model cannot use, e.g. on an indefinite-tail model, falls back inside)
+            mode = str(rng.choice(["auto", "auto", "ozaki", "product", "trsm"]))
+            if mode == "auto":
+                os.environ.pop("GPR_VAR_MODE", None)
+            else:
+                os.environ["GPR_VAR_MODE"] = mode
+            modes.append(mode[0])
             f, v, gr, tx, ty = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True, tangent=True)
+            os.environ.pop("GPR_VAR_MODE", None)
             f1 = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2])
             sub = slice(0, min(q, 400))
             fo, vo, go = o.predict(Q[sub, 0], Q[sub, 1], Q[sub, 2], var=True, grad=True, threads=8)
@@ -100,8 +110,8 @@ for case in range(cases):
         status = "ok" if worst <= 1.0 else "VIOLATION"
         if worst > 1.0:
             bad.append((seed, {k: round(v, 2) for k, v in errs.items() if v > 1.0}))
-        print("case %3d seed %4d n=%4d %-10s noise=%d normals=%d appends=%s cond=%.1e tail=%d%s worst=%.3f %s" % (
-            case, seed, n, kind, noise, normals, steps, cond, m.n_tail, " (indefinite)" if indefinite else "", worst, status), flush=True)
+        print("case %3d seed %4d n=%4d %-10s noise=%d normals=%d appends=%s var=%s cond=%.1e tail=%d%s worst=%.3f %s" % (
+            case, seed, n, kind, noise, normals, steps, "".join(modes), cond, m.n_tail, " (indefinite)" if indefinite else "", worst, status), flush=True)
     except Exception as e:     # noqa: BLE001
         bad.append((seed, repr(e)))
         print("case %3d seed %4d EXCEPTION %r" % (case, seed, e), flush=True)
