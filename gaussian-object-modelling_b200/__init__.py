@@ -40,7 +40,7 @@ class KernelT(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "cov_ms", "chol_ms", "solve_ms", "normals_ms", "fit_total_ms", "linv_ms",
-        "predict_mean_ms", "predict_var_ms", "predict_total_ms", "h2d_ms", "d2h_ms", "append_ms", "ozaki_ms", "ozaki_slices")]
+        "predict_mean_ms", "predict_var_ms", "predict_total_ms", "h2d_ms", "d2h_ms", "append_ms", "ozaki_ms", "ozaki_slices", "ozaki_issued_fraction")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -112,7 +112,7 @@ def lib():
         L.gpr_selftest_leaf.argtypes = [_dp, _dp, C.POINTER(ci)]
         L.gpr_selftest_factor.argtypes = [_dp, ci, _dp, ci, C.POINTER(C.c_longlong)]
         L.gpr_selftest_peak.argtypes = [ci, ci, _dp]
-        L.gpr_selftest_i8gemm.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
+        L.gpr_selftest_i8gemm.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
         L.gpr_selftest_factor_trace.argtypes = [ci, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         _lib = L
     return _lib
@@ -451,7 +451,7 @@ def selftest_factor(A, want_inverse=False, serial=False):
     return np.tril(A), (None if X is None else np.ascontiguousarray(X)), piv.value
 
 
-def selftest_i8gemm(A, B, levels=None, tri=False):
+def selftest_i8gemm(A, B, levels=None, tri=False, skip_zero_blocks=False):
     """Raw level accumulators of the INT8 tensor-core engine: A (S, M, K), B (S, N, K) int8 -> C (levels, M, N) int32 with
     C[l] = sum_{t+u=l} A[t] @ B[u].T (row tile r of a lower-triangular A only visits k < 128 (r + 1))."""
     A = np.ascontiguousarray(A, dtype=np.int8)
@@ -460,7 +460,7 @@ def selftest_i8gemm(A, B, levels=None, tri=False):
     N = B.shape[1]
     levels = S if levels is None else levels
     Cm = np.zeros((levels, M, N), dtype=np.int32)
-    _check(lib().gpr_selftest_i8gemm(A.ctypes.data, B.ctypes.data, S, levels, M, N, K, int(tri), Cm.ctypes.data))
+    _check(lib().gpr_selftest_i8gemm(A.ctypes.data, B.ctypes.data, S, levels, M, N, K, int(tri), int(skip_zero_blocks), Cm.ctypes.data))
     return Cm
 
 

@@ -197,6 +197,7 @@ struct ModelDev {            // what predict needs, per device
     bool have = false, have_linv = false, have_tail = false, have_fac = false, own_fac = false;
     // int8 slices of X = L^-1 and its per-row power-of-two scales, for the variance on the INT8 tensor cores (gpr_ozaki.cu)
     signed char* oz_xs = nullptr; double* oz_scale = nullptr; int oz_S = 0, oz_base = 0; size_t oz_ld = 0, oz_n = 0;   // oz_n: model size the slices were cut for
+    unsigned char* oz_nz = nullptr; double oz_exec = 1.0;      // nonzero-slice map per (row tile, k-block); fraction of the MMAs that are issued
 };
 
 struct gpr_model {
@@ -261,8 +262,8 @@ static void free_factor(gpr_model* m) {
         cudaFree(d.xyz); cudaFree(d.alpha); cudaFree(d.tZ); cudaFree(d.tSinv);
         big_free(m->ctx, d.dev, d.linv, m->cap * m->cap * sizeof(double));
         if (d.own_fac) { big_free(m->ctx, d.dev, d.lfac, m->cap * m->cap * sizeof(double)); cudaFree(d.dinv); }
-        cudaFree(d.oz_xs); cudaFree(d.oz_scale);
-        d.oz_xs = nullptr; d.oz_scale = nullptr; d.oz_S = 0; d.oz_ld = 0;
+        cudaFree(d.oz_xs); cudaFree(d.oz_scale); cudaFree(d.oz_nz);
+        d.oz_xs = nullptr; d.oz_scale = nullptr; d.oz_nz = nullptr; d.oz_S = 0; d.oz_ld = 0;
         d.xyz = d.alpha = d.linv = d.tZ = d.tSinv = d.lfac = d.dinv = nullptr;
         d.have = d.have_linv = d.have_tail = d.have_fac = d.own_fac = false;
     }
@@ -689,14 +690,31 @@ static int ensure_ozaki_slices(gpr_model* m, size_t di, int S, int base254, cuda
     ModelDev& md = m->devs[di];
     if (md.oz_xs && md.oz_S == S && md.oz_base == base254 && md.oz_ld == m->cap && md.oz_n == m->n) return GPR_OK;     // an append changes n: re-slice
     CU(cudaSetDevice(md.dev));
-    cudaFree(md.oz_xs); cudaFree(md.oz_scale);
-    md.oz_xs = nullptr; md.oz_scale = nullptr; md.oz_S = 0;
+    cudaFree(md.oz_xs); cudaFree(md.oz_scale); cudaFree(md.oz_nz);
+    md.oz_xs = nullptr; md.oz_scale = nullptr; md.oz_nz = nullptr; md.oz_S = 0;
     const size_t ld = m->cap;
     CU(cudaMalloc((void**)&md.oz_xs, (size_t)S * ld * ld));
     CU(cudaMalloc((void**)&md.oz_scale, 2 * ld * sizeof(double)));          // scales | row-max scratch
     CU(launch_ozaki_slice_x(md.linv, ld, m->nb * TB, S, base254, md.oz_xs, md.oz_scale,
                             reinterpret_cast<unsigned long long*>(md.oz_scale + ld), st));
+    // which digit slices vanish entirely in which (row tile, k-block): their MMAs are skipped (gpr_ozaki.cu)
+    const int nrt = m->nb, kbl = (int)(ld / 64);
+    CU(cudaMalloc((void**)&md.oz_nz, (size_t)nrt * kbl));
+    CU(launch_ozaki_mask(md.oz_xs, ld, ld * ld, S, nrt, kbl, md.oz_nz, (size_t)kbl, st));
+    std::vector<unsigned char> hnz((size_t)nrt * kbl);
+    CU(cudaMemcpyAsync(hnz.data(), md.oz_nz, hnz.size(), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    {
+        double issued = 0.0, total = 0.0;
+        for (int rt = 0; rt < nrt; ++rt)
+            for (int kb = 0; kb < 2 * (rt + 1); ++kb)
+                for (int t = 0; t < S; ++t) {
+                    const double pairs = (double)(S - t);                       // pairs (t, u) with t + u < S
+                    total += pairs;
+                    if (kb == 0 || ((hnz[(size_t)rt * kbl + kb] >> t) & 1)) issued += pairs;
+                }
+        md.oz_exec = total > 0 ? issued / total : 1.0;
+    }
     md.oz_S = S; md.oz_base = base254; md.oz_ld = ld; md.oz_n = m->n;
     return GPR_OK;
 }
@@ -893,7 +911,7 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
                     CU(launch_ozaki_slice_panel(ws->panel, pld, (int)bq, m->nb * TB, 1.0 / cs, oz_S, oz_base254, ws->oz_ks, ld, pld, st));
                     CU(cudaEventRecord(ws->ev[5], st));
                     CU(launch_ozaki_product(md.oz_xs, ld, ld * ld, m->nb, ws->oz_ks, ld, pld * ld, pld, (int)bq, pld, (size_t)m->nb * TB, 1,
-                                            oz_S, oz_base254, md.oz_scale, cs, ws->partial, ws->oz_ctrl, nullptr, 0, st));
+                                            oz_S, oz_base254, md.oz_scale, cs, ws->partial, ws->oz_ctrl, nullptr, 0, st, md.oz_nz, ld / 64));
                     CU(cudaEventRecord(ws->ev[6], st));
                     oz_timed = true;
                     CU(launch_var_finalize(ws->partial, pld, m->nb, (int)bq, m->k0, v, st));
@@ -963,7 +981,11 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         t_var += ev_ms(ws->ev[2], ws->ev[3]); t_d2h += ev_ms(ws->ev[3], ws->ev[4]);
         if (oz_timed) t_oz += ev_ms(ws->ev[5], ws->ev[6]);
     }
-    { std::lock_guard<std::mutex> lk(ctx->tmu); ctx->timings.ozaki_ms = t_oz; ctx->timings.ozaki_slices = t_oz > 0 ? (double)oz_S : 0.0; }
+    {
+        std::lock_guard<std::mutex> lk(ctx->tmu);
+        ctx->timings.ozaki_ms = t_oz; ctx->timings.ozaki_slices = t_oz > 0 ? (double)oz_S : 0.0;
+        ctx->timings.ozaki_issued_fraction = t_oz > 0 ? md.oz_exec : 0.0;
+    }
     if (use_oz) {
         int ctrl[2] = {0, 0};
         CU(cudaMemcpy(ctrl, ws->oz_ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
@@ -2431,7 +2453,8 @@ int gpr_selftest_factor_trace(int nb, long long* h_trace, long long* leaf_cycles
 // INT8 tensor-core engine self-test (gpr_ozaki.cu): raw level accumulators C[l] = sum_{t+u=l} A_t B_u^T for int8 slice
 // tensors A [S][M][K], B [S][N][K] (host, K contiguous); M multiple of 128, N of 64, K of 64; tri: A lower triangular by
 // 128-row tiles (row tile r only visits k < 128 (r + 1)).  hC: [levels][M][N] int32.
-int gpr_selftest_i8gemm(const signed char* hA, const signed char* hB, int S, int levels, int M, int Nq, int K, int tri, int* hC) {
+int gpr_selftest_i8gemm(const signed char* hA, const signed char* hB, int S, int levels, int M, int Nq, int K, int tri, int skip_zero_blocks,
+                        int* hC) {
     if (!hA || !hB || !hC || M % 128 || Nq % 16 || K % 64 || S < 1 || S > 8 || levels != S) return fail(GPR_ERR_INVALID, "bad shape");
     signed char *A, *B; int *C, *ctrl; double *scale, *partial;
     const size_t qpad = (size_t)(Nq + 127) / 128 * 128;
@@ -2446,14 +2469,19 @@ int gpr_selftest_i8gemm(const signed char* hA, const signed char* hB, int S, int
     CU(cudaMemset(C, 0, (size_t)S * M * Nq * sizeof(int)));
     std::vector<double> ones(M, 1.0);
     CU(cudaMemcpy(scale, ones.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice));
+    unsigned char* nz = nullptr;
+    if (skip_zero_blocks) {
+        CU(cudaMalloc((void**)&nz, (size_t)(M / 128) * (K / 64)));
+        CU(launch_ozaki_mask(A, (size_t)K, (size_t)M * K, S, M / 128, K / 64, nz, (size_t)(K / 64), 0));
+    }
     // the tensor of B has exactly Nq rows: query tiles reaching beyond it are zero-filled by TMA
     CU(launch_ozaki_product(A, (size_t)K, (size_t)M * K, M / 128, B, (size_t)K, (size_t)Nq * K, (size_t)Nq, Nq, qpad, (size_t)K, tri, S, 0, scale,
-                            1.0, partial, ctrl, C, (size_t)Nq, 0));
+                            1.0, partial, ctrl, C, (size_t)Nq, 0, nz, (size_t)(K / 64)));
     CU(cudaDeviceSynchronize());
     int hctrl[2];
     CU(cudaMemcpy(hctrl, ctrl, sizeof hctrl, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(hC, C, (size_t)S * M * Nq * sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(ctrl); cudaFree(scale); cudaFree(partial);
+    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(ctrl); cudaFree(scale); cudaFree(partial); cudaFree(nz);
     if (hctrl[1] != 0) return fail(GPR_ERR_CUDA, "INT8 tensor-core kernel aborted (a pipeline wait timed out)");
     return GPR_OK;
 }

@@ -80,7 +80,10 @@ long long ozaki_max_k(int S, int base254);
 cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a_slice, int nrt, const signed char* Bs, size_t b_pitch,
                                  size_t b_slice, size_t b_rows, int q, size_t q_pad, size_t k_extent, int tri, int S, int base254,
                                  const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, size_t dbg_ld,
-                                 cudaStream_t st);
+                                 cudaStream_t st, const unsigned char* nzA = nullptr, size_t nz_pitch = 0);
+// nz[rt*pitch + kb] bit t: slice t of (row tile rt, 64-wide k-block kb) of As holds a nonzero digit (all-zero blocks are skipped)
+cudaError_t launch_ozaki_mask(const signed char* As, size_t a_pitch, size_t a_slice, int S, int nrt, int kblocks, unsigned char* nz,
+                              size_t pitch, cudaStream_t st);
 cudaError_t launch_ozaki_slice_x(const double* X, size_t ld, int n_rows, int S, int base254, signed char* Xs, double* row_scale,
                                  unsigned long long* rowmax, cudaStream_t st);
 cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q, int n_k, double inv_scale, int S, int base254,

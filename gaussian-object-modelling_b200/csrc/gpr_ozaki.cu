@@ -56,6 +56,8 @@ struct OzArgs {
     size_t dbg_ld;
     int gr, gq;                   // co-scheduled group: gr row tiles x gq query tiles
     double wl[8];                 // level weights 1 / (F^2 B^l)
+    const unsigned char* nzA;     // optional [nrt][nz_pitch]: bit t set iff slice t of (row tile, 64-wide k-block) has a nonzero digit
+    size_t nz_pitch;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -210,8 +212,15 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
             if (tcount > 0 && !mbar_wait(&accum_empty, (tcount - 1) & 1)) { ok = false; break; }   // epilogue has drained TMEM
             tc_fence_after();
+            // Digit slices of A that are entirely zero in a (row tile, k-block) — far from the diagonal the entries of L^-1 are
+            // small against their row maximum, so the leading digits vanish (36 % of the blocks at n = 16384) — contribute
+            // nothing: their MMAs are skipped.  The first k-block of a task never skips (it zero-initialises every level).
+            const unsigned char* nzrow = a.nzA ? a.nzA + (size_t)rt * a.nz_pitch : nullptr;
+            uint32_t mask_next = 0xFFu;
             for (int kb = 0; kb < nkb; ++kb, ++j) {
                 const uint32_t s = j % (uint32_t)stages, u = j / (uint32_t)stages;
+                const uint32_t mask = mask_next;
+                mask_next = (nzrow && kb + 1 < nkb) ? (uint32_t)__ldg(nzrow + kb + 1) : 0xFFu;
                 if (!mbar_wait(&full_bar[s], u & 1)) { ok = false; break; }
                 tc_fence_after();
                 const uint32_t sa = smem_u32(base + (size_t)s * STAGE_BYTES);
@@ -222,6 +231,7 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int l = 0; l < LEVELS; ++l) {
 #pragma unroll
                     for (int t = 0; t <= l; ++t) {
+                        if (!((mask >> t) & 1u)) continue;
 #pragma unroll
                         for (int ks = 0; ks < OZ_BK / 32; ++ks) {
                             const uint64_t da = ((uint64_t)DESC_HI << 32) | (a_lo + (uint32_t)(t * (OZ_A_SLICE_BYTES >> 4) + 2 * ks));
@@ -358,6 +368,37 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     }
 }
 
+// nz[rt * pitch + kb] bit t = slice t of rows [128 rt, 128 rt + 128) x k [64 kb, 64 kb + 64) holds a nonzero digit.
+// One CTA per (k-block, row tile); slices [t][row][k] with row pitch a_pitch and slice pitch a_slice.
+__global__ void __launch_bounds__(256) oz_mask_kernel(const signed char* __restrict__ As, size_t a_pitch, size_t a_slice, int S,
+                                                       unsigned char* __restrict__ nz, size_t pitch) {
+    __shared__ unsigned int sm;
+    const int kb = blockIdx.x, rt = blockIdx.y;
+    if (threadIdx.x == 0) sm = 0u;
+    __syncthreads();
+    unsigned int bits = 0u;
+    for (int t = 0; t < S; ++t) {
+        const signed char* base = As + (size_t)t * a_slice + (size_t)rt * OZ_BM * a_pitch + (size_t)kb * OZ_BK;
+        bool any = false;
+        for (int e = threadIdx.x; e < OZ_BM * (OZ_BK / 16); e += 256) {            // 128 rows x 4 chunks of 16 bytes
+            const int r = e >> 2, c = e & 3;
+            const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)r * a_pitch + 16 * c);
+            any = any || (v.x | v.y | v.z | v.w) != 0u;
+        }
+        if (any) bits |= 1u << t;
+    }
+    if (bits) atomicOr(&sm, bits);
+    __syncthreads();
+    if (threadIdx.x == 0) nz[(size_t)rt * pitch + kb] = (unsigned char)sm;
+}
+
+cudaError_t launch_ozaki_mask(const signed char* As, size_t a_pitch, size_t a_slice, int S, int nrt, int kblocks, unsigned char* nz,
+                              size_t pitch, cudaStream_t st) {
+    if (nrt <= 0 || kblocks <= 0) return cudaSuccess;
+    oz_mask_kernel<<<dim3((unsigned)kblocks, (unsigned)nrt), 256, 0, st>>>(As, a_pitch, a_slice, S, nz, pitch);
+    return cudaGetLastError();
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -419,7 +460,7 @@ static cudaError_t launch_oz(const CUtensorMap& tmA, const CUtensorMap& tmB, con
 cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a_slice, int nrt, const signed char* Bs, size_t b_pitch,
                                  size_t b_slice, size_t b_rows, int q, size_t q_pad, size_t k_extent, int tri, int S, int base254,
                                  const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, size_t dbg_ld,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, const unsigned char* nzA, size_t nz_pitch) {
     if (S < 1 || S > 8) return cudaErrorInvalidValue;
     if ((long long)k_extent > ozaki_max_k(S, base254)) return cudaErrorInvalidValue;       // an accumulator could overflow
     const int BN = ozaki_tile_n(S);
@@ -433,6 +474,7 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
     a.S = S; a.levels = S; a.stages = ozaki_stages(S, BN);
     a.nrt = nrt; a.nqt = (int)((q + BN - 1) / BN); a.tri = tri; a.kblocks = (int)(k_extent / OZ_BK);
     a.row_scale = row_scale; a.col_scale = col_scale; a.partial = partial; a.q_pad = q_pad; a.ctrl = ctrl; a.dbg = dbg; a.dbg_ld = dbg_ld;
+    a.nzA = nzA; a.nz_pitch = nz_pitch;
     const double F = base254 ? 127.0 : 64.0, B = base254 ? 254.0 : 128.0;
     double w = 1.0 / (F * F);
     for (int l = 0; l < 8; ++l) { a.wl[l] = w; w /= B; }

@@ -18,8 +18,10 @@ int gpr_selftest_factor_trace(int n_tiles, long long* h_trace, long long* leaf_c
 int gpr_selftest_peak(int which, int ctas_per_sm, double* tflops);
 
 /* INT8 tensor-core engine (gpr_ozaki.cu: tcgen05.mma kind::i8 + TMEM + TMA): raw level accumulators
- * C[l] = sum_{t+u=l} A_t B_u^T for int8 slice tensors A [S][M][K], B [S][N][K] (K contiguous); hC: [levels][M][N]. */
-int gpr_selftest_i8gemm(const signed char* hA, const signed char* hB, int S, int levels, int M, int N, int K, int tri, int* hC);
+ * C[l] = sum_{t+u=l} A_t B_u^T for int8 slice tensors A [S][M][K], B [S][N][K] (K contiguous); hC: [levels][M][N].
+ * skip_zero_blocks: build the nonzero-slice map of A and skip the MMAs of all-zero (row tile, k-block, slice) blocks. */
+int gpr_selftest_i8gemm(const signed char* hA, const signed char* hB, int S, int levels, int M, int N, int K, int tri,
+                        int skip_zero_blocks, int* hC);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,8 @@ typedef struct {
     double append_ms;               /* last gpr_append: device time of the incremental update incl. the alpha re-solve */
     double ozaki_ms;                /* last predict on the primary device: time inside the INT8 tensor-core variance kernel (0 if another form ran) */
     double ozaki_slices;            /* ... and the number of int8 slices per operand it used (6: base-254 digits, 7 or more: base 128 / escalated) */
+    double ozaki_issued_fraction;   /* ... and the share of its slice-pair MMAs actually issued (digit slices of L^-1 that are all zero in a
+                                       (128-row, 64-k) block are skipped) */
 } gpr_timings;
 
 /* ---- context ------------------------------------------------------------------------------ */
