@@ -474,7 +474,8 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
     a.S = S; a.levels = S; a.stages = ozaki_stages(S, BN);
     a.nrt = nrt; a.nqt = (int)((q + BN - 1) / BN); a.tri = tri; a.kblocks = (int)(k_extent / OZ_BK);
     a.row_scale = row_scale; a.col_scale = col_scale; a.partial = partial; a.q_pad = q_pad; a.ctrl = ctrl; a.dbg = dbg; a.dbg_ld = dbg_ld;
-    a.nzA = nzA; a.nz_pitch = nz_pitch;
+    static const bool noskip = getenv("GPR_OZ_NOSKIP") && atoi(getenv("GPR_OZ_NOSKIP")) != 0;      // A/B switch for measurements
+    a.nzA = noskip ? nullptr : nzA; a.nz_pitch = nz_pitch;
     const double F = base254 ? 127.0 : 64.0, B = base254 ? 254.0 : 128.0;
     double w = 1.0 / (F * F);
     for (int l = 0; l < 8; ++l) { a.wl[l] = w; w /= B; }

@@ -15,6 +15,6 @@ Q = W.grid_slab(256, 100, 104)[:4 * 148 * 128]
 for rep in range(3):
     f, v = reg.evaluate(m, Q[:, 0], Q[:, 1], Q[:, 2], var=True)
 t = ctx.timings()
-print(json.dumps({"gr": $GR, "gq": 148 // $GR, "int8_kernel_ms_per_batch": t["ozaki_ms"] / 4, "var_ms_per_batch": t["predict_var_ms"] / 4, "slices": t["ozaki_slices"]}), flush=True)
+print(json.dumps({"gr": $GR, "gq": 148 // $GR, "noskip": os.environ.get("GPR_OZ_NOSKIP", "0"), "int8_kernel_ms_per_batch": t["ozaki_ms"] / 4, "var_ms_per_batch": t["predict_var_ms"] / 4, "slices": t["ozaki_slices"], "issued_fraction": t["ozaki_issued_fraction"]}), flush=True)
 PY
 done 2>&1 | grep -v "^$" | tee gpurun_out/oz_group_sweep.log
