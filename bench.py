@@ -244,7 +244,10 @@ def main():
             tot = 1e3 * (time.perf_counter() - t0)
             tt = ctx.timings()
             ttfv[mode] = {"total_ms": tot, "fit_wall_ms": t_fit, "first_batch_queries": q1, "first_batch_wall_ms": tot - t_fit,
-                          "of_which_linv_ms": tt["linv_ms"] if mode == "default" else 0.0, "variance_ms": tt["predict_var_ms"]}
+                          "of_which_linv_ms": tt["linv_ms"] if mode == "default" else 0.0, "variance_ms": tt["predict_var_ms"],
+                          # the device-side part (CUDA events): what remains once the one-time multi-GB allocations of a fresh
+                          # process (panel, L^-1, int8 slices: their host cost varies from box to box) are taken out
+                          "device_ms": tt["fit_total_ms"] + (tt["linv_ms"] if mode == "default" else 0.0) + tt["predict_mean_ms"] + tt["predict_var_ms"]}
             if mode == "trsm":
                 assert model.state().linv is None                # nothing built L^-1
         os.environ.pop("GPR_VAR_MODE", None)
