@@ -8,7 +8,7 @@ timeout 900 python -m pytest tests -m gpu -x -q -k "two_devices or replicated or
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2_$TAG.json 2> gpurun_out/bench_n2_$TAG.err; echo "bench rc=$?"; python - <<'PY'
 import json
 try:
-    d=json.load(open('gpurun_out/bench_n2_%s.json' % '$TAG'))
+    d=json.load(open('gpurun_out/bench_n2_'+'$TAG'+'.json'))
     for k in ('value','ms_per_step','fit_ms','broadcast_ms','broadcast_GBps','broadcast_exposed_ms','fit_publish','full_grid','time_to_first_variance_ms'):
         print(k, d.get(k))
 except Exception as e:
