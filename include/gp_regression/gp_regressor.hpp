@@ -115,6 +115,19 @@ inline void vec_to(Eigen::VectorXd& dst, const std::vector<double>& src) {
 
 }  // namespace detail
 
+// Extension: the x, y, z fields of a PCD file (ascii / binary / binary_compressed) as a Data with empty labels — what the
+// reference's node obtains from PCL (pcl::io::loadPCDFile, src/gp_node.cpp:557); no PCL needed (gpr_pcd_read_xyz).
+inline Data::Ptr loadPCD(const std::string& path) {
+    double *x = nullptr, *y = nullptr, *z = nullptr;
+    size_t n = 0;
+    const int rc = gpr_pcd_read_xyz(path.c_str(), &x, &y, &z, &n);
+    if (rc != GPR_OK) detail::raise(rc);
+    Data::Ptr d = std::make_shared<Data>();
+    d->coord_x.assign(x, x + n); d->coord_y.assign(y, y + n); d->coord_z.assign(z, z + n);
+    gpr_free(x); gpr_free(y); gpr_free(z);
+    return d;
+}
+
 template <typename CovType>
 class GPRegressor {
 public:

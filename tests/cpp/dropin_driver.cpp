@@ -114,7 +114,17 @@ int main(int argc, char** argv) {
                   << ga.compute(one) << ' ' << ga.computediff(one) << ' ' << la.compute(one) << ' ' << la.computediff(one) << "\n";
         return 0;
     }
-    if (argc < 3) { std::cerr << "usage: dropin_driver <in.txt> <out.txt> | --errors\n"; return 2; }
+    if (argc >= 3 && !std::strcmp(argv[1], "--pcd")) {          // host only: the PCD reader behind loadPCD
+        try {
+            Data::Ptr d = loadPCD(argv[2]);
+            double sx = 0, sy = 0, sz = 0;
+            for (size_t i = 0; i < d->coord_x.size(); ++i) { sx += d->coord_x[i]; sy += d->coord_y[i]; sz += d->coord_z[i]; }
+            std::cout.precision(17);
+            std::cout << "pcd " << d->coord_x.size() << ' ' << sx << ' ' << sy << ' ' << sz << ' ' << d->label.size() << "\n";
+        } catch (const GPRegressionException& e) { std::cout << "exception " << e.what() << "\n"; }
+        return 0;
+    }
+    if (argc < 3) { std::cerr << "usage: dropin_driver <in.txt> <out.txt> | --errors | --pcd <file.pcd>\n"; return 2; }
     std::ifstream in(argv[1]);
     std::ofstream out(argv[2]);
     int kind; double p0, p1;

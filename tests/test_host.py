@@ -223,6 +223,13 @@ def test_c_abi_pcd_reader(gpr, tmp_path):
         got = gpr.pcd_read_xyz(tmp_path / name)
         assert got.dtype == np.float64 and np.array_equal(got, xyz.astype(np.float64)), name
         assert np.array_equal(got, gpr.workloads.read_pcd_xyz(str(tmp_path / name)))       # the Python reader of the benches
+    # the C++ header's loadPCD (drop-in side of the same reader)
+    exe = _build_driver(str(tmp_path))
+    out = subprocess.run([exe, "--pcd", str(tmp_path / "c.pcd")], capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "pcd" and int(out[1]) == n and int(out[5]) == 0
+    assert np.allclose([float(v) for v in out[2:5]], xyz.astype(np.float64).sum(axis=0), rtol=1e-12, atol=1e-12)
+    out = subprocess.run([exe, "--pcd", str(tmp_path / "missing.pcd")], capture_output=True, text=True, check=True).stdout
+    assert out.startswith("exception") and "cannot open" in out
     (tmp_path / "bad.pcd").write_bytes((hdr % (n, n, "binary_compressed")).encode() + struct.pack("<II", len(comp), len(soa)) + comp[:-7])
     (tmp_path / "short.pcd").write_bytes((hdr % (n, n, "binary")).encode() + rec.tobytes()[:-5])
     (tmp_path / "nofields.pcd").write_bytes(b"VERSION 0.7\nDATA ascii\n1 2 3\n")
