@@ -224,6 +224,8 @@ struct gpr_model {
     size_t n_normals = 0;
     bool oz_disabled = false;        // the INT8 tensor-core variance failed its FP64 spot check on this model: FP64 paths only
     int oz_bump = 0;                 // extra slices this model needs beyond the default (raised by a failed spot check)
+    std::vector<std::pair<int, void*>> retired;   // (device, buffer): slice buffers replaced while concurrent predict calls may
+                                                  // still read them (slice escalation); freed with the model
     std::mutex mu;
     // Micro-batcher of the callers' q = 1 pattern (hundreds of concurrent threads with one query each on one shared
     // model, src/gp_node.cpp:1027-1038): concurrent small requests are combined into one batched launch.
@@ -250,6 +252,8 @@ static KernParams make_kp(gpr_kernel_t k) {
 static double kernel_at_zero(const KernParams& kp) { return kp.kind == 0 ? kp.R3 : kp.amp; }
 
 static void free_factor(gpr_model* m) {
+    for (auto& r : m->retired) { cudaSetDevice(r.first); cudaFree(r.second); }
+    m->retired.clear();
     if (m->devs.empty()) return;
     cudaSetDevice(m->devs[0].dev);
     cudaFree(m->label); cudaFree(m->s2); cudaFree(m->zfwd); cudaFree(m->Dinv); cudaFree(m->scratch);
@@ -690,7 +694,14 @@ static int ensure_ozaki_slices(gpr_model* m, size_t di, int S, int base254, cuda
     ModelDev& md = m->devs[di];
     if (md.oz_xs && md.oz_S == S && md.oz_base == base254 && md.oz_ld == m->cap && md.oz_n == m->n) return GPR_OK;     // an append changes n: re-slice
     CU(cudaSetDevice(md.dev));
-    cudaFree(md.oz_xs); cudaFree(md.oz_scale); cudaFree(md.oz_nz);
+    // Same model, other slice count (escalation after a failed spot check): predict calls of other threads may be running on
+    // the old buffers, so they are retired (freed with the model) instead of freed now.  A changed model (append / growth:
+    // exclusive by the API's contract) frees them at once.
+    const bool same_model = md.oz_n == m->n && md.oz_ld == m->cap;
+    for (void* p : {(void*)md.oz_xs, (void*)md.oz_scale, (void*)md.oz_nz}) {
+        if (!p) continue;
+        if (same_model) m->retired.emplace_back(md.dev, p); else cudaFree(p);
+    }
     md.oz_xs = nullptr; md.oz_scale = nullptr; md.oz_nz = nullptr; md.oz_S = 0;
     const size_t ld = m->cap;
     CU(cudaMalloc((void**)&md.oz_xs, (size_t)S * ld * ld));
