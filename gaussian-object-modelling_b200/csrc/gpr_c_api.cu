@@ -768,17 +768,17 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
         const char* mode_env = getenv("GPR_VAR_MODE");
         static const long oz_min_q = getenv("GPR_OZAKI_MIN_Q") ? atol(getenv("GPR_OZAKI_MIN_Q")) : 16384;
         static const long min_q = getenv("GPR_TRSM_MIN_Q") ? atol(getenv("GPR_TRSM_MIN_Q")) : 4096;
-        // digit system: base 254 (|digit| <= 127, 8 bits per slice: 6 slices) while no int32 accumulator can overflow
-        // (k <= 22016), else base 128 (|digit| <= 64, 7 bits per slice: 7 slices; k <= 74752).  GPR_OZAKI_BASE / _SLICES override.
+        // digit system: base 254 (|digit| <= 127, ~8 bits per slice: 6 slices).  Up to k = 22016 no int32 accumulator can
+        // overflow; longer rows run the k-chunked kernel, which drains the accumulators into FP64 every 344 k-blocks.
+        // GPR_OZAKI_BASE=128 selects |digit| <= 64 (7 slices, unchunked up to k = 74752); GPR_OZAKI_SLICES overrides the count.
         const long long kext = (long long)m->nb * TB;
-        oz_base254 = kext <= ozaki_max_k(6, 1) ? 1 : 0;
+        oz_base254 = 1;
         if (const char* e = getenv("GPR_OZAKI_BASE")) oz_base254 = atoi(e) == 254 ? 1 : 0;
         int bump;
         { std::lock_guard<std::mutex> lk(m->mu); bump = m->oz_bump; }
         oz_S = std::min(8, (oz_base254 ? 6 : 7) + bump);
         if (const char* e = getenv("GPR_OZAKI_SLICES")) oz_S = std::max(2, std::min(8, atoi(e) + bump));
-        if (oz_base254 && kext > ozaki_max_k(oz_S, 1) && !getenv("GPR_OZAKI_BASE")) { oz_base254 = 0; oz_S = std::min(8, oz_S + 1); }
-        const bool oz_fits = kext <= ozaki_max_k(oz_S, oz_base254);
+        const bool oz_fits = ozaki_supported(oz_S, oz_base254, kext);
         const bool can_trsm = m->devs[0].have_fac;
         if (mode_env && !strcmp(mode_env, "ozaki")) use_oz = oz_fits;
         else if (mode_env && !strcmp(mode_env, "trsm")) use_trsm = can_trsm;
@@ -944,11 +944,10 @@ static int predict_on_device(gpr_model* m, size_t di, const PredictIO& io, doubl
                     // (x128 / x254 finer) if the accumulators still cannot overflow — remembered on the model — else this batch
                     // and everything after it on this model go through the FP64 product form.
                     const bool forced_slices = getenv("GPR_OZAKI_SLICES") != nullptr;
-                    int nS = oz_S + 1, nbase = oz_base254;
-                    if (nbase && (long long)m->nb * TB > ozaki_max_k(nS, 1)) nbase = 0;
-                    if (!forced_slices && nS <= 8 && (long long)m->nb * TB <= ozaki_max_k(nS, nbase)) {
+                    const int nS = oz_S + 1;
+                    if (!forced_slices && ozaki_supported(nS, oz_base254, (long long)m->nb * TB)) {
                         { std::lock_guard<std::mutex> lk(m->mu); m->oz_bump += 1; }
-                        oz_S = nS; oz_base254 = nbase;
+                        oz_S = nS;
                         rc = prep_oz();
                         if (rc) return rc;
                         continue;

@@ -77,6 +77,7 @@ cudaError_t launch_var_finalize(const double* partial, size_t panel_ld, int nb, 
 // K3'' (gpr_ozaki.cu): the variance product on the INT8 tensor cores (tcgen05 kind::i8 + TMEM + TMA), FP64-equivalent by slicing.
 int ozaki_tile_n(int S);
 long long ozaki_max_k(int S, int base254);
+bool ozaki_supported(int S, int base254, long long k_extent);
 cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a_slice, int nrt, const signed char* Bs, size_t b_pitch,
                                  size_t b_slice, size_t b_rows, int q, size_t q_pad, size_t k_extent, int tri, int S, int base254,
                                  const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, size_t dbg_ld,

@@ -9,8 +9,11 @@
 // where every bracket is an exact integer computed by int8 MMAs and the S levels are recombined in FP64 in the epilogue,
 // which also reduces the squared column norms per 128-row tile exactly like the DMMA kernels
 // (partial[row tile][query] -> var_finalize_kernel).  Two digit systems:
-//   base 254: F = 127, |digit| <= 127 (7.99 bits per slice); exact while S * 127^2 * k < 2^31, i.e. k <= 22016 for S = 6;
-//   base 128: F = 64,  |digit| <= 64  (7 bits per slice);    exact while S * 64^2 * k < 2^31, i.e. k <= 74752 for S = 7.
+//   base 254: F = 127, |digit| <= 127 (7.99 bits per slice); an int32 accumulator holds S * 127^2 * k < 2^31, i.e. k <= 22016 for S = 6;
+//   base 128: F = 64,  |digit| <= 64  (7 bits per slice);    S * 64^2 * k < 2^31, i.e. k <= 74752 for S = 7.
+// Longer rows (config 5: n = 65536) run the CHUNKED variant of the kernel: the k range of a task is cut into chunks of at
+// most that length, after each of which the epilogue drains the int32 accumulators into FP64 running sums (registers; 64-query
+// tiles) — still exact integer arithmetic per chunk, one FP64 rounding per chunk and level on top (<= 1e-16 relative).
 // Slices beyond level S - 1 are dropped: truncation ~ B^(-S) relative to (row max of X) x (max of K*) x sqrt(k); the slice
 // count is chosen against the variance tolerance (profiles/ozaki_slicing_study_r2.json, tools/ozaki_study.py), and every
 // call is spot-checked against the FP64 tensor pipe by the caller (gpr_c_api.cu).
@@ -58,6 +61,8 @@ struct OzArgs {
     double wl[8];                 // level weights 1 / (F^2 B^l)
     const unsigned char* nzA;     // optional [nrt][nz_pitch]: bit t set iff slice t of (row tile, 64-wide k-block) has a nonzero digit
     size_t nz_pitch;
+    int kchunk;                   // k-blocks (of 64) after which the int32 accumulators are drained into FP64 (they could overflow
+                                  // beyond); >= the longest row for the unchunked kernel
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -128,7 +133,7 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int M, int N) {
 // issue loop (template on the slice count) and the separate producer warp.
 constexpr int OZ_NTHREADS = 192;
 
-template <int S, int BN>
+template <int S, int BN, bool CHUNKED>
 __global__ void __launch_bounds__(OZ_NTHREADS, 1)
 ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a) {
     extern __shared__ __align__(1024) uint8_t oz_smem[];
@@ -210,23 +215,28 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int rt, qt;
             if (!decode(task, it & 1, rt, qt)) continue;
             const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
-            if (tcount > 0 && !mbar_wait(&accum_empty, (tcount - 1) & 1)) { ok = false; break; }   // epilogue has drained TMEM
-            tc_fence_after();
             // Digit slices of A that are entirely zero in a (row tile, k-block) — far from the diagonal the entries of L^-1 are
             // small against their row maximum, so the leading digits vanish (36 % of the blocks at n = 16384) — contribute
             // nothing: their MMAs are skipped.  The first k-block of a task never skips (it zero-initialises every level).
+            // Long rows (CHUNKED): the k range is cut into chunks after each of which the epilogue drains the int32 accumulators
+            // into FP64, so that no accumulator can overflow; each chunk is one accumulate / commit / drain cycle.
             const unsigned char* nzrow = a.nzA ? a.nzA + (size_t)rt * a.nz_pitch : nullptr;
+            const int kch = CHUNKED ? a.kchunk : nkb;
+          for (int c0 = 0; c0 < nkb && ok; c0 += kch) {
+            const int c1 = c0 + kch < nkb ? c0 + kch : nkb;
+            if (tcount > 0 && !mbar_wait(&accum_empty, (tcount - 1) & 1)) { ok = false; break; }   // epilogue has drained TMEM
+            tc_fence_after();
             uint32_t mask_next = 0xFFu;
-            for (int kb = 0; kb < nkb; ++kb, ++j) {
+            for (int kb = c0; kb < c1; ++kb, ++j) {
                 const uint32_t s = j % (uint32_t)stages, u = j / (uint32_t)stages;
                 const uint32_t mask = mask_next;
-                mask_next = (nzrow && kb + 1 < nkb) ? (uint32_t)__ldg(nzrow + kb + 1) : 0xFFu;
+                mask_next = (nzrow && kb + 1 < c1) ? (uint32_t)__ldg(nzrow + kb + 1) : 0xFFu;
                 if (!mbar_wait(&full_bar[s], u & 1)) { ok = false; break; }
                 tc_fence_after();
                 const uint32_t sa = smem_u32(base + (size_t)s * STAGE_BYTES);
                 const uint32_t a_lo = (((sa >> 4) & 0x3FFFu) | (1u << 16));
                 const uint32_t b_lo = a_lo + (uint32_t)(S * OZ_A_SLICE_BYTES >> 4);
-                const uint32_t keep = kb > 0 ? 1u : 0u;
+                const uint32_t keep = kb > c0 ? 1u : 0u;
 #pragma unroll
                 for (int l = 0; l < LEVELS; ++l) {
 #pragma unroll
@@ -243,8 +253,9 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_commit(&empty_bar[s]);                            // stage free once these MMAs have read it
             }
             if (!ok) break;
-            umma_commit(&accum_full);                                  // all MMAs of the task done -> epilogue
+            umma_commit(&accum_full);                                  // all MMAs of the chunk done -> epilogue
             ++tcount;
+          }
         }
         if (!ok) atomicExch(a.ctrl + 1, 1);
     } else if (warp >= 2) {
@@ -258,45 +269,94 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (task >= ntasks) break;
             int rt, qt;
             if (!decode(task, it & 1, rt, qt)) continue;
-            if (!mbar_wait(&accum_full, tcount & 1)) { ok = false; break; }
-            ++tcount;
-            tc_fence_after();
             const int row = rt * OZ_BM + q4 * 32 + lane;
             const double rs = a.row_scale[row] * a.col_scale;
+            if constexpr (!CHUNKED) {
+                if (!mbar_wait(&accum_full, tcount & 1)) { ok = false; break; }
+                ++tcount;
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < OZ_BN / 16; ++c) {
-                double acc[16];
+                for (int c = 0; c < OZ_BN / 16; ++c) {
+                    double acc[16];
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.0;
+                    for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.0;
 #pragma unroll
-                for (int l = LEVELS - 1; l >= 0; --l) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem + lane_base + (uint32_t)(l * OZ_BN + 16 * c), v);
-                    const double wl = a.wl[l];
+                    for (int l = LEVELS - 1; l >= 0; --l) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem + lane_base + (uint32_t)(l * OZ_BN + 16 * c), v);
+                        const double wl = a.wl[l];
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) acc[jj] = fma((double)(int)v[jj], wl, acc[jj]);
-                    if (a.dbg) {
-                        int* o = a.dbg + ((size_t)l * a.nrt * OZ_BM + row) * a.dbg_ld;
+                        for (int jj = 0; jj < 16; ++jj) acc[jj] = fma((double)(int)v[jj], wl, acc[jj]);
+                        if (a.dbg) {
+                            int* o = a.dbg + ((size_t)l * a.nrt * OZ_BM + row) * a.dbg_ld;
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const size_t col = (size_t)qt * OZ_BN + 16 * c + jj;
-                            if (col < a.dbg_ld) o[col] = (int)v[jj];
+                            for (int jj = 0; jj < 16; ++jj) {
+                                const size_t col = (size_t)qt * OZ_BN + 16 * c + jj;
+                                if (col < a.dbg_ld) o[col] = (int)v[jj];
+                            }
                         }
                     }
-                }
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                    const double vv = acc[jj] * rs;
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const double vv = acc[jj] * rs;
+                        double sv = vv * vv;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                        if (lane == 0) sred[q4][16 * c + jj] = sv;
+                    }
+                }
+                // TMEM is drained: the MMA issuer may start the next task
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
+            } else {
+                // one drain per k-chunk into FP64 running sums (registers), squares and reduction after the last chunk
+                const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
+                double vacc[OZ_BN];
+#pragma unroll
+                for (int jj = 0; jj < OZ_BN; ++jj) vacc[jj] = 0.0;
+                for (int c0 = 0; c0 < nkb && ok; c0 += a.kchunk) {
+                    if (!mbar_wait(&accum_full, tcount & 1)) { ok = false; break; }
+                    ++tcount;
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < OZ_BN / 16; ++c) {
+                        double acc[16];
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.0;
+#pragma unroll
+                        for (int l = LEVELS - 1; l >= 0; --l) {
+                            uint32_t v[16];
+                            tmem_ld16(tmem + lane_base + (uint32_t)(l * OZ_BN + 16 * c), v);
+                            const double wl = a.wl[l];
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) acc[jj] = fma((double)(int)v[jj], wl, acc[jj]);
+                            if (a.dbg) {                                        // debug dump: the accumulators are SUMMED over the chunks
+                                int* o = a.dbg + ((size_t)l * a.nrt * OZ_BM + row) * a.dbg_ld;
+#pragma unroll
+                                for (int jj = 0; jj < 16; ++jj) {
+                                    const size_t col = (size_t)qt * OZ_BN + 16 * c + jj;
+                                    if (col < a.dbg_ld) o[col] = (c0 == 0 ? 0 : o[col]) + (int)v[jj];
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) vacc[16 * c + jj] += acc[jj];
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
+                }
+                if (!ok) break;
+#pragma unroll
+                for (int jj = 0; jj < OZ_BN; ++jj) {
+                    const double vv = vacc[jj] * rs;
                     double sv = vv * vv;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-                    if (lane == 0) sred[q4][16 * c + jj] = sv;
+                    if (lane == 0) sred[q4][jj] = sv;
                 }
             }
-            // TMEM is drained: the MMA issuer may start the next task
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps
             const int et = tid - 64;
             if (et < OZ_BN && (size_t)qt * OZ_BN + et < a.q_pad)
@@ -436,21 +496,28 @@ int ozaki_stages(int S, int BN) {
 }
 int ozaki_tile_n(int S) { return S * 80 <= OZ_TMEM_COLS ? 80 : 64; }
 // Largest k extent for which every level accumulator stays below 2^31 in the worst case.
+// Can the engine run S slices over k_extent columns?  Within ozaki_max_k always; beyond it only the slice counts the
+// k-chunked kernel is instantiated for.
+bool ozaki_supported(int S, int base254, long long k_extent) {
+    if (S < 1 || S > 8) return false;
+    return k_extent <= ozaki_max_k(S, base254) || S <= 2 || S >= 6;
+}
+
 long long ozaki_max_k(int S, int base254) {
     const long long d = base254 ? 127 : 64;
     return ((1LL << 31) - 1) / ((long long)S * d * d);
 }
 
-template <int S, int BN>
+template <int S, int BN, bool CHUNKED>
 static cudaError_t launch_oz(const CUtensorMap& tmA, const CUtensorMap& tmB, const OzArgs& a, int grid, size_t smem, cudaStream_t st) {
     static PerDeviceOnce attr_done;
     const int cur = PerDeviceOnce::current();
     if (!attr_done.done(cur)) {
-        cudaError_t e = cudaFuncSetAttribute(ozaki_var_kernel<S, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ozaki_var_kernel<S, BN, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done.set(cur);
     }
-    ozaki_var_kernel<S, BN><<<grid, OZ_NTHREADS, smem, st>>>(tmA, tmB, a);
+    ozaki_var_kernel<S, BN, CHUNKED><<<grid, OZ_NTHREADS, smem, st>>>(tmA, tmB, a);
     return cudaGetLastError();
 }
 
@@ -462,8 +529,13 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
                                  const double* row_scale, double col_scale, double* partial, int* ctrl, int* dbg, size_t dbg_ld,
                                  cudaStream_t st, const unsigned char* nzA, size_t nz_pitch) {
     if (S < 1 || S > 8) return cudaErrorInvalidValue;
-    if ((long long)k_extent > ozaki_max_k(S, base254)) return cudaErrorInvalidValue;       // an accumulator could overflow
-    const int BN = ozaki_tile_n(S);
+    // Beyond ozaki_max_k an int32 accumulator could overflow: the chunked kernel drains the accumulators into FP64 every
+    // kchunk k-blocks (64-query tiles: the FP64 running sums live in the epilogue threads' registers).
+    // GPR_OZ_KCHUNK=<even number of k-blocks> forces the chunked kernel with that chunk length (tests of the chunk logic).
+    const char* kc_env = getenv("GPR_OZ_KCHUNK");
+    const int kc_forced = kc_env ? (atoi(kc_env) & ~1) : 0;
+    const bool chunked = (long long)k_extent > ozaki_max_k(S, base254) || (kc_forced > 0 && (S <= 2 || S >= 6));
+    const int BN = chunked ? 64 : ozaki_tile_n(S);
     const size_t smem = (size_t)220 * 1024 + 1024;
     CUtensorMap tmA, tmB;
     cudaError_t e = make_map(&tmA, As, k_extent, (size_t)nrt * OZ_BM, S, a_pitch, a_slice, OZ_BM);
@@ -476,6 +548,8 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
     a.row_scale = row_scale; a.col_scale = col_scale; a.partial = partial; a.q_pad = q_pad; a.ctrl = ctrl; a.dbg = dbg; a.dbg_ld = dbg_ld;
     static const bool noskip = getenv("GPR_OZ_NOSKIP") && atoi(getenv("GPR_OZ_NOSKIP")) != 0;      // A/B switch for measurements
     a.nzA = noskip ? nullptr : nzA; a.nz_pitch = nz_pitch;
+    a.kchunk = chunked ? (int)((ozaki_max_k(S, base254) / OZ_BK) & ~1LL) : (1 << 30);
+    if (chunked && kc_forced > 0 && kc_forced < a.kchunk) a.kchunk = kc_forced;
     const double F = base254 ? 127.0 : 64.0, B = base254 ? 254.0 : 128.0;
     double w = 1.0 / (F * F);
     for (int l = 0; l < 8; ++l) { a.wl[l] = w; w /= B; }
@@ -494,15 +568,25 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
     if (e != cudaSuccess) return e;
     const int tasks = ((npairs + a.gr - 1) / a.gr) * ((a.nqt + a.gq - 1) / a.gq) * a.gr * a.gq;
     const int grid = tasks < sms ? tasks : sms;
+    if (chunked) {
+        switch (S) {
+            case 1: return launch_oz<1, 64, true>(tmA, tmB, a, grid, smem, st);       // (self-test of the chunk logic)
+            case 2: return launch_oz<2, 64, true>(tmA, tmB, a, grid, smem, st);
+            case 6: return launch_oz<6, 64, true>(tmA, tmB, a, grid, smem, st);
+            case 7: return launch_oz<7, 64, true>(tmA, tmB, a, grid, smem, st);
+            case 8: return launch_oz<8, 64, true>(tmA, tmB, a, grid, smem, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (S) {
-        case 1: return launch_oz<1, 80>(tmA, tmB, a, grid, smem, st);
-        case 2: return launch_oz<2, 80>(tmA, tmB, a, grid, smem, st);
-        case 3: return launch_oz<3, 80>(tmA, tmB, a, grid, smem, st);
-        case 4: return launch_oz<4, 80>(tmA, tmB, a, grid, smem, st);
-        case 5: return launch_oz<5, 80>(tmA, tmB, a, grid, smem, st);
-        case 6: return launch_oz<6, 80>(tmA, tmB, a, grid, smem, st);
-        case 7: return launch_oz<7, 64>(tmA, tmB, a, grid, smem, st);
-        default: return launch_oz<8, 64>(tmA, tmB, a, grid, smem, st);
+        case 1: return launch_oz<1, 80, false>(tmA, tmB, a, grid, smem, st);
+        case 2: return launch_oz<2, 80, false>(tmA, tmB, a, grid, smem, st);
+        case 3: return launch_oz<3, 80, false>(tmA, tmB, a, grid, smem, st);
+        case 4: return launch_oz<4, 80, false>(tmA, tmB, a, grid, smem, st);
+        case 5: return launch_oz<5, 80, false>(tmA, tmB, a, grid, smem, st);
+        case 6: return launch_oz<6, 80, false>(tmA, tmB, a, grid, smem, st);
+        case 7: return launch_oz<7, 64, false>(tmA, tmB, a, grid, smem, st);
+        default: return launch_oz<8, 64, false>(tmA, tmB, a, grid, smem, st);
     }
 }
 

@@ -46,7 +46,7 @@ typedef struct {
     double h2d_ms, d2h_ms;
     double append_ms;               /* last gpr_append: device time of the incremental update incl. the alpha re-solve */
     double ozaki_ms;                /* last predict on the primary device: time inside the INT8 tensor-core variance kernel (0 if another form ran) */
-    double ozaki_slices;            /* ... and the number of int8 slices per operand it used (6: base-254 digits, 7 or more: base 128 / escalated) */
+    double ozaki_slices;            /* ... and the number of int8 slices per operand it used (6: base-254 digits, 7 or more: escalated / base 128) */
     double ozaki_issued_fraction;   /* ... and the share of its slice-pair MMAs actually issued (digit slices of L^-1 that are all zero in a
                                        (128-row, 64-k) block are skipped) */
 } gpr_timings;
@@ -147,7 +147,7 @@ int gpr_sample_chart(gpr_ctx* ctx, gpr_model* m, const double* frames, const siz
 /* Builds L^-1 now.  It is otherwise built by the first call that needs it.  The variance (n^2 flop per query) has three
  * forms, chosen per call (GPR_VAR_MODE=ozaki|product|trsm forces one):
  *   >= 16384 queries (GPR_OZAKI_MIN_Q): product with L^-1 on the INT8 tensor cores (tcgen05 kind::i8 + TMEM + TMA),
- *      FP64-equivalent by Ozaki slicing (6 slices of base-254 digits for n <= 22016, else 7 slices of base-128 digits:
+ *      FP64-equivalent by Ozaki slicing (6 slices of base-254 digits; rows longer than 22016 drain the int32 accumulators in chunks:
  *      ~1e-9 of the variance; GPR_OZAKI_SLICES / GPR_OZAKI_BASE override), ~2.9x the FP64 tensor-pipe rate; needs L^-1 and its
  *      int8 slices (built once per model); every call re-computes its first query tile on the FP64 tensor pipe and, if the
  *      two differ by > 1e-8, adds a slice for this model (remembered) or, failing that, falls back to the FP64 product form;

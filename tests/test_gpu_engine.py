@@ -103,3 +103,26 @@ def test_int8_tensor_core_engine_is_exact(gpr, S, M, N, K, tri):
     for l in range(S):
         E = sum(A64[t] @ B[l - t].astype(np.int64).T for t in range(l + 1))
         assert np.array_equal(C[l].astype(np.int64), E), l
+
+
+@pytest.mark.parametrize("S,M,N,K,tri,kchunk", [(2, 256, 128, 1024, False, 4), (6, 512, 192, 1024, True, 2),
+                                                (7, 384, 64, 1536, True, 6), (8, 256, 320, 2048, False, 10)])
+def test_int8_engine_with_chunked_accumulation_is_exact(gpr, monkeypatch, S, M, N, K, tri, kchunk):
+    """Rows longer than the int32 accumulators allow (k > 22016 at 6 slices of |d| <= 127) run the k-chunked kernel: the
+    accumulators are drained every `kchunk` k-blocks.  GPR_OZ_KCHUNK forces that kernel with a short chunk, so that tasks
+    span several chunks (and, for `tri`, a ragged last chunk); the summed level accumulators must equal the int64 product."""
+    monkeypatch.setenv("GPR_OZ_KCHUNK", str(kchunk))
+    rng = np.random.default_rng(S * 77 + K)
+    A = rng.integers(-127, 128, size=(S, M, K), dtype=np.int8)
+    B = rng.integers(-127, 128, size=(S, N, K), dtype=np.int8)
+    # zero blocks, among them the first block of a chunk (which must not be skipped: it initialises the accumulators)
+    for (t, r, kb) in [(0, 0, kchunk), (0, 1, 0), (1, 1, kchunk + 1), (0, M // 128 - 1, K // 64 - 1)]:
+        A[t, r * 128:(r + 1) * 128, kb * 64:(kb + 1) * 64] = 0
+    C = gpr.selftest_i8gemm(A, B, S, tri, skip_zero_blocks=True)
+    A64 = A.astype(np.int64)
+    if tri:
+        for r in range(M // 128):
+            A64[:, r * 128:(r + 1) * 128, 128 * (r + 1):] = 0
+    for l in range(S):
+        E = sum(A64[t] @ B[l - t].astype(np.int64).T for t in range(l + 1))
+        assert np.array_equal(C[l].astype(np.int64), E), l
