@@ -50,6 +50,24 @@ METRIC = "query_pts_per_sec_mean_var"
 UNIT = "points/s"
 
 
+def fit_roofline(extras, dmma_peak, dgemm):
+    """The factorisation (n^3/3 flop).  All-FP64 tile kernel: against the DMMA issue peak.  INT8-assisted (the default for
+    n >= 8192): ~83 % of the flops run as exact int8 slice products on tcgen05 (7 base-254 digits), the panels on the FP64 pipe
+    — an FP64-equivalent rate, reported against the same FP64 peaks (it can exceed them; that is the point) and never clamped."""
+    i8 = extras.get("fit_int8_slices", 0)
+    r = {"kernel": ("launch_cholesky_int8: ozaki_var_kernel<%d,64,chunked,update> (INT8 tensor cores, left of each 16-tile panel) + "
+                    "chol_tiles_kernel (FP64 tensor pipe, panels) + oz_slice_kernel; n^3/3 flop" % i8) if i8
+         else "chol_tiles_kernel (tile-task Cholesky, n^3/3 flop)",
+         "bound": "tensor", "achieved": extras["fit_chol_tflops"], "peak": dmma_peak,
+         "unit": "TFLOP/s (FP64-equivalent)" if i8 else "TFLOP/s",
+         "frac": extras["fit_chol_tflops"] / dmma_peak, "frac_vs_cublas": extras["fit_chol_tflops"] / dgemm,
+         "ms": extras["fit_chol_ms"], "share_of_fit": extras["fit_chol_ms"] / extras["fit_ms"], "traffic": None,
+         "int8_slices": i8}
+    if i8:
+        r["peak_note"] = "peak = measured FP64 DMMA issue rate; frac > 1 means the factorisation ran faster than any all-FP64 one can on this GPU"
+    return r
+
+
 def workload_config(extra=None):
     cfg = {"workload": "config3: synthetic sphere cloud n=16384, ThinPlate(R=4.2), sigma2=0.1, mean+variance over the "
                        "256^3 grid on [-1.2,1.2]^3 (z-slab shards)",
@@ -218,6 +236,7 @@ def main():
                 extras["fit_wall_ms_first_call"] = wall
             else:
                 fits.append((t["fit_total_ms"], t["cov_ms"], t["chol_ms"], t["solve_ms"], wall))
+                extras["fit_int8_slices"] = int(t["fit_int8_slices"])
         best = min(fits)
         extras.update(fit_ms=best[0], fit_cov_ms=best[1], fit_chol_ms=best[2], fit_solve_ms=best[3],
                       fit_wall_ms_e2e=min(f[4] for f in fits),      # host wall of gpr_fit (H2D of the cloud, allocation, D2H of alpha)
@@ -522,11 +541,7 @@ def main():
                 "gpu_launches": (5 * BATCHES_PER_STEP + 2) * args.steps if default_is_int8 else 4 * BATCHES_PER_STEP * args.steps,
                 "clocks": clocks,
                 "roofline": roof,
-                "roofline_fit": {"kernel": "chol_tiles_kernel (tile-task Cholesky, n^3/3 flop)", "bound": "tensor",
-                                 "achieved": extras["fit_chol_tflops"], "peak": dmma_peak, "unit": "TFLOP/s",
-                                 "frac": extras["fit_chol_tflops"] / dmma_peak, "frac_vs_cublas": extras["fit_chol_tflops"] / dgemm,
-                                 "ms": extras["fit_chol_ms"], "share_of_fit": extras["fit_chol_ms"] / extras["fit_ms"],
-                                 "traffic": None}}
+                "roofline_fit": fit_roofline(extras, dmma_peak, dgemm)}
         line.update(extras)
         if full_grid:
             line["full_grid"] = full_grid

@@ -40,7 +40,8 @@ class KernelT(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "cov_ms", "chol_ms", "solve_ms", "normals_ms", "fit_total_ms", "linv_ms",
-        "predict_mean_ms", "predict_var_ms", "predict_total_ms", "h2d_ms", "d2h_ms", "append_ms", "ozaki_ms", "ozaki_slices", "ozaki_issued_fraction")]
+        "predict_mean_ms", "predict_var_ms", "predict_total_ms", "h2d_ms", "d2h_ms", "append_ms", "ozaki_ms", "ozaki_slices", "ozaki_issued_fraction",
+        "fit_int8_slices")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -222,6 +222,7 @@ struct gpr_model {
     std::vector<ModelDev> devs;
     std::vector<double> hx, hy, hz, hlabel, hs2, h_alpha, h_normals;   // h_normals: n_normals x 3 column-major
     size_t n_normals = 0;
+    int fit_int8_slices = 0;         // digit slices of the INT8-assisted factorisation that produced L (0: all-FP64)
     bool oz_disabled = false;        // the INT8 tensor-core variance failed its FP64 spot check on this model: FP64 paths only
     int oz_bump = 0;                 // extra slices this model needs beyond the default (raised by a failed spot check)
     std::vector<std::pair<int, void*>> retired;   // (device, buffer): slice buffers replaced while concurrent predict calls may
@@ -393,6 +394,27 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     struct Rel { DeviceCtx* d; Workspace* w; ~Rel() { ws_release(d, w); } } rel{dc, ws};
     cudaStream_t st = ws->st;
 
+    // INT8-assisted factorisation (decided here so that its slice workspace is allocated before the timed phases start)
+    bool want_i8 = false;
+    int i8_panel = 0, i8_S = 7;
+    if (!ctx->chol_serial) {
+        static const long i8_min_n = getenv("GPR_FIT_INT8_MIN_N") ? atol(getenv("GPR_FIT_INT8_MIN_N")) : 8192;
+        const char* fm = getenv("GPR_FIT_MODE");
+        want_i8 = fm ? !strcmp(fm, "int8") : (long)n >= i8_min_n;
+        i8_panel = getenv("GPR_FIT_PANEL") ? atoi(getenv("GPR_FIT_PANEL")) : std::max(8, std::min(32, nb / 8));
+        if (const char* e = getenv("GPR_FIT_SLICES")) i8_S = std::max(6, std::min(8, atoi(e)));
+        if (i8_panel < 1 || i8_panel >= nb) want_i8 = false;
+    }
+    struct I8Buf {                                               // returned to the context's buffer cache on every exit path
+        gpr_ctx* c; int dev; signed char* p = nullptr; size_t bytes = 0; cudaStream_t s;
+        ~I8Buf() { if (p) { cudaStreamSynchronize(s); big_free(c, dev, p, bytes); } }
+    } i8_buf{ctx, dc->dev, nullptr, 0, st};
+    if (want_i8) {
+        i8_buf.bytes = (size_t)i8_S * N * N;
+        CU(big_alloc(ctx, dc->dev, (void**)&i8_buf.p, i8_buf.bytes));
+        if (!ws->oz_ctrl) CU(cudaMalloc((void**)&ws->oz_ctrl, 4 * sizeof(int)));
+    }
+
     // Internal point order.  Normally the caller's order (perm empty).  When the factorisation meets a
     // non-positive pivot with too many points after it for the trailing-block elimination, the offending point
     // is moved to the END of the internal order and the factorisation is retried: after at most MAX_TAIL moves
@@ -436,6 +458,8 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
     double Rbits_host = 0.0;
     int info[4] = {0, 0, 0, 0};
     size_t moved = 0;
+    bool i8_failed = false;
+    m->fit_int8_slices = 0;
     std::vector<int> counts;                 // conflict counts per point (caller's order), computed on the first failure
     for (;;) {
         CU(launch_cov_build(md.xyz, md.xyz + N, md.xyz + 2 * N, m->s2, (int)n, nb, 0, m->L, N, rbits, m->kp, st));
@@ -445,9 +469,31 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
         }
         // first attempt: every finished tile also goes to the registered peer replicas (gpr_ctx_set_fit_peers)
         const bool publish = moved == 0 && ctx->peers.n > 0 && ctx->peer_N == N && !ctx->chol_serial;
-        CU(launch_cholesky(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st, nullptr, publish ? &ctx->peers : nullptr));
-        CU(cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        // Large models: the flops left of each panel of tile columns run on the INT8 tensor cores (launch_cholesky_int8,
+        // FP64-equivalent: 7 digit slices of base 254).  GPR_FIT_MODE=fp64|int8 forces a path, GPR_FIT_INT8_MIN_N (8192),
+        // GPR_FIT_PANEL (tile columns per panel) and GPR_FIT_SLICES (7) tune it.  First attempt only: a matrix that turns out
+        // not to be positive definite is re-factorised in FP64, whose pivot report the indefinite-tail logic below is tuned on.
+        const bool use_i8 = want_i8 && moved == 0 && !i8_failed;
+        if (use_i8) {
+            signed char* Ls = i8_buf.p;
+            double dmax = m->k0;
+            if (m->has_s2) { double smax = 0.0; for (double v : m->hs2) smax = std::max(smax, v); dmax += smax; }
+            dmax = std::max(dmax, 1.0);                            // padding rows carry a unit diagonal
+            cudaError_t ce = launch_cholesky_int8(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, st, publish ? &ctx->peers : nullptr, Ls,
+                                                  i8_S, dmax, i8_panel, ws->oz_ctrl);
+            int octl[2] = {0, 0};
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(octl, ws->oz_ctrl, sizeof(octl), cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            CU(ce);
+            if (octl[1] != 0) return fail(GPR_ERR_CUDA, "INT8 update kernel of the factorisation aborted (barrier wait timed out)");
+            if (info[1] != 0 || info[2] != 0) { i8_failed = true; info[1] = info[2] = 0; continue; }
+            m->fit_int8_slices = i8_S;
+        } else {
+            CU(launch_cholesky(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, ctx->chol_serial, st, nullptr, publish ? &ctx->peers : nullptr));
+            CU(cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
         ctx->last_fit_published = publish && info[1] == 0;
         if (info[1] == 0) break;                                   // positive definite
         const size_t p = (size_t)info[1] - 1;                      // internal index of the failing pivot
@@ -613,6 +659,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
         t.solve_ms = ev_ms(ws->ev[3], ws->ev[4]);
         t.normals_ms = ev_ms(ws->ev[4], ws->ev[5]);
         t.fit_total_ms = ev_ms(ws->ev[1], ws->ev[5]);
+        t.fit_int8_slices = (double)m->fit_int8_slices;
     }
     return GPR_OK;
 }
@@ -2396,7 +2443,23 @@ int gpr_selftest_factor(double* hA, int nb, double* h_linv, int serial, long lon
     CU(cudaMalloc((void**)&D, (size_t)nb * TB * TB * sizeof(double)));
     CU(cudaMalloc((void**)&scratch, (8 + (size_t)nb * nb) * sizeof(int)));
     CU(cudaMemcpy(A, hA, N * N * sizeof(double), cudaMemcpyHostToDevice));
-    CU(launch_cholesky(A, N, nb, D, scratch, sms, serial, 0));
+    if (serial >= 100) {
+        // INT8-assisted factorisation: serial = 100 * (tile columns per panel) + (digit slices)
+        const int P = serial / 100, S = serial % 100;
+        double dmax = 0.0;
+        for (size_t i = 0; i < N; ++i) dmax = std::max(dmax, hA[i * N + i]);
+        signed char* Ls; int* ctrl;
+        CU(cudaMalloc((void**)&Ls, (size_t)S * N * N));
+        CU(cudaMalloc((void**)&ctrl, 4 * sizeof(int)));
+        CU(launch_cholesky_int8(A, N, nb, D, scratch, sms, 0, nullptr, Ls, S, dmax, P, ctrl));
+        CU(cudaDeviceSynchronize());
+        int hc[2];
+        CU(cudaMemcpy(hc, ctrl, sizeof hc, cudaMemcpyDeviceToHost));
+        cudaFree(Ls); cudaFree(ctrl);
+        if (hc[1]) return fail(GPR_ERR_CUDA, "int8 update kernel timed out");
+    } else {
+        CU(launch_cholesky(A, N, nb, D, scratch, sms, serial, 0));
+    }
     CU(cudaDeviceSynchronize());
     int info[4];
     CU(cudaMemcpy(info, scratch, sizeof info, cudaMemcpyDeviceToHost));

@@ -31,7 +31,11 @@ struct CholArgs {
     size_t ld;
     int nb;           // N / 128
     double* Dinv;     // nb tiles of 128x128: inverse of each diagonal block of L
-    int* ready;       // nb*nb flags, [i*nb + j]
+    int* ready;       // flags, [i*ready_ld + j]
+    int ready_ld;     // nb for a whole factorisation; the enclosing matrix's nb for a panel launch
+    int ncols;        // only the first ncols tile columns are factorised (nb for a whole factorisation): panel launches of the
+                      // INT8-assisted factorisation (launch_cholesky_int8), where A, Dinv and ready point at the panel's corner
+    int row0;         // global row of A's first row (pivot reports)
     int* counter;     // tasks claimed so far by this launch
     int task_begin;   // tasks [task_begin, task_end) are executed by this launch
     int task_end;
@@ -79,6 +83,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
             const int t = a.task_begin + atomicAdd(a.counter, 1);
             int ti = 0, tj = 0;
             if (t < a.task_end) chol_task_decode(t, a.nb, ti, tj);
+            if (tj >= a.ncols) ti = -1;                      // diagonal task of the column after a panel: not part of this launch
             s_task = t; s_i = ti; s_j = tj;
             s_abort = ld_volatile(a.abort) != 0;
             s_fail = 1 << 20;
@@ -87,6 +92,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
         }
         __syncthreads();
         if (GPR_SH(s_task) >= a.task_end || s_abort) return;
+        if (GPR_SH(s_i) < 0) { __syncthreads(); continue; }
 
         Acc acc;
         acc_zero(acc);
@@ -95,8 +101,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
             // (almost always all but the last one or two).  They are accumulated by the wait-free mainloop
             // (the same instantiation as the variance kernel).
             const int i = GPR_SH(s_i), j = GPR_SH(s_j);
-            const int* fi = a.ready + (size_t)i * a.nb;
-            const int* fj = a.ready + (size_t)j * a.nb;
+            const int* fi = a.ready + (size_t)i * a.ready_ld;
+            const int* fj = a.ready + (size_t)j * a.ready_ld;
             const int upto = ready_prefix(j, [&](int t) { return ld_acquire(fi + t) != 0 && ld_acquire(fj + t) != 0; }, &s_upto);
             if (!tile_mainloop<STREAM_M, STREAM_M>(acc, a.A + (size_t)i * TB, a.ld, a.A + (size_t)j * TB, a.ld, 8 * upto, smem,
                                                    &s_abort, NoWait())) return;
@@ -105,8 +111,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
         for (int kb = GPR_SH(s_upto); kb < GPR_SH(s_j); ++kb) {
             const int i = GPR_SH(s_i), j = GPR_SH(s_j);
             if (tid == 0) {
-                if (!spin_wait(a.ready + (size_t)i * a.nb + kb, a.abort) ||
-                    (i != j && !spin_wait(a.ready + (size_t)j * a.nb + kb, a.abort))) s_abort = 1;
+                if (!spin_wait(a.ready + (size_t)i * a.ready_ld + kb, a.abort) ||
+                    (i != j && !spin_wait(a.ready + (size_t)j * a.ready_ld + kb, a.abort))) s_abort = 1;
             }
             __syncthreads();
             if (s_abort) return;
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
             potrf128_smem(T, s_inv, &s_fail);
             if (s_fail < TB) {
                 if (tid == 0) {
-                    atomicCAS(a.info, 0, j * TB + s_fail + 1);
+                    atomicCAS(a.info, 0, a.row0 + j * TB + s_fail + 1);
                     atomicExch(a.abort, 1);
                 }
                 return;
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
             store_lower_tile(T, a.Dinv + (size_t)j * TB * TB, TB);
             for (int pr = 0; pr < a.n_peers; ++pr) store_lower_tile(T, a.peerDinv[pr] + (size_t)j * TB * TB, TB);
         } else {
-            if (tid == 0 && !spin_wait(a.ready + (size_t)j * a.nb + j, a.abort)) s_abort = 1;
+            if (tid == 0 && !spin_wait(a.ready + (size_t)j * a.ready_ld + j, a.abort)) s_abort = 1;
             __syncthreads();
             if (s_abort) return;
             acc_zero(acc);
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) chol_tiles_kernel(CholArgs a) {
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            st_release(a.ready + (size_t)i * a.nb + j, 1);
+            st_release(a.ready + (size_t)i * a.ready_ld + j, 1);
             if (a.trace) a.trace[4 * (size_t)task_id + 3] = globaltimer_ns();
         }
     }
@@ -280,6 +286,7 @@ cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scr
     if (e != cudaSuccess) return e;
     CholArgs a;
     a.A = A; a.ld = ld; a.nb = nb; a.Dinv = Dinv; a.trace = trace;
+    a.ready_ld = nb; a.ncols = nb; a.row0 = 0;
     a.n_peers = 0;
     for (int pr = 0; pr < MAX_CHOL_PEERS; ++pr) { a.peerA[pr] = nullptr; a.peerDinv[pr] = nullptr; }
     if (peers && !serial) {
@@ -315,6 +322,59 @@ cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scr
         t0 += len;
     }
     return cudaGetLastError();
+}
+
+// INT8-assisted factorisation.  Left-looking by panels of P tile columns:
+//   for each panel [c0, c0 + P):   A[c0.., panel] -= L[c0.., 0:c0] L[panel, 0:c0]^T      INT8 tensor cores, exact integer products
+//                                  of base-254 digit slices of L, recombined in FP64 (gpr_ozaki.cu MODE 1)
+//                                  panel factorised by chol_tiles_kernel (FP64 tensor pipe; k restricted to the panel)
+//                                  finished panel cut into int8 digit slices (one common power-of-two scale: |L_ik| <= sqrt(K_ii))
+// With S = 7 digits of base 254 the dropped part of every product is below 254^-7 = 1.5e-17 of scale^2 per term — the size
+// of the FP64 rounding of the same sum (1.1e-16 of the partial sums) — so the factor is as accurate as the all-FP64 one,
+// at ~2x the DMMA rate for the (1 - ~1.5 P / nb) share of the flops that lies left of the panels.  Still one producer per
+// tile and integer (order-independent) sums: bit-reproducible.  A non-positive pivot is reported like launch_cholesky does
+// (the later launches of the sequence then leave at once: the abort flag stays up).
+cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, cudaStream_t st,
+                                 const CholPeers* peers, signed char* Ls, int S, double diag_max, int panel_tiles, int* ctrl) {
+    cudaError_t e = ensure_attrs();
+    if (e != cudaSuccess) return e;
+    if (panel_tiles < 1 || !(diag_max > 0.0)) return cudaErrorInvalidValue;
+    e = cudaMemsetAsync(scratch, 0, sizeof(int) * (4 + (size_t)nb * nb), st);
+    if (e != cudaSuccess) return e;
+    int ex = 0;
+    frexp(sqrt(diag_max), &ex);                              // 2^ex > sqrt(max K_ii) >= every |L_ik|
+    const double scale = ldexp(1.0, ex);
+    const size_t N = (size_t)nb * TB;
+    for (int c0 = 0; c0 < nb; c0 += panel_tiles) {
+        const int ncols = nb - c0 < panel_tiles ? nb - c0 : panel_tiles;
+        const size_t r0 = (size_t)c0 * TB;
+        e = launch_ozaki_syrk_update(Ls, ld, ld * N, S, r0, N, (size_t)ncols * TB, A, ld, scale * scale, ctrl, st);
+        if (e != cudaSuccess) return e;
+        CholArgs a;
+        a.A = A + r0 * ld + r0; a.ld = ld; a.nb = nb - c0; a.Dinv = Dinv + (size_t)c0 * TB * TB; a.trace = nullptr;
+        a.ready = scratch + 4 + (size_t)c0 * nb + c0; a.ready_ld = nb; a.ncols = ncols; a.row0 = (int)r0;
+        a.counter = scratch; a.info = scratch + 1; a.abort = scratch + 2;
+        a.n_peers = 0;
+        for (int pr = 0; pr < MAX_CHOL_PEERS; ++pr) { a.peerA[pr] = nullptr; a.peerDinv[pr] = nullptr; }
+        if (peers) {
+            a.n_peers = peers->n < MAX_CHOL_PEERS ? peers->n : MAX_CHOL_PEERS;
+            for (int pr = 0; pr < a.n_peers; ++pr) { a.peerA[pr] = peers->L[pr] + r0 * ld + r0; a.peerDinv[pr] = peers->Dinv[pr] + (size_t)c0 * TB * TB; }
+        }
+        // tasks of the first ncols columns in chol_task_decode order (the diagonal task of column ncols, which that order places
+        // among them, is skipped by the kernel)
+        int ntasks = 1;
+        for (int j = 0; j < ncols && j < a.nb - 1; ++j) ntasks += a.nb - j;
+        a.task_begin = 0; a.task_end = ntasks;
+        if (c0 > 0) { e = cudaMemsetAsync(scratch, 0, sizeof(int), st); if (e != cudaSuccess) return e; }
+        chol_tiles_kernel<<<ntasks < num_sms ? ntasks : num_sms, NTHREADS, TILE_SMEM_BYTES, st>>>(a);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (c0 + ncols < nb) {
+            e = launch_ozaki_slice_lpanel(A, ld, r0, N, (size_t)ncols * TB, 1.0 / scale, S, Ls, ld, ld * N, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_dinv_from_l(const double* L, size_t ld, int nb, double* Dinv, cudaStream_t st) {

@@ -16,6 +16,11 @@ constexpr int MAX_CHOL_PEERS = 7;
 struct CholPeers { int n; double* L[MAX_CHOL_PEERS]; double* Dinv[MAX_CHOL_PEERS]; };
 cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, int serial,
                             cudaStream_t st, long long* trace = nullptr, const CholPeers* peers = nullptr);
+// The same factorisation with the bulk of the flops on the INT8 tensor cores: panels of `panel_tiles` tile columns are factorised
+// by the FP64 tile kernel, everything to the left of a panel is applied to it beforehand as one sliced-integer product
+// (gpr_ozaki.cu MODE 1).  Ls: S * N * N bytes of slice workspace (N = nb * 128); diag_max >= max K_ii; ctrl: 2 ints.
+cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, cudaStream_t st,
+                                 const CholPeers* peers, signed char* Ls, int S, double diag_max, int panel_tiles, int* ctrl);
 cudaError_t launch_dinv_from_l(const double* L, size_t ld, int nb, double* Dinv, cudaStream_t st);
 cudaError_t launch_linv(const double* L, double* X, size_t ld, int nb, const double* Dinv, int* scratch, int num_sms,
                         cudaStream_t st);
@@ -87,6 +92,10 @@ cudaError_t launch_ozaki_mask(const signed char* As, size_t a_pitch, size_t a_sl
                               size_t pitch, cudaStream_t st);
 cudaError_t launch_ozaki_slice_x(const double* X, size_t ld, int n_rows, int S, int base254, signed char* Xs, double* row_scale,
                                  unsigned long long* rowmax, cudaStream_t st);
+cudaError_t launch_ozaki_slice_lpanel(const double* A, size_t ld, size_t r0, size_t n_rows, size_t width, double inv_scale, int S,
+                                      signed char* Ls, size_t pitch, size_t slice, cudaStream_t st);
+cudaError_t launch_ozaki_syrk_update(const signed char* Ls, size_t pitch, size_t slice, int S, size_t r0, size_t n_rows, size_t width,
+                                     double* A, size_t ld, double scale2, int* ctrl, cudaStream_t st);
 cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q, int n_k, double inv_scale, int S, int base254,
                                      signed char* Ks, size_t k_pitch, size_t q_pad, cudaStream_t st);
 // K5 (gpr_append.cu): one slab of k <= 32 appended points at rows [n0, n0+k); ws: append_workspace_doubles(cap).

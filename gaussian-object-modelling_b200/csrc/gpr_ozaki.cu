@@ -63,6 +63,8 @@ struct OzArgs {
     size_t nz_pitch;
     int kchunk;                   // k-blocks (of 64) after which the int32 accumulators are drained into FP64 (they could overflow
                                   // beyond); >= the longest row for the unchunked kernel
+    double* C;                    // MODE 1 (symmetric update of the factorisation): C[col * ldc + row] -= col_scale * product, rows of
+    size_t ldc;                   // the A operand x rows of the B operand, tiles on or below the diagonal only
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -133,7 +135,10 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int M, int N) {
 // issue loop (template on the slice count) and the separate producer warp.
 constexpr int OZ_NTHREADS = 192;
 
-template <int S, int BN, bool CHUNKED>
+// MODE 0: variance (squared column norms of the product per row tile -> partial).  MODE 1: C -= product (the trailing update
+// of the INT8-assisted Cholesky, launch_ozaki_syrk_update): both operands are row ranges of the same slice tensor, tasks above
+// the diagonal are skipped, the epilogue carries -C / scale in its FP64 running sums (loaded before the first wait).
+template <int S, int BN, bool CHUNKED, int MODE>
 __global__ void __launch_bounds__(OZ_NTHREADS, 1)
 ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a) {
     extern __shared__ __align__(1024) uint8_t oz_smem[];
@@ -180,6 +185,7 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int pr = rg * a.gr + w % a.gr;
         qt = qg * a.gq + w / a.gr;
         rt = h == 0 ? a.nrt - 1 - pr : pr;
+        if (MODE == 1 && qt * BN >= (rt + 1) * OZ_BM) return false;                  // tile entirely above the diagonal
         return pr < npairs && qt < a.nqt && !(h == 1 && pr == a.nrt - 1 - pr);       // odd nrt: the middle row tile is its own pair
     };
 
@@ -270,7 +276,7 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int rt, qt;
             if (!decode(task, it & 1, rt, qt)) continue;
             const int row = rt * OZ_BM + q4 * 32 + lane;
-            const double rs = a.row_scale[row] * a.col_scale;
+            const double rs = MODE == 1 ? a.col_scale : a.row_scale[row] * a.col_scale;
             if constexpr (!CHUNKED) {
                 if (!mbar_wait(&accum_full, tcount & 1)) { ok = false; break; }
                 ++tcount;
@@ -313,8 +319,15 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // one drain per k-chunk into FP64 running sums (registers), squares and reduction after the last chunk
                 const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
                 double vacc[OZ_BN];
+                double* crow = MODE == 1 ? a.C + (size_t)qt * OZ_BN * a.ldc + row : nullptr;
+                if constexpr (MODE == 1) {
+                    const double irs = -1.0 / rs;                               // rs is a power of two: exact
 #pragma unroll
-                for (int jj = 0; jj < OZ_BN; ++jj) vacc[jj] = 0.0;
+                    for (int jj = 0; jj < OZ_BN; ++jj) vacc[jj] = __ldcg(crow + (size_t)jj * a.ldc) * irs;
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < OZ_BN; ++jj) vacc[jj] = 0.0;
+                }
                 for (int c0 = 0; c0 < nkb && ok; c0 += a.kchunk) {
                     if (!mbar_wait(&accum_full, tcount & 1)) { ok = false; break; }
                     ++tcount;
@@ -348,13 +361,19 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&accum_empty)) : "memory");
                 }
                 if (!ok) break;
+                if constexpr (MODE == 1) {
 #pragma unroll
-                for (int jj = 0; jj < OZ_BN; ++jj) {
-                    const double vv = vacc[jj] * rs;
-                    double sv = vv * vv;
+                    for (int jj = 0; jj < OZ_BN; ++jj) crow[(size_t)jj * a.ldc] = -(vacc[jj] * rs);
+                    continue;
+                } else {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-                    if (lane == 0) sred[q4][jj] = sv;
+                    for (int jj = 0; jj < OZ_BN; ++jj) {
+                        const double vv = vacc[jj] * rs;
+                        double sv = vv * vv;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                        if (lane == 0) sred[q4][jj] = sv;
+                    }
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps
@@ -409,10 +428,11 @@ __device__ __forceinline__ void oz_slice(double v, int S, double first, double b
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ M, size_t ld, int rows, int cols,
                                                         const double* __restrict__ scale_rows, double inv_scale, int tri,
                                                         int S, double first, double base, signed char* __restrict__ out, size_t out_ld,
-                                                        size_t out_slice) {
+                                                        size_t out_slice, int fill_upper) {
     __shared__ double tile[64][65];
     const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-    if (tri && c0 > r0 + 63) return;                     // block entirely above the diagonal: left zero by the memset
+    if (tri && c0 > r0 + 63 && !fill_upper) return;      // block entirely above the diagonal: left zero by the memset (or, with
+                                                         // fill_upper, written as zeros: the buffer is not cleared beforehand)
     for (int e = threadIdx.x; e < 64 * 64; e += 256) {
         const int rr = e & 63, cc = e >> 6;
         const int r = r0 + rr, c = c0 + cc;
@@ -508,16 +528,16 @@ long long ozaki_max_k(int S, int base254) {
     return ((1LL << 31) - 1) / ((long long)S * d * d);
 }
 
-template <int S, int BN, bool CHUNKED>
+template <int S, int BN, bool CHUNKED, int MODE = 0>
 static cudaError_t launch_oz(const CUtensorMap& tmA, const CUtensorMap& tmB, const OzArgs& a, int grid, size_t smem, cudaStream_t st) {
     static PerDeviceOnce attr_done;
     const int cur = PerDeviceOnce::current();
     if (!attr_done.done(cur)) {
-        cudaError_t e = cudaFuncSetAttribute(ozaki_var_kernel<S, BN, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ozaki_var_kernel<S, BN, CHUNKED, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done.set(cur);
     }
-    ozaki_var_kernel<S, BN, CHUNKED><<<grid, OZ_NTHREADS, smem, st>>>(tmA, tmB, a);
+    ozaki_var_kernel<S, BN, CHUNKED, MODE><<<grid, OZ_NTHREADS, smem, st>>>(tmA, tmB, a);
     return cudaGetLastError();
 }
 
@@ -548,6 +568,7 @@ cudaError_t launch_ozaki_product(const signed char* As, size_t a_pitch, size_t a
     a.row_scale = row_scale; a.col_scale = col_scale; a.partial = partial; a.q_pad = q_pad; a.ctrl = ctrl; a.dbg = dbg; a.dbg_ld = dbg_ld;
     static const bool noskip = getenv("GPR_OZ_NOSKIP") && atoi(getenv("GPR_OZ_NOSKIP")) != 0;      // A/B switch for measurements
     a.nzA = noskip ? nullptr : nzA; a.nz_pitch = nz_pitch;
+    a.C = nullptr; a.ldc = 0;
     a.kchunk = chunked ? (int)((ozaki_max_k(S, base254) / OZ_BK) & ~1LL) : (1 << 30);
     if (chunked && kc_forced > 0 && kc_forced < a.kchunk) a.kchunk = kc_forced;
     const double F = base254 ? 127.0 : 64.0, B = base254 ? 254.0 : 128.0;
@@ -601,7 +622,7 @@ cudaError_t launch_ozaki_slice_x(const double* X, size_t ld, int n_rows, int S, 
     oz_rowmax_kernel<<<dim3((n_rows + 255) / 256, (n_rows + 255) / 256), 256, 0, st>>>(X, ld, n_rows, rowmax);
     oz_rowscale_kernel<<<(int)((ld + 255) / 256), 256, 0, st>>>(rowmax, (int)ld, row_scale);
     oz_slice_kernel<<<dim3((n_rows + 63) / 64, (n_rows + 63) / 64), 256, 0, st>>>(X, ld, n_rows, n_rows, row_scale, 0.0, 1, S,
-                                                                                base254 ? 127.0 : 64.0, base254 ? 254.0 : 128.0, Xs, ld, ld * ld);
+                                                                                base254 ? 127.0 : 64.0, base254 ? 254.0 : 128.0, Xs, ld, ld * ld, 0);
     return cudaGetLastError();
 }
 
@@ -611,8 +632,61 @@ cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q
     // here the "rows" of the slice tensor are the queries and its "columns" the points: M(row = query, col = k) = panel[k*ld + query]
     oz_slice_kernel<<<dim3((q + 63) / 64, (n_k + 63) / 64), 256, 0, st>>>(panel, panel_ld, q, n_k, nullptr, inv_scale, 0, S,
                                                                         base254 ? 127.0 : 64.0, base254 ? 254.0 : 128.0, Ks, k_pitch,
-                                                                        q_pad * k_pitch);
+                                                                        q_pad * k_pitch, 0);
     return cudaGetLastError();
+}
+
+// ---- INT8-assisted Cholesky (gpr_factor.cu: launch_cholesky_int8) ---------------------------------------------------------
+// Slices of a finished panel of L: rows [r0, n_rows) x columns [r0, r0 + width) of the column-major factor A (leading dimension
+// ld; r0 on the diagonal, so local entries with column > row are structural zeros and are WRITTEN as zeros) into
+// Ls[t][row][k] (k pitch `pitch`, slice pitch `slice`), one common power-of-two scale (|L_ik| <= sqrt(K_ii) <= 1 / inv_scale).
+cudaError_t launch_ozaki_slice_lpanel(const double* A, size_t ld, size_t r0, size_t n_rows, size_t width, double inv_scale, int S,
+                                      signed char* Ls, size_t pitch, size_t slice, cudaStream_t st) {
+    if (n_rows <= r0 || width == 0) return cudaSuccess;
+    const int rows = (int)(n_rows - r0), cols = (int)width;
+    oz_slice_kernel<<<dim3((rows + 63) / 64, (cols + 63) / 64), 256, 0, st>>>(A + r0 * ld + r0, ld, rows, cols, nullptr, inv_scale, 1, S,
+                                                                            127.0, 254.0, Ls + r0 * pitch + r0, pitch, slice, 1);
+    return cudaGetLastError();
+}
+
+// C[r0.., r0 .. r0 + width) -= scale2 * sum_{k < r0} L[row, k] L[col, k] on the INT8 tensor cores, from the slices of the
+// finished columns k < r0 (base-254 digits): the left-looking update of the next panel.  Only tiles on or below the diagonal.
+cudaError_t launch_ozaki_syrk_update(const signed char* Ls, size_t pitch, size_t slice, int S, size_t r0, size_t n_rows, size_t width,
+                                     double* A, size_t ld, double scale2, int* ctrl, cudaStream_t st) {
+    if (r0 == 0 || n_rows <= r0 || width == 0) return cudaSuccess;
+    if (S < 6 || S > 8 || r0 % OZ_BM || n_rows % OZ_BM || width % OZ_BM) return cudaErrorInvalidValue;
+    constexpr int BN = 64;
+    const size_t smem = (size_t)220 * 1024 + 1024;
+    CUtensorMap tmA, tmB;
+    cudaError_t e = make_map(&tmA, Ls + r0 * pitch, r0, n_rows - r0, S, pitch, slice, OZ_BM);
+    if (e != cudaSuccess) return e;
+    e = make_map(&tmB, Ls + r0 * pitch, r0, width, S, pitch, slice, BN);
+    if (e != cudaSuccess) return e;
+    OzArgs a;
+    a.S = S; a.levels = S; a.stages = ozaki_stages(S, BN);
+    a.nrt = (int)((n_rows - r0) / OZ_BM); a.nqt = (int)(width / BN); a.tri = 0; a.kblocks = (int)(r0 / OZ_BK);
+    a.row_scale = nullptr; a.col_scale = scale2; a.partial = nullptr; a.q_pad = 0; a.ctrl = ctrl; a.dbg = nullptr; a.dbg_ld = 0;
+    a.nzA = nullptr; a.nz_pitch = 0;
+    a.C = A + r0 * ld + r0; a.ldc = ld;
+    a.kchunk = (int)((ozaki_max_k(S, 1) / OZ_BK) & ~1LL);
+    double w = 1.0 / (127.0 * 127.0);
+    for (int l = 0; l < 8; ++l) { a.wl[l] = w; w /= 254.0; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    a.gr = 10; a.gq = sms / a.gr > 0 ? sms / a.gr : 1;
+    const int npairs = (a.nrt + 1) / 2;
+    if (a.gq > a.nqt) a.gq = a.nqt;
+    if (a.gr > npairs) a.gr = npairs;
+    e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const int tasks = ((npairs + a.gr - 1) / a.gr) * ((a.nqt + a.gq - 1) / a.gq) * a.gr * a.gq;
+    const int grid = tasks < sms ? tasks : sms;
+    switch (S) {
+        case 6: return launch_oz<6, 64, true, 1>(tmA, tmB, a, grid, smem, st);
+        case 7: return launch_oz<7, 64, true, 1>(tmA, tmB, a, grid, smem, st);
+        default: return launch_oz<8, 64, true, 1>(tmA, tmB, a, grid, smem, st);
+    }
 }
 
 }  // namespace gpr

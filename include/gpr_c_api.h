@@ -49,6 +49,7 @@ typedef struct {
     double ozaki_slices;            /* ... and the number of int8 slices per operand it used (6: base-254 digits, 7 or more: escalated / base 128) */
     double ozaki_issued_fraction;   /* ... and the share of its slice-pair MMAs actually issued (digit slices of L^-1 that are all zero in a
                                        (128-row, 64-k) block are skipped) */
+    double fit_int8_slices;         /* last fit: digit slices of the INT8-assisted factorisation (0: the all-FP64 tile Cholesky ran) */
 } gpr_timings;
 
 /* ---- context ------------------------------------------------------------------------------ */

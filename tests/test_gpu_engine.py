@@ -69,6 +69,44 @@ def test_tile_cholesky_is_bit_reproducible(gpr):
     assert np.array_equal(L1, L2) and np.array_equal(L1, L3)     # scheduling never changes the arithmetic
 
 
+def _kernel_matrix(n, seed, nugget):
+    """Gaussian-kernel matrix of random points: smooth kernel + small nugget = the ill-conditioned kind of matrix a GP fit meets."""
+    rng = np.random.default_rng(seed)
+    P = rng.random((n, 3))
+    D2 = ((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)
+    return np.exp(-D2 / 0.5) + nugget * np.eye(n)
+
+
+@pytest.mark.parametrize("nb,panel,S,nugget", [(12, 4, 7, 1e-6), (12, 5, 7, 1e-3), (24, 8, 7, 1e-5), (16, 3, 8, 1e-6), (8, 8, 7, 1e-4)])
+def test_int8_assisted_cholesky_is_as_accurate_as_fp64(gpr, nb, panel, S, nugget):
+    """launch_cholesky_int8: the flops left of each panel of tile columns run on the INT8 tensor cores (base-254 digit slices of
+    L, exact integer products, FP64 recombination), the panels themselves on the FP64 tile kernel.  Its backward error
+    ||L L^T - A|| must match the all-FP64 factorisation's on ill-conditioned kernel matrices; one panel = the FP64 kernel itself."""
+    n = 128 * nb
+    A = _kernel_matrix(n, 100 + nb, nugget)
+    L64, _, p64 = gpr.selftest_factor(A, False, False)
+    L8, _, p8 = gpr.selftest_factor(A, False, 100 * panel + S)
+    assert p64 == 0 and p8 == 0
+    if panel >= nb:
+        assert np.array_equal(L8, L64)
+        return
+    An = np.linalg.norm(A)
+    b64 = np.linalg.norm(L64 @ L64.T - A) / An
+    b8 = np.linalg.norm(L8 @ L8.T - A) / An
+    print(nb, panel, S, "backward error fp64 %.3e int8-assisted %.3e" % (b64, b8), "factor difference %.3e" % relerr(L8, L64))
+    assert b8 <= 2.0 * b64 + 2e-16
+    assert relerr(L8, L64) <= 1e-6                    # both are within cond(A) * eps of the exact factor
+    L8b, _, _ = gpr.selftest_factor(A, False, 100 * panel + S)
+    assert np.array_equal(L8, L8b)                    # integer sums + one producer per tile: bit-reproducible
+
+
+def test_int8_assisted_cholesky_reports_a_bad_pivot_in_a_later_panel(gpr):
+    A = _spd(128 * 8, 5)
+    A[700, 700] = -1.0
+    _, _, piv = gpr.selftest_factor(A, False, 100 * 2 + 7)
+    assert piv == 701
+
+
 def test_tile_cholesky_rejects_indefinite(gpr):
     A = _spd(128 * 4, 5)
     A[300, 300] = -1.0
