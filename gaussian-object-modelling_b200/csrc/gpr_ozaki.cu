@@ -178,14 +178,27 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // the CTAs that run together stay in step — which is what lets them share operand tiles through L2.
     const int npairs = (a.nrt + 1) / 2;
     const int rgroups = (npairs + a.gr - 1) / a.gr;
-    const int ntasks = rgroups * qgroups * per_group;
+    // MODE 1: every task has the same length (k < r0), so the valid (row tile, query tile) pairs are simply enumerated compactly
+    // and dealt round-robin: first the row tiles below the diagonal block (nqt tasks each, bottom up), then the diagonal block's
+    // row tiles rt < nqt * BN / 128 with their 2 (rt + 1) tiles on or below the diagonal.
+    const int dblk = MODE == 1 ? a.nqt * BN / OZ_BM : 0;                            // row tiles of the diagonal block
+    const int full_tasks = MODE == 1 ? (a.nrt - dblk) * a.nqt : 0;
+    const int ntasks = MODE == 1 ? full_tasks + dblk * (dblk + 1) * (OZ_BM / BN) / 2 : rgroups * qgroups * per_group;
     auto decode = [&](int task, int h, int& rt, int& qt) {
+        if (MODE == 1) {
+            if (h) return false;
+            if (task < full_tasks) { rt = a.nrt - 1 - task / a.nqt; qt = task % a.nqt; return true; }
+            int t = task - full_tasks;
+            rt = dblk - 1;
+            while (t >= (OZ_BM / BN) * (rt + 1)) { t -= (OZ_BM / BN) * (rt + 1); --rt; }
+            qt = t;
+            return true;
+        }
         const int g = task / per_group, w = task % per_group;
         const int rg = g / qgroups, qg = g % qgroups;
         const int pr = rg * a.gr + w % a.gr;
         qt = qg * a.gq + w / a.gr;
         rt = h == 0 ? a.nrt - 1 - pr : pr;
-        if (MODE == 1 && qt * BN >= (rt + 1) * OZ_BM) return false;                  // tile entirely above the diagonal
         return pr < npairs && qt < a.nqt && !(h == 1 && pr == a.nrt - 1 - pr);       // odd nrt: the middle row tile is its own pair
     };
 
@@ -211,7 +224,6 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!ok) atomicExch(a.ctrl + 1, 1);
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
-        const uint32_t idesc = umma_idesc_i8(OZ_BM, OZ_BN);
         constexpr uint32_t DESC_HI = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);      // SBO | version 1 | SWIZZLE_64B
         uint32_t j = 0, tcount = 0;
         bool ok = true;
@@ -243,16 +255,24 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t a_lo = (((sa >> 4) & 0x3FFFu) | (1u << 16));
                 const uint32_t b_lo = a_lo + (uint32_t)(S * OZ_A_SLICE_BYTES >> 4);
                 const uint32_t keep = kb > c0 ? 1u : 0u;
+                // Slice t of A meets slices u = 0 .. S-1-t of B, whose products belong to the levels t .. S-1: the B slices lie
+                // back to back in the stage (BN rows of 64 bytes each, a multiple of the swizzle atom) and the level accumulators
+                // back to back in TMEM, so ONE instruction with N = cnt * BN covers cnt slices of B at once (cnt * BN <= 256).
+                // Against one instruction per (t, u) pair that is the same tensor work with far fewer reads of the A tile from
+                // shared memory (S = 6: 9 instead of 21 per 32-k step) — the operand path, not the tensor pipe, was the busiest unit.
+                constexpr int MAXC = 256 / OZ_BN;
 #pragma unroll
-                for (int l = 0; l < LEVELS; ++l) {
+                for (int t = 0; t < S; ++t) {
+                    if (!((mask >> t) & 1u)) continue;
 #pragma unroll
-                    for (int t = 0; t <= l; ++t) {
-                        if (!((mask >> t) & 1u)) continue;
+                    for (int u0 = 0; u0 < S - t; u0 += MAXC) {
+                        const int cnt = (S - t - u0) < MAXC ? (S - t - u0) : MAXC;
+                        const uint32_t idesc_c = umma_idesc_i8(OZ_BM, cnt * OZ_BN);
 #pragma unroll
                         for (int ks = 0; ks < OZ_BK / 32; ++ks) {
                             const uint64_t da = ((uint64_t)DESC_HI << 32) | (a_lo + (uint32_t)(t * (OZ_A_SLICE_BYTES >> 4) + 2 * ks));
-                            const uint64_t db = ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)((l - t) * (OZ_B_SLICE_BYTES >> 4) + 2 * ks));
-                            umma_i8(tmem + (uint32_t)(l * OZ_BN), da, db, idesc, (t == 0 && ks == 0) ? keep : 1u);
+                            const uint64_t db = ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)(u0 * (OZ_B_SLICE_BYTES >> 4) + 2 * ks));
+                            umma_i8(tmem + (uint32_t)((t + u0) * OZ_BN), da, db, idesc_c, (t == 0 && ks == 0) ? keep : 1u);
                         }
                     }
                 }
@@ -680,7 +700,8 @@ cudaError_t launch_ozaki_syrk_update(const signed char* Ls, size_t pitch, size_t
     if (a.gr > npairs) a.gr = npairs;
     e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    const int tasks = ((npairs + a.gr - 1) / a.gr) * ((a.nqt + a.gq - 1) / a.gq) * a.gr * a.gq;
+    const int dblk = a.nqt * BN / OZ_BM;
+    const int tasks = (a.nrt - dblk) * a.nqt + dblk * (dblk + 1) * (OZ_BM / BN) / 2;
     const int grid = tasks < sms ? tasks : sms;
     switch (S) {
         case 6: return launch_oz<6, 64, true, 1>(tmA, tmB, a, grid, smem, st);

@@ -39,7 +39,7 @@ def fit(mode, panel=None, slices=None, reps=3):
 t64, a64, f64, v64 = fit("fp64")
 out["fp64"] = {"chol_ms": t64["chol_ms"], "fit_total_ms": t64["fit_total_ms"], "solve_ms": t64["solve_ms"]}
 print(json.dumps(out["fp64"]), flush=True)
-combos = [(16, 7)] if len(sys.argv) > 2 and sys.argv[2] == "quick" else [(8, 7), (12, 7), (16, 7), (24, 7), (32, 7), (16, 6), (16, 8)]
+combos = [(16, 7)] if len(sys.argv) > 2 and sys.argv[2] == "quick" else [(4, 7), (6, 7), (8, 7), (10, 7), (12, 7), (16, 7), (24, 7), (8, 6), (8, 8)]
 for panel, S in combos:
     t, a, f, v = fit("int8", panel, S)
     r = {"panel_tiles": panel, "slices": S, "chol_ms": t["chol_ms"], "fit_total_ms": t["fit_total_ms"], "fit_int8_slices": t["fit_int8_slices"],
