@@ -341,6 +341,8 @@ cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int
     if (panel_tiles < 1 || !(diag_max > 0.0)) return cudaErrorInvalidValue;
     e = cudaMemsetAsync(scratch, 0, sizeof(int) * (4 + (size_t)nb * nb), st);
     if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);       // [1]: raised by an INT8 update whose barrier wait timed out (sticky)
+    if (e != cudaSuccess) return e;
     int ex = 0;
     frexp(sqrt(diag_max), &ex);                              // 2^ex > sqrt(max K_ii) >= every |L_ik|
     const double scale = ldexp(1.0, ex);

@@ -698,8 +698,7 @@ cudaError_t launch_ozaki_syrk_update(const signed char* Ls, size_t pitch, size_t
     const int npairs = (a.nrt + 1) / 2;
     if (a.gq > a.nqt) a.gq = a.nqt;
     if (a.gr > npairs) a.gr = npairs;
-    e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);
-    if (e != cudaSuccess) return e;
+    // ctrl is cleared once by launch_cholesky_int8 (the abort flag of the whole sequence is sticky)
     const int dblk = a.nqt * BN / OZ_BM;
     const int tasks = (a.nrt - dblk) * a.nqt + dblk * (dblk + 1) * (OZ_BM / BN) / 2;
     const int grid = tasks < sms ? tasks : sms;
