@@ -347,8 +347,12 @@ cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int
     frexp(sqrt(diag_max), &ex);                              // 2^ex > sqrt(max K_ii) >= every |L_ik|
     const double scale = ldexp(1.0, ex);
     const size_t N = (size_t)nb * TB;
-    for (int c0 = 0; c0 < nb; c0 += panel_tiles) {
-        const int ncols = nb - c0 < panel_tiles ? nb - c0 : panel_tiles;
+    // The last panels have so few row tiles below them that the tile kernel is bound by its dependency chain (~100 us per
+    // column) whatever their width: the final `last_tiles` columns are one panel (two INT8 launches and slicing passes fewer).
+    static const int last_tiles = getenv("GPR_FIT_LAST") ? atoi(getenv("GPR_FIT_LAST")) : 48;
+    for (int c0 = 0, ncols = 0; c0 < nb; c0 += ncols) {
+        ncols = nb - c0 < panel_tiles ? nb - c0 : panel_tiles;
+        if (nb - c0 <= last_tiles) ncols = nb - c0;
         const size_t r0 = (size_t)c0 * TB;
         e = launch_ozaki_syrk_update(Ls, ld, ld * N, S, r0, N, (size_t)ncols * TB, A, ld, scale * scale, ctrl, st);
         if (e != cudaSuccess) return e;

@@ -20,6 +20,8 @@ want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
         ("lts__t_sector_hit_rate.pct", "L2 hit %"),
         ("sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "DMMA pipe %"),
         ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 pipe %"),
+        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe (tcgen05) %"),
+        ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem->tensor operand path %"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
         ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %")]
@@ -38,6 +40,9 @@ lines = ["# ncu summary: %s" % rep.split("/")[-1], "",
          "One fit at n = %d + one mean+variance batch of %d queries (tools/prof_target.py), `ncu --set full "
          "--clock-control none`. Durations are cold-cache, serialised ncu replays: compare shares, not absolutes." % (n, q), "",
          "| kernel | " + " | ".join(w[1] for w in want) + " | algorithmic work | achieved |", "|---|" + "---|" * (len(want) + 2)]
+n_chol = sum(1 for r in rows[2:] if "chol_tiles_kernel" in r[col["Kernel Name"]])
+if n_chol > 1:        # INT8-assisted factorisation: the tile kernel only factorises panels, n^3/3 is the work of the whole sequence
+    del alg["chol_tiles_kernel"]
 for r in rows[2:]:
     name = r[col["Kernel Name"]]
     short = name.split("(")[0].replace("void ", "").replace("gpr::", "")

@@ -8,7 +8,7 @@ $BCMD > gpurun_out/plain_bench_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv $BCMD > gpurun_out/ncu_bench_$TAG.log 2>&1
 echo "ncu list rc=$?"
 python tools/prof_target.py > gpurun_out/plain_prof_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -c 24 -f -o gpurun_out/prof_$TAG python tools/prof_target.py > gpurun_out/ncu_prof_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -c 64 -f -o gpurun_out/prof_$TAG python tools/prof_target.py > gpurun_out/ncu_prof_$TAG.log 2>&1
 echo "ncu full rc=$?"
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
 for k in ozaki_var var_trsm chol_tiles; do
