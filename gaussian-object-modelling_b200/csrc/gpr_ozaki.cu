@@ -433,14 +433,6 @@ __global__ void oz_rowscale_kernel(const unsigned long long* rowmax, int n, doub
 }
 // One value -> S signed digits in base B with first scale F (F = B / 2): v in [-1, 1];  d_0 = rint(F v), r = F v - d_0 in
 // [-1/2, 1/2];  d_t = rint(B r) in [-F, F], r = B r - d_t ...   (B = 128, F = 64 or B = 254, F = 127: all digits fit int8)
-__device__ __forceinline__ void oz_slice(double v, int S, double first, double base, signed char* out, size_t stride) {
-    double r = v * first;
-    for (int t = 0; t < S; ++t) {
-        const double it = rint(r);
-        out[(size_t)t * stride] = (signed char)(int)it;
-        r = (r - it) * base;
-    }
-}
 // Slices of a column-major FP64 matrix M (element (row r, col c) at M[c*ld + r]) into K-major int8 tensors
 // out[t][r][c] (c contiguous, row pitch out_ld, slice pitch out_slice): 64 x 64 tiles through shared memory so that both the
 // FP64 reads (along r) and the byte writes (along c) are coalesced.  scale_rows: per-row power-of-two scale (X), or
@@ -449,22 +441,58 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
                                                         const double* __restrict__ scale_rows, double inv_scale, int tri,
                                                         int S, double first, double base, signed char* __restrict__ out, size_t out_ld,
                                                         size_t out_slice, int fill_upper) {
-    __shared__ double tile[64][65];
+    // one buffer, two uses: the FP64 tile (transposed on the way in), then — once every thread holds its 16 values in
+    // registers — the digit bytes [slice][row][64 k], which leave as 16-byte stores (byte stores to global memory made this
+    // kernel latency-bound: 1.5 ms per K* panel at 35 % of the DRAM bandwidth)
+    __shared__ __align__(16) double tile[64 * 65];
+    signed char* dig = reinterpret_cast<signed char*>(tile);
     const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
     if (tri && c0 > r0 + 63 && !fill_upper) return;      // block entirely above the diagonal: left zero by the memset (or, with
                                                          // fill_upper, written as zeros: the buffer is not cleared beforehand)
     for (int e = threadIdx.x; e < 64 * 64; e += 256) {
         const int rr = e & 63, cc = e >> 6;
         const int r = r0 + rr, c = c0 + cc;
-        tile[rr][cc] = (r < rows && c < cols && !(tri && c > r)) ? M[(size_t)c * ld + r] : 0.0;
+        tile[rr * 65 + cc] = (r < rows && c < cols && !(tri && c > r)) ? M[(size_t)c * ld + r] : 0.0;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-        const int cc = e & 63, rr = e >> 6;
-        const int r = r0 + rr, c = c0 + cc;
-        if (r >= rows || c >= cols) continue;
-        const double sc = scale_rows ? 1.0 / scale_rows[r] : inv_scale;
-        oz_slice(tile[rr][cc] * sc, S, first, base, out + (size_t)r * out_ld + c, out_slice);
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = threadIdx.x + 256 * i, cc = e & 63, rr = e >> 6;
+        const int r = r0 + rr;
+        const double sc = scale_rows ? (r < rows ? 1.0 / scale_rows[r] : 0.0) : inv_scale;
+        v[i] = tile[rr * 65 + cc] * sc;
+    }
+    __syncthreads();
+    // digit t of all 16 values before digit t + 1 of any: 16 independent dependency chains in flight per thread
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= first;
+    // rint() and the conversion to int without the slow FP64 conversion instructions: v + 1.5 * 2^52 rounds v to the nearest
+    // integer (ties to even, like rint) and leaves it, as a two's complement number, in the low word of the sum (|v| < 2^31).
+    constexpr double MAGIC = 6755399441055744.0;
+    for (int t = 0; t < S; ++t) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const double m = __dadd_rn(v[i], MAGIC);
+            const double it = __dsub_rn(m, MAGIC);
+            dig[t * (64 * 64) + threadIdx.x + 256 * i] = (signed char)__double2loint(m);      // index = rr * 64 + cc
+            v[i] = (v[i] - it) * base;
+        }
+    }
+    __syncthreads();
+    // [slice][rr][64 bytes] -> global rows of 64 bytes, 16 bytes per thread (rows / columns past the matrix are not written)
+    const bool full = r0 + 64 <= rows && c0 + 64 <= cols && (out_ld % 16 == 0) && (out_slice % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) + c0) % 16 == 0);
+    if (full) {
+        for (int e = threadIdx.x; e < S * 64 * 4; e += 256) {
+            const int q = e & 3, rr = (e >> 2) & 63, t = e >> 8;
+            const uint4 w = *reinterpret_cast<const uint4*>(dig + (t * 64 + rr) * 64 + 16 * q);
+            *reinterpret_cast<uint4*>(out + (size_t)t * out_slice + (size_t)(r0 + rr) * out_ld + c0 + 16 * q) = w;
+        }
+    } else {
+        for (int e = threadIdx.x; e < S * 64 * 64; e += 256) {
+            const int cc = e & 63, rr = (e >> 6) & 63, t = e >> 12;
+            if (r0 + rr < rows && c0 + cc < cols) out[(size_t)t * out_slice + (size_t)(r0 + rr) * out_ld + c0 + cc] = dig[e];
+        }
     }
 }
 

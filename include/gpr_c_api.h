@@ -63,7 +63,11 @@ long long gpr_last_pivot(void);            /* thread-local, valid after GPR_ERR_
 int gpr_last_timings(const gpr_ctx* ctx, gpr_timings* out);
 
 /* ---- fit: GPRegressor::create<withNormals>  (gp_regressor.hpp:110-182) ---------------------- */
-/* x,y,z,label: n host doubles each; sigma2: n host doubles or NULL (Data::sigma2 empty, :154). */
+/* x,y,z,label: n host doubles each; sigma2: n host doubles or NULL (Data::sigma2 empty, :154).
+ * The factorisation of models with n >= 8192 (GPR_FIT_INT8_MIN_N) runs INT8-assisted: panels of 16 tile columns on the FP64
+ * tensor pipe, everything left of a panel as exact int8 digit-slice products on tcgen05 (7 base-254 digits: the dropped part
+ * is below the FP64 rounding of the same sums); GPR_FIT_MODE=fp64 forces the all-FP64 tile Cholesky.  gpr_timings.fit_int8_slices
+ * says which ran.  A matrix that turns out not to be positive definite is always re-factorised (and reported) in FP64. */
 int gpr_fit(gpr_ctx* ctx, const double* x, const double* y, const double* z, const double* label,
             const double* sigma2_or_null, size_t n, gpr_kernel_t kernel, int with_normals, gpr_model** out);
 int gpr_model_destroy(gpr_model* m);

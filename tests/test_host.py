@@ -60,6 +60,20 @@ def test_synthetic_generators(gpr):
     assert len(b) == 3 and b[0][0].shape == (32, 3) and np.all(b[0][2] == 0.05)
 
 
+def test_publish_policy(monkeypatch):
+    """The factor is pushed to the replicas from inside the fit only while that hides in the factorisation time."""
+    import gpr_b200  # noqa: F401  (registers the package alias)
+    from gaussian_object_modelling_b200 import distributed as D
+    monkeypatch.delenv("GPR_FIT_PUBLISH", raising=False)
+    assert D.publish_pays(16384, 1) and D.publish_pays(16384, 2)
+    assert not D.publish_pays(16384, 3) and not D.publish_pays(16384, 7)
+    assert D.publish_pays(65536, 7) and not D.publish_pays(3000, 1) and not D.publish_pays(16384, 0)
+    monkeypatch.setenv("GPR_FIT_PUBLISH", "1")
+    assert D.publish_pays(3000, 7)
+    monkeypatch.setenv("GPR_FIT_PUBLISH", "0")
+    assert not D.publish_pays(65536, 1)
+
+
 def test_shard_ranges_cover_queries():
     from gaussian_object_modelling_b200 import distributed as D
     for q in (1, 7, 1000, 256 ** 3):
