@@ -425,9 +425,12 @@ def main():
         assert vmin > 0.0
         full_grid = {"full_grid_s": fg_s, "queries": total_q, "points_per_s": total_q / fg_s, "fit_wall_ms": fg_fit_ms,
                      "broadcast_ms": fg_bc_ms, "points_in_shell_abs_f_le_0.01": shell, "scaling": "strong",
-                     "what": "replica set-up (IPC handles) -> fit on rank 0 publishing L and Dinv into the replicas from inside the "
-                             "Cholesky kernel -> {x|y|z, alpha} broadcast -> mean+variance of ALL 256^3 lattice points "
-                             "(z-slab shards); host wall of the slowest rank"}
+                     "what": ("fit on rank 0" if world == 1 else
+                              "replica set-up (IPC handles) -> fit on rank 0 publishing L and Dinv into the replicas from inside the "
+                              "factorisation -> {x|y|z, alpha} broadcast" if D.publish_pays(N_TRAIN, world - 1) else
+                              "fit on rank 0 -> NCCL broadcast of {x|y|z, alpha, L, Dinv} (publishing %d copies from inside the "
+                              "factorisation would not hide in it: distributed.publish_pays)" % (world - 1))
+                             + " -> mean+variance of ALL 256^3 lattice points (z-slab shards); host wall of the slowest rank"}
         del Qfull, fo_g, vo_g
 
     if rank == 0:
