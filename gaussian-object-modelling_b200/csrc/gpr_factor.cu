@@ -349,7 +349,7 @@ cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int
     const size_t N = (size_t)nb * TB;
     // The last panels have so few row tiles below them that the tile kernel is bound by its dependency chain (~100 us per
     // column) whatever their width: the final `last_tiles` columns are one panel (two INT8 launches and slicing passes fewer).
-    static const int last_tiles = getenv("GPR_FIT_LAST") ? atoi(getenv("GPR_FIT_LAST")) : 48;
+    const int last_tiles = getenv("GPR_FIT_LAST") ? atoi(getenv("GPR_FIT_LAST")) : 48;
     for (int c0 = 0, ncols = 0; c0 < nb; c0 += ncols) {
         ncols = nb - c0 < panel_tiles ? nb - c0 : panel_tiles;
         if (nb - c0 <= last_tiles) ncols = nb - c0;
