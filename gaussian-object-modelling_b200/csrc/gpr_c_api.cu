@@ -410,7 +410,7 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
         ~I8Buf() { if (p) { cudaStreamSynchronize(s); big_free(c, dev, p, bytes); } }
     } i8_buf{ctx, dc->dev, nullptr, 0, st};
     if (want_i8) {
-        i8_buf.bytes = (size_t)i8_S * N * N;
+        i8_buf.bytes = ozaki_fit_workspace_bytes(i8_S, N);
         CU(big_alloc(ctx, dc->dev, (void**)&i8_buf.p, i8_buf.bytes));
         if (!ws->oz_ctrl) CU(cudaMalloc((void**)&ws->oz_ctrl, 4 * sizeof(int)));
     }
@@ -476,11 +476,8 @@ static int fit_from_host(gpr_model* m, bool keep_R) {
         const bool use_i8 = want_i8 && moved == 0 && !i8_failed;
         if (use_i8) {
             signed char* Ls = i8_buf.p;
-            double dmax = m->k0;
-            if (m->has_s2) { double smax = 0.0; for (double v : m->hs2) smax = std::max(smax, v); dmax += smax; }
-            dmax = std::max(dmax, 1.0);                            // padding rows carry a unit diagonal
             cudaError_t ce = launch_cholesky_int8(m->L, N, nb, m->Dinv, m->scratch, dc->num_sms, st, publish ? &ctx->peers : nullptr, Ls,
-                                                  i8_S, dmax, i8_panel, ws->oz_ctrl);
+                                                  i8_S, i8_panel, getenv("GPR_FIT_LAST") ? atoi(getenv("GPR_FIT_LAST")) : 48, ws->oz_ctrl);
             int octl[2] = {0, 0};
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(octl, ws->oz_ctrl, sizeof(octl), cudaMemcpyDeviceToHost, st);
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(info, m->scratch, sizeof(info), cudaMemcpyDeviceToHost, st);
@@ -2446,12 +2443,10 @@ int gpr_selftest_factor(double* hA, int nb, double* h_linv, int serial, long lon
     if (serial >= 100) {
         // INT8-assisted factorisation: serial = 100 * (tile columns per panel) + (digit slices)
         const int P = serial / 100, S = serial % 100;
-        double dmax = 0.0;
-        for (size_t i = 0; i < N; ++i) dmax = std::max(dmax, hA[i * N + i]);
         signed char* Ls; int* ctrl;
-        CU(cudaMalloc((void**)&Ls, (size_t)S * N * N));
+        CU(cudaMalloc((void**)&Ls, ozaki_fit_workspace_bytes(S, N)));
         CU(cudaMalloc((void**)&ctrl, 4 * sizeof(int)));
-        CU(launch_cholesky_int8(A, N, nb, D, scratch, sms, 0, nullptr, Ls, S, dmax, P, ctrl));
+        CU(launch_cholesky_int8(A, N, nb, D, scratch, sms, 0, nullptr, Ls, S, P, 0, ctrl));
         CU(cudaDeviceSynchronize());
         int hc[2];
         CU(cudaMemcpy(hc, ctrl, sizeof hc, cudaMemcpyDeviceToHost));

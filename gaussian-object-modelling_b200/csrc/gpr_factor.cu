@@ -324,37 +324,41 @@ cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scr
     return cudaGetLastError();
 }
 
+size_t ozaki_fit_workspace_bytes(int S, size_t N) { return (size_t)S * N * N + N * sizeof(double); }
+
 // INT8-assisted factorisation.  Left-looking by panels of P tile columns:
 //   for each panel [c0, c0 + P):   A[c0.., panel] -= L[c0.., 0:c0] L[panel, 0:c0]^T      INT8 tensor cores, exact integer products
 //                                  of base-254 digit slices of L, recombined in FP64 (gpr_ozaki.cu MODE 1)
 //                                  panel factorised by chol_tiles_kernel (FP64 tensor pipe; k restricted to the panel)
-//                                  finished panel cut into int8 digit slices (one common power-of-two scale: |L_ik| <= sqrt(K_ii))
-// With S = 7 digits of base 254 the dropped part of every product is below 254^-7 = 1.5e-17 of scale^2 per term — the size
+//                                  finished panel cut into int8 digit slices; row i is scaled by the power of two above
+//                                  sqrt(K_ii), read from the diagonal beforehand (|L_ik| <= sqrt(K_ii) for an SPD matrix: nothing
+//                                  has to be known about L before it exists, and rows of very different size keep all their digits)
+// With S = 7 digits of base 254 the dropped part of every product is below 254^-7 = 1.5e-17 of sqrt(K_ii K_jj) per term — the size
 // of the FP64 rounding of the same sum (1.1e-16 of the partial sums) — so the factor is as accurate as the all-FP64 one,
 // at ~2x the DMMA rate for the (1 - ~1.5 P / nb) share of the flops that lies left of the panels.  Still one producer per
 // tile and integer (order-independent) sums: bit-reproducible.  A non-positive pivot is reported like launch_cholesky does
 // (the later launches of the sequence then leave at once: the abort flag stays up).
 cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, cudaStream_t st,
-                                 const CholPeers* peers, signed char* Ls, int S, double diag_max, int panel_tiles, int* ctrl) {
+                                 const CholPeers* peers, signed char* Ls, int S, int panel_tiles, int last_tiles, int* ctrl) {
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
-    if (panel_tiles < 1 || !(diag_max > 0.0)) return cudaErrorInvalidValue;
+    if (panel_tiles < 1) return cudaErrorInvalidValue;
     e = cudaMemsetAsync(scratch, 0, sizeof(int) * (4 + (size_t)nb * nb), st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(ctrl, 0, 2 * sizeof(int), st);       // [1]: raised by an INT8 update whose barrier wait timed out (sticky)
     if (e != cudaSuccess) return e;
-    int ex = 0;
-    frexp(sqrt(diag_max), &ex);                              // 2^ex > sqrt(max K_ii) >= every |L_ik|
-    const double scale = ldexp(1.0, ex);
     const size_t N = (size_t)nb * TB;
+    double* row_scale = reinterpret_cast<double*>(Ls + (size_t)S * N * N);          // tail of the workspace (8-byte aligned: N % 128 == 0)
+    e = launch_ozaki_diag_scale(A, ld, (int)N, row_scale, st);
+    if (e != cudaSuccess) return e;
     // The last panels have so few row tiles below them that the tile kernel is bound by its dependency chain (~100 us per
-    // column) whatever their width: the final `last_tiles` columns are one panel (two INT8 launches and slicing passes fewer).
-    const int last_tiles = getenv("GPR_FIT_LAST") ? atoi(getenv("GPR_FIT_LAST")) : 48;
+    // column) whatever their width: the final `last_tiles` columns are one panel (two INT8 launches and slicing passes fewer;
+    // the fit passes 48, GPR_FIT_LAST overrides).
     for (int c0 = 0, ncols = 0; c0 < nb; c0 += ncols) {
         ncols = nb - c0 < panel_tiles ? nb - c0 : panel_tiles;
         if (nb - c0 <= last_tiles) ncols = nb - c0;
         const size_t r0 = (size_t)c0 * TB;
-        e = launch_ozaki_syrk_update(Ls, ld, ld * N, S, r0, N, (size_t)ncols * TB, A, ld, scale * scale, ctrl, st);
+        e = launch_ozaki_syrk_update(Ls, ld, ld * N, S, r0, N, (size_t)ncols * TB, A, ld, row_scale, ctrl, st);
         if (e != cudaSuccess) return e;
         CholArgs a;
         a.A = A + r0 * ld + r0; a.ld = ld; a.nb = nb - c0; a.Dinv = Dinv + (size_t)c0 * TB * TB; a.trace = nullptr;
@@ -376,7 +380,7 @@ cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (c0 + ncols < nb) {
-            e = launch_ozaki_slice_lpanel(A, ld, r0, N, (size_t)ncols * TB, 1.0 / scale, S, Ls, ld, ld * N, st);
+            e = launch_ozaki_slice_lpanel(A, ld, r0, N, (size_t)ncols * TB, row_scale, S, Ls, ld, ld * N, st);
             if (e != cudaSuccess) return e;
         }
     }

@@ -296,7 +296,8 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int rt, qt;
             if (!decode(task, it & 1, rt, qt)) continue;
             const int row = rt * OZ_BM + q4 * 32 + lane;
-            const double rs = MODE == 1 ? a.col_scale : a.row_scale[row] * a.col_scale;
+            // MODE 1: both operands carry per-row power-of-two scales (row_scale indexed from the panel's first row)
+            const double rs = MODE == 1 ? a.row_scale[row] : a.row_scale[row] * a.col_scale;
             if constexpr (!CHUNKED) {
                 if (!mbar_wait(&accum_full, tcount & 1)) { ok = false; break; }
                 ++tcount;
@@ -340,10 +341,11 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int nkb = a.tri ? 2 * (rt + 1) : a.kblocks;
                 double vacc[OZ_BN];
                 double* crow = MODE == 1 ? a.C + (size_t)qt * OZ_BN * a.ldc + row : nullptr;
+                const double* cs = MODE == 1 ? a.row_scale + (size_t)qt * OZ_BN : nullptr;      // scales of this tile's columns
                 if constexpr (MODE == 1) {
-                    const double irs = -1.0 / rs;                               // rs is a power of two: exact
+                    const double irs = -1.0 / rs;                               // powers of two: exact
 #pragma unroll
-                    for (int jj = 0; jj < OZ_BN; ++jj) vacc[jj] = __ldcg(crow + (size_t)jj * a.ldc) * irs;
+                    for (int jj = 0; jj < OZ_BN; ++jj) vacc[jj] = __ldcg(crow + (size_t)jj * a.ldc) * (irs / __ldg(cs + jj));
                 } else {
 #pragma unroll
                     for (int jj = 0; jj < OZ_BN; ++jj) vacc[jj] = 0.0;
@@ -383,7 +385,7 @@ ozaki_var_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (!ok) break;
                 if constexpr (MODE == 1) {
 #pragma unroll
-                    for (int jj = 0; jj < OZ_BN; ++jj) crow[(size_t)jj * a.ldc] = -(vacc[jj] * rs);
+                    for (int jj = 0; jj < OZ_BN; ++jj) crow[(size_t)jj * a.ldc] = -(vacc[jj] * (rs * __ldg(cs + jj)));
                     continue;
                 } else {
 #pragma unroll
@@ -685,22 +687,38 @@ cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q
 }
 
 // ---- INT8-assisted Cholesky (gpr_factor.cu: launch_cholesky_int8) ---------------------------------------------------------
+// Per-row scales of the factor-to-be: row_scale[i] = the power of two above sqrt(K_ii) (|L_ik| <= sqrt(K_ii) for an SPD matrix;
+// 1 for a non-positive diagonal entry — that factorisation fails anyway).  Read from the diagonal BEFORE the factorisation.
+__global__ void oz_diag_scale_kernel(const double* __restrict__ A, size_t ld, int n, double* __restrict__ row_scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = A[(size_t)i * ld + i];
+    int e = 0;
+    if (d > 0.0) frexp(sqrt(d), &e);
+    row_scale[i] = d > 0.0 ? ldexp(1.0, e) : 1.0;
+}
+cudaError_t launch_ozaki_diag_scale(const double* A, size_t ld, int n, double* row_scale, cudaStream_t st) {
+    oz_diag_scale_kernel<<<(n + 255) / 256, 256, 0, st>>>(A, ld, n, row_scale);
+    return cudaGetLastError();
+}
+
 // Slices of a finished panel of L: rows [r0, n_rows) x columns [r0, r0 + width) of the column-major factor A (leading dimension
 // ld; r0 on the diagonal, so local entries with column > row are structural zeros and are WRITTEN as zeros) into
-// Ls[t][row][k] (k pitch `pitch`, slice pitch `slice`), one common power-of-two scale (|L_ik| <= sqrt(K_ii) <= 1 / inv_scale).
-cudaError_t launch_ozaki_slice_lpanel(const double* A, size_t ld, size_t r0, size_t n_rows, size_t width, double inv_scale, int S,
+// Ls[t][row][k] (k pitch `pitch`, slice pitch `slice`), row i divided by row_scale[i] (launch_ozaki_diag_scale).
+cudaError_t launch_ozaki_slice_lpanel(const double* A, size_t ld, size_t r0, size_t n_rows, size_t width, const double* row_scale, int S,
                                       signed char* Ls, size_t pitch, size_t slice, cudaStream_t st) {
     if (n_rows <= r0 || width == 0) return cudaSuccess;
     const int rows = (int)(n_rows - r0), cols = (int)width;
-    oz_slice_kernel<<<dim3((rows + 63) / 64, (cols + 63) / 64), 256, 0, st>>>(A + r0 * ld + r0, ld, rows, cols, nullptr, inv_scale, 1, S,
+    oz_slice_kernel<<<dim3((rows + 63) / 64, (cols + 63) / 64), 256, 0, st>>>(A + r0 * ld + r0, ld, rows, cols, row_scale + r0, 0.0, 1, S,
                                                                             127.0, 254.0, Ls + r0 * pitch + r0, pitch, slice, 1);
     return cudaGetLastError();
 }
 
-// C[r0.., r0 .. r0 + width) -= scale2 * sum_{k < r0} L[row, k] L[col, k] on the INT8 tensor cores, from the slices of the
-// finished columns k < r0 (base-254 digits): the left-looking update of the next panel.  Only tiles on or below the diagonal.
+// C[r0.., r0 .. r0 + width) -= sum_{k < r0} L[row, k] L[col, k] on the INT8 tensor cores, from the slices of the finished
+// columns k < r0 (base-254 digits of L[i, :] / row_scale[i]): the left-looking update of the next panel.  Only tiles on or
+// below the diagonal.
 cudaError_t launch_ozaki_syrk_update(const signed char* Ls, size_t pitch, size_t slice, int S, size_t r0, size_t n_rows, size_t width,
-                                     double* A, size_t ld, double scale2, int* ctrl, cudaStream_t st) {
+                                     double* A, size_t ld, const double* row_scale, int* ctrl, cudaStream_t st) {
     if (r0 == 0 || n_rows <= r0 || width == 0) return cudaSuccess;
     if (S < 6 || S > 8 || r0 % OZ_BM || n_rows % OZ_BM || width % OZ_BM) return cudaErrorInvalidValue;
     constexpr int BN = 64;
@@ -713,7 +731,7 @@ cudaError_t launch_ozaki_syrk_update(const signed char* Ls, size_t pitch, size_t
     OzArgs a;
     a.S = S; a.levels = S; a.stages = ozaki_stages(S, BN);
     a.nrt = (int)((n_rows - r0) / OZ_BM); a.nqt = (int)(width / BN); a.tri = 0; a.kblocks = (int)(r0 / OZ_BK);
-    a.row_scale = nullptr; a.col_scale = scale2; a.partial = nullptr; a.q_pad = 0; a.ctrl = ctrl; a.dbg = nullptr; a.dbg_ld = 0;
+    a.row_scale = row_scale + r0; a.col_scale = 1.0; a.partial = nullptr; a.q_pad = 0; a.ctrl = ctrl; a.dbg = nullptr; a.dbg_ld = 0;
     a.nzA = nullptr; a.nz_pitch = 0;
     a.C = A + r0 * ld + r0; a.ldc = ld;
     a.kchunk = (int)((ozaki_max_k(S, 1) / OZ_BK) & ~1LL);

@@ -100,6 +100,32 @@ def test_int8_assisted_cholesky_is_as_accurate_as_fp64(gpr, nb, panel, S, nugget
     assert np.array_equal(L8, L8b)                    # integer sums + one producer per tile: bit-reproducible
 
 
+def test_int8_assisted_cholesky_keeps_rows_of_very_different_size_accurate(gpr):
+    """Per-point noise / very different diagonal entries: every row of L is sliced against its own power-of-two scale
+    (above sqrt(K_ii)), so a row 10^6 times smaller than the largest keeps all its digits.  Measured on A = D K D with
+    D = diag(10^u), u in [-3, 3]: the error of L L^T, entry (i, j) relative to d_i d_j, matches the all-FP64 factorisation's
+    (one common scale would lose log2(d_max / d_i) bits in row i)."""
+    n = 128 * 10
+    rng = np.random.default_rng(7)
+    K = _kernel_matrix(n, 21, 1e-4)
+    d = 10.0 ** rng.uniform(-3.0, 3.0, n)
+    A = K * d[:, None] * d[None, :]
+    L64, _, p64 = gpr.selftest_factor(A, False, False)
+    L8, _, p8 = gpr.selftest_factor(A, False, 100 * 3 + 7)
+    assert p64 == 0 and p8 == 0
+    # the 48 smallest rows behind the first panel, L L^T evaluated in extended precision (a float64 product would drown the signal)
+    rows = 384 + np.argsort(d[384:])[:48]
+    Al = A.astype(np.longdouble)
+
+    def scaled(L):
+        Ll = L.astype(np.longdouble)
+        # columns behind the first panel only: entries (i, j < 384) involve nothing but the first panel, which is all-FP64
+        return float(np.abs((Ll[rows] @ Ll[384:].T - Al[rows, 384:]) / (d[rows, None] * d[None, 384:])).max())
+    e64, e8 = scaled(L64), scaled(L8)
+    print("scaled backward error of the smallest rows: fp64 %.3e, int8-assisted %.3e" % (e64, e8))
+    assert e8 <= 3.0 * e64 + 1e-16            # one common scale: ~1e-11 here
+
+
 def test_int8_assisted_cholesky_reports_a_bad_pivot_in_a_later_panel(gpr):
     A = _spd(128 * 8, 5)
     A[700, 700] = -1.0
