@@ -42,7 +42,17 @@ for case in range(cases):
             s2 = np.full(n, 1e-3)                     # noise-free thin-plate at this size is too ill-conditioned for any tolerance
         normals = bool(rng.random() < 0.5)
         reg = g.GPRegressor(kind, p0, p1, ctx=ctx)
-        m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2, with_normals=normals)
+        # the factorisation: the library's own choice (all-FP64 at these sizes) or, for a third of the cases with at least
+        # three tile columns, forced INT8-assisted with panels of 1-2 tile columns (ragged sizes, all kernels, per-point
+        # noise; an indefinite matrix must fall back to the FP64 factorisation and its trailing-block logic)
+        fit_i8 = n > 256 and rng.random() < 0.34
+        if fit_i8:
+            os.environ.update(GPR_FIT_MODE="int8", GPR_FIT_PANEL=str(int(rng.integers(1, 3))), GPR_FIT_LAST="0")
+        try:
+            m = reg.create(P[:, 0], P[:, 1], P[:, 2], y, s2, with_normals=normals)
+        finally:
+            for k_env in ("GPR_FIT_MODE", "GPR_FIT_PANEL", "GPR_FIT_LAST"):
+                os.environ.pop(k_env, None)
         o = oracle.Oracle(P[:, 0], P[:, 1], P[:, 2], y, s2, kind, p0, p1, factor="llt", with_normals=normals)
         indefinite = o.info != 0
         if indefinite:      # e.g. a nearly noise-free thin-plate matrix with a slightly negative eigenvalue: the reference's
@@ -110,8 +120,8 @@ for case in range(cases):
         status = "ok" if worst <= 1.0 else "VIOLATION"
         if worst > 1.0:
             bad.append((seed, {k: round(v, 2) for k, v in errs.items() if v > 1.0}))
-        print("case %3d seed %4d n=%4d %-10s noise=%d normals=%d appends=%s var=%s cond=%.1e tail=%d%s worst=%.3f %s" % (
-            case, seed, n, kind, noise, normals, steps, "".join(modes), cond, m.n_tail, " (indefinite)" if indefinite else "", worst, status), flush=True)
+        print("case %3d seed %4d n=%4d %-10s noise=%d normals=%d fit=%s appends=%s var=%s cond=%.1e tail=%d%s worst=%.3f %s" % (
+            case, seed, n, kind, noise, normals, "i8" if fit_i8 else "f64", steps, "".join(modes), cond, m.n_tail, " (indefinite)" if indefinite else "", worst, status), flush=True)
     except Exception as e:     # noqa: BLE001
         bad.append((seed, repr(e)))
         print("case %3d seed %4d EXCEPTION %r" % (case, seed, e), flush=True)
