@@ -324,7 +324,7 @@ cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scr
     return cudaGetLastError();
 }
 
-size_t ozaki_fit_workspace_bytes(int S, size_t N) { return (size_t)S * N * N + N * sizeof(double); }
+size_t ozaki_fit_workspace_bytes(int S, size_t N) { return (size_t)S * N * N + N * sizeof(double) + (N / 128) * (N / 64); }
 
 // INT8-assisted factorisation.  Left-looking by panels of P tile columns:
 //   for each panel [c0, c0 + P):   A[c0.., panel] -= L[c0.., 0:c0] L[panel, 0:c0]^T      INT8 tensor cores, exact integer products
@@ -351,6 +351,11 @@ cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int
     double* row_scale = reinterpret_cast<double*>(Ls + (size_t)S * N * N);          // tail of the workspace (8-byte aligned: N % 128 == 0)
     e = launch_ozaki_diag_scale(A, ld, (int)N, row_scale, st);
     if (e != cudaSuccess) return e;
+    // zero-slice map of the slices (one byte per (128-row tile, 64-k block), bit t = slice t holds a nonzero digit): an entry of L
+    // is small against its row's scale once a few columns have been eliminated, so its leading digits vanish in whole blocks
+    // and the update skips their MMAs
+    unsigned char* nz = reinterpret_cast<unsigned char*>(row_scale + N);
+    const size_t nz_pitch = N / 64;
     // The last panels have so few row tiles below them that the tile kernel is bound by its dependency chain (~100 us per
     // column) whatever their width: the final `last_tiles` columns are one panel (two INT8 launches and slicing passes fewer;
     // the fit passes 48, GPR_FIT_LAST overrides).
@@ -358,7 +363,7 @@ cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int
         ncols = nb - c0 < panel_tiles ? nb - c0 : panel_tiles;
         if (nb - c0 <= last_tiles) ncols = nb - c0;
         const size_t r0 = (size_t)c0 * TB;
-        e = launch_ozaki_syrk_update(Ls, ld, ld * N, S, r0, N, (size_t)ncols * TB, A, ld, row_scale, ctrl, st);
+        e = launch_ozaki_syrk_update(Ls, ld, ld * N, S, r0, N, (size_t)ncols * TB, A, ld, row_scale, ctrl, st, nz, nz_pitch);
         if (e != cudaSuccess) return e;
         CholArgs a;
         a.A = A + r0 * ld + r0; a.ld = ld; a.nb = nb - c0; a.Dinv = Dinv + (size_t)c0 * TB * TB; a.trace = nullptr;
@@ -381,6 +386,9 @@ cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int
         if (e != cudaSuccess) return e;
         if (c0 + ncols < nb) {
             e = launch_ozaki_slice_lpanel(A, ld, r0, N, (size_t)ncols * TB, row_scale, S, Ls, ld, ld * N, st);
+            if (e != cudaSuccess) return e;
+            e = launch_ozaki_mask(Ls + r0 * ld + r0, ld, ld * N, S, (int)((N - r0) / TB), ncols * TB / 64, nz + (r0 / TB) * nz_pitch + r0 / 64,
+                                  nz_pitch, st);
             if (e != cudaSuccess) return e;
         }
     }

@@ -18,7 +18,8 @@ cudaError_t launch_cholesky(double* A, size_t ld, int nb, double* Dinv, int* scr
                             cudaStream_t st, long long* trace = nullptr, const CholPeers* peers = nullptr);
 // The same factorisation with the bulk of the flops on the INT8 tensor cores: panels of `panel_tiles` tile columns are factorised
 // by the FP64 tile kernel, everything to the left of a panel is applied to it beforehand as one sliced-integer product
-// (gpr_ozaki.cu MODE 1).  Ls: S * N * N bytes of slice workspace (N = nb * 128) followed by N doubles (the per-row scales):
+// (gpr_ozaki.cu MODE 1).  Ls: S * N * N bytes of slice workspace (N = nb * 128) followed by N doubles (the per-row scales)
+// and the (N / 128) x (N / 64) byte map of all-zero slice blocks:
 // ozaki_fit_workspace_bytes(S, N); ctrl: 2 ints.  The final last_tiles tile columns are factorised as one panel.
 size_t ozaki_fit_workspace_bytes(int S, size_t N);
 cudaError_t launch_cholesky_int8(double* A, size_t ld, int nb, double* Dinv, int* scratch, int num_sms, cudaStream_t st,
@@ -98,7 +99,8 @@ cudaError_t launch_ozaki_diag_scale(const double* A, size_t ld, int n, double* r
 cudaError_t launch_ozaki_slice_lpanel(const double* A, size_t ld, size_t r0, size_t n_rows, size_t width, const double* row_scale, int S,
                                       signed char* Ls, size_t pitch, size_t slice, cudaStream_t st);
 cudaError_t launch_ozaki_syrk_update(const signed char* Ls, size_t pitch, size_t slice, int S, size_t r0, size_t n_rows, size_t width,
-                                     double* A, size_t ld, const double* row_scale, int* ctrl, cudaStream_t st);
+                                     double* A, size_t ld, const double* row_scale, int* ctrl, cudaStream_t st,
+                                     const unsigned char* nz = nullptr, size_t nz_pitch = 0);
 cudaError_t launch_ozaki_slice_panel(const double* panel, size_t panel_ld, int q, int n_k, double inv_scale, int S, int base254,
                                      signed char* Ks, size_t k_pitch, size_t q_pad, cudaStream_t st);
 // K5 (gpr_append.cu): one slab of k <= 32 appended points at rows [n0, n0+k); ws: append_workspace_doubles(cap).

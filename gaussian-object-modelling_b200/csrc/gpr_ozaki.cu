@@ -717,8 +717,11 @@ cudaError_t launch_ozaki_slice_lpanel(const double* A, size_t ld, size_t r0, siz
 // C[r0.., r0 .. r0 + width) -= sum_{k < r0} L[row, k] L[col, k] on the INT8 tensor cores, from the slices of the finished
 // columns k < r0 (base-254 digits of L[i, :] / row_scale[i]): the left-looking update of the next panel.  Only tiles on or
 // below the diagonal.
+// nz (optional): the zero-slice map of Ls (launch_ozaki_mask: [row tile][64-k block], rows from 0, pitch nz_pitch) — the
+// leading digits of most of L vanish (its entries shrink with the column index while the scale is that of the row).
 cudaError_t launch_ozaki_syrk_update(const signed char* Ls, size_t pitch, size_t slice, int S, size_t r0, size_t n_rows, size_t width,
-                                     double* A, size_t ld, const double* row_scale, int* ctrl, cudaStream_t st) {
+                                     double* A, size_t ld, const double* row_scale, int* ctrl, cudaStream_t st,
+                                     const unsigned char* nz, size_t nz_pitch) {
     if (r0 == 0 || n_rows <= r0 || width == 0) return cudaSuccess;
     if (S < 6 || S > 8 || r0 % OZ_BM || n_rows % OZ_BM || width % OZ_BM) return cudaErrorInvalidValue;
     constexpr int BN = 64;
@@ -732,7 +735,8 @@ cudaError_t launch_ozaki_syrk_update(const signed char* Ls, size_t pitch, size_t
     a.S = S; a.levels = S; a.stages = ozaki_stages(S, BN);
     a.nrt = (int)((n_rows - r0) / OZ_BM); a.nqt = (int)(width / BN); a.tri = 0; a.kblocks = (int)(r0 / OZ_BK);
     a.row_scale = row_scale + r0; a.col_scale = 1.0; a.partial = nullptr; a.q_pad = 0; a.ctrl = ctrl; a.dbg = nullptr; a.dbg_ld = 0;
-    a.nzA = nullptr; a.nz_pitch = 0;
+    static const bool noskip = getenv("GPR_OZ_NOSKIP") && atoi(getenv("GPR_OZ_NOSKIP")) != 0;
+    a.nzA = (nz && !noskip) ? nz + (r0 / OZ_BM) * nz_pitch : nullptr; a.nz_pitch = nz_pitch;
     a.C = A + r0 * ld + r0; a.ldc = ld;
     a.kchunk = (int)((ozaki_max_k(S, 1) / OZ_BK) & ~1LL);
     double w = 1.0 / (127.0 * 127.0);
