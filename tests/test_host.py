@@ -256,3 +256,58 @@ def test_c_abi_pcd_reader(gpr, tmp_path):
         for name in ("mugD", "kettle", "jug"):
             gold = np.load(os.path.join(ROOT, "tests", "golden", name + "_xyz.npy")).astype(np.float64)
             assert np.array_equal(gpr.pcd_read_xyz(os.path.join(res, name + ".pcd")), gold)
+
+
+def test_digit_slicing_scheme_on_the_cpu():
+    """The integer-slicing arithmetic of the INT8 kernels (csrc/gpr_ozaki.cu), emulated with numpy: (i) the rounding
+    without conversion instructions, v + 1.5*2^52 - 1.5*2^52, equals rint(v) and leaves the integer in the low word of
+    the sum; (ii) S base-254 digits reconstruct a scaled value to 0.5 / (127 * 254^(S-1)); (iii) a left-looking Cholesky
+    whose updates use the sliced factor (7 digits, per-row power-of-two scales, levels t + u < 7 only, exact integer
+    products) is as accurate as the plain float64 one — the scheme of launch_cholesky_int8 at a size numpy handles."""
+    rng = np.random.default_rng(11)
+    v = np.concatenate([rng.uniform(-127.5, 127.5, 4000), np.arange(-127, 128) + 0.5, np.arange(-127, 128) - 0.5])
+    MAGIC = 6755399441055744.0
+    m = v + MAGIC
+    assert np.array_equal(m - MAGIC, np.rint(v))
+    low = (m.view(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.int32)
+    assert np.array_equal(low.astype(np.float64), np.rint(v))
+
+    def digits(x, S, base=254.0):                       # x in [-1, 1]
+        r, out = x * (base / 2.0), []
+        for _ in range(S):
+            it = np.rint(r)
+            out.append(it.astype(np.int64))
+            r = (r - it) * base
+        return out
+
+    x = rng.uniform(-1.0, 1.0, 2000)
+    for S in (6, 7):
+        d = digits(x, S)
+        assert max(int(np.abs(t).max()) for t in d) <= 127
+        rec = sum(t.astype(np.longdouble) / (np.longdouble(127.0) * np.longdouble(254.0) ** i) for i, t in enumerate(d))
+        assert float(np.abs(rec - x.astype(np.longdouble)).max()) <= 0.5 / (127.0 * 254.0 ** (S - 1)) + 3e-16   # + the rounding of the digit recursion itself
+
+    n, P, S = 192, 48, 7
+    pts = rng.random((n, 3))
+    K = np.exp(-((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1) / 0.5) + 1e-5 * np.eye(n)
+    dscale = 10.0 ** rng.uniform(-2.0, 2.0, n)
+    A = K * dscale[:, None] * dscale[None, :]
+    s = 2.0 ** (np.floor(np.log2(np.sqrt(A.diagonal()))) + 1)          # power of two above sqrt(K_ii)
+    L = np.zeros((n, n))
+    W = A.copy()
+    for c0 in range(0, n, P):
+        c1 = min(n, c0 + P)
+        if c0:
+            D = digits(L[c0:, :c0] / s[c0:, None], S)                  # slices of the finished columns, rows from c0 on
+            upd = np.zeros((n - c0, c1 - c0))
+            for l in range(S):                                         # levels t + u = l < S, exact int64 products
+                acc = sum(D[t] @ D[l - t][:c1 - c0].T for t in range(l + 1))
+                upd += acc.astype(np.float64) / (127.0 ** 2 * 254.0 ** l)
+            W[c0:, c0:c1] -= upd * s[c0:, None] * s[None, c0:c1]
+        for j in range(c0, c1):                                        # the panel itself in float64, k restricted to the panel
+            W[j, j] = np.sqrt(W[j, j] - L[j, c0:j] @ L[j, c0:j])
+            L[j, j] = W[j, j]
+            L[j + 1:, j] = (W[j + 1:, j] - L[j + 1:, c0:j] @ L[j, c0:j]) / L[j, j]
+    L64 = np.linalg.cholesky(A)
+    err = lambda F: np.abs((F.astype(np.longdouble) @ F.T.astype(np.longdouble) - A) / (dscale[:, None] * dscale[None, :])).max()
+    assert err(L) <= 3.0 * err(L64) + 1e-16
